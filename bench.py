@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the iskra hot path (gather + push + boundary + deposit + MCC
++ rho all-reduce + field solve) on N B200s, with the HBM roofline of the dominant kernel and the
+CPU port timed beside it.  Contract: see the task statement / DESIGN.md "Measurement".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4] [--particles-per-gpu P]
+  python bench.py --impl reference ...      # the reference's CPU algorithm (oracle port) on host cores
+Under torchrun one rank per GPU; rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_PARTICLE_STEP = 88.0   # read x,y,vx,vy,vz,wg + write x,y,vx,vy,vz (FP64)
+METRIC = "particle-steps/sec (push+gather+deposit+MCC)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c4"])
+    ap.add_argument("--particles-per-gpu", type=int, default=None)
+    ap.add_argument("--cells", type=int, default=None)
+    ap.add_argument("--sort-interval", type=int, default=8)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-particles", type=int, default=4_000_000)
+    return ap.parse_args()
+
+
+def workload_defaults(a):
+    if a.workload == "c5":
+        return a.particles_per_gpu or 125_000_000, a.cells or 2048
+    return a.particles_per_gpu or 100_000_000, a.cells or 1024
+
+
+def config_dict(a, ppg, cells, n_gpus, extra=None):
+    names = {"c5": "C5 shard: 2D XY RF discharge + MCC (BASELINE configs[4]), %dx%d grid, %.3g particles per GPU "
+                   "(1e9 over 8 GPUs), index-slice sharding, rho all-reduce, replicated field solve",
+             "c4": "C4: 2D XY two-stream (BASELINE configs[3]), %dx%d grid, %.3g particles per GPU, periodic"}
+    d = {"workload": names[a.workload] % (cells, cells, ppg), "grid_cells": [cells, cells],
+         "particles_per_gpu": ppg, "particles_total": ppg * n_gpus, "sort_interval": a.sort_interval,
+         "l2": "inputs (%.1f GB of particle columns per GPU) are far larger than the 126 MB L2" % (ppg * 52 / 1e9),
+         "parallelism": "particle index slices x%d, fields replicated" % n_gpus}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port (the reference itself is pure Julia and cannot run here)
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(a, cells, n_particles, steps, warmup):
+    """Times the C restatement (OpenMP over all host cores) on a bounded sample of the workload:
+    MCC + gather + push + boundary + deposit on n_particles rows, same grid, same tables.  The field
+    solve is left out: the reference's dense LU cannot exist at this grid size."""
+    from iskra_b200 import datasets
+    from oracle import c_oracle as CO
+    from oracle import pic_oracle as O
+    Lc = CO.lib()
+    cores = Lc.orc_num_threads()
+    rng = np.random.default_rng(0)
+    n_each = n_particles // 2
+    if a.workload == "c5":
+        dh, dt = 6.7 * 0.01 / 128, 1 / (400 * 13.56e6)
+        spec = [("e-", -O.qe, O.me, 30000.0, 0.0), ("He+", O.qe, 3.99 * O.mp, 300.0, 0.0)]
+        bmode = (2, 1)
+    else:
+        w = 2 * math.pi * 9e3 * math.sqrt(2e-6 * 1e24)
+        dh = 5e-3 * O.c0 / w
+        dt = 0.4 * dh / 1e7 / math.sqrt(2.0)
+        spec = [("e-", -O.qe, O.me, 300.0, 1e7), ("He+", O.qe, 4.002602 * O.me / 5.48579903e-04, 300.0, 0.0)]
+        bmode = (1, 1)
+    nx = ny = cells + 1
+    cg = CO.make_grid(nx, ny, dh, dh)
+    sp = []
+    for name, q, m, T, drift in spec:
+        s = CO.CSpecies(int(n_each * 1.1) + 64, q, m, 1.0)
+        v = rng.standard_normal((3, n_each)) * O.thermal_speed(T, m)
+        if drift:
+            v[0, : n_each // 2] += drift
+            v[0, n_each // 2:] -= drift
+        s.set(rng.random(n_each) * cells * dh, rng.random(n_each) * cells * dh, v[0], v[1], v[2])
+        sp.append(s)
+    nn = nx * ny
+    E = (rng.standard_normal(3 * nn) * 10.0)
+    E[2 * nn:] = 0.0
+    mccs = []
+    if a.workload == "c5":
+        tn = 9.64e20 * np.ones(nn)
+        el = datasets.helium_electron()
+        io = datasets.helium_ion()
+        kinds_e = [(0, 0.0), (3, 19.82), (3, 20.61), (4, 24.587)]
+        mccs.append(CO.CMcc(sp[0], [(k, thr, t[:, 0], t[:, 1], sp[1] if k == 4 else None)
+                                    for (k, thr), t in zip(kinds_e, el)], 0.0, 3.99 * O.mp, 300.0, tn))
+        mccs.append(CO.CMcc(sp[1], [(k, 0.0, t[:, 0], t[:, 1], None) for k, t in zip((1, 0), io)],
+                            0.0, 3.99 * O.mp, 300.0, tn))
+    rngc = CO.make_rng(1)
+    u = np.zeros(nn)
+    bm = (C.c_int32 * 2)(*bmode)
+
+    # OpenMP only if it actually helps on this host (shared vCPUs often make it slower): probe once
+    probe = CO.CSpecies(200_064, spec[0][1], spec[0][2], 1.0)
+    pv = rng.standard_normal((3, 200_000)) * 1e5
+    tt = []
+    for fn in (Lc.orc_advance, Lc.orc_advance_mt):
+        probe.set(rng.random(200_000) * cells * dh, rng.random(200_000) * cells * dh, pv[0], pv[1], pv[2])
+        fn(probe.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), (C.c_int32 * 2)(1, 1))
+        t0 = time.perf_counter()
+        fn(probe.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), (C.c_int32 * 2)(1, 1))
+        tt.append(time.perf_counter() - t0)
+    use_mt = cores > 1 and tt[1] < 0.8 * tt[0]
+    adv = Lc.orc_advance_mt if use_mt else Lc.orc_advance
+    dep = Lc.orc_deposit_mt if use_mt else Lc.orc_deposit
+    if not use_mt:
+        cores = 1
+
+    def one_step():
+        cnt = sum(s.np for s in sp)
+        for m in mccs:
+            m.perform(cg, E, dt, rngc, want_nu=False)
+        for s in sp:
+            adv(s.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), bm)
+        for s in sp:
+            dep(C.byref(cg), s.ref(), CO.dp(u))
+        return cnt
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        done += one_step()
+    el_s = time.perf_counter() - t0
+    return {"value": done / el_s, "unit": "particle-steps/s", "cores": int(cores), "kind": "port",
+            "sample": "C oracle (%d thread(s); OpenMP used only when faster on this host): MCC + gather + push + boundary + deposit on %d particles, "
+                      "%dx%d grid, %d steps; field solve excluded (reference dense LU impossible at this size)"
+                      % (cores, n_particles, cells, cells, steps),
+            "seconds": el_s, "steps": steps}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ppg, cells = workload_defaults(a)
+    r = cpu_port_run(a, cells, a.cpu_particles, a.steps, a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "particle-steps/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * r["seconds"] / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(a, ppg, cells, a.gpus, {"cpu_sample_particles": a.cpu_particles}),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.p = device, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for ln in out.splitlines():
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: iskra_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from iskra_b200 import workloads
+
+    ppg, cells = workload_defaults(a)
+    t_build = time.perf_counter()
+    wl = (workloads.build_c5(ppg, cells, n_gpus_total=8, device=local) if a.workload == "c5"
+          else workloads.build_c4(ppg, cells, device=local))
+    rt = wl.rt
+    rt.use_torch_stream()
+    wl.prepare(a.sort_interval)
+    rt.synchronize()
+    build_s = time.perf_counter() - t_build
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    wl.step(a.warmup)
+    rt.synchronize()
+    np_before = wl.n_particles()
+    rt.profile(True)
+    rt.profile_read()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = rt.launch_count()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    wl.step(a.steps)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    l1 = rt.launch_count()
+    adv_ms, adv_launches = rt.profile_read()
+    rt.profile(False)
+    np_after = wl.n_particles()
+    rt.synchronize()
+    psteps_local = 0.5 * (np_before + np_after) * a.steps
+
+    t = torch.tensor([ms, psteps_local, float(l1 - l0)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_max, psteps, launches = tmax[0].item(), tsum[1].item(), tsum[2].item()
+    else:
+        ms_max, psteps, launches = ms, psteps_local, float(l1 - l0)
+    value = psteps / (ms_max * 1e-3)
+
+    # roofline of the dominant kernel (fused advance), this rank
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "kernel": "k_advance_tiled", "peak_source": peak_src}
+    if adv_launches > 0 and adv_ms > 0:
+        per_launch_particles = psteps_local / adv_launches
+        per_launch_s = adv_ms * 1e-3 / adv_launches
+        ach = ALGO_BYTES_PER_PARTICLE_STEP * per_launch_particles / per_launch_s / 1e9
+        roof.update({"achieved": ach, "frac": ach / peak, "avg_launch_ms": 1e3 * per_launch_s,
+                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * per_launch_particles,
+                     "kernel_share_of_step": adv_ms / ms})
+    tr = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(a.workload)
+        except Exception:
+            pass
+
+    # end-to-end through the reference-facing API with HOST buffers
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, wl, torch, dist, world)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cpu = cpu_port_run(a, cells, a.cpu_particles, 3, 1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(a, ppg, cells, world, {"setup_seconds": build_s}),
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(a, wl, torch, dist, world):
+    """Same metric through the host-facing API: species arrays start in PINNED HOST memory; the
+    timed region uploads them (iskb_species_upload), runs K steps -- each with the host->device RF
+    electrode value and a device->host read of the live particle counts (what the reference's
+    iteration() returns every step) -- and downloads the particle state back to the host."""
+    from iskra_b200 import _lib as L
+    rt = wl.rt
+    kin = wl.kinetic()
+    try:
+        bufs = []
+        for s in kin:
+            n = s.np
+            x = torch.empty((2, s.N), dtype=torch.float64, pin_memory=True)
+            v = torch.empty((3, s.N), dtype=torch.float64, pin_memory=True)
+            xn, vn = x.numpy(), v.numpy()
+            L.check(rt.lib.iskb_species_download(s._h, L.ptr(xn), L.ptr(vn), None, None, s.N))
+            n = s.np
+            bufs.append((s, xn, vn, n))
+    except Exception as ex:   # pinned allocation can fail on small hosts
+        return {"value": None, "unit": "particle-steps/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                "note": "pinned host buffers unavailable: %s" % ex}
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for s, xn, vn, n in bufs:
+        L.check(rt.lib.iskb_species_upload(s._h, L.ptr(xn), L.ptr(vn), None, None, n, s.N))
+        h2d += n * 5 * 8
+    psteps = 0
+    for _ in range(a.steps):
+        wl.step(1)
+        h2d += 8
+        cnt = 0
+        for s, _, _, _ in bufs:
+            cnt += s._query_np()
+            d2h += 16
+        psteps += cnt
+    for s, xn, vn, n in bufs:
+        L.check(rt.lib.iskb_species_download(s._h, L.ptr(xn), L.ptr(vn), None, None, s.N))
+        d2h += s.np * 5 * 8
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    t = torch.tensor([el, float(psteps)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        el, psteps = tm[0].item(), ts[1].item()
+    return {"value": psteps / el, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d / a.steps,
+            "d2h_bytes_per_step": d2h / a.steps, "seconds": el,
+            "note": "solve()-style call from pinned host arrays: upload x,v once, %d steps with per-step RF value "
+                    "H2D and live-count D2H, download x,v once; bytes are per-rank averages over the steps" % a.steps}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -1,0 +1,202 @@
+/* iskra_b200 -- C ABI of the B200-native particle hot path of bchaber/iskra.
+ *
+ * This header is the drop-in boundary.  The reference (pure Julia) has no FFI today: the
+ * path sits behind multiple dispatch on generic functions of its ParticleInCell,
+ * FiniteDifferenceMethod, RegularGrids and Chemistry modules.  Every entry point below
+ * names the reference function (file:line under /root/reference) whose work it replaces;
+ * the Julia-side `ccall` methods a maintainer would add are in INTEGRATION.md and
+ * julia/ParticleInCellB200.jl, the Python/ctypes mirror used by the tests is iskra_b200/.
+ *
+ * Conventions
+ *   - plain C, opaque handles, no exceptions cross the boundary; every function returns an
+ *     int32 status (ISKB_OK = 0, errors < 0); iskb_last_error() gives the message.
+ *   - all host arrays are COLUMN-MAJOR exactly as Julia lays them out: x :: N x 2, v :: N x 3
+ *     (kinetic.jl:2-3) with leading dimension `ld` (= the species capacity N for the
+ *     reference's arrays), grid fields nx x ny (x 3) with i fastest.
+ *   - host pointers are only read/written during the call (the library copies); device state
+ *     (particles, rho, phi, E, sigma tables, RNG counters) lives in HBM inside the handles.
+ *   - indices returned to the host are 1-based like the reference's.
+ *   - calls on one context are stream-ordered on the stream given to iskb_set_stream()
+ *     (default: a private non-blocking stream); calls that return host data synchronise.
+ *   - single caller thread per context (the reference loop is single-threaded,
+ *     ParticleInCell.jl:84-139).
+ */
+#ifndef ISKRA_B200_H
+#define ISKRA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct iskb_ctx iskb_ctx;
+typedef struct iskb_species iskb_species;
+typedef struct iskb_mcc iskb_mcc;
+
+/* status codes */
+#define ISKB_OK 0
+#define ISKB_E_INVALID (-1)      /* bad argument / call order */
+#define ISKB_E_CUDA (-2)         /* CUDA runtime error (message has the cudaError string) */
+#define ISKB_E_CAPACITY (-3)     /* species capacity exceeded (reference: BoundsError, mcc.jl:195-197, TODO:2) */
+#define ISKB_E_PMAX (-4)         /* max_Pt > 1/N            (reference: @assert, mcc.jl:244-246) */
+#define ISKB_E_PK (-5)           /* P_k > 1                 (reference: @assert, mcc.jl:273-279) */
+#define ISKB_E_OOB (-6)          /* live particle outside the grid at gather/deposit (reference: BoundsError) */
+#define ISKB_E_NCCL (-7)         /* NCCL missing or failed */
+#define ISKB_E_UNSUPPORTED (-8)  /* configuration outside the implemented scope */
+#define ISKB_E_SINGULAR (-9)     /* dense Poisson operator is singular */
+
+/* boundary handling per axis after the push (ParticleInCell/src/pic/surfaces/wrap.jl) */
+#define ISKB_BND_NONE 0
+#define ISKB_BND_WRAP 1          /* wrap!    wrap.jl:20-33 */
+#define ISKB_BND_DISCARD 2       /* discard! wrap.jl:1-18  */
+
+/* grid edge kinds, order left,right,bottom,top (RegularGrids.jl:11,55-57) */
+#define ISKB_BC_OPEN 0
+#define ISKB_BC_PERIODIC 1
+
+/* edges for iskb_poisson_apply_dirichlet_edge */
+#define ISKB_EDGE_LEFT 0         /* i = 1  */
+#define ISKB_EDGE_RIGHT 1        /* i = nx */
+#define ISKB_EDGE_BOTTOM 2       /* j = 1  */
+#define ISKB_EDGE_TOP 3          /* j = ny */
+
+/* collision kinds (Chemistry/src/mcc.jl:4-8) */
+#define ISKB_MCC_ELASTIC_ISOTROPIC 0
+#define ISKB_MCC_ELASTIC_BACKWARD 1
+#define ISKB_MCC_INELASTIC_BACKWARD 2
+#define ISKB_MCC_EXCITATION 3
+#define ISKB_MCC_IONIZATION 4
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+int32_t iskb_version(void);
+const char *iskb_last_error(void);
+/* One context per process/GPU; replaces the implicit single address space of
+ * ParticleInCell.solve (ParticleInCell.jl:84-100: phi, rho, E, B = zeros(size(grid)...)). */
+int32_t iskb_create(int32_t device, iskb_ctx **out);
+int32_t iskb_destroy(iskb_ctx *ctx);
+/* Run all work of this context on the caller's CUDA stream (a cudaStream_t); NULL restores
+ * the private stream. */
+int32_t iskb_set_stream(iskb_ctx *ctx, void *cuda_stream);
+int32_t iskb_synchronize(iskb_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int32_t iskb_launch_count(iskb_ctx *ctx, int64_t *out);
+
+/* Time the dominant kernel (fused advance) with CUDA events on the launching stream.
+ * iskb_profile_read synchronises, returns the accumulated milliseconds and launch count since the
+ * last read, and resets both. */
+int32_t iskb_profile_enable(iskb_ctx *ctx, int32_t on);
+int32_t iskb_profile_read(iskb_ctx *ctx, double *ms_advance, int64_t *launches_advance);
+
+/* ---- multi-GPU: particles sharded by index slice, rho all-reduced --------- */
+/* The reference has no communication layer; this is new.  id128 is an ncclUniqueId. */
+int32_t iskb_comm_unique_id(void *id128);
+int32_t iskb_comm_init(iskb_ctx *ctx, int32_t n_ranks, int32_t rank, const void *id128);
+
+/* ---- grid: create_uniform_grid(xx, yy; left, right, bottom, top)  RegularGrids.jl:55-69 -- */
+/* Also fixes cell_volume(grid) (RegularGrids.jl:26-38) and allocates rho, phi, E in HBM.     */
+int32_t iskb_grid_set(iskb_ctx *ctx, int32_t nx, int32_t ny, double dx, double dy,
+                      double ox, double oy, const int32_t bcs[4]);
+int32_t iskb_cell_volume(iskb_ctx *ctx, double *V_out /* nx*ny */);
+
+/* ---- field solve: FiniteDifferenceMethod/src/generalized_poisson.jl ---------------------- */
+/* create_poisson_solver(grid, eps0)  :27-30 -> :34-68 (5-point operator, all edges open) */
+int32_t iskb_poisson_create(iskb_ctx *ctx, double eps0);
+/* apply_periodic(ps, axis)  :286-324  (axis 1 couples j=1<->ny, axis 2 couples i=1<->nx) */
+int32_t iskb_poisson_apply_periodic(iskb_ctx *ctx, int32_t axis);
+/* apply_dirichlet(ps, nodes::BitArray, phi0)  :205-215 ; mask is nx*ny bytes, column-major */
+int32_t iskb_poisson_apply_dirichlet(iskb_ctx *ctx, const uint8_t *mask, double phi0);
+/* Same for a whole edge without shipping a mask (the per-step RF drive of
+ * problem/11_rf_discharge.jl:95). */
+int32_t iskb_poisson_apply_dirichlet_edge(iskb_ctx *ctx, int32_t edge, double phi0);
+/* Dense matrix exactly as the reference assembles it (debug / parity): A is nn*nn column-major */
+int32_t iskb_poisson_get_dense(iskb_ctx *ctx, double *A_out, double *b_out);
+/* 1 = separable fast solver, 2 = dense inverse; decided from the boundary structure */
+int32_t iskb_poisson_mode(iskb_ctx *ctx, int32_t *mode_out);
+/* phi = calculate_electric_potential(solver, -rho) :372-378 ; E = calculate_electric_field(solver, phi)
+ * :398-410 ; B = calculate_magnetic_field == 0 :412-419 is never materialised.
+ * (ParticleInCell.jl:126-128).  rho -> phi -> E stays in HBM. */
+int32_t iskb_field_solve(iskb_ctx *ctx);
+/* any pointer may be NULL; E is nx*ny*3 column-major (Ez == 0) */
+int32_t iskb_fields_download(iskb_ctx *ctx, double *rho, double *phi, double *E);
+int32_t iskb_fields_upload(iskb_ctx *ctx, const double *rho, const double *phi, const double *E);
+
+/* ---- species: KineticSpecies{2,3}  ParticleInCell/src/pic/kinetic.jl:1-18 ----------------- */
+/* create_kinetic_species(name, N, q, m, weight)  problem/configuration.jl:95-102 */
+int32_t iskb_species_create(iskb_ctx *ctx, int64_t capacity, double q, double m, double w0,
+                            iskb_species **out);
+/* x: np x 2, v: np x 3 with leading dimension ld; wg, id: `capacity` entries or NULL (defaults
+ * ones*w0 and 1..N, kinetic.jl:15-18).  Sets species.np = np. */
+int32_t iskb_species_upload(iskb_species *sp, const double *x, const double *v, const double *wg,
+                            const uint32_t *id, int64_t np, int64_t ld);
+/* Live particles come back in rows 1..np (device order; compare keyed by id); any pointer may
+ * be NULL. */
+int32_t iskb_species_download(iskb_species *sp, double *x, double *v, double *wg, uint32_t *id,
+                              int64_t ld);
+int32_t iskb_species_np(iskb_species *sp, int64_t *np_out);
+/* sample!(src::MaxwellianSource, species, dt)  sources.jl:24-34 with n given: appends n
+ * particles x = rand*wx + dx, v = randn*wv + dv  (device Philox stream, key = seed). */
+int32_t iskb_species_sample_maxwellian(iskb_species *sp, int64_t n, const double wx[2],
+                                       const double dx[2], const double wv[3], const double dv[3],
+                                       uint64_t seed);
+/* iHe.x .= e.x ; iHe.np = e.np   (problem/10_two_streams.jl:66-68); v filled with v_fill */
+int32_t iskb_species_copy_positions(iskb_species *dst, iskb_species *src, const double v_fill[3]);
+/* density field n of the last iskb_density()/iskb_step() (part.n, kinetic.jl:4) */
+int32_t iskb_species_density_download(iskb_species *sp, double *n_out);
+
+/* ---- per-step operators (each usable on its own for parity tests) ------------------------ */
+/* particle_cell(px, p, dh)  ParticleInCell.jl:28-35 : 1-based lower-left node and fractions */
+int32_t iskb_cell_index(iskb_species *sp, int32_t *i_out, int32_t *j_out, double *hx_out,
+                        double *hy_out);
+/* Stable counting (radix) sort of the live particles by cell key; new, enables tiled deposition.
+ * perm_out[k] (0-based) = previous row of the particle now in row k.  Key layout: DESIGN.md. */
+int32_t iskb_sort_by_cell(iskb_species *sp, uint32_t *perm_out);
+/* grid_to_particle(grid, part, (i,j)->E[i,j,:])  cloud_in_cell.jl:20-36 ; out is np x 3, ld = np */
+int32_t iskb_gather(iskb_species *sp, double *partE_out);
+/* push_particles!(::BorisPusher{:xy}, part, E, B, dt)  pushers.jl:8-11,37-50 with B == 0.
+ * partE (np x 3, ld = np) may be NULL: then E is gathered on the fly from the context's field. */
+int32_t iskb_push(iskb_species *sp, const double *partE, double dt);
+/* discard!(part, grid; dims) then wrap!(part, grid; dims)  wrap.jl:1-33 ; mode per axis */
+int32_t iskb_boundary(iskb_species *sp, int32_t mode_x, int32_t mode_y, int64_t *n_removed);
+/* density(species, grid) = particle_to_grid(species, grid, p->wg[p]) ./ cell_volume(grid)
+ * kinetic.jl:53, cloud_in_cell.jl:1-18.  n_out (nx*ny) may be NULL. */
+int32_t iskb_density(iskb_species *sp, double *n_out);
+/* fill!(rho, 0) ; rho .+= part.n .* part.q  ParticleInCell.jl:118-121 */
+int32_t iskb_rho_zero(iskb_ctx *ctx);
+int32_t iskb_rho_accumulate(iskb_ctx *ctx, iskb_species *sp);
+/* sum of rho over ranks (no-op for one rank) */
+int32_t iskb_rho_allreduce(iskb_ctx *ctx);
+
+/* ---- fused fast path: the loop body of ParticleInCell.solve  ParticleInCell.jl:102-135 ---- */
+/* after_push hook (ParticleInCell.jl:41; problem scripts override it), applied to every species */
+int32_t iskb_set_after_push(iskb_ctx *ctx, int32_t mode_x, int32_t mode_y);
+/* re-sort every `interval` steps (0 = never) */
+int32_t iskb_set_sort_interval(iskb_ctx *ctx, int32_t interval);
+/* n_steps iterations of: MCC (registered interactions, in order) -> advance! every species
+ * (gather, push, after_push) -> density / rho -> all-reduce -> phi -> E. */
+int32_t iskb_step(iskb_ctx *ctx, double dt, int32_t n_steps);
+
+/* ---- MCC: Chemistry/src/mcc.jl ----------------------------------------------------------- */
+/* mcc(reactions) -> MonteCarloCollisions(collisions)  mcc.jl:313-320, :27-51.
+ * One source species colliding with one fluid target (accept, :291-311).  Process k has
+ * kind[k], threshold[k] (eV) and a CrossSection table (cross_section.jl:3-14) of table_len[k]
+ * rows stored back to back in eps[] / sigma[].  ion_product[k] is the product species != source
+ * of an ionisation (or NULL).  target_n is the fluid density on the nodes (nx*ny). */
+int32_t iskb_mcc_create(iskb_ctx *ctx, iskb_species *source, double target_q, double target_m,
+                        double target_T, const double *target_n, int32_t n_proc,
+                        const int32_t *kind, const double *threshold, const int32_t *table_len,
+                        const double *eps, const double *sigma, iskb_species *const *ion_product,
+                        uint64_t seed, iskb_mcc **out);
+/* mcc.max_sigma_g and mcc.m  (mcc.jl:20-21) */
+int32_t iskb_mcc_constants(iskb_mcc *mcc, double *max_sigma_g, double *m_eV);
+/* PIC.perform!(mcc, E, dt, config)  mcc.jl:231-289.  nu_out: nx*ny*N collision counters of
+ * this call (may be NULL).  Per-particle Philox null-collision test, see DESIGN.md (H7). */
+int32_t iskb_mcc_perform(iskb_mcc *mcc, double dt, double *nu_out, int64_t *n_candidates,
+                         int64_t *n_collisions);
+/* totals accumulated by iskb_step since creation: [candidates, collisions, per-process...] */
+int32_t iskb_mcc_totals(iskb_mcc *mcc, int64_t *out /* 2 + N */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISKRA_B200_H */

@@ -1,0 +1,199 @@
+"""Host mirror of the Chemistry module API for the MCC path (Chemistry/src/{mcc,cross_section,
+reactions}.jl).  Set-up stays on the host (as it stays Julia in the reference); perform! runs on
+the device."""
+import ctypes as C
+import re
+
+import numpy as np
+
+from . import _lib as L
+from .particle_in_cell import is_fluid
+
+
+class CrossSection:
+    """CrossSection(nodes)  cross_section.jl:3-14: sigma(eps) table, piecewise linear, Flat() outside."""
+
+    def __init__(self, nodes, ys=None):
+        if ys is not None:
+            nodes = np.stack([np.asarray(nodes, dtype=np.float64), np.asarray(ys, dtype=np.float64)], axis=1)
+        self.nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        if self.nodes.ndim != 2 or self.nodes.shape[1] != 2 or len(self.nodes) < 2:
+            raise ValueError("CrossSection needs an (n>=2, 2) table")
+
+    def __call__(self, x):
+        xs, ys = self.nodes[:, 0], self.nodes[:, 1]
+        return np.interp(x, xs, ys)          # host convenience only; the device evaluates its own copy
+
+    def maximum(self):
+        return float(self.nodes[:, 1].max())
+
+
+class MCC:
+    """collision type tags  mcc.jl:4-8"""
+
+    class ElasticIsotropic:
+        kind, energy = L.MCC_ELASTIC_ISOTROPIC, 0.0
+
+    class ElasticBackward:
+        kind, energy = L.MCC_ELASTIC_BACKWARD, 0.0
+
+    class InelasticBackward:
+        kind, energy = L.MCC_INELASTIC_BACKWARD, 0.0
+
+    class Excitation:
+        kind = L.MCC_EXCITATION
+
+        def __init__(self, energy):
+            self.energy = float(energy)
+
+    class Ionization:
+        kind = L.MCC_IONIZATION
+
+        def __init__(self, energy):
+            self.energy = float(energy)
+
+
+class ChemicalReaction:
+    """ChemicalReaction  reactions.jl:7-12"""
+
+    def __init__(self, type_, rate, reactants, stoichiometry):
+        self.type, self.rate, self.reactants, self.stoichiometry = type_, rate, reactants, stoichiometry
+
+
+def reactions(entries, species):
+    """Python stand-in for the @reactions macro (reactions.jl:3-101).
+
+    entries: iterable of (rate, "a + b --> c + d", type-or-None); species: name -> object, in the
+    order they first appear in the block (the macro's OrderedDict `mapping`, reactions.jl:16)."""
+    out = []
+    mapping = []
+    for entry in entries:
+        rate, eqn = entry[0], entry[1]
+        type_ = entry[2] if len(entry) > 2 else None
+        lhs, rhs = re.split(r"-->|->", eqn)
+        reacs, prods = {}, {}
+        for side, d in ((lhs, reacs), (rhs, prods)):
+            for tok in side.split("+"):
+                tok = tok.strip()
+                if not tok:
+                    continue
+                mm = re.match(r"^(\d+)\s*\*?\s*(\w+)$", tok)
+                coeff, name = (int(mm.group(1)), mm.group(2)) if mm else (1, tok)
+                if name not in mapping:
+                    mapping.append(name)
+                d[name] = d.get(name, 0) + coeff
+        reactants, stoich = [], []
+        for name in mapping:                                     # reactions.jl:39-51
+            P, R = prods.get(name, 0), reacs.get(name, 0)
+            if name in reacs:
+                reactants.append((species[name], R))
+            if P - R != 0:
+                stoich.append((species[name], P - R))
+        out.append(ChemicalReaction(type_, rate, reactants, stoich))
+    return out
+
+
+class Collision:
+    """MCC.Collision{T}  mcc.jl:9-15"""
+
+    def __init__(self, type_, rate, source, target, products):
+        self.type, self.rate, self.source, self.target, self.products = type_, rate, source, target, products
+
+
+def accept(reaction):
+    """accept(reaction)  mcc.jl:291-311"""
+    source = target = None
+    if len(reaction.reactants) != 2:
+        raise AssertionError("Monte Carlo Collisions support only two reacting species: one fluid and one kinetic")
+    for r, _ in reaction.reactants:
+        if is_fluid(r):
+            target = r
+        else:
+            source = r
+    products = [p for p, c in reaction.stoichiometry if c > 0]
+    if source is None:
+        raise ValueError("Reaction without particle species")
+    if target is None:
+        raise ValueError("Reaction without fluid species")
+    type_ = reaction.type if reaction.type is not None else MCC.ElasticIsotropic()
+    return Collision(type_, reaction.rate, source, target, products)
+
+
+class MonteCarloCollisions:
+    """MonteCarloCollisions  mcc.jl:18-51 -- tables and constants are built by the device library."""
+
+    def __init__(self, collisions, seed=0):
+        self.collisions = collisions
+        self.seed = int(seed)
+        self._h = None
+        self._rt = None
+        self.max_sigma_g = None
+        self.m = None
+
+    def _bind(self, config):
+        if self._h is not None:
+            return
+        grid = config.grid
+        rt = grid._rt
+        first = self.collisions[0]
+        source, target = first.source, first.target
+        source._push(grid)
+        N = len(self.collisions)
+        kinds = np.array([c.type.kind for c in self.collisions], dtype=np.int32)
+        thr = np.array([c.type.energy for c in self.collisions], dtype=np.float64)
+        lens = np.array([len(c.rate.nodes) for c in self.collisions], dtype=np.int32)
+        eps = np.ascontiguousarray(np.concatenate([c.rate.nodes[:, 0] for c in self.collisions]))
+        sig = np.ascontiguousarray(np.concatenate([c.rate.nodes[:, 1] for c in self.collisions]))
+        prods = (L.vp * N)()
+        for k, c in enumerate(self.collisions):
+            prods[k] = None
+            if c.type.kind == L.MCC_IONIZATION:
+                for p in c.products:                                 # mcc.jl:201-204
+                    if p is not source:
+                        p._push(grid)
+                        prods[k] = p._h
+        tn = np.asfortranarray(target.n, dtype=np.float64)
+        if tn.shape != tuple(grid.n):
+            raise ValueError("target density must live on the grid nodes %s" % (grid.n,))
+        h = L.vp()
+        L.check(rt.lib.iskb_mcc_create(rt.h, source._h, target.q, target.m, target.T, L.ptr(tn), N, L.ptr(kinds),
+                                       L.ptr(thr), L.ptr(lens), L.ptr(eps), L.ptr(sig), prods, self.seed,
+                                       C.byref(h)))
+        self._h, self._rt = h, rt
+        a, b = L.f64(), L.f64()
+        L.check(rt.lib.iskb_mcc_constants(h, C.byref(a), C.byref(b)))
+        self.max_sigma_g, self.m = a.value, b.value
+
+    def perform_(self, E, dt, config, want_nu=True):
+        """PIC.perform!(mcc, E, dt, config)  mcc.jl:231-289 -> (nu, n_candidates, n_collisions)."""
+        self._bind(config)
+        grid = config.grid
+        if E is not None:
+            grid._rt.set_fields(E=E)
+        source = self.collisions[0].source
+        source._push(grid)
+        for c in self.collisions:
+            for p in c.products:
+                if not is_fluid(p):
+                    p._push(grid)
+        nx, ny = grid.n
+        N = len(self.collisions)
+        nu = np.zeros((nx, ny, N), order="F") if want_nu else None
+        nc, ncoll = L.i64(), L.i64()
+        L.check(self._rt.lib.iskb_mcc_perform(self._h, float(dt), L.ptr(nu), C.byref(nc), C.byref(ncoll)))
+        source._touched_on_device()
+        for c in self.collisions:
+            for p in c.products:
+                if not is_fluid(p):
+                    p._touched_on_device()
+        return nu, nc.value, ncoll.value
+
+    def totals(self):
+        out = np.zeros(2 + len(self.collisions), dtype=np.int64)
+        L.check(self._rt.lib.iskb_mcc_totals(self._h, L.ptr(out)))
+        return out
+
+
+def mcc(reaction_list, seed=0):
+    """mcc(reactions)  mcc.jl:313-320"""
+    return MonteCarloCollisions([accept(r) for r in reaction_list], seed=seed)

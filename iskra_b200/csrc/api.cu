@@ -1,0 +1,485 @@
+// C-ABI entry points: context, grid, fields, species storage, and the fused step.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "pic_device.cuh"
+
+int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit, bool from_begin);
+int32_t launch_advance_tiled(iskb_species *sp, double dt, int mode_x, int mode_y);
+
+// ---- errors -------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void iskb_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int32_t iskb_fail(int32_t code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char *iskb_last_error(void) { return g_err; }
+extern "C" int32_t iskb_version(void) { return 100; }
+// test hook: the Philox4x32-10 block function on the host (known-answer tests run without a GPU)
+extern "C" void iskb_debug_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const Philox4 o = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  for (int k = 0; k < 4; ++k) out[k] = o.c[k];
+}
+
+// ---- small kernels ------------------------------------------------------------------------------
+namespace {
+constexpr int TPB = 256;
+
+__global__ void k_cell_volume(int nx, int ny, double dx, double dy, int b0, int b1, int b2, int b3, double *V) {
+  const int64_t nn = (int64_t)nx * ny;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(n % nx), j = (int)(n / nx);
+    double v = 0.0 + dx * dy;                         // RegularGrids.jl:29-30
+    if (b0 != ISKB_BC_PERIODIC && i == 0) v *= 0.5;   // :33
+    if (b1 != ISKB_BC_PERIODIC && i == nx - 1) v *= 0.5;
+    if (b2 != ISKB_BC_PERIODIC && j == 0) v *= 0.5;
+    if (b3 != ISKB_BC_PERIODIC && j == ny - 1) v *= 0.5;
+    V[n] = v;
+  }
+}
+
+__global__ void k_init_species(double *wg, uint32_t *id, int64_t cap, double w0) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < cap;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    wg[p] = w0;                 // ones(N) * weight, configuration.jl:99
+    id[p] = (uint32_t)(p + 1);  // particle_uuids, kinetic.jl:15
+  }
+}
+
+__global__ void k_E_interleave(const double *__restrict__ E, int64_t nn, double2 *E2) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn;
+       n += (int64_t)gridDim.x * blockDim.x)
+    E2[n] = make_double2(E[n], E[n + nn]);
+}
+__global__ void k_E_split(const double2 *__restrict__ E2, int64_t nn, double *E) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    const double2 e = E2[n];
+    E[n] = e.x;
+    E[n + nn] = e.y;
+    E[n + 2 * nn] = 0.0;
+  }
+}
+
+// sample!(MaxwellianSource)  sources.jl:31-32 : x = rand*wx + dx ; v = randn*wv + dv
+__global__ void k_sample(double *x, double *y, double *vx, double *vy, double *vz, int64_t first, int64_t n,
+                         double wx0, double wx1, double dx0, double dx1, double wv0, double wv1, double wv2,
+                         double dv0, double dv1, double dv2, uint32_t k0, uint32_t k1, uint32_t call) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const Philox4 a = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), call, 0u, k0, k1);
+    const Philox4 b = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), call, 1u, k0, k1);
+    const Philox4 c = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), call, 2u, k0, k1);
+    const int64_t p = first + t;
+    x[p] = __dadd_rn(__dmul_rn(u01_53(a.c[0], a.c[1]), wx0), dx0);
+    y[p] = __dadd_rn(__dmul_rn(u01_53(a.c[2], a.c[3]), wx1), dx1);
+    const double r0 = sqrt(-2.0 * log(u01_open(b.c[0], b.c[1])));
+    const double r1 = sqrt(-2.0 * log(u01_open(c.c[0], c.c[1])));
+    double s0, c0, s1, c1;
+    sincospi(2.0 * u01_53(b.c[2], b.c[3]), &s0, &c0);
+    sincospi(2.0 * u01_53(c.c[2], c.c[3]), &s1, &c1);
+    vx[p] = __dadd_rn(__dmul_rn(r0 * c0, wv0), dv0);
+    vy[p] = __dadd_rn(__dmul_rn(r0 * s0, wv1), dv1);
+    vz[p] = __dadd_rn(__dmul_rn(r1 * c1, wv2), dv2);
+  }
+}
+
+__global__ void k_fill3(double *vx, double *vy, double *vz, int64_t n, double a, double b, double c) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    vx[p] = a; vy[p] = b; vz[p] = c;
+  }
+}
+
+__global__ void k_set_counts(int64_t *cnt, int64_t nslots, int64_t ndead) {
+  cnt[CNT_NSLOTS] = nslots;
+  cnt[CNT_NDEAD] = ndead;
+  cnt[CNT_BEGIN] = nslots;
+}
+
+int blocks_for(const iskb_ctx *c, int64_t n) {
+  int64_t b = (n + TPB - 1) / TPB;
+  if (b > (int64_t)c->n_sm * 8) b = (int64_t)c->n_sm * 8;
+  return b < 1 ? 1 : (int)b;
+}
+}  // namespace
+
+// ---- lifecycle ----------------------------------------------------------------------------------
+extern "C" int32_t iskb_create(int32_t device, iskb_ctx **out) {
+  if (!out) return iskb_fail(ISKB_E_INVALID, "out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return iskb_fail(ISKB_E_CUDA, "no CUDA device available (%s); iskra_b200 has no CPU fallback",
+                     cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return iskb_fail(ISKB_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+  CU_TRY(cudaSetDevice(device));
+  iskb_ctx *c = new iskb_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  c->n_sm = prop.multiProcessorCount;
+  CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  CU_TRY(cudaMalloc(&c->d_status, sizeof(int)));
+  CU_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
+  CU_TRY(cudaMallocHost(&c->h_status, sizeof(int)));
+  CU_TRY(cudaMallocHost(&c->h_scratch, 16 * sizeof(int64_t)));
+  *out = c;
+  return ISKB_OK;
+}
+
+static void free_species(iskb_species *s) {
+  for (int q = 0; q < 6; ++q) { cudaFree(s->col[q]); cudaFree(s->alt[q]); }
+  cudaFree(s->id); cudaFree(s->alt_id); cudaFree(s->d_cnt); cudaFree(s->d_u); cudaFree(s->d_n);
+  for (int k = 0; k < 2; ++k) { cudaFree(s->d_key[k]); cudaFree(s->d_idx[k]); }
+  cudaFree(s->d_hist);
+  delete s;
+}
+
+extern "C" int32_t iskb_destroy(iskb_ctx *c) {
+  if (!c) return ISKB_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  comm_destroy(c);
+  for (iskb_mcc *m : c->mccs) {
+    cudaFree(m->d_tn); cudaFree(m->d_eps); cudaFree(m->d_sig); cudaFree(m->d_stats); cudaFree(m->d_nu);
+    delete m;
+  }
+  for (iskb_species *s : c->species) free_species(s);
+  poisson_free(c);
+  cudaFree(c->d_V); cudaFree(c->d_rho); cudaFree(c->d_phi); cudaFree(c->d_E2); cudaFree(c->d_status);
+  cudaFreeHost(c->h_status); cudaFreeHost(c->h_scratch);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_set_stream(iskb_ctx *c, void *s) {
+  if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_synchronize(iskb_ctx *c) {
+  if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return ctx_check_status(c);
+}
+
+extern "C" int32_t iskb_launch_count(iskb_ctx *c, int64_t *out) {
+  if (!c || !out) return iskb_fail(ISKB_E_INVALID, "null");
+  *out = c->launches;
+  return ISKB_OK;
+}
+
+int32_t prof_begin(iskb_ctx *c) {
+  if (!c->profile) return ISKB_OK;
+  if (c->prof_used + 2 > c->prof_ev.size()) {
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreate(&a));
+    CU_TRY(cudaEventCreate(&b));
+    c->prof_ev.push_back(a);
+    c->prof_ev.push_back(b);
+  }
+  CU_TRY(cudaEventRecord(c->prof_ev[c->prof_used], c->stream));
+  return ISKB_OK;
+}
+int32_t prof_end(iskb_ctx *c) {
+  if (!c->profile) return ISKB_OK;
+  CU_TRY(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->stream));
+  c->prof_used += 2;
+  c->prof_launches++;
+  return ISKB_OK;
+}
+extern "C" int32_t iskb_profile_enable(iskb_ctx *c, int32_t on) {
+  if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  c->profile = on != 0;
+  return ISKB_OK;
+}
+extern "C" int32_t iskb_profile_read(iskb_ctx *c, double *ms, int64_t *launches) {
+  if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  for (size_t k = 0; k + 1 < c->prof_used; k += 2) {
+    float t = 0.f;
+    CU_TRY(cudaEventElapsedTime(&t, c->prof_ev[k], c->prof_ev[k + 1]));
+    c->prof_ms += t;
+  }
+  c->prof_used = 0;
+  if (ms) *ms = c->prof_ms;
+  if (launches) *launches = c->prof_launches;
+  c->prof_ms = 0.0;
+  c->prof_launches = 0;
+  return ISKB_OK;
+}
+
+int32_t ctx_check_status(iskb_ctx *c) {
+  CU_TRY(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  const int st = *c->h_status;
+  if (!st) return ISKB_OK;
+  CU_TRY(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
+  if (st & ISKB_ST_CAPACITY) return iskb_fail(ISKB_E_CAPACITY, "species capacity exceeded while appending particles");
+  if (st & ISKB_ST_PK) return iskb_fail(ISKB_E_PK, "collision probability P_k > 1 (energy outside of the range)");
+  return iskb_fail(ISKB_E_OOB, "a live particle lies outside the grid (reference would raise BoundsError)");
+}
+
+// ---- grid ---------------------------------------------------------------------------------------
+extern "C" int32_t iskb_grid_set(iskb_ctx *c, int32_t nx, int32_t ny, double dx, double dy, double ox, double oy,
+                                 const int32_t bcs[4]) {
+  if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  if (nx < 2 || ny < 2 || !(dx > 0) || !(dy > 0)) return iskb_fail(ISKB_E_INVALID, "grid needs nx, ny >= 2 and dh > 0");
+  if (c->has_grid) return iskb_fail(ISKB_E_INVALID, "grid already set for this context");
+  CU_TRY(cudaSetDevice(c->device));
+  c->g.nx = nx; c->g.ny = ny; c->g.dx = dx; c->g.dy = dy; c->g.ox = ox; c->g.oy = oy;
+  c->g.Lx = (double)(nx - 1) * dx;   // wrap.jl:3-4  Lx = nx*dx with nx = grid.n[i]-1
+  c->g.Ly = (double)(ny - 1) * dy;
+  for (int k = 0; k < 4; ++k) c->bcs[k] = bcs ? bcs[k] : ISKB_BC_OPEN;
+  const int64_t nn = (int64_t)nx * ny;
+  CU_TRY(cudaMalloc(&c->d_V, nn * sizeof(double)));
+  CU_TRY(cudaMalloc(&c->d_rho, nn * sizeof(double)));
+  CU_TRY(cudaMalloc(&c->d_phi, nn * sizeof(double)));
+  CU_TRY(cudaMalloc(&c->d_E2, nn * sizeof(double2)));
+  CU_TRY(cudaMemsetAsync(c->d_rho, 0, nn * sizeof(double), c->stream));   // zeros, ParticleInCell.jl:97-99
+  CU_TRY(cudaMemsetAsync(c->d_phi, 0, nn * sizeof(double), c->stream));
+  CU_TRY(cudaMemsetAsync(c->d_E2, 0, nn * sizeof(double2), c->stream));
+  k_cell_volume<<<blocks_for(c, nn), TPB, 0, c->stream>>>(nx, ny, dx, dy, c->bcs[0], c->bcs[1], c->bcs[2], c->bcs[3], c->d_V);
+  LAUNCH_CHECK(c);
+  c->has_grid = true;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_cell_volume(iskb_ctx *c, double *V_out) {
+  if (!c || !c->has_grid || !V_out) return iskb_fail(ISKB_E_INVALID, "no grid");
+  CU_TRY(cudaMemcpyAsync(V_out, c->d_V, (int64_t)c->g.nx * c->g.ny * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_fields_download(iskb_ctx *c, double *rho, double *phi, double *E) {
+  if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  double *tmp = nullptr;
+  if (rho) CU_TRY(cudaMemcpyAsync(rho, c->d_rho, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (phi) CU_TRY(cudaMemcpyAsync(phi, c->d_phi, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (E) {
+    CU_TRY(cudaMalloc(&tmp, 3 * nn * sizeof(double)));
+    k_E_split<<<blocks_for(c, nn), TPB, 0, c->stream>>>(c->d_E2, nn, tmp);
+    LAUNCH_CHECK(c);
+    CU_TRY(cudaMemcpyAsync(E, tmp, 3 * nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  cudaFree(tmp);
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_fields_upload(iskb_ctx *c, const double *rho, const double *phi, const double *E) {
+  if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  double *tmp = nullptr;
+  if (rho) CU_TRY(cudaMemcpyAsync(c->d_rho, rho, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (phi) CU_TRY(cudaMemcpyAsync(c->d_phi, phi, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (E) {
+    CU_TRY(cudaMalloc(&tmp, 2 * nn * sizeof(double)));
+    CU_TRY(cudaMemcpyAsync(tmp, E, 2 * nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_E_interleave<<<blocks_for(c, nn), TPB, 0, c->stream>>>(tmp, nn, c->d_E2);
+    LAUNCH_CHECK(c);
+  }
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  cudaFree(tmp);
+  return ISKB_OK;
+}
+
+// ---- species ------------------------------------------------------------------------------------
+extern "C" int32_t iskb_species_create(iskb_ctx *c, int64_t capacity, double q, double m, double w0,
+                                       iskb_species **out) {
+  if (!c || !c->has_grid || !out) return iskb_fail(ISKB_E_INVALID, "iskb_grid_set must be called first");
+  if (capacity < 1 || capacity > 0xfffffff0ll) return iskb_fail(ISKB_E_INVALID, "capacity out of range");
+  CU_TRY(cudaSetDevice(c->device));
+  iskb_species *s = new iskb_species();
+  s->ctx = c; s->cap = capacity; s->q = q; s->m = m; s->w0 = w0;
+  for (int k = 0; k < 6; ++k) {
+    CU_TRY(cudaMalloc(&s->col[k], capacity * sizeof(double)));
+    if (k < 5) CU_TRY(cudaMemsetAsync(s->col[k], 0, capacity * sizeof(double), c->stream));   // zeros(N,D), zeros(N,V)
+  }
+  CU_TRY(cudaMalloc(&s->id, capacity * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&s->d_cnt, CNT_N * sizeof(int64_t)));
+  CU_TRY(cudaMemsetAsync(s->d_cnt, 0, CNT_N * sizeof(int64_t), c->stream));
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  CU_TRY(cudaMalloc(&s->d_u, nn * sizeof(double)));
+  CU_TRY(cudaMalloc(&s->d_n, nn * sizeof(double)));
+  CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
+  CU_TRY(cudaMemsetAsync(s->d_n, 0, nn * sizeof(double), c->stream));
+  k_init_species<<<blocks_for(c, capacity), TPB, 0, c->stream>>>(s->col[5], s->id, capacity, w0);
+  LAUNCH_CHECK(c);
+  c->species.push_back(s);
+  *out = s;
+  return ISKB_OK;
+}
+
+int32_t sp_ensure_alt(iskb_species *s) {
+  if (s->alt[0]) return ISKB_OK;
+  for (int k = 0; k < 6; ++k) CU_TRY(cudaMalloc(&s->alt[k], s->cap * sizeof(double)));
+  CU_TRY(cudaMalloc(&s->alt_id, s->cap * sizeof(uint32_t)));
+  return ISKB_OK;
+}
+
+int32_t sp_sync_counts(iskb_species *s) {
+  iskb_ctx *c = s->ctx;
+  if (!s->counts_stale) return ISKB_OK;
+  CU_TRY(cudaMemcpyAsync(c->h_scratch, s->d_cnt, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  s->h_nslots = c->h_scratch[CNT_NSLOTS];
+  s->h_ndead = c->h_scratch[CNT_NDEAD];
+  s->counts_stale = false;
+  return ISKB_OK;
+}
+
+static int32_t set_counts(iskb_species *s, int64_t nslots, int64_t ndead) {
+  iskb_ctx *c = s->ctx;
+  k_set_counts<<<1, 1, 0, c->stream>>>(s->d_cnt, nslots, ndead);
+  LAUNCH_CHECK(c);
+  s->h_nslots = nslots; s->h_ndead = ndead; s->counts_stale = false;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_species_upload(iskb_species *s, const double *x, const double *v, const double *wg,
+                                       const uint32_t *id, int64_t np, int64_t ld) {
+  if (!s) return iskb_fail(ISKB_E_INVALID, "null species");
+  iskb_ctx *c = s->ctx;
+  if (np < 0 || np > s->cap) return iskb_fail(ISKB_E_CAPACITY, "np = %lld exceeds capacity %lld", (long long)np, (long long)s->cap);
+  if (np > 0 && (!x || !v || ld < np)) return iskb_fail(ISKB_E_INVALID, "x, v required with ld >= np");
+  const size_t b = (size_t)np * sizeof(double);
+  if (np > 0) {
+    CU_TRY(cudaMemcpyAsync(s->col[0], x, b, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(s->col[1], x + ld, b, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(s->col[2], v, b, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(s->col[3], v + ld, b, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(s->col[4], v + 2 * ld, b, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (wg) CU_TRY(cudaMemcpyAsync(s->col[5], wg, s->cap * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (id) CU_TRY(cudaMemcpyAsync(s->id, id, s->cap * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  ISKB_TRY(set_counts(s, np, 0));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_species_download(iskb_species *s, double *x, double *v, double *wg, uint32_t *id, int64_t ld) {
+  if (!s) return iskb_fail(ISKB_E_INVALID, "null species");
+  iskb_ctx *c = s->ctx;
+  ISKB_TRY(sp_compact(s));
+  const int64_t np = s->h_nslots;
+  if ((x || v) && ld < np) return iskb_fail(ISKB_E_INVALID, "ld < np");
+  const size_t b = (size_t)np * sizeof(double);
+  if (x && np) {
+    CU_TRY(cudaMemcpyAsync(x, s->col[0], b, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(x + ld, s->col[1], b, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (v && np) {
+    CU_TRY(cudaMemcpyAsync(v, s->col[2], b, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(v + ld, s->col[3], b, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(v + 2 * ld, s->col[4], b, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (wg) CU_TRY(cudaMemcpyAsync(wg, s->col[5], s->cap * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (id) CU_TRY(cudaMemcpyAsync(id, s->id, s->cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return ctx_check_status(c);
+}
+
+extern "C" int32_t iskb_species_np(iskb_species *s, int64_t *np_out) {
+  if (!s || !np_out) return iskb_fail(ISKB_E_INVALID, "null");
+  ISKB_TRY(sp_sync_counts(s));
+  *np_out = s->h_nslots - s->h_ndead;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_species_sample_maxwellian(iskb_species *s, int64_t n, const double wx[2], const double dx[2],
+                                                  const double wv[3], const double dv[3], uint64_t seed) {
+  if (!s || !wx || !wv) return iskb_fail(ISKB_E_INVALID, "null");
+  iskb_ctx *c = s->ctx;
+  ISKB_TRY(sp_compact(s));
+  const int64_t free_rows = s->cap - s->h_nslots;
+  if (n > free_rows) n = free_rows;                      // sources.jl:30  minimum([size(px,1), ...])
+  if (n <= 0) return ISKB_OK;
+  const double z2[2] = {0, 0}, z3[3] = {0, 0, 0};
+  if (!dx) dx = z2;
+  if (!dv) dv = z3;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (0x85EBCA6Bu * (uint32_t)(c->rank + 1));
+  k_sample<<<blocks_for(c, n), TPB, 0, c->stream>>>(s->col[0], s->col[1], s->col[2], s->col[3], s->col[4], s->h_nslots, n,
+                                                   wx[0], wx[1], dx[0], dx[1], wv[0], wv[1], wv[2], dv[0], dv[1], dv[2],
+                                                   k0, k1, (uint32_t)(s->sample_calls++));
+  LAUNCH_CHECK(c);
+  return set_counts(s, s->h_nslots + n, 0);
+}
+
+extern "C" int32_t iskb_species_copy_positions(iskb_species *dst, iskb_species *src, const double v_fill[3]) {
+  if (!dst || !src || dst->ctx != src->ctx) return iskb_fail(ISKB_E_INVALID, "bad species");
+  iskb_ctx *c = dst->ctx;
+  ISKB_TRY(sp_compact(src));
+  const int64_t n = src->h_nslots;
+  if (n > dst->cap) return iskb_fail(ISKB_E_CAPACITY, "destination capacity too small");
+  CU_TRY(cudaMemcpyAsync(dst->col[0], src->col[0], n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(dst->col[1], src->col[1], n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  const double z[3] = {0, 0, 0};
+  if (!v_fill) v_fill = z;
+  if (n) {
+    k_fill3<<<blocks_for(c, n), TPB, 0, c->stream>>>(dst->col[2], dst->col[3], dst->col[4], n, v_fill[0], v_fill[1], v_fill[2]);
+    LAUNCH_CHECK(c);
+  }
+  return set_counts(dst, n, 0);
+}
+
+// ---- fused step: ParticleInCell.jl:102-135 ------------------------------------------------------
+extern "C" int32_t iskb_set_after_push(iskb_ctx *c, int32_t mx, int32_t my) {
+  if (!c || mx < 0 || mx > 2 || my < 0 || my > 2) return iskb_fail(ISKB_E_INVALID, "bad boundary mode");
+  c->after_push[0] = mx; c->after_push[1] = my;
+  return ISKB_OK;
+}
+extern "C" int32_t iskb_set_sort_interval(iskb_ctx *c, int32_t interval) {
+  if (!c || interval < 0) return iskb_fail(ISKB_E_INVALID, "bad interval");
+  c->sort_interval = interval;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_rho_allreduce(iskb_ctx *c) {
+  if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
+  if (c->n_ranks == 1) return ISKB_OK;
+  return comm_allreduce_sum(c, c->d_rho, (int64_t)c->g.nx * c->g.ny);
+}
+
+extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
+  if (!c || !c->has_grid || !c->ps.created) return iskb_fail(ISKB_E_INVALID, "grid and Poisson solver must be set");
+  CU_TRY(cudaSetDevice(c->device));
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  ISKB_TRY(poisson_prepare(c));
+  for (int it = 0; it < n_steps; ++it) {
+    const bool tiled = c->sort_interval > 0;
+    if (tiled && (c->step_count % c->sort_interval) == 0)
+      for (iskb_species *s : c->species) ISKB_TRY(sp_sort(s, nullptr));
+    for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));       // :109-111
+    for (iskb_species *s : c->species) {                                   // :113-115
+      CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
+      if (tiled) ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
+      else ISKB_TRY(launch_advance_simple(s, dt, c->after_push[0], c->after_push[1], true, false));
+    }
+    ISKB_TRY(launch_rho_finalize(c));                                      // :118-124
+    if (c->n_ranks > 1) ISKB_TRY(comm_allreduce_sum(c, c->d_rho, nn));
+    ISKB_TRY(poisson_solve(c));                                            // :126-128
+    c->step_count++;
+  }
+  return ISKB_OK;
+}

@@ -1,0 +1,186 @@
+// iskra_b200 internal declarations shared by the .cu translation units.
+// Device state of the hot path: particle SoA columns, rho/phi/E, the
+// Poisson operator in separable form, sigma tables and RNG counters -- all resident in HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/iskra_b200.h"
+
+// status bits OR-ed by kernels into ctx->d_status
+#define ISKB_ST_OOB 1
+#define ISKB_ST_CAPACITY 2
+#define ISKB_ST_PK 4
+
+void iskb_set_error(const char *fmt, ...);
+int32_t iskb_fail(int32_t code, const char *fmt, ...);
+
+#define CU_TRY(expr)                                                                        \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return iskb_fail(ISKB_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                       __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define ISKB_TRY(expr)            \
+  do {                            \
+    int32_t rc__ = (expr);        \
+    if (rc__ != ISKB_OK) return rc__; \
+  } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                   \
+  do {                                                                                      \
+    (ctx)->launches++;                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                   \
+    if (e__ != cudaSuccess)                                                                 \
+      return iskb_fail(ISKB_E_CUDA, "kernel launch failed: %s (%s:%d)",                     \
+                       cudaGetErrorString(e__), __FILE__, __LINE__);                        \
+  } while (0)
+
+// Grid description passed by value to kernels (RegularGrids.jl:7-15).
+struct GridDev {
+  int nx, ny;          // nodes
+  double dx, dy;       // dh
+  double ox, oy;       // origin (used by wrap!/discard! only, wrap.jl:5,24)
+  double Lx, Ly;       // (n-1)*dh  (wrap.jl:3-4)
+};
+
+// Axis kinds of the separable operator (generalized_poisson.jl:34-68, 205-215, 286-324)
+struct PoissonState {
+  bool created = false;
+  double eps0 = 0.0;
+  bool periodic_i = false;   // apply_periodic(ps, 2): couples i=1 <-> i=nx
+  bool periodic_j = false;   // apply_periodic(ps, 1): couples j=1 <-> j=ny
+  std::vector<uint8_t> isdir;   // host copy: node is Dirichlet
+  std::vector<double> dval;     // host copy: Dirichlet value
+  bool structure_dirty = true;  // operator structure changed -> rebuild solver
+  bool values_dirty = true;     // only Dirichlet values changed -> re-upload dval
+  int mode = 0;                 // 1 separable, 2 dense
+  // device
+  uint8_t *d_isdir = nullptr;
+  double *d_dval = nullptr;
+  // --- separable solver (transform along the contiguous axis of the working layout) ---
+  bool transposed = false;      // working layout is (ny x nx)
+  int na = 0, nb = 0;           // working sizes: transform axis a (contiguous), solve axis b
+  int a0 = 0, ma = 0;           // unknown range along a: [a0, a0+ma)
+  int b0 = 0, mb = 0;           // unknown range along b
+  bool b_cyclic = false;
+  bool singular = false;
+  bool use_fft = false;         // DST-I by FFT (ma+1 power of two)
+  double *d_V = nullptr;        // ma x ma orthonormal eigenvectors (column-major), V[p,k]
+  double *d_Vt = nullptr;       // transpose of V
+  double *d_lam = nullptr;      // ma eigenvalues of the a-axis operator
+  double *d_gam = nullptr;      // Sherman-Morrison gamma per mode
+  double *d_msing = nullptr;    // Thomas factors of the pinned singular mode
+  int singular_mode = -1;
+  double *d_cp = nullptr;       // Thomas c' table  (ma x mb)
+  double *d_q = nullptr;        // Sherman-Morrison q table (ma x mb), cyclic only
+  double *d_qden = nullptr;     // 1/(1 + v.q) per mode
+  double *d_w1 = nullptr, *d_w2 = nullptr, *d_w3 = nullptr;   // work arrays (nx*ny)
+  double2 *d_tw = nullptr;      // FFT twiddles
+  // --- dense solver ---
+  double *d_Ainv = nullptr;
+  int64_t nn_dense = 0;
+};
+
+struct iskb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  int64_t launches = 0;
+  int n_sm = 148;
+  // grid + fields
+  bool has_grid = false;
+  GridDev g{};
+  int bcs[4] = {0, 0, 0, 0};
+  double *d_V = nullptr;      // cell_volume, RegularGrids.jl:26-38
+  double *d_rho = nullptr, *d_phi = nullptr;
+  double2 *d_E2 = nullptr;    // (Ex,Ey) interleaved per node; Ez == 0 is not stored
+  int *d_status = nullptr;
+  int *h_status = nullptr;    // pinned
+  int64_t *h_scratch = nullptr;  // pinned, 16 int64
+  PoissonState ps;
+  std::vector<iskb_species *> species;
+  std::vector<iskb_mcc *> mccs;
+  int after_push[2] = {ISKB_BND_WRAP, ISKB_BND_WRAP};   // default hook wrap!, ParticleInCell.jl:41
+  int sort_interval = 0;
+  int64_t step_count = 0;
+  // optional per-kernel timing of the dominant (advance) kernel, CUDA events on the launch stream
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;     // pairs (start, stop)
+  size_t prof_used = 0;
+  double prof_ms = 0.0;
+  int64_t prof_launches = 0;
+  // comm (NCCL through dlopen, see comm.cu)
+  int n_ranks = 1, rank = 0;
+  void *nccl_comm = nullptr;
+};
+
+// counters living in device memory (kernels read loop bounds from here)
+enum { CNT_NSLOTS = 0, CNT_NDEAD = 1, CNT_BEGIN = 2, CNT_N = 8 };
+
+struct iskb_species {
+  iskb_ctx *ctx = nullptr;
+  int64_t cap = 0;
+  double q = 0, m = 0, w0 = 0;
+  double *col[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // x y vx vy vz wg
+  uint32_t *id = nullptr;
+  double *alt[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // sort ping-pong
+  uint32_t *alt_id = nullptr;
+  int64_t *d_cnt = nullptr;     // CNT_*
+  int64_t h_nslots = 0, h_ndead = 0;   // host mirror, valid when !counts_stale
+  bool counts_stale = false;
+  double *d_u = nullptr;        // deposited weights  (particle_to_grid, cloud_in_cell.jl:1-18)
+  double *d_n = nullptr;        // density n = u ./ V (kinetic.jl:53)
+  // sort scratch
+  uint32_t *d_key[2] = {nullptr, nullptr}, *d_idx[2] = {nullptr, nullptr};
+  uint32_t *d_hist = nullptr;
+  int64_t hist_cap = 0;
+  uint64_t sample_calls = 0;
+};
+
+struct MccProc {
+  int kind;
+  double threshold;
+  int offset, len;      // into the concatenated tables
+  iskb_species *product;
+};
+
+struct iskb_mcc {
+  iskb_ctx *ctx = nullptr;
+  iskb_species *source = nullptr;
+  double tq = 0, tm = 0, tT = 0;
+  int N = 0;
+  std::vector<MccProc> procs;
+  double max_sigma_g = 0, m_eV = 0;
+  double max_n0 = 0;
+  uint64_t seed = 0;
+  uint64_t calls = 0;
+  double *d_tn = nullptr;       // target density on nodes
+  double *d_eps = nullptr, *d_sig = nullptr;
+  void *d_procs = nullptr;      // MccProcDev[N]
+  unsigned long long *d_stats = nullptr;   // [0] candidates, [1] collisions, [2+k] per process
+  float *d_nu = nullptr;        // nx*ny*N counters of the last perform (lazy)
+  int64_t totals[2 + 16] = {0};
+};
+
+// ---- internal entry points across translation units ------------------------------------------
+int32_t sp_sync_counts(iskb_species *sp);
+int32_t sp_compact(iskb_species *sp);
+int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host);
+int32_t sp_ensure_alt(iskb_species *sp);
+int32_t ctx_check_status(iskb_ctx *ctx);
+int32_t poisson_prepare(iskb_ctx *ctx);
+int32_t poisson_solve(iskb_ctx *ctx);
+int32_t poisson_free(iskb_ctx *ctx);
+int32_t mcc_launch(iskb_mcc *mcc, double dt, bool count_nu);
+int32_t comm_allreduce_sum(iskb_ctx *ctx, double *d_buf, int64_t n);
+int32_t comm_destroy(iskb_ctx *ctx);
+int32_t launch_advance(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit,
+                       int64_t first_slot_from_cnt_begin);
+int32_t launch_rho_finalize(iskb_ctx *ctx);
+int32_t prof_begin(iskb_ctx *ctx);
+int32_t prof_end(iskb_ctx *ctx);

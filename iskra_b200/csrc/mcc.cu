@@ -1,0 +1,415 @@
+// Monte-Carlo null-collision step, Chemistry/src/mcc.jl:231-289, on the device.
+//
+// The reference draws Nc = N*max_Pt*np candidates *with replacement* from one sequential
+// MersenneTwister stream (mcc.jl:248-251).  Here every particle row gets its own counter-based
+// Philox4x32-10 stream keyed (seed, rank) with counter (row, call#, draw#): a row is a candidate
+// with probability N*max_Pt, then process selection, acceptance test and kinematics follow the
+// reference line by line.  Per particle and process the collision probability is
+// 1 - exp(-n sigma_k g dt) in both schemes; they differ at second order in P, so
+// parity for this step is statistical by construction.
+//
+// Only the candidate decision touches every row, and it needs no particle data: one Philox call
+// decides four rows.  Candidate rows (a few %) then read x, v and the sigma tables.
+#include <algorithm>
+#include <cmath>
+
+#include "pic_device.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr double QE_MCC = 1.60217646e-19;   // mcc.jl:26
+constexpr double KB_MCC = 1.3806503e-23;    // mcc.jl:75
+
+struct SpDev {
+  double *col[6];
+  int64_t *cnt;
+  int64_t cap;
+};
+
+struct ProcDev {
+  int kind;
+  double threshold;
+  int offset, len;
+  int prod;        // index into MccDev::prod or -1
+  int n_prod;      // round(source.w0 / product.w0)   mcc.jl:205-207
+};
+
+struct MccDev {
+  SpDev src;
+  SpDev prod[4];
+  ProcDev proc[8];
+  int N;
+  const double *eps, *sig, *tn;
+  const double2 *E2;
+  GridDev g;
+  double tqm;        // target.q / target.m            mcc.jl:266
+  double vth_t;      // thermal_speed(target.T, target.m)  mcc.jl:74-77
+  double mr1, mr2;   // mass ratios                    mcc.jl:131-132
+  double m_eV;       // mass(source)                   mcc.jl:26
+  double dt;
+  double p_cand;     // N * max_Pt
+  uint32_t p_cand_u32;
+  uint32_t k0, k1;   // Philox key
+  uint32_t call;
+  unsigned long long *stats;
+  float *nu;         // nullable
+  int *status;
+};
+
+struct Rng {   // per-row stream: counter = (row_lo, row_hi, call, draw)
+  uint32_t r0, r1, call, k0, k1, draw;
+  uint32_t buf[4];
+  int have;
+  __device__ Rng(int64_t row, uint32_t call_, uint32_t k0_, uint32_t k1_, uint32_t first_draw)
+      : r0((uint32_t)row), r1((uint32_t)(row >> 32)), call(call_), k0(k0_), k1(k1_), draw(first_draw), have(0) {}
+  __device__ uint32_t next32() {
+    if (!have) {
+      const Philox4 o = philox4x32_10(r0, r1, call, draw++, k0, k1);
+      buf[0] = o.c[0]; buf[1] = o.c[1]; buf[2] = o.c[2]; buf[3] = o.c[3];
+      have = 4;
+    }
+    return buf[--have];
+  }
+  __device__ double u01() { const uint32_t a = next32(), b = next32(); return u01_53(a, b); }
+  __device__ void randn2(double &z0, double &z1) {   // Box-Muller
+    const uint32_t a = next32(), b = next32(), c = next32(), d = next32();
+    const double r = sqrt(-2.0 * log(u01_open(a, b)));
+    double s, co;
+    sincospi(2.0 * u01_53(c, d), &s, &co);
+    z0 = r * co;
+    z1 = r * s;
+  }
+};
+
+// cross_section.jl:8-14: LinearInterpolation(xs, ys; extrapolation_bc = Flat())
+__device__ double xsec_eval(const double *__restrict__ xs, const double *__restrict__ ys, int n, double x) {
+  if (x <= xs[0]) return ys[0];
+  if (x >= xs[n - 1]) return ys[n - 1];
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (xs[mid] <= x) lo = mid; else hi = mid;
+  }
+  const double f = (x - xs[lo]) / (xs[lo + 1] - xs[lo]);
+  return (1.0 - f) * ys[lo] + f * ys[lo + 1];
+}
+
+__device__ __forceinline__ double norm3(const double *v) { return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+
+// euler_angles :89-106, unrotated :83-87, [sc*ce sc*se cc] * T  (:112, :126)
+__device__ void scatter3(const double *v, double sc, double cc, double se, double ce, double *out) {
+  const double nv = norm3(v);
+  const double ct = v[2] / nv;
+  const double st = sqrt(1.0 - ct * ct);
+  double cp, sp;
+  if (st == 0.0) { cp = 1.0; sp = 0.0; }
+  else { cp = v[0] / nv / st; sp = v[1] / nv / st; }
+  const double r0 = sc * ce, r1 = sc * se, r2 = cc;
+  out[0] = (r0 * (cp * ct) + r1 * (-sp)) + r2 * (cp * st);
+  out[1] = (r0 * (-sp * ct) + r1 * cp) + r2 * (sp * st);
+  out[2] = (r0 * (-st) + r1 * 0.0) + r2 * ct;
+}
+__device__ void isotropic_scattering(const double *v, Rng &g, double *out) {   // :53-62, :108-113
+  double sc, cc, se, ce;
+  sincos(2.0 * M_PI * g.u01(), &sc, &cc);
+  sincos(2.0 * M_PI * g.u01(), &se, &ce);
+  scatter3(v, sc, cc, se, ce, out);
+}
+__device__ void diffuse_reflection(const double *v, Rng &g, double *out) {     // :64-72, :122-127
+  const double sc = sqrt(g.u01());
+  const double cc = -sqrt(1.0 - sc * sc);
+  double se, ce;
+  sincos(2.0 * M_PI * g.u01(), &se, &ce);
+  scatter3(v, sc, cc, se, ce, out);
+}
+
+__device__ bool append_row(const SpDev &s, double x, double y, const double *v, int *status) {
+  const int64_t slot = (int64_t)atomicAdd((unsigned long long *)&s.cnt[CNT_NSLOTS], 1ull);
+  if (slot >= s.cap) {
+    atomicAdd((unsigned long long *)&s.cnt[CNT_NSLOTS], (unsigned long long)(-1ll));
+    atomicOr(status, ISKB_ST_CAPACITY);
+    return false;
+  }
+  s.col[0][slot] = x; s.col[1][slot] = y;
+  s.col[2][slot] = v[0]; s.col[3][slot] = v[1]; s.col[4][slot] = v[2];
+  // wg and id of the slot stay as parked there (kinetic.jl:29-37 "dst has already correct ID")
+  return true;
+}
+
+// perform!(collision, p, ...)  mcc.jl:129-229
+__device__ void collide(const MccDev &m, const ProcDev &pc, int64_t p, Rng &g) {
+  double sv[3] = {m.src.col[2][p], m.src.col[3][p], m.src.col[4][p]};
+  if (pc.kind <= ISKB_MCC_INELASTIC_BACKWARD) {
+    double tv[3], z;
+    g.randn2(tv[0], tv[1]);
+    g.randn2(tv[2], z);
+    double vr[3], w[3], dir[3];
+    for (int k = 0; k < 3; ++k) {
+      tv[k] *= m.vth_t;
+      vr[k] = sv[k] - tv[k];
+      w[k] = m.mr1 * sv[k] + m.mr2 * tv[k];
+    }
+    double mag = norm3(vr);
+    if (pc.kind == ISKB_MCC_ELASTIC_ISOTROPIC) isotropic_scattering(vr, g, dir);
+    else if (pc.kind == ISKB_MCC_ELASTIC_BACKWARD) diffuse_reflection(vr, g, dir);
+    else { mag = g.u01() * mag; diffuse_reflection(vr, g, dir); }
+    for (int k = 0; k < 3; ++k) m.src.col[2 + k][p] = w[k] + m.mr2 * (mag * dir[k]);
+    return;
+  }
+  const double sE = 0.5 * m.m_eV * ((sv[0] * sv[0] + sv[1] * sv[1]) + sv[2] * sv[2]) - pc.threshold;
+  if (sE < 0) return;                                   // :179-182, :220-223
+  if (pc.kind == ISKB_MCC_EXCITATION) {
+    const double ev = sqrt(2.0 / m.m_eV) * sqrt(sE);
+    double dir[3];
+    isotropic_scattering(sv, g, dir);
+    for (int k = 0; k < 3; ++k) m.src.col[2 + k][p] = ev * dir[k];
+    return;
+  }
+  // ionization :184-212
+  const double e1E = sE * g.u01(), e2E = sE - e1E;
+  const double alpha = sqrt(2.0 / m.m_eV), e1v = alpha * sqrt(e1E), e2v = alpha * sqrt(e2E);
+  double d1[3], d2[3];
+  diffuse_reflection(sv, g, d1);
+  for (int k = 0; k < 3; ++k) { sv[k] = e1v * d1[k]; m.src.col[2 + k][p] = sv[k]; }
+  diffuse_reflection(sv, g, d2);
+  const double x = m.src.col[0][p], y = m.src.col[1][p];
+  double nv[3] = {e2v * d2[0], e2v * d2[1], e2v * d2[2]};
+  if (!append_row(m.src, x, y, nv, m.status)) return;
+  double tv[3], z;
+  g.randn2(tv[0], tv[1]);
+  g.randn2(tv[2], z);
+  for (int k = 0; k < 3; ++k) tv[k] *= m.vth_t;
+  if (pc.prod >= 0)
+    for (int c = 0; c < pc.n_prod; ++c)
+      if (!append_row(m.prod[pc.prod], x, y, tv, m.status)) return;
+}
+
+__global__ void k_snapshot_begin(int64_t *cnt) { cnt[CNT_BEGIN] = cnt[CNT_NSLOTS]; }
+
+__global__ void k_mcc(MccDev m) {
+  const int64_t n = m.src.cnt[CNT_BEGIN];   // rows that existed when the step started
+  unsigned long long my_cand = 0, my_coll = 0;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q * 4 < n;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    // one Philox call decides candidacy of rows 4q..4q+3 (counter draw index 0 of row 4q)
+    const Philox4 o = philox4x32_10((uint32_t)(q * 4), (uint32_t)((q * 4) >> 32), m.call, 0u, m.k0, m.k1);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int64_t p = q * 4 + s;
+      if (p >= n || o.c[s] >= m.p_cand_u32) continue;
+      const double px = m.src.col[0][p];
+      if (is_dead(px)) continue;
+      ++my_cand;
+      int i, j;
+      double hx, hy;
+      cell1(px, m.g.dx, i, hx);
+      cell1(m.src.col[1][p], m.g.dy, j, hy);
+      if (!cell_in_grid(i, j, m.g.nx, m.g.ny)) { atomicOr(m.status, ISKB_ST_OOB); continue; }
+      const int64_t node = (int64_t)(i - 1) + (int64_t)(j - 1) * m.g.nx;   // lower-left node :252-253
+      const double dens = m.tn[node];
+      if (dens < 0) continue;                                               // :254-257
+      Rng g(p, m.call, m.k0, m.k1, 1u);
+      const double U = g.u01();                                             // :260
+      int k = (int)floor(m.N * U + 1.0);                                    // :261
+      if (k > m.N) k = m.N;
+      const ProcDev pc = m.proc[k - 1];
+      const double2 e = m.E2[node];
+      double d[3];
+      d[0] = (m.tqm * e.x) * m.dt - m.src.col[2][p];                        // :266-267
+      d[1] = (m.tqm * e.y) * m.dt - m.src.col[3][p];
+      d[2] = (m.tqm * 0.0) * m.dt - m.src.col[4][p];
+      const double gg = norm3(d);
+      const double eps = 0.5 * m.m_eV * (gg * gg);                          // :268
+      const double skg = xsec_eval(m.eps + pc.offset, m.sig + pc.offset, pc.len, eps) * gg;
+      double Pk = 1.0 - exp(-dens * skg * m.dt);                            // :271
+      Pk /= m.p_cand;                                                       // :272  N*max_Pt
+      if (Pk > 1.0) { atomicOr(m.status, ISKB_ST_PK); continue; }           // :273-279
+      if (U > (double)k / m.N - Pk) {                                       // :281
+        collide(m, pc, p, g);
+        ++my_coll;
+        atomicAdd(&m.stats[2 + (k - 1)], 1ull);
+        if (m.nu) atomicAdd(&m.nu[node + (int64_t)(k - 1) * m.g.nx * m.g.ny], 1.0f);   // :283
+      }
+    }
+  }
+  if (my_cand) atomicAdd(&m.stats[0], my_cand);
+  if (my_coll) atomicAdd(&m.stats[1], my_coll);
+}
+
+SpDev spdev(const iskb_species *s) {
+  SpDev d;
+  for (int q = 0; q < 6; ++q) d.col[q] = s->col[q];
+  d.cnt = s->d_cnt;
+  d.cap = s->cap;
+  return d;
+}
+
+double xsec_eval_host(const double *xs, const double *ys, int n, double x) {
+  if (x <= xs[0]) return ys[0];
+  if (x >= xs[n - 1]) return ys[n - 1];
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (xs[mid] <= x) lo = mid; else hi = mid; }
+  const double f = (x - xs[lo]) / (xs[lo + 1] - xs[lo]);
+  return (1.0 - f) * ys[lo] + f * ys[lo + 1];
+}
+
+}  // namespace
+
+int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
+  iskb_ctx *c = mc->ctx;
+  iskb_species *src = mc->source;
+  const int N = mc->N;
+  const double max_Pt = 1.0 - exp(-mc->max_n0 * mc->max_sigma_g * dt);     // mcc.jl:243
+  if (max_Pt > 1.0 / N)
+    return iskb_fail(ISKB_E_PMAX, "Maximum probability (%g) is greater than 1/%d", max_Pt, N);   // :244-246
+  MccDev m;
+  m.src = spdev(src);
+  int nprod = 0;
+  for (int k = 0; k < N; ++k) {
+    const MccProc &p = mc->procs[(size_t)k];
+    ProcDev &d = m.proc[k];
+    d.kind = p.kind; d.threshold = p.threshold; d.offset = p.offset; d.len = p.len;
+    d.prod = -1; d.n_prod = 0;
+    if (p.kind == ISKB_MCC_IONIZATION && p.product && p.product != src) {
+      if (nprod >= 4) return iskb_fail(ISKB_E_UNSUPPORTED, "too many ionisation products");
+      m.prod[nprod] = spdev(p.product);
+      d.prod = nprod++;
+      d.n_prod = (int)std::rint(src->w0 / p.product->w0);                  // :205-207
+      p.product->counts_stale = true;
+    }
+    if (p.kind == ISKB_MCC_IONIZATION) src->counts_stale = true;
+  }
+  m.N = N;
+  m.eps = mc->d_eps; m.sig = mc->d_sig; m.tn = mc->d_tn; m.E2 = c->d_E2; m.g = c->g;
+  m.tqm = mc->tq / mc->tm;
+  m.vth_t = sqrt(2 * KB_MCC * mc->tT / mc->tm);
+  m.mr1 = src->m / (src->m + mc->tm);
+  m.mr2 = mc->tm / (src->m + mc->tm);
+  m.m_eV = mc->m_eV;
+  m.dt = dt;
+  m.p_cand = N * max_Pt;
+  const double pc32 = m.p_cand * 4294967296.0;
+  m.p_cand_u32 = pc32 >= 4294967295.0 ? 0xffffffffu : (uint32_t)pc32;
+  m.k0 = (uint32_t)mc->seed;
+  m.k1 = (uint32_t)(mc->seed >> 32) ^ (0x9E3779B9u * (uint32_t)(c->rank + 1));
+  m.call = (uint32_t)(mc->calls++);
+  m.stats = mc->d_stats;
+  m.status = c->d_status;
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  m.nu = nullptr;
+  if (count_nu) {
+    if (!mc->d_nu) CU_TRY(cudaMalloc(&mc->d_nu, nn * N * sizeof(float)));
+    CU_TRY(cudaMemsetAsync(mc->d_nu, 0, nn * N * sizeof(float), c->stream));
+    m.nu = mc->d_nu;
+  }
+  k_snapshot_begin<<<1, 1, 0, c->stream>>>(src->d_cnt);
+  LAUNCH_CHECK(c);
+  const int64_t bound = src->counts_stale ? src->cap : src->h_nslots;
+  int64_t blocks = (bound / 4 + TPB) / TPB;
+  if (blocks > (int64_t)c->n_sm * 8) blocks = (int64_t)c->n_sm * 8;
+  if (blocks < 1) blocks = 1;
+  k_mcc<<<(int)blocks, TPB, 0, c->stream>>>(m);
+  LAUNCH_CHECK(c);
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_mcc_create(iskb_ctx *c, iskb_species *source, double target_q, double target_m,
+                                   double target_T, const double *target_n, int32_t n_proc, const int32_t *kind,
+                                   const double *threshold, const int32_t *table_len, const double *eps,
+                                   const double *sigma, iskb_species *const *ion_product, uint64_t seed,
+                                   iskb_mcc **out) {
+  if (!c || !c->has_grid || !source || !out || n_proc < 1 || n_proc > 8 || !target_n || !kind || !table_len ||
+      !eps || !sigma)
+    return iskb_fail(ISKB_E_INVALID, "iskb_mcc_create: bad arguments (1..8 processes, grid set first)");
+  iskb_mcc *mc = new iskb_mcc();
+  mc->ctx = c;
+  mc->source = source;
+  mc->tq = target_q; mc->tm = target_m; mc->tT = target_T;
+  mc->N = n_proc;
+  mc->seed = seed;
+  int off = 0;
+  for (int k = 0; k < n_proc; ++k) {
+    if (table_len[k] < 2) { delete mc; return iskb_fail(ISKB_E_INVALID, "cross-section table needs >= 2 rows"); }
+    MccProc p;
+    p.kind = kind[k];
+    p.threshold = threshold ? threshold[k] : 0.0;
+    p.offset = off;
+    p.len = table_len[k];
+    p.product = ion_product ? ion_product[k] : nullptr;
+    mc->procs.push_back(p);
+    off += table_len[k];
+  }
+  // MonteCarloCollisions(collisions)  mcc.jl:27-51
+  mc->m_eV = source->m / QE_MCC;
+  std::vector<double> e(1, 0.0);
+  e.insert(e.end(), eps, eps + off);
+  std::sort(e.begin(), e.end());
+  e.erase(std::unique(e.begin(), e.end()), e.end());
+  const double alpha = sqrt(2.0 / mc->m_eV);
+  double best = -INFINITY;
+  for (double ee : e) {
+    const double v = alpha * sqrt(ee);
+    double sg = 0.0;
+    for (const MccProc &p : mc->procs) sg += xsec_eval_host(eps + p.offset, sigma + p.offset, p.len, ee) * v;
+    best = std::fmax(best, sg);
+  }
+  mc->max_sigma_g = best;
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  mc->max_n0 = -INFINITY;
+  for (int64_t k = 0; k < nn; ++k) mc->max_n0 = std::fmax(mc->max_n0, target_n[k]);   // :242
+  CU_TRY(cudaMalloc(&mc->d_tn, nn * sizeof(double)));
+  CU_TRY(cudaMalloc(&mc->d_eps, off * sizeof(double)));
+  CU_TRY(cudaMalloc(&mc->d_sig, off * sizeof(double)));
+  CU_TRY(cudaMalloc(&mc->d_stats, (2 + 8) * sizeof(unsigned long long)));
+  CU_TRY(cudaMemcpyAsync(mc->d_tn, target_n, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(mc->d_eps, eps, off * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemcpyAsync(mc->d_sig, sigma, off * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaMemsetAsync(mc->d_stats, 0, (2 + 8) * sizeof(unsigned long long), c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  c->mccs.push_back(mc);
+  *out = mc;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_mcc_constants(iskb_mcc *mc, double *max_sigma_g, double *m_eV) {
+  if (!mc) return iskb_fail(ISKB_E_INVALID, "null mcc");
+  if (max_sigma_g) *max_sigma_g = mc->max_sigma_g;
+  if (m_eV) *m_eV = mc->m_eV;
+  return ISKB_OK;
+}
+
+static int32_t read_stats(iskb_mcc *mc, unsigned long long *h) {
+  iskb_ctx *c = mc->ctx;
+  CU_TRY(cudaMemcpyAsync(h, mc->d_stats, (2 + 8) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_mcc_perform(iskb_mcc *mc, double dt, double *nu_out, int64_t *n_candidates,
+                                    int64_t *n_collisions) {
+  if (!mc) return iskb_fail(ISKB_E_INVALID, "null mcc");
+  iskb_ctx *c = mc->ctx;
+  unsigned long long before[10], after[10];
+  ISKB_TRY(read_stats(mc, before));
+  ISKB_TRY(mcc_launch(mc, dt, nu_out != nullptr));
+  ISKB_TRY(read_stats(mc, after));
+  if (n_candidates) *n_candidates = (int64_t)(after[0] - before[0]);
+  if (n_collisions) *n_collisions = (int64_t)(after[1] - before[1]);
+  if (nu_out) {
+    const int64_t tot = (int64_t)c->g.nx * c->g.ny * mc->N;
+    std::vector<float> h((size_t)tot);
+    CU_TRY(cudaMemcpyAsync(h.data(), mc->d_nu, tot * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    for (int64_t k = 0; k < tot; ++k) nu_out[k] = h[(size_t)k];
+  }
+  return ctx_check_status(c);
+}
+
+extern "C" int32_t iskb_mcc_totals(iskb_mcc *mc, int64_t *out) {
+  if (!mc || !out) return iskb_fail(ISKB_E_INVALID, "null");
+  unsigned long long h[10];
+  ISKB_TRY(read_stats(mc, h));
+  for (int k = 0; k < 2 + mc->N; ++k) out[k] = (int64_t)h[k];
+  return ISKB_OK;
+}

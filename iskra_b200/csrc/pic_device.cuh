@@ -1,0 +1,110 @@
+// Per-particle device arithmetic of the hot path.  Every function keeps the reference's
+// operation order and uses the *_rn intrinsics (never contracted into FMAs) so that results
+// are bit-identical to the Julia code / the oracle.
+#pragma once
+#include "common.cuh"
+
+__device__ __forceinline__ bool is_dead(double x) { return x != x; }   // dead slots carry x = NaN
+
+// particle_cell(px, p, dh)  ParticleInCell.jl:28-35:  f = 1 + x/dh ; i = floor(f) ; h = f - i
+__device__ __forceinline__ void cell1(double x, double d, int &i, double &h) {
+  const double f = __dadd_rn(1.0, __ddiv_rn(x, d));
+  const double fl = floor(f);
+  i = (int)fl;
+  h = __dsub_rn(f, fl);
+}
+
+struct CicW {
+  double w00, w10, w01, w11;
+};
+// weights formed first: (1-hx)*(1-hy), hx*(1-hy), (1-hx)*hy, hx*hy  (cloud_in_cell.jl:11-14,29-32)
+__device__ __forceinline__ CicW cic_weights(double hx, double hy) {
+  const double ax = __dsub_rn(1.0, hx), ay = __dsub_rn(1.0, hy);
+  CicW w;
+  w.w00 = __dmul_rn(ax, ay);
+  w.w10 = __dmul_rn(hx, ay);
+  w.w01 = __dmul_rn(ax, hy);
+  w.w11 = __dmul_rn(hx, hy);
+  return w;
+}
+
+// grid_to_particle, cloud_in_cell.jl:29-32: left-to-right sum of weight*value
+__device__ __forceinline__ double cic_gather(const CicW &w, double u00, double u10, double u01,
+                                             double u11) {
+  double s = __dadd_rn(__dmul_rn(w.w00, u00), __dmul_rn(w.w10, u10));
+  s = __dadd_rn(s, __dmul_rn(w.w01, u01));
+  return __dadd_rn(s, __dmul_rn(w.w11, u11));
+}
+
+// push_in_cartesian!  pushers.jl:37-50 with B == 0 (generalized_poisson.jl:412-419):
+//   v- = ((0.5dt)*qm)*E + v ; v+ = v- (+0.0 twice) ; v = ((dt*E)*qm)*0.5 + v+ ; x = dt*v + x
+__device__ __forceinline__ double push_v(double v, double e, double c1, double qm, double dt) {
+  double vm = __dadd_rn(__dmul_rn(c1, e), v);
+  vm = __dadd_rn(vm, 0.0);   // :44 v' = v- + v- x B ; :46 v+ = v- + v' x s   (B = s = 0)
+  return __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(dt, e), qm), 0.5), vm);
+}
+__device__ __forceinline__ double push_x(double x, double v, double dt) {
+  return __dadd_rn(__dmul_rn(dt, v), x);
+}
+
+// Julia Base mod(x, y) for Float64 (float.jl) and fld = round((x - mod(x,y))/y) (div.jl).
+__device__ __forceinline__ double jl_fld(double x, double y) {
+  const double r = fmod(x, y);
+  double md;
+  if (r == 0.0) md = copysign(r, y);
+  else if ((r > 0.0) != (y > 0.0)) md = __dadd_rn(r, y);
+  else md = r;
+  return rint(__ddiv_rn(__dsub_rn(x, md), y));
+}
+
+// One axis of discard!/wrap!  (wrap.jl:1-33).  Returns true when the particle is discarded.
+// Fast path: 0 <= x-o < L  <=>  fld(x-o, L) == 0 (DESIGN.md "boundary fast path").
+__device__ __forceinline__ bool boundary_axis(double &x, double o, double L, int mode) {
+  if (mode == ISKB_BND_NONE) return false;
+  const double xs = __dsub_rn(x, o);
+  if (xs >= 0.0 && xs < L) return false;
+  const double a = jl_fld(xs, L);
+  if (a != 0.0) {
+    if (mode == ISKB_BND_DISCARD) return true;
+    x = __dsub_rn(x, __dmul_rn(a, L));
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool cell_in_grid(int i, int j, int nx, int ny) {
+  return i >= 1 && i <= nx - 1 && j >= 1 && j <= ny - 1;
+}
+
+// ---- Philox4x32-10 counter-based RNG (Salmon et al. 2011), written from the published spec ---
+struct Philox4 {
+  uint32_t c[4];
+};
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                          uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += W0;
+    k1 += W1;
+  }
+  Philox4 o;
+  o.c[0] = c0; o.c[1] = c1; o.c[2] = c2; o.c[3] = c3;
+  return o;
+}
+// uniform in [0,1) with 53 bits (like Julia's rand(Float64) range)
+__host__ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
+  const uint64_t b = (((uint64_t)hi << 32) | lo) >> 11;
+  return (double)b * (1.0 / 9007199254740992.0);
+}
+// uniform in (0,1] for log()
+__host__ __device__ __forceinline__ double u01_open(uint32_t hi, uint32_t lo) {
+  const uint64_t b = (((uint64_t)hi << 32) | lo) >> 11;
+  return ((double)b + 1.0) * (1.0 / 9007199254740992.0);
+}

@@ -1,0 +1,680 @@
+// Device field solve rho -> phi -> E for the reference's 5-point operator
+// (FiniteDifferenceMethod/src/generalized_poisson.jl).  The reference assembles a dense nn x nn
+// matrix and LU-factors it every step (:34-68, :201-203, :372-378); that is 8.8 TB at 1025^2
+// nodes.  The operator is separable whenever the Dirichlet nodes are whole edges:
+//     A = (T_i (x) I + I (x) T_j) / dx^2          (dx == dy required, :65 "TODO")
+// with T = path / ring / Dirichlet-lifted tridiagonals, so we solve it exactly by
+//     (1) an orthonormal eigen-transform along one axis (closed-form sine/cosine bases;
+//         FP64 GEMM, or an FFT-based DST-I when the interior length + 1 is a power of two),
+//     (2) one (cyclic) tridiagonal Thomas solve per mode along the other axis, with the
+//         elimination factors precomputed once per boundary structure,
+//     (3) the inverse transform.
+// Arbitrary Dirichlet masks on small grids fall back to a dense inverse computed once per
+// boundary structure on the host and a device GEMV per step.
+// Fully periodic / all-open operators are singular; the reference's LU then returns a solution
+// polluted by the null vector.  Here the constant mode of the right-hand side is
+// projected out and phi has zero mean -- E is unaffected by the gauge.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+enum AxisKind { AX_PATH = 0, AX_RING = 1, AX_DD = 2, AX_DL = 3, AX_DR = 4 };
+
+struct AxisInfo {
+  AxisKind kind;
+  int n;       // nodes
+  int lo, m;   // unknown range [lo, lo+m)
+};
+
+// ---------------------------------------------------------------------------------------------
+// host: dense assembly exactly as the reference (debug, parity and the dense fallback)
+// ---------------------------------------------------------------------------------------------
+void assemble_dense(const iskb_ctx *c, std::vector<double> &A, std::vector<double> &b) {
+  const PoissonState &ps = c->ps;
+  const int nx = c->g.nx, ny = c->g.ny;
+  const int64_t nn = (int64_t)nx * ny;
+  A.assign((size_t)(nn * nn), 0.0);
+  b.assign((size_t)nn, 0.0);
+  auto at = [&](int64_t r, int64_t col) -> double & { return A[(size_t)(r + col * nn)]; };
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i < nx; ++i) {                       // :42-61
+      const int64_t r = i + (int64_t)j * nx;
+      if (i < nx - 1) { at(r, r) -= 1.0; at(r, r + 1) += 1.0; }
+      if (i > 0) { at(r, r) -= 1.0; at(r, r - 1) += 1.0; }
+      if (j < ny - 1) { at(r, r) -= 1.0; at(r, r + nx) += 1.0; }
+      if (j > 0) { at(r, r) -= 1.0; at(r, r - nx) += 1.0; }
+    }
+  const double d2 = c->g.dx * c->g.dx;                   // :65
+  for (auto &v : A) v /= d2;
+  if (ps.periodic_j) {                                   // apply_periodic(ps, 1) :291-306
+    const double cc = (0.5 + 0.5) / (c->g.dx * c->g.dx);
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = jj == 0 ? 0 : ny - 1;
+      for (int i = 0; i < nx; ++i) {
+        const int64_t r = i + (int64_t)j * nx;
+        if (j == ny - 1) { at(r, r) -= cc; at(r, i) += cc; }
+        if (j == 0) { at(r, r) -= cc; at(r, i + (int64_t)(ny - 1) * nx) += cc; }
+      }
+    }
+  }
+  if (ps.periodic_i) {                                   // apply_periodic(ps, 2) :308-323
+    const double cc = (0.5 + 0.5) / (c->g.dy * c->g.dy);
+    for (int j = 0; j < ny; ++j)
+      for (int ii = 0; ii < 2; ++ii) {
+        const int i = ii == 0 ? 0 : nx - 1;
+        const int64_t r = i + (int64_t)j * nx;
+        if (i == nx - 1) { at(r, r) -= cc; at(r, (int64_t)j * nx) += cc; }
+        if (i == 0) { at(r, r) -= cc; at(r, (nx - 1) + (int64_t)j * nx) += cc; }
+      }
+  }
+  for (int64_t r = 0; r < nn; ++r)
+    if (ps.isdir[(size_t)r]) {                           // apply_dirichlet :205-215
+      for (int64_t col = 0; col < nn; ++col) at(r, col) = 0.0;
+      at(r, r) = 1.0;
+      b[(size_t)r] = ps.dval[(size_t)r];
+    }
+}
+
+// Gauss-Jordan inverse with partial pivoting, column-major.  Returns false if singular.
+bool invert_dense(std::vector<double> &A, int64_t n) {
+  std::vector<double> inv((size_t)(n * n), 0.0);
+  for (int64_t k = 0; k < n; ++k) inv[(size_t)(k + k * n)] = 1.0;
+  double amax = 0.0;
+  for (double v : A) amax = std::fmax(amax, std::fabs(v));
+  std::vector<double> colk((size_t)n);
+  for (int64_t k = 0; k < n; ++k) {
+    int64_t piv = k;
+    double best = std::fabs(A[(size_t)(k + k * n)]);
+    for (int64_t r = k + 1; r < n; ++r) {
+      const double a = std::fabs(A[(size_t)(r + k * n)]);
+      if (a > best) { best = a; piv = r; }
+    }
+    if (!(best > 1e-13 * amax)) return false;
+    if (piv != k)
+      for (int64_t col = 0; col < n; ++col) {
+        std::swap(A[(size_t)(k + col * n)], A[(size_t)(piv + col * n)]);
+        std::swap(inv[(size_t)(k + col * n)], inv[(size_t)(piv + col * n)]);
+      }
+    const double ip = 1.0 / A[(size_t)(k + k * n)];
+    for (int64_t col = 0; col < n; ++col) {
+      A[(size_t)(k + col * n)] *= ip;
+      inv[(size_t)(k + col * n)] *= ip;
+    }
+    for (int64_t r = 0; r < n; ++r) colk[(size_t)r] = A[(size_t)(r + k * n)];
+    for (int64_t col = 0; col < n; ++col) {
+      const double ak = A[(size_t)(k + col * n)], ik = inv[(size_t)(k + col * n)];
+      if (ak == 0.0 && ik == 0.0) continue;
+      double *Ac = &A[(size_t)(col * n)], *Ic = &inv[(size_t)(col * n)];
+      for (int64_t r = 0; r < n; ++r) {
+        if (r == k) continue;
+        const double f = colk[(size_t)r];
+        if (f == 0.0) continue;
+        Ac[r] -= f * ak;
+        Ic[r] -= f * ik;
+      }
+    }
+  }
+  A.swap(inv);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: closed-form orthonormal eigen-decompositions of the 1-D operators
+// ---------------------------------------------------------------------------------------------
+void axis_eigen(const AxisInfo &ax, std::vector<double> &V, std::vector<double> &lam) {
+  const int m = ax.m;
+  V.assign((size_t)m * m, 0.0);
+  lam.assign((size_t)m, 0.0);
+  const long double PI = 3.141592653589793238462643383279502884L;
+  auto set = [&](int p, int k, long double v) { V[(size_t)p + (size_t)k * m] = (double)v; };
+  // angles are reduced in exact integer arithmetic before the long-double sin/cos
+  auto ang = [&](long long num, long long den) { return PI * (long double)(num % (2 * den)) / (long double)den; };
+  switch (ax.kind) {
+    case AX_RING: {
+      const int n = m;
+      int col = 0;
+      for (int k = 0; k <= n / 2; ++k) {
+        const long double l = -2.0L + 2.0L * cosl(ang(2LL * k, n));
+        if (k == 0 || (n % 2 == 0 && k == n / 2)) {
+          const long double s = 1.0L / sqrtl((long double)n);
+          for (int p = 0; p < n; ++p) set(p, col, s * cosl(ang(2LL * k * p, n)));
+          lam[(size_t)col++] = (double)l;
+        } else {
+          const long double s = sqrtl(2.0L / n);
+          for (int p = 0; p < n; ++p) set(p, col, s * cosl(ang(2LL * k * p, n)));
+          lam[(size_t)col++] = (double)l;
+          for (int p = 0; p < n; ++p) set(p, col, s * sinl(ang(2LL * k * p, n)));
+          lam[(size_t)col++] = (double)l;
+        }
+      }
+      break;
+    }
+    case AX_PATH: {
+      const int n = m;
+      for (int k = 0; k < n; ++k) {
+        const long double s = k == 0 ? 1.0L / sqrtl((long double)n) : sqrtl(2.0L / n);
+        for (int p = 0; p < n; ++p) set(p, k, s * cosl(ang((long long)k * (2 * p + 1), 2LL * n)));
+        lam[(size_t)k] = (double)(-2.0L + 2.0L * cosl(ang(k, n)));
+      }
+      break;
+    }
+    case AX_DD: {
+      const long double s = sqrtl(2.0L / (m + 1));
+      for (int k = 1; k <= m; ++k) {
+        for (int p = 1; p <= m; ++p) set(p - 1, k - 1, s * sinl(ang((long long)k * p, m + 1)));
+        lam[(size_t)(k - 1)] = (double)(-2.0L + 2.0L * cosl(ang(k, m + 1)));
+      }
+      break;
+    }
+    case AX_DL:
+    case AX_DR: {
+      const long double s = 2.0L / sqrtl(2.0L * m + 1.0L);
+      for (int k = 1; k <= m; ++k) {
+        for (int p = 1; p <= m; ++p) {
+          const int row = ax.kind == AX_DL ? p - 1 : m - p;
+          set(row, k - 1, s * sinl(ang((long long)(2 * k - 1) * p, 2LL * m + 1)));
+        }
+        lam[(size_t)(k - 1)] = (double)(-2.0L + 2.0L * cosl(ang(2 * k - 1, 2LL * m + 1)));
+      }
+      break;
+    }
+  }
+}
+
+// diagonal of the tridiagonal along an axis restricted to its unknown range (off-diagonals = 1)
+void axis_diag(const AxisInfo &ax, std::vector<double> &d) {
+  d.assign((size_t)ax.m, -2.0);
+  if (ax.kind == AX_PATH) { d[0] = -1.0; d[(size_t)ax.m - 1] = -1.0; if (ax.m == 1) d[0] = 0.0; }
+  if (ax.kind == AX_DL) d[(size_t)ax.m - 1] = -1.0;
+  if (ax.kind == AX_DR) d[0] = -1.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device kernels
+// ---------------------------------------------------------------------------------------------
+struct SolveDims {
+  int nx, ny;
+  int transposed;   // working axis a is j when set
+  int a0, ma, b0, mb;
+  double scale;     // dx^2 / eps0
+};
+
+__device__ __forceinline__ int64_t node_of(const SolveDims &s, int a, int b) {
+  return s.transposed ? (int64_t)b + (int64_t)a * s.nx : (int64_t)a + (int64_t)b * s.nx;
+}
+
+// R[a,b] = dx^2 * b_rhs - (Dirichlet neighbours), b_rhs = (-rho)/eps0   (:375 with f = -rho)
+__global__ void k_build_rhs(SolveDims s, const double *__restrict__ rho, const uint8_t *__restrict__ isdir,
+                            const double *__restrict__ dval, double *R) {
+  const int64_t tot = (int64_t)s.ma * s.mb;
+  const int na = s.transposed ? s.ny : s.nx, nb = s.transposed ? s.nx : s.ny;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < tot;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int ka = (int)(t % s.ma), kb = (int)(t / s.ma);
+    const int a = s.a0 + ka, b = s.b0 + kb;
+    double r = -(rho[node_of(s, a, b)]) * s.scale;
+    if (a - 1 >= 0 && isdir[node_of(s, a - 1, b)]) r -= dval[node_of(s, a - 1, b)];
+    if (a + 1 < na && isdir[node_of(s, a + 1, b)]) r -= dval[node_of(s, a + 1, b)];
+    if (b - 1 >= 0 && isdir[node_of(s, a, b - 1)]) r -= dval[node_of(s, a, b - 1)];
+    if (b + 1 < nb && isdir[node_of(s, a, b + 1)]) r -= dval[node_of(s, a, b + 1)];
+    R[t] = r;
+  }
+}
+
+__global__ void k_store_phi(SolveDims s, const double *__restrict__ X, const uint8_t *__restrict__ isdir,
+                            const double *__restrict__ dval, double *phi) {
+  const int64_t nn = (int64_t)s.nx * s.ny;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    if (isdir[n]) {
+      phi[n] = dval[n];
+      continue;
+    }
+    const int i = (int)(n % s.nx), j = (int)(n / s.nx);
+    const int a = s.transposed ? j : i, b = s.transposed ? i : j;
+    phi[n] = X[(int64_t)(a - s.a0) + (int64_t)(b - s.b0) * s.ma];
+  }
+}
+
+// C[M x N] = A[M x K] * B[K x N], all column-major, FP64, 64x64x16 tiles, 4x4 per thread.
+__global__ void __launch_bounds__(256) k_dgemm(int M, int N, int K, const double *__restrict__ A, int lda,
+                                               const double *__restrict__ B, int ldb, double *C, int ldc) {
+  __shared__ double As[16][64 + 4];
+  __shared__ double Bs[16][64 + 4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e % 64, kk = e / 64;
+      const int gm = m0 + r, gk = k0 + kk;
+      As[kk][r] = (gm < M && gk < K) ? A[(int64_t)gm + (int64_t)gk * lda] : 0.0;
+    }
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int kk = e % 16, cidx = e / 16;
+      const int gk = k0 + kk, gn = n0 + cidx;
+      Bs[kk][cidx] = (gk < K && gn < N) ? B[(int64_t)gk + (int64_t)gn * ldb] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = As[kk][tx + 16 * q];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) b[q] = Bs[kk][ty + 16 * q];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[q][r] = fma(a[q], b[r], acc[q][r]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int gm = m0 + tx + 16 * q, gn = n0 + ty + 16 * r;
+      if (gm < M && gn < N) C[(int64_t)gm + (int64_t)gn * ldc] = acc[q][r];
+    }
+}
+
+// One thread per mode k: Thomas along b with precomputed factors; cyclic via Sherman-Morrison.
+// W[k + q*ma] holds the transformed rhs on entry and the transformed solution on exit.
+__global__ void k_thomas(int ma, int mb, int cyclic, int singular_mode, const double *__restrict__ mt,
+                         const double *__restrict__ qt, const double *__restrict__ qden,
+                         const double *__restrict__ gam, const double *__restrict__ msing, double *W) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ma) return;
+  if (k == singular_mode) {
+    // T x = r with T singular (null vector = const): project r, pin x_0 = 0, remove the mean
+    double mean = 0.0;
+    for (int q = 0; q < mb; ++q) mean += W[k + (int64_t)q * ma];
+    mean /= mb;
+    double y = 0.0;
+    for (int q = 1; q < mb; ++q) {
+      y = ((W[k + (int64_t)q * ma] - mean) - y) * msing[q];
+      W[k + (int64_t)q * ma] = y;
+    }
+    double x = 0.0, sum = 0.0;
+    for (int q = mb - 1; q >= 1; --q) {
+      x = W[k + (int64_t)q * ma] - msing[q] * x;
+      W[k + (int64_t)q * ma] = x;
+      sum += x;
+    }
+    const double xm = sum / mb;
+    W[k] = -xm;
+    for (int q = 1; q < mb; ++q) W[k + (int64_t)q * ma] -= xm;
+    return;
+  }
+  double y = 0.0;
+  for (int q = 0; q < mb; ++q) {
+    const int64_t o = k + (int64_t)q * ma;
+    y = (W[o] - y) * mt[o];
+    W[o] = y;
+  }
+  double x = 0.0;
+  for (int q = mb - 1; q >= 0; --q) {
+    const int64_t o = k + (int64_t)q * ma;
+    x = W[o] - (q == mb - 1 ? 0.0 : mt[o] * x);
+    W[o] = x;
+  }
+  if (cyclic) {
+    const double f = (W[k] + W[k + (int64_t)(mb - 1) * ma] / gam[k]) * qden[k];
+    for (int q = 0; q < mb; ++q) {
+      const int64_t o = k + (int64_t)q * ma;
+      W[o] -= qt[o] * f;
+    }
+  }
+}
+
+// dense fallback: b = isdir ? dval : (-rho)/eps0 ; phi = Ainv * b
+__global__ void k_dense_rhs(const double *__restrict__ rho, const uint8_t *__restrict__ isdir,
+                            const double *__restrict__ dval, double eps0, int64_t nn, double *b) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn;
+       n += (int64_t)gridDim.x * blockDim.x)
+    b[n] = isdir[n] ? dval[n] : (-rho[n]) / eps0;
+}
+__global__ void k_dense_gemv(const double *__restrict__ Ainv, const double *__restrict__ b, int64_t nn,
+                             double *phi) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= nn) return;
+  double s = 0.0;
+  for (int64_t cidx = 0; cidx < nn; ++cidx) s = fma(Ainv[r + cidx * nn], b[cidx], s);
+  phi[r] = s;
+}
+
+// calculate_electric_field!  generalized_poisson.jl:398-410 ; E2 = (Ex, Ey) per node
+__global__ void k_efield(int nx, int ny, double dx, double dy, const double *__restrict__ phi, double2 *E2) {
+  const int64_t nn = (int64_t)nx * ny;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(n % nx), j = (int)(n / nx);
+    double ex, ey;
+    if (i == 0) ex = __ddiv_rn(__dsub_rn(phi[n], phi[n + 1]), dx);                      // :404
+    else if (i == nx - 1) ex = __ddiv_rn(__dsub_rn(phi[n - 1], phi[n]), dx);            // :405
+    else ex = __ddiv_rn(__dsub_rn(phi[n - 1], phi[n + 1]), __dmul_rn(2.0, dx));         // :402
+    if (j == 0) ey = __ddiv_rn(__dsub_rn(phi[n], phi[n + nx]), dy);                     // :406
+    else if (j == ny - 1) ey = __ddiv_rn(__dsub_rn(phi[n - nx], phi[n]), dy);           // :407
+    else ey = __ddiv_rn(__dsub_rn(phi[n - nx], phi[n + nx]), __dmul_rn(2.0, dy));       // :403
+    E2[n] = make_double2(ex, ey);
+  }
+}
+
+// per-step update of one Dirichlet edge (the RF drive, 11_rf_discharge.jl:95) without re-uploading
+__global__ void k_set_edge(int nx, int ny, int edge, double v, double *dval) {
+  const int len = edge < 2 ? ny : nx;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < len; t += gridDim.x * blockDim.x) {
+    int64_t n;
+    if (edge == ISKB_EDGE_LEFT) n = (int64_t)t * nx;
+    else if (edge == ISKB_EDGE_RIGHT) n = (nx - 1) + (int64_t)t * nx;
+    else if (edge == ISKB_EDGE_BOTTOM) n = t;
+    else n = t + (int64_t)(ny - 1) * nx;
+    dval[n] = v;
+  }
+}
+
+int blocks_for(const iskb_ctx *c, int64_t n) {
+  int64_t b = (n + TPB - 1) / TPB;
+  if (b > (int64_t)c->n_sm * 8) b = (int64_t)c->n_sm * 8;
+  return b < 1 ? 1 : (int)b;
+}
+
+template <typename T>
+int32_t upload(T **dptr, const std::vector<T> &h, cudaStream_t st) {
+  if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+  if (h.empty()) return ISKB_OK;
+  CU_TRY(cudaMalloc(dptr, h.size() * sizeof(T)));
+  CU_TRY(cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return ISKB_OK;
+}
+
+}  // namespace
+
+int32_t poisson_free(iskb_ctx *c) {
+  PoissonState &ps = c->ps;
+  double **ptrs[] = {&ps.d_dval, &ps.d_V, &ps.d_lam, &ps.d_cp, &ps.d_q, &ps.d_qden, &ps.d_w1, &ps.d_w2,
+                     &ps.d_w3, &ps.d_Ainv, &ps.d_Vt, &ps.d_gam, &ps.d_msing};
+  for (auto p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+  if (ps.d_isdir) { cudaFree(ps.d_isdir); ps.d_isdir = nullptr; }
+  if (ps.d_tw) { cudaFree(ps.d_tw); ps.d_tw = nullptr; }
+  return ISKB_OK;
+}
+
+static bool classify_axis(bool periodic, bool dir_lo, bool dir_hi, int n, AxisInfo &ax) {
+  ax.n = n;
+  if (periodic) {
+    if (dir_lo || dir_hi) return false;   // mixing on one axis: not separable in closed form
+    ax.kind = AX_RING; ax.lo = 0; ax.m = n;
+  } else if (dir_lo && dir_hi) { ax.kind = AX_DD; ax.lo = 1; ax.m = n - 2; }
+  else if (dir_lo) { ax.kind = AX_DL; ax.lo = 1; ax.m = n - 1; }
+  else if (dir_hi) { ax.kind = AX_DR; ax.lo = 0; ax.m = n - 1; }
+  else { ax.kind = AX_PATH; ax.lo = 0; ax.m = n; }
+  return ax.m >= 1;
+}
+
+static int32_t prepare_dense(iskb_ctx *c) {
+  PoissonState &ps = c->ps;
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  if (nn > 8192) return iskb_fail(ISKB_E_UNSUPPORTED,
+                                  "Dirichlet nodes are not whole edges and the grid (%lld nodes) is too large "
+                                  "for the dense fallback", (long long)nn);
+  std::vector<double> A, b;
+  assemble_dense(c, A, b);
+  if (!invert_dense(A, nn)) return iskb_fail(ISKB_E_SINGULAR, "dense Poisson operator is singular");
+  ISKB_TRY(upload(&ps.d_Ainv, A, c->stream));
+  ps.nn_dense = nn;
+  if (!ps.d_w1) CU_TRY(cudaMalloc(&ps.d_w1, nn * sizeof(double)));
+  ps.mode = 2;
+  return ISKB_OK;
+}
+
+int32_t poisson_prepare(iskb_ctx *c) {
+  PoissonState &ps = c->ps;
+  if (!ps.created) return iskb_fail(ISKB_E_INVALID, "iskb_poisson_create must be called first");
+  const int nx = c->g.nx, ny = c->g.ny;
+  const int64_t nn = (int64_t)nx * ny;
+  if (ps.structure_dirty) {
+    {
+      std::vector<uint8_t> &m = ps.isdir;
+      if (ps.d_isdir) { cudaFree(ps.d_isdir); ps.d_isdir = nullptr; }
+      CU_TRY(cudaMalloc(&ps.d_isdir, nn));
+      CU_TRY(cudaMemcpyAsync(ps.d_isdir, m.data(), nn, cudaMemcpyHostToDevice, c->stream));
+    }
+    // which whole edges are Dirichlet, and is every Dirichlet node on such an edge?
+    bool eL = true, eR = true, eB = true, eT = true;
+    for (int j = 0; j < ny; ++j) { eL &= ps.isdir[(size_t)(0 + (int64_t)j * nx)] != 0; eR &= ps.isdir[(size_t)((nx - 1) + (int64_t)j * nx)] != 0; }
+    for (int i = 0; i < nx; ++i) { eB &= ps.isdir[(size_t)i] != 0; eT &= ps.isdir[(size_t)(i + (int64_t)(ny - 1) * nx)] != 0; }
+    bool whole = true;
+    for (int j = 0; j < ny && whole; ++j)
+      for (int i = 0; i < nx; ++i)
+        if (ps.isdir[(size_t)(i + (int64_t)j * nx)]) {
+          const bool cov = (eL && i == 0) || (eR && i == nx - 1) || (eB && j == 0) || (eT && j == ny - 1);
+          if (!cov) { whole = false; break; }
+        }
+    AxisInfo axi{}, axj{};
+    bool sep = whole && c->g.dx == c->g.dy;
+    sep = sep && classify_axis(ps.periodic_i, eL, eR, nx, axi) && classify_axis(ps.periodic_j, eB, eT, ny, axj);
+    // choose the transform axis: the solve axis needs >= 3 unknowns when cyclic, >= 1 otherwise
+    auto ok_solve = [](const AxisInfo &b) { return b.kind == AX_RING ? b.m >= 3 : b.m >= 1; };
+    int choice = -1;   // 0: transform along i, 1: transform along j
+    if (sep) {
+      const bool can0 = ok_solve(axj), can1 = ok_solve(axi);
+      if (can0 && can1) choice = axi.m <= axj.m ? 0 : 1;   // transform along the shorter axis
+      else if (can0) choice = 0;
+      else if (can1) choice = 1;
+    }
+    if (choice < 0) {
+      ISKB_TRY(prepare_dense(c));
+    } else {
+      const AxisInfo &A = choice == 0 ? axi : axj, &B = choice == 0 ? axj : axi;
+      ps.transposed = choice == 1;
+      ps.na = A.n; ps.nb = B.n; ps.a0 = A.lo; ps.ma = A.m; ps.b0 = B.lo; ps.mb = B.m;
+      ps.b_cyclic = B.kind == AX_RING;
+      const bool a_null = A.kind == AX_RING || A.kind == AX_PATH;
+      const bool b_null = B.kind == AX_RING || B.kind == AX_PATH;
+      ps.singular = a_null && b_null;
+      std::vector<double> V, lam, db;
+      axis_eigen(A, V, lam);
+      axis_diag(B, db);
+      std::vector<double> Vt((size_t)A.m * A.m);
+      for (int p = 0; p < A.m; ++p)
+        for (int k = 0; k < A.m; ++k) Vt[(size_t)k + (size_t)p * A.m] = V[(size_t)p + (size_t)k * A.m];
+      ps.singular_mode = -1;
+      if (ps.singular)
+        for (int k = 0; k < A.m; ++k) if (std::fabs(lam[(size_t)k]) < 1e-14) ps.singular_mode = k;
+      // Thomas factors per mode (and Sherman-Morrison vectors when cyclic)
+      const int ma = A.m, mb = B.m;
+      std::vector<double> mt((size_t)ma * mb), qt, qden, gam, msing;
+      if (ps.b_cyclic) { qt.assign((size_t)ma * mb, 0.0); qden.assign((size_t)ma, 0.0); gam.assign((size_t)ma, 1.0); }
+      std::vector<double> d((size_t)mb), qv((size_t)mb);
+      for (int k = 0; k < ma; ++k) {
+        if (k == ps.singular_mode) {
+          for (int q = 0; q < mb; ++q) mt[(size_t)k + (size_t)q * ma] = 0.0;
+          continue;
+        }
+        for (int q = 0; q < mb; ++q) d[(size_t)q] = db[(size_t)q] + lam[(size_t)k];
+        double g = 1.0;
+        if (ps.b_cyclic) {
+          g = -d[0];
+          gam[(size_t)k] = g;
+          d[0] -= g;
+          d[(size_t)mb - 1] -= 1.0 / g;
+        }
+        double cprev = 0.0;
+        for (int q = 0; q < mb; ++q) {
+          const double mq = 1.0 / (d[(size_t)q] - cprev);
+          mt[(size_t)k + (size_t)q * ma] = mq;
+          cprev = mq;
+        }
+        if (ps.b_cyclic) {
+          // solve A' q = u, u = (g, 0, ..., 0, 1)
+          double y = 0.0;
+          for (int q = 0; q < mb; ++q) {
+            const double u = q == 0 ? g : (q == mb - 1 ? 1.0 : 0.0);
+            y = (u - y) * mt[(size_t)k + (size_t)q * ma];
+            qv[(size_t)q] = y;
+          }
+          double x = 0.0;
+          for (int q = mb - 1; q >= 0; --q) {
+            x = qv[(size_t)q] - (q == mb - 1 ? 0.0 : mt[(size_t)k + (size_t)q * ma] * x);
+            qv[(size_t)q] = x;
+          }
+          for (int q = 0; q < mb; ++q) qt[(size_t)k + (size_t)q * ma] = qv[(size_t)q];
+          qden[(size_t)k] = 1.0 / (1.0 + qv[0] + qv[(size_t)mb - 1] / g);
+        }
+      }
+      if (ps.singular_mode >= 0) {
+        // pinned system on q = 1..mb-1: diag = db[q] (lambda = 0), no cyclic corner
+        msing.assign((size_t)mb, 0.0);
+        double cprev = 0.0;
+        for (int q = 1; q < mb; ++q) {
+          const double mq = 1.0 / (db[(size_t)q] - cprev);
+          msing[(size_t)q] = mq;
+          cprev = mq;
+        }
+      }
+      ISKB_TRY(upload(&ps.d_V, V, c->stream));
+      ISKB_TRY(upload(&ps.d_Vt, Vt, c->stream));
+      ISKB_TRY(upload(&ps.d_lam, lam, c->stream));
+      ISKB_TRY(upload(&ps.d_cp, mt, c->stream));
+      ISKB_TRY(upload(&ps.d_q, qt, c->stream));
+      ISKB_TRY(upload(&ps.d_qden, qden, c->stream));
+      ISKB_TRY(upload(&ps.d_gam, gam, c->stream));
+      ISKB_TRY(upload(&ps.d_msing, msing, c->stream));
+      if (ps.d_w1) { cudaFree(ps.d_w1); ps.d_w1 = nullptr; }
+      if (ps.d_w2) { cudaFree(ps.d_w2); ps.d_w2 = nullptr; }
+      CU_TRY(cudaMalloc(&ps.d_w1, (size_t)ma * mb * sizeof(double)));
+      CU_TRY(cudaMalloc(&ps.d_w2, (size_t)ma * mb * sizeof(double)));
+      ps.mode = 1;
+    }
+    ps.structure_dirty = false;
+    ps.values_dirty = true;
+  }
+  if (ps.values_dirty) {
+    if (!ps.d_dval) CU_TRY(cudaMalloc(&ps.d_dval, nn * sizeof(double)));
+    CU_TRY(cudaMemcpyAsync(ps.d_dval, ps.dval.data(), nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));   // host vector may change right after
+    ps.values_dirty = false;
+  }
+  return ISKB_OK;
+}
+
+int32_t poisson_solve(iskb_ctx *c) {
+  ISKB_TRY(poisson_prepare(c));
+  PoissonState &ps = c->ps;
+  const int nx = c->g.nx, ny = c->g.ny;
+  const int64_t nn = (int64_t)nx * ny;
+  if (ps.mode == 2) {
+    k_dense_rhs<<<blocks_for(c, nn), TPB, 0, c->stream>>>(c->d_rho, ps.d_isdir, ps.d_dval, ps.eps0, nn, ps.d_w1);
+    LAUNCH_CHECK(c);
+    k_dense_gemv<<<(int)((nn + 127) / 128), 128, 0, c->stream>>>(ps.d_Ainv, ps.d_w1, nn, c->d_phi);
+    LAUNCH_CHECK(c);
+  } else {
+    SolveDims s{nx, ny, ps.transposed ? 1 : 0, ps.a0, ps.ma, ps.b0, ps.mb, c->g.dx * c->g.dx / ps.eps0};
+    const int64_t tot = (int64_t)ps.ma * ps.mb;
+    k_build_rhs<<<blocks_for(c, tot), TPB, 0, c->stream>>>(s, c->d_rho, ps.d_isdir, ps.d_dval, ps.d_w1);
+    LAUNCH_CHECK(c);
+    dim3 gg((ps.ma + 63) / 64, (ps.mb + 63) / 64);
+    k_dgemm<<<gg, 256, 0, c->stream>>>(ps.ma, ps.mb, ps.ma, ps.d_Vt, ps.ma, ps.d_w1, ps.ma, ps.d_w2, ps.ma);
+    LAUNCH_CHECK(c);
+    k_thomas<<<(ps.ma + 63) / 64, 64, 0, c->stream>>>(ps.ma, ps.mb, ps.b_cyclic ? 1 : 0, ps.singular_mode, ps.d_cp,
+                                                     ps.d_q, ps.d_qden, ps.d_gam, ps.d_msing, ps.d_w2);
+    LAUNCH_CHECK(c);
+    k_dgemm<<<gg, 256, 0, c->stream>>>(ps.ma, ps.mb, ps.ma, ps.d_V, ps.ma, ps.d_w2, ps.ma, ps.d_w1, ps.ma);
+    LAUNCH_CHECK(c);
+    k_store_phi<<<blocks_for(c, nn), TPB, 0, c->stream>>>(s, ps.d_w1, ps.d_isdir, ps.d_dval, c->d_phi);
+    LAUNCH_CHECK(c);
+  }
+  k_efield<<<blocks_for(c, nn), TPB, 0, c->stream>>>(nx, ny, c->g.dx, c->g.dy, c->d_phi, c->d_E2);
+  LAUNCH_CHECK(c);
+  return ISKB_OK;
+}
+
+// ---- C ABI ------------------------------------------------------------------------------------
+extern "C" int32_t iskb_poisson_create(iskb_ctx *c, double eps0) {
+  if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "iskb_grid_set must be called first");
+  PoissonState &ps = c->ps;
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  ps.created = true;
+  ps.eps0 = eps0;
+  ps.periodic_i = ps.periodic_j = false;
+  ps.isdir.assign((size_t)nn, 0);
+  ps.dval.assign((size_t)nn, 0.0);
+  ps.structure_dirty = ps.values_dirty = true;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_poisson_apply_periodic(iskb_ctx *c, int32_t axis) {
+  if (!c || !c->ps.created) return iskb_fail(ISKB_E_INVALID, "no Poisson solver");
+  if (axis == 1) c->ps.periodic_j = true;        // :291-306 couples j = 1 <-> ny
+  else if (axis == 2) c->ps.periodic_i = true;   // :308-323 couples i = 1 <-> nx
+  else return iskb_fail(ISKB_E_INVALID, "axis must be 1 or 2");
+  c->ps.structure_dirty = true;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_poisson_apply_dirichlet(iskb_ctx *c, const uint8_t *mask, double phi0) {
+  if (!c || !c->ps.created || !mask) return iskb_fail(ISKB_E_INVALID, "no Poisson solver / mask");
+  PoissonState &ps = c->ps;
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  for (int64_t n = 0; n < nn; ++n)
+    if (mask[n]) {
+      if (!ps.isdir[(size_t)n]) { ps.isdir[(size_t)n] = 1; ps.structure_dirty = true; }
+      ps.dval[(size_t)n] = phi0;
+      ps.values_dirty = true;
+    }
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_poisson_apply_dirichlet_edge(iskb_ctx *c, int32_t edge, double phi0) {
+  if (!c || !c->ps.created) return iskb_fail(ISKB_E_INVALID, "no Poisson solver");
+  PoissonState &ps = c->ps;
+  const int nx = c->g.nx, ny = c->g.ny;
+  auto setn = [&](int64_t n) {
+    if (!ps.isdir[(size_t)n]) { ps.isdir[(size_t)n] = 1; ps.structure_dirty = true; }
+    ps.dval[(size_t)n] = phi0;
+  };
+  switch (edge) {
+    case ISKB_EDGE_LEFT: for (int j = 0; j < ny; ++j) setn((int64_t)j * nx); break;
+    case ISKB_EDGE_RIGHT: for (int j = 0; j < ny; ++j) setn((nx - 1) + (int64_t)j * nx); break;
+    case ISKB_EDGE_BOTTOM: for (int i = 0; i < nx; ++i) setn(i); break;
+    case ISKB_EDGE_TOP: for (int i = 0; i < nx; ++i) setn(i + (int64_t)(ny - 1) * nx); break;
+    default: return iskb_fail(ISKB_E_INVALID, "bad edge");
+  }
+  if (!ps.structure_dirty && !ps.values_dirty && ps.d_dval) {
+    // solver already built and only this edge's value changed: patch the device copy in place
+    const int len = edge < 2 ? ny : nx;
+    k_set_edge<<<(len + 255) / 256, 256, 0, c->stream>>>(nx, ny, edge, phi0, ps.d_dval);
+    LAUNCH_CHECK(c);
+    return ISKB_OK;
+  }
+  ps.values_dirty = true;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_poisson_get_dense(iskb_ctx *c, double *A_out, double *b_out) {
+  if (!c || !c->ps.created) return iskb_fail(ISKB_E_INVALID, "no Poisson solver");
+  std::vector<double> A, b;
+  assemble_dense(c, A, b);
+  if (A_out) memcpy(A_out, A.data(), A.size() * sizeof(double));
+  if (b_out) memcpy(b_out, b.data(), b.size() * sizeof(double));
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_poisson_mode(iskb_ctx *c, int32_t *mode_out) {
+  if (!c || !mode_out) return iskb_fail(ISKB_E_INVALID, "null");
+  ISKB_TRY(poisson_prepare(c));
+  *mode_out = c->ps.mode;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_field_solve(iskb_ctx *c) {
+  if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
+  return poisson_solve(c);
+}

@@ -1,0 +1,329 @@
+// Stable LSD radix sort of the particle rows by cell key, and stable compaction of discarded
+// rows (the reference's remove!, kinetic.jl:20-27, keeps `id` a permutation of 1..N; here the
+// discarded rows are parked behind the live ones with their ids, which preserves the same
+// invariant -- SURVEY.md H5).  New relative to the reference: sorting exists only to make the
+// tiled shared-memory deposition possible.
+//
+// Sort key (DESIGN.md "cell key"): cells are grouped in 8x8 tiles, tile-major, then row-major
+// inside the tile: key = ((ty*tiles_x + tx) << 6) | ((cy & 7) << 3) | (cx & 7) with
+// cx = i-1, cy = j-1 from particle_cell (ParticleInCell.jl:28-35).  Out-of-grid rows get key_max and
+// dead rows key_max+1, so they land at the end.  The sort is stable in the previous row order, so the resulting
+// permutation is a pure function of the cell indices (bit-exact contract of north_star).
+#include "pic_device.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_WARPS = TPB / 32;
+constexpr int RS_TILE = TPB * RS_ITEMS;   // 4096 keys per block
+
+__global__ void k_cell_keys(const double *__restrict__ x, const double *__restrict__ y, int64_t n,
+                            GridDev g, int tiles_x, uint32_t key_max, uint32_t *keys) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const double px = x[p];
+    uint32_t key = key_max + 1u;   // dead rows go last, behind live out-of-grid rows (key_max)
+    if (!is_dead(px)) {
+      key = key_max;
+      int i, j;
+      double hx, hy;
+      cell1(px, g.dx, i, hx);
+      cell1(y[p], g.dy, j, hy);
+      if (cell_in_grid(i, j, g.nx, g.ny)) {
+        const uint32_t cx = (uint32_t)(i - 1), cy = (uint32_t)(j - 1);
+        key = (((cy >> 3) * (uint32_t)tiles_x + (cx >> 3)) << 6) | ((cy & 7u) << 3) | (cx & 7u);
+      }
+    }
+    keys[p] = key;
+  }
+}
+
+__global__ void k_dead_keys(const double *__restrict__ x, int64_t n, uint32_t *keys) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
+       p += (int64_t)gridDim.x * blockDim.x)
+    keys[p] = is_dead(x[p]) ? 1u : 0u;
+}
+
+__global__ void k_radix_hist(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t *hist,
+                             int nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll 4
+  for (int t = 0; t < RS_ITEMS; ++t) {
+    const int64_t p = base + t * TPB + threadIdx.x;
+    if (p < n) atomicAdd(&h[(keys[p] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// ---- exclusive scan over uint32 (3 kernels) ----------------------------------------------------
+constexpr int SC_PER_BLOCK = 2048;   // 256 threads x 8
+
+__global__ void k_scan_reduce(const uint32_t *__restrict__ in, int64_t n, uint32_t *partial) {
+  __shared__ uint32_t s[TPB];
+  const int64_t base = (int64_t)blockIdx.x * SC_PER_BLOCK + threadIdx.x * 8;
+  uint32_t a = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) if (base + k < n) a += in[base + k];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = TPB / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+
+__global__ void k_scan_partials(uint32_t *partial, int np) {   // single block, exclusive in place
+  __shared__ uint32_t s[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < np; base += 1024) {
+    const int k = base + threadIdx.x;
+    const uint32_t v = k < np ? partial[k] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      uint32_t t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (k < np) partial[k] = carry + s[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += s[1023];
+    __syncthreads();
+  }
+}
+
+__global__ void k_scan_down(uint32_t *data, int64_t n, const uint32_t *__restrict__ partial) {
+  __shared__ uint32_t s[TPB];
+  const int64_t base = (int64_t)blockIdx.x * SC_PER_BLOCK + threadIdx.x * 8;
+  uint32_t v[8];
+  uint32_t a = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = base + k < n ? data[base + k] : 0;
+    a += v[k];
+  }
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 1; o < TPB; o <<= 1) {
+    uint32_t t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+    __syncthreads();
+    s[threadIdx.x] += t;
+    __syncthreads();
+  }
+  uint32_t run = partial[blockIdx.x] + s[threadIdx.x] - a;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (base + k < n) data[base + k] = run;
+    run += v[k];
+  }
+}
+
+// ---- stable scatter of one 8-bit digit ---------------------------------------------------------
+__global__ void k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ idx_in,
+                                uint32_t *keys_out, uint32_t *idx_out, int64_t n, int shift,
+                                const uint32_t *__restrict__ offs, int nblocks) {
+  __shared__ uint32_t wcnt[RS_WARPS][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int k = threadIdx.x; k < RS_WARPS * 256; k += TPB) (&wcnt[0][0])[k] = 0;
+  __syncthreads();
+  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (RS_ITEMS * 32);
+  uint32_t key[RS_ITEMS];
+  // phase 1: per-warp digit counts (warp-private rows; one writer per digit and iteration)
+#pragma unroll
+  for (int t = 0; t < RS_ITEMS; ++t) {
+    const int64_t p = wbase + t * 32 + lane;
+    const bool valid = p < n;
+    key[t] = valid ? keys_in[p] : 0xffffffffu;
+    const uint32_t d = valid ? ((key[t] >> shift) & 255u) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (peers & lt) == 0) wcnt[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // exclusive prefix across warps + global base of (digit, block)
+  {
+    const int d = threadIdx.x;
+    uint32_t run = offs[(int64_t)d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t c = wcnt[w][d];
+      wcnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // phase 2: stable ranks and scatter
+#pragma unroll
+  for (int t = 0; t < RS_ITEMS; ++t) {
+    const int64_t p = wbase + t * 32 + lane;
+    const bool valid = p < n;
+    const uint32_t d = valid ? ((key[t] >> shift) & 255u) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (valid && lane == leader) {
+      old = wcnt[warp][d];
+      wcnt[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    if (valid) {
+      const uint32_t dest = old + __popc(peers & lt);
+      keys_out[dest] = key[t];
+      idx_out[dest] = idx_in ? idx_in[p] : (uint32_t)p;
+    }
+    __syncwarp();
+  }
+}
+
+struct Cols {
+  const double *in[6];
+  double *out[6];
+  const uint32_t *id_in;
+  uint32_t *id_out;
+};
+
+__global__ void k_permute(Cols c, const uint32_t *__restrict__ idx, int64_t n) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+       k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t s = idx[k];
+    double v[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) v[q] = c.in[q][s];
+    const uint32_t id = c.id_in[s];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) c.out[q][k] = v[q];
+    c.id_out[k] = id;
+  }
+}
+
+__global__ void k_counts_after_sort(int64_t *cnt) {
+  cnt[CNT_NSLOTS] -= cnt[CNT_NDEAD];
+  cnt[CNT_NDEAD] = 0;
+}
+
+int32_t exclusive_scan_u32(iskb_ctx *c, uint32_t *d, int64_t n, uint32_t *partial) {
+  const int nb = (int)((n + SC_PER_BLOCK - 1) / SC_PER_BLOCK);
+  k_scan_reduce<<<nb, TPB, 0, c->stream>>>(d, n, partial);
+  LAUNCH_CHECK(c);
+  k_scan_partials<<<1, 1024, 0, c->stream>>>(partial, nb);
+  LAUNCH_CHECK(c);
+  k_scan_down<<<nb, TPB, 0, c->stream>>>(d, n, partial);
+  LAUNCH_CHECK(c);
+  return ISKB_OK;
+}
+
+int32_t ensure_sort_scratch(iskb_species *sp) {
+  if (!sp->d_key[0]) {
+    for (int k = 0; k < 2; ++k) {
+      CU_TRY(cudaMalloc(&sp->d_key[k], sp->cap * sizeof(uint32_t)));
+      CU_TRY(cudaMalloc(&sp->d_idx[k], sp->cap * sizeof(uint32_t)));
+    }
+    const int64_t nblocks = (sp->cap + RS_TILE - 1) / RS_TILE;
+    const int64_t hn = 256 * nblocks;
+    sp->hist_cap = hn + (hn + SC_PER_BLOCK - 1) / SC_PER_BLOCK + 16;
+    CU_TRY(cudaMalloc(&sp->d_hist, sp->hist_cap * sizeof(uint32_t)));
+  }
+  return sp_ensure_alt(sp);
+}
+
+// keys already in d_key[0][0..n); runs `passes` 8-bit passes, permutes all columns, fixes counters
+int32_t sort_by_keys(iskb_species *sp, int64_t n, int passes, uint32_t *perm_out_host) {
+  iskb_ctx *c = sp->ctx;
+  const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
+  const int64_t hn = 256 * (int64_t)nblocks;
+  int cur = 0;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = 8 * pass;
+    k_radix_hist<<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], n, shift, sp->d_hist, nblocks);
+    LAUNCH_CHECK(c);
+    ISKB_TRY(exclusive_scan_u32(c, sp->d_hist, hn, sp->d_hist + hn));
+    k_radix_scatter<<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], pass == 0 ? nullptr : sp->d_idx[cur],
+                                                    sp->d_key[cur ^ 1], sp->d_idx[cur ^ 1], n, shift,
+                                                    sp->d_hist, nblocks);
+    LAUNCH_CHECK(c);
+    cur ^= 1;
+  }
+  Cols cols;
+  for (int q = 0; q < 6; ++q) {
+    cols.in[q] = sp->col[q];
+    cols.out[q] = sp->alt[q];
+  }
+  cols.id_in = sp->id;
+  cols.id_out = sp->alt_id;
+  int blocks = (int)((n + TPB - 1) / TPB);
+  if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
+  k_permute<<<blocks, TPB, 0, c->stream>>>(cols, sp->d_idx[cur], n);
+  LAUNCH_CHECK(c);
+  // rows >= n (parked ids / default weights) must survive the buffer swap
+  if (sp->cap > n) {
+    CU_TRY(cudaMemcpyAsync(sp->alt_id + n, sp->id + n, (sp->cap - n) * sizeof(uint32_t),
+                           cudaMemcpyDeviceToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(sp->alt[5] + n, sp->col[5] + n, (sp->cap - n) * sizeof(double),
+                           cudaMemcpyDeviceToDevice, c->stream));
+  }
+  for (int q = 0; q < 6; ++q) std::swap(sp->col[q], sp->alt[q]);
+  std::swap(sp->id, sp->alt_id);
+  k_counts_after_sort<<<1, 1, 0, c->stream>>>(sp->d_cnt);
+  LAUNCH_CHECK(c);
+  const int64_t nlive = n - sp->h_ndead;
+  if (perm_out_host && nlive > 0)
+    CU_TRY(cudaMemcpyAsync(perm_out_host, sp->d_idx[cur], nlive * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                           c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  sp->h_nslots = nlive;
+  sp->h_ndead = 0;
+  sp->counts_stale = false;
+  return ISKB_OK;
+}
+
+}  // namespace
+
+int32_t sp_compact(iskb_species *sp) {
+  ISKB_TRY(sp_sync_counts(sp));
+  if (sp->h_ndead == 0) return ISKB_OK;
+  iskb_ctx *c = sp->ctx;
+  ISKB_TRY(ensure_sort_scratch(sp));
+  const int64_t n = sp->h_nslots;
+  int blocks = (int)((n + TPB - 1) / TPB);
+  if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
+  k_dead_keys<<<blocks, TPB, 0, c->stream>>>(sp->col[0], n, sp->d_key[0]);
+  LAUNCH_CHECK(c);
+  return sort_by_keys(sp, n, 1, nullptr);
+}
+
+int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host) {
+  iskb_ctx *c = sp->ctx;
+  if (!c->has_grid) return iskb_fail(ISKB_E_INVALID, "iskb_grid_set must be called first");
+  ISKB_TRY(sp_sync_counts(sp));
+  const int64_t n = sp->h_nslots;
+  if (n == 0) return ISKB_OK;
+  ISKB_TRY(ensure_sort_scratch(sp));
+  const int tiles_x = (c->g.nx - 1 + 7) / 8, tiles_y = (c->g.ny - 1 + 7) / 8;
+  const uint64_t kmax64 = (uint64_t)tiles_x * tiles_y * 64u;
+  if (kmax64 >= 0xffffffffull) return iskb_fail(ISKB_E_UNSUPPORTED, "grid too large for 32-bit cell keys");
+  const uint32_t key_max = (uint32_t)kmax64;
+  int bits = 1;
+  while ((1ull << bits) <= (uint64_t)key_max + 1u) ++bits;
+  const int passes = (bits + 7) / 8;
+  int blocks = (int)((n + TPB - 1) / TPB);
+  if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
+  k_cell_keys<<<blocks, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], n, c->g, tiles_x, key_max, sp->d_key[0]);
+  LAUNCH_CHECK(c);
+  return sort_by_keys(sp, n, passes, perm_out_host);
+}
+
+extern "C" int32_t iskb_sort_by_cell(iskb_species *sp, uint32_t *perm_out) {
+  if (!sp) return iskb_fail(ISKB_E_INVALID, "null species");
+  ISKB_TRY(sp_compact(sp));   // perm_out refers to the compacted (download) row order
+  return sp_sort(sp, perm_out);
+}

@@ -1,0 +1,53 @@
+"""SYNTHETIC cross-section tables (input data, clearly not LXCat).
+
+The reference reads datasets/Biagi-7.1.txt and datasets/Phelps.txt (Chemistry/src/biagi71-He.jl:2-5,
+phelps-He.jl:2-3, biagi71-Ar.jl:2-5); those files are not in the repository and cannot be fetched.
+The tables below are smooth analytic shapes on the printed energy extents and thresholds of
+docs/capacitively_induced_discharge.ipynb:145-156, scaled so that max_sigma_g of the electron set
+equals the printed 8.976965143603543e-14 to ~1e-3.  The same tables feed the oracle and the device
+path, so parity is unaffected by their shape.
+"""
+import numpy as np
+
+
+def _table(e0, e1, n, fn):
+    eps = np.unique(np.concatenate([[e0], np.geomspace(max(e0, 1e-3), e1, n), [e1]]))
+    return np.stack([eps, fn(eps)], axis=1)
+
+
+def helium_electron(scale=1.0):
+    """sigma_1..sigma_4 for e + He: elastic, two excitations (19.82, 20.61 eV), ionisation (24.587 eV)."""
+    s = 6.35e-20 * scale
+    el = _table(0.0, 965.0509, 96, lambda e: s / (1.0 + (e / 25.0)) ** 1.1)
+
+    def bump(thr, amp):
+        def f(e):
+            x = np.maximum(e - thr, 0.0)
+            return amp * x / (x + 30.0) ** 2 * 30.0
+        return f
+    ex1 = _table(19.82, 984.8709, 64, bump(19.82, 2.5e-22 * scale))
+    ex2 = _table(20.61, 985.6609, 64, bump(20.61, 6.0e-22 * scale))
+    ion = _table(24.59, 989.6379, 64, bump(24.59, 1.4e-20 * scale))
+    return el, ex1, ex2, ion
+
+
+def helium_ion(scale=1.0):
+    """sigma_e2 (backscatter, 1e-4..1e4 eV) and sigma_e1 (isotropic, 0..1e4 eV) for He+ + He."""
+    back = _table(1e-4, 1e4, 96, lambda e: 2.3e-19 * scale / (1.0 + e) ** 0.16)
+    iso = _table(0.0, 1e4, 96, lambda e: 1.6e-19 * scale / (1.0 + e) ** 0.16)
+    return back, iso
+
+
+def argon_electron(scale=1.0):
+    """sigma_1..sigma_4 for e + Ar: elastic, excitations (11.55, 13.00 eV), ionisation (15.7 eV)."""
+    el = _table(0.0, 1000.0, 96, lambda e: 1.5e-19 * scale * (0.08 + e / 12.0) / (1.0 + (e / 12.0) ** 2))
+
+    def bump(thr, amp):
+        def f(e):
+            x = np.maximum(e - thr, 0.0)
+            return amp * x / (x + 40.0) ** 2 * 40.0
+        return f
+    ex1 = _table(11.55, 1000.0, 64, bump(11.55, 4e-21 * scale))
+    ex2 = _table(13.00, 1000.0, 64, bump(13.00, 8e-21 * scale))
+    ion = _table(15.7, 1000.0, 64, bump(15.7, 1.1e-19 * scale))
+    return el, ex1, ex2, ion

@@ -1,0 +1,75 @@
+"""Host mirror of FiniteDifferenceMethod/src/generalized_poisson.jl for the path."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class PoissonSolver:
+    """PoissonSolver{:xy,2}  generalized_poisson.jl:11-20 -- the operator lives on the device in
+    separable form (or as a dense inverse for irregular Dirichlet masks)."""
+
+    def __init__(self, grid, eps0):
+        self.grid, self.eps0 = grid, float(eps0)
+        self._rt = grid._rt
+        self.dh = grid.dh
+        L.check(self._rt.lib.iskb_poisson_create(self._rt.h, self.eps0))
+
+    @property
+    def mode(self):
+        m = L.i32()
+        L.check(self._rt.lib.iskb_poisson_mode(self._rt.h, C.byref(m)))
+        return {1: "separable", 2: "dense"}[m.value]
+
+    def dense(self):
+        """(A, b) exactly as the reference assembles them (debug / parity)."""
+        nn = len(self.grid)
+        A = np.zeros((nn, nn), order="F")
+        b = np.zeros(nn)
+        L.check(self._rt.lib.iskb_poisson_get_dense(self._rt.h, L.ptr(A), L.ptr(b)))
+        return A, b
+
+
+def create_poisson_solver(grid, eps0):
+    """create_poisson_solver(grid::CartesianGrid{2}, eps0)  :27-30"""
+    return PoissonSolver(grid, eps0)
+
+
+def apply_periodic(ps, axis):
+    """apply_periodic(ps, axis)  :286-324"""
+    L.check(ps._rt.lib.iskb_poisson_apply_periodic(ps._rt.h, int(axis)))
+
+
+def apply_dirichlet(ps, nodes, phi0):
+    """apply_dirichlet(ps, nodes::BitArray, phi0)  :205-215.  Whole-edge masks take the cheap path."""
+    nodes = np.asarray(nodes, dtype=bool)
+    nx, ny = ps.grid.n
+    for edge, sel in ((L.EDGE_LEFT, (0, slice(None))), (L.EDGE_RIGHT, (nx - 1, slice(None))),
+                      (L.EDGE_BOTTOM, (slice(None), 0)), (L.EDGE_TOP, (slice(None), ny - 1))):
+        m = np.zeros((nx, ny), dtype=bool)
+        m[sel] = True
+        if np.array_equal(m, nodes):
+            L.check(ps._rt.lib.iskb_poisson_apply_dirichlet_edge(ps._rt.h, edge, float(phi0)))
+            return
+    mask = np.asfortranarray(nodes.astype(np.uint8))
+    L.check(ps._rt.lib.iskb_poisson_apply_dirichlet(ps._rt.h, L.ptr(mask), float(phi0)))
+
+
+def calculate_electric_potential(ps, f):
+    """phi = calculate_electric_potential(ps, f) with f = -rho  :372-378 (ParticleInCell.jl:126)."""
+    rho = -np.asfortranarray(f, dtype=np.float64)
+    ps._rt.set_fields(rho=rho)
+    L.check(ps._rt.lib.iskb_field_solve(ps._rt.h))
+    return ps._rt.fields(rho=False, E=False)[1]
+
+
+def calculate_electric_field(ps, phi=None):
+    """E = calculate_electric_field(ps, phi)  :398-410 -- E of the last solve (phi is on the device)."""
+    return ps._rt.fields(rho=False, phi=False)[2]
+
+
+def calculate_magnetic_field(ps):
+    """calculate_magnetic_field  :412-419: identically zero."""
+    nx, ny = ps.grid.n
+    return np.zeros((nx, ny, 3), order="F")

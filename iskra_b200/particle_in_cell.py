@@ -1,0 +1,338 @@
+"""Host mirror of the ParticleInCell module API that problem/*.jl scripts call
+(ParticleInCell/src/ParticleInCell.jl and pic/*.jl), backed by the device library.
+
+Julia's `f!` functions are spelled `f_` here.  KineticSpecies keeps lazily-synced host mirrors so
+that script idioms like `e.np = 0`, `iHe.x .= e.x` (problem/10_two_streams.jl:62-68) keep working:
+reading `.x/.v/.wg/.id` pulls from the device if it is newer and marks the host copy as the
+authority until the next device operation pushes it back.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+from .units_and_constants import kB
+
+
+# ---- species ------------------------------------------------------------------------------------
+class KineticSpecies:
+    """KineticSpecies{2,3}  pic/kinetic.jl:1-18."""
+
+    def __init__(self, name, N, D=2, V=3):
+        if (D, V) != (2, 3):
+            raise NotImplementedError("only KineticSpecies{2,3} is on the hot path (SURVEY.md 8a)")
+        self.name = name
+        self.N = int(N)
+        self._x = np.zeros((N, 2), order="F")
+        self._v = np.zeros((N, 3), order="F")
+        self._wg = np.ones(N)
+        self._id = np.arange(1, N + 1, dtype=np.uint32)      # particle_uuids, kinetic.jl:15
+        self._np = 0
+        self.n = np.zeros((0, 0))
+        self.m = 0.0
+        self.q = 0.0
+        self.w0 = 1.0
+        self._rt = None
+        self._h = None
+        self._host_newer = True
+        self._dev_newer = False
+
+    def __repr__(self):
+        return self.name
+
+    # -- lazy sync -----------------------------------------------------------------------------
+    def _bind(self, grid):
+        rt = grid._rt
+        if self._rt is rt:
+            return
+        if self._rt is not None:
+            raise RuntimeError("species %s is already bound to another grid" % self.name)
+        h = L.vp()
+        L.check(rt.lib.iskb_species_create(rt.h, self.N, self.q, self.m, self.w0, C.byref(h)))
+        self._rt, self._h = rt, h
+        self._host_newer = True
+
+    def _push(self, grid=None):
+        """make the device copy current"""
+        if grid is not None:
+            self._bind(grid)
+        if self._rt is None:
+            raise RuntimeError("species %s is not bound to a grid yet" % self.name)
+        if self._host_newer:
+            L.check(self._rt.lib.iskb_species_upload(self._h, L.ptr(self._x), L.ptr(self._v), L.ptr(self._wg),
+                                                     L.ptr(self._id), self._np, self.N))
+            self._host_newer = False
+            self._dev_newer = False
+
+    def _pull(self):
+        """make the host copy current"""
+        if self._dev_newer:
+            L.check(self._rt.lib.iskb_species_download(self._h, L.ptr(self._x), L.ptr(self._v), L.ptr(self._wg),
+                                                       L.ptr(self._id), self.N))
+            self._np = self._query_np()
+            self._dev_newer = False
+
+    def _query_np(self):
+        v = L.i64()
+        L.check(self._rt.lib.iskb_species_np(self._h, C.byref(v)))
+        return v.value
+
+    def _touched_on_device(self):
+        self._dev_newer = True
+
+    @property
+    def np(self):
+        if self._dev_newer:
+            return self._query_np()
+        return self._np
+
+    @np.setter
+    def np(self, value):
+        self._pull()
+        self._np = int(value)
+        self._host_newer = True
+
+    def _host(name):
+        def get(self):
+            self._pull()
+            self._host_newer = True     # the caller may write through the returned array
+            return getattr(self, name)
+
+        def set_(self, value):
+            self._pull()
+            getattr(self, name)[...] = value
+            self._host_newer = True
+        return property(get, set_)
+
+    x = _host("_x")
+    v = _host("_v")
+    wg = _host("_wg")
+    id = _host("_id")
+
+
+class FluidSpecies:
+    """FluidSpecies  pic/fluid.jl:1-11 -- on the path only as the read-only MCC target."""
+
+    def __init__(self, name, mu, q, m, n, T):
+        self.name, self.mu, self.q, self.m, self.T = name, float(mu), float(q), float(m), float(T)
+        self.n = np.asfortranarray(n, dtype=np.float64)
+
+    def __repr__(self):
+        return self.name
+
+
+def is_fluid(species):
+    return isinstance(species, FluidSpecies)
+
+
+def create_kinetic_species(name, N, q, m, weight, D=2, V=3):
+    """problem/configuration.jl:95-102"""
+    sp = KineticSpecies(name, N, D, V)
+    sp.q, sp.m = float(q), float(m)
+    sp._wg *= weight
+    sp.w0 = float(weight)
+    return sp
+
+
+# ---- sources ------------------------------------------------------------------------------------
+class MaxwellianSource:
+    """MaxwellianSource{D,V}  pic/sources.jl:8-22"""
+
+    def __init__(self, rate, wx, wv, dx=None, dv=None):
+        self.rate = float(rate)
+        self.wx = np.asarray(wx, dtype=np.float64).reshape(-1)
+        self.wv = np.asarray(wv, dtype=np.float64).reshape(-1)
+        self.dx = np.zeros_like(self.wx) if dx is None else np.asarray(dx, dtype=np.float64).reshape(-1)
+        self.dv = np.zeros_like(self.wv) if dv is None else np.asarray(dv, dtype=np.float64).reshape(-1)
+        self.seed = 0
+
+
+def thermal_speed(T, m):
+    """problem/configuration.jl:79-81"""
+    return math.sqrt(2 * kB * T / m)
+
+
+def create_thermalized_beam(species, x, vb, dx=None, T=300.0, rate=1.0):
+    """problem/configuration.jl:89-93"""
+    vth = thermal_speed(T, species.m) * np.ones(3)
+    return MaxwellianSource(rate, x, vth, dx=dx, dv=vb)
+
+
+_sample_calls = [0]
+
+
+def sample_(src, species, dt, grid=None, seed=None):
+    """sample!(src, species, dt)  pic/sources.jl:24-34 -- drawn on the device (Philox)."""
+    n = int(math.floor(src.rate * dt))            # :30
+    species._push(grid)
+    if seed is None:
+        _sample_calls[0] += 1
+        seed = (src.seed << 20) + _sample_calls[0]
+    L.check(species._rt.lib.iskb_species_sample_maxwellian(species._h, n, L.ptr(src.wx), L.ptr(src.dx),
+                                                           L.ptr(src.wv), L.ptr(src.dv), int(seed)))
+    species._touched_on_device()
+
+
+def init(src, species, dt, grid=None):
+    """init(src, species, dt)  ParticleInCell.jl:47-49"""
+    sample_(src, species, dt, grid)
+
+
+# ---- operators ----------------------------------------------------------------------------------
+def particle_cell(part, grid):
+    """particle_cell for every live particle  ParticleInCell.jl:28-35 -> (i, j, hx, hy), 1-based."""
+    part._push(grid)
+    n = part.np
+    i = np.zeros(n, dtype=np.int32)
+    j = np.zeros(n, dtype=np.int32)
+    hx = np.zeros(n)
+    hy = np.zeros(n)
+    L.check(part._rt.lib.iskb_cell_index(part._h, L.ptr(i), L.ptr(j), L.ptr(hx), L.ptr(hy)))
+    return i, j, hx, hy
+
+
+def grid_to_particle(grid, part, u=None):
+    """grid_to_particle(grid, part, (i,j)->E[i,j,:])  cloud_in_cell.jl:20-36.  `u`: (nx,ny,3) node
+    array to gather, or None for the field currently on the device."""
+    part._push(grid)
+    if u is not None:
+        grid._rt.set_fields(E=u)
+    n = part.np
+    out = np.zeros((n, 3), order="F")
+    if n:
+        L.check(part._rt.lib.iskb_gather(part._h, L.ptr(out)))
+    return out
+
+
+def particle_to_grid(part, grid):
+    """particle_to_grid(part, grid, p->wg[p])  cloud_in_cell.jl:1-18"""
+    return density(part, grid) * __import__("iskra_b200").regular_grids.cell_volume(grid)
+
+
+def density(species, grid):
+    """density(species, grid)  kinetic.jl:53 / fluid.jl:11"""
+    if is_fluid(species):
+        return species.n
+    species._push(grid)
+    n = np.zeros(grid.n, order="F")
+    L.check(species._rt.lib.iskb_density(species._h, L.ptr(n)))
+    species.n = n
+    return n
+
+
+class BorisPusher:
+    """BorisPusher{:xy}  pushers.jl:4-5"""
+
+
+def create_boris_pusher():
+    return BorisPusher()
+
+
+def push_particles_(pusher, part, E, B, dt, grid=None):
+    """push_particles!(pusher, part, E, B, dt)  pushers.jl:8-11.  E: (np,3) per-particle field, or
+    None to gather from the device field on the fly.  B must be zero (generalized_poisson.jl:412-419)."""
+    if B is not None and np.any(np.asarray(B) != 0):
+        raise NotImplementedError("B != 0 is outside the hot path (calculate_magnetic_field == 0)")
+    part._push(grid)
+    pe = None if E is None else np.asfortranarray(E, dtype=np.float64)
+    L.check(part._rt.lib.iskb_push(part._h, L.ptr(pe), float(dt)))
+    part._touched_on_device()
+
+
+def _modes(dims, mode):
+    dims = (1, 2) if dims is None else tuple(dims)
+    return (mode if 1 in dims else L.BND_NONE, mode if 2 in dims else L.BND_NONE)
+
+
+def wrap_(part, grid, dims=None):
+    """wrap!(part, grid; dims)  surfaces/wrap.jl:20-33"""
+    part._push(grid)
+    mx, my = _modes(dims, L.BND_WRAP)
+    L.check(part._rt.lib.iskb_boundary(part._h, mx, my, None))
+    part._touched_on_device()
+
+
+def discard_(part, grid, dims=None):
+    """discard!(part, grid; dims)  surfaces/wrap.jl:1-18 -> number removed"""
+    part._push(grid)
+    mx, my = _modes(dims, L.BND_DISCARD)
+    removed = L.i64()
+    L.check(part._rt.lib.iskb_boundary(part._h, mx, my, C.byref(removed)))
+    part._touched_on_device()
+    return removed.value
+
+
+def sort_by_cell_(part, grid):
+    """New (no reference counterpart): stable sort of the rows by cell; returns the permutation."""
+    part._push(grid)
+    perm = np.zeros(part.np, dtype=np.uint32)
+    L.check(part._rt.lib.iskb_sort_by_cell(part._h, L.ptr(perm)))
+    part._touched_on_device()
+    return perm
+
+
+# ---- hooks and loop (ParticleInCell.jl:37-45, 51-72, 84-139) --------------------------------------
+class Hooks:
+    def __init__(self):
+        self.enter_loop = lambda: None
+        self.after_loop = lambda it, t, dt: None
+        self.exit_loop = lambda: None
+        self.after_push = lambda part, grid: wrap_(part, grid)   # default, ParticleInCell.jl:41
+
+
+hooks = Hooks()
+
+
+def advance_(part, E, B, dt, config):
+    """advance!(part::KineticSpecies, E, B, dt, config)  ParticleInCell.jl:51-72 (operator by operator)."""
+    grid = config.grid
+    if E is not None:
+        grid._rt.set_fields(E=E)
+    push_particles_(config.pusher, part, None, None, dt, grid)     # gather :57 + push :59 fused
+    hooks.after_push(part, grid)                                    # :61
+
+
+def perform_(interaction, E, dt, config):
+    """extension point perform!(interaction, E, dt, config)  ParticleInCell.jl:44"""
+    return interaction.perform_(E, dt, config)
+
+
+def solve(config, dt=1e-5, timesteps=200, after_push=None, sort_interval=0, fused=True):
+    """solve(config, dt, timesteps)  ParticleInCell.jl:84-139.
+
+    fused=True runs the loop body as one device call per step (iskb_step) and still fires
+    after_loop every step, so scripts' iteration() (diagnostics, RF Dirichlet update) keep working.
+    `after_push` = (mode_x, mode_y) boundary modes replacing the after_push hook on that path."""
+    grid, rt = config.grid, config.grid._rt
+    dt = float(dt)
+    hooks.enter_loop()                                                        # :95
+    kinetic = [s for s in config.species if not is_fluid(s)]
+    for s in kinetic:
+        s._push(grid)
+    for inter in config.interactions:
+        inter._bind(config)
+    if fused:
+        mx, my = after_push if after_push is not None else (L.BND_WRAP, L.BND_WRAP)
+        rt.set_after_push(mx, my)
+        rt.set_sort_interval(sort_interval)
+    for it in range(1, timesteps + 1):
+        if fused:
+            rt.step(dt, 1)
+            for s in kinetic:
+                s._touched_on_device()
+        else:
+            for inter in config.interactions:                                 # :109-111
+                inter.perform_(None, dt, config)
+            for part in kinetic:                                              # :113-115
+                advance_(part, None, None, dt, config)
+            L.check(rt.lib.iskb_rho_zero(rt.h))                               # :118
+            for part in kinetic:                                              # :119-124
+                part._push(grid)
+                L.check(rt.lib.iskb_density(part._h, None))
+                L.check(rt.lib.iskb_rho_accumulate(rt.h, part._h))
+            L.check(rt.lib.iskb_rho_allreduce(rt.h))
+            L.check(rt.lib.iskb_field_solve(rt.h))                            # :126-128
+        hooks.after_loop(it, it * dt - dt, dt)                                # :134
+    rt.synchronize()
+    hooks.exit_loop()                                                         # :137

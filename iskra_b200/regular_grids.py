@@ -1,0 +1,50 @@
+"""Host mirror of RegularGrids/src/RegularGrids.jl for the path (CartesianGrid{2} only)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .runtime import Runtime
+
+_BC = {"open": L.BC_OPEN, "periodic": L.BC_PERIODIC}
+
+
+class UniformGrid:
+    """UniformGrid{:xy,2}  RegularGrids.jl:7-15.  Creating it allocates rho/phi/E on the device."""
+
+    def __init__(self, xx, yy, left="open", right="open", bottom="open", top="open", device=None):
+        xx = np.asarray(xx, dtype=np.float64)
+        yy = np.asarray(yy, dtype=np.float64)
+        self.n = (len(xx), len(yy))
+        dx = float(xx[1] - xx[0]) if len(xx) > 1 else 1.0      # :60
+        dy = float(yy[1] - yy[0]) if len(yy) > 1 else 1.0      # :61
+        self.dh = (dx, dy)
+        self.bcs = ((left, right), (bottom, top))
+        self.origin = (float(xx[0]), float(yy[0]))
+        self.coords = (np.repeat(xx[:, None], len(yy), 1), np.repeat(yy[None, :], len(xx), 0))
+        self.data = {}
+        self._rt = Runtime(device)
+        self._rt.grid = self
+        bcs = (C.c_int32 * 4)(_BC[left], _BC[right], _BC[bottom], _BC[top])
+        L.check(self._rt.lib.iskb_grid_set(self._rt.h, self.n[0], self.n[1], dx, dy, self.origin[0], self.origin[1], bcs))
+
+    def size(self):
+        return self.n
+
+    def __len__(self):
+        return self.n[0] * self.n[1]
+
+
+CartesianGrid = UniformGrid
+
+
+def create_uniform_grid(xx, yy, left="open", right="open", bottom="open", top="open", device=None):
+    """create_uniform_grid(xx, yy; left, right, bottom, top)  RegularGrids.jl:55-69"""
+    return UniformGrid(xx, yy, left, right, bottom, top, device)
+
+
+def cell_volume(g):
+    """cell_volume(g::CartesianGrid{2})  RegularGrids.jl:26-38 (computed on the device)."""
+    V = np.zeros(g.n, order="F")
+    L.check(g._rt.lib.iskb_cell_volume(g._rt.h, L.ptr(V)))
+    return V

@@ -57,6 +57,7 @@ def lib():
     global _lib
     if _lib is None:
         build()
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # spinning threads hurt on shared vCPUs
         L = C.CDLL(_SO)
         L.orc_num_threads.restype = C.c_int
         L.orc_discard.restype = C.c_int64
