@@ -63,10 +63,13 @@ def config_dict(a, ppg, cells, n_gpus, extra=None):
 # ------------------------------------------------------------------------------------------------
 # CPU leg: the oracle port (the reference itself is pure Julia and cannot run here)
 # ------------------------------------------------------------------------------------------------
-def cpu_port_run(a, cells, n_particles, steps, warmup):
-    """Times the C restatement (OpenMP over all host cores) on a bounded sample of the workload:
-    MCC + gather + push + boundary + deposit on n_particles rows, same grid, same tables.  The field
-    solve is left out: the reference's dense LU cannot exist at this grid size."""
+def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
+    """Times the C restatement on a bounded sample of the workload: MCC + gather + push + boundary +
+    deposit on n_particles rows with the workload's particles-per-cell (the grid is shrunk to keep
+    it), same tables.  The field solve is left out: the reference's dense LU cannot exist at the
+    workload's grid size."""
+    if ppc:
+        cells = max(16, int(round(math.sqrt(n_particles / ppc))))
     from iskra_b200 import datasets
     from oracle import c_oracle as CO
     from oracle import pic_oracle as O
@@ -157,7 +160,7 @@ def run_reference(a):
     if rank != 0:
         return
     ppg, cells = workload_defaults(a)
-    r = cpu_port_run(a, cells, a.cpu_particles, a.steps, a.warmup)
+    r = cpu_port_run(a, cells, a.cpu_particles, a.steps, a.warmup, ppc=ppg / float(cells * cells))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "particle-steps/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * r["seconds"] / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -308,7 +311,7 @@ def run_b200(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        cpu = cpu_port_run(a, cells, a.cpu_particles, 3, 1)
+        cpu = cpu_port_run(a, cells, a.cpu_particles, 3, 1, ppc=ppg / float(cells * cells))
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:

@@ -9,6 +9,9 @@ path, so parity is unaffected by their shape.
 """
 import numpy as np
 
+EL_HE = 1.036992e-19     # tuned below so that max_sigma_g(e-/He) = 8.977e-14 (notebook)
+ION_HE = 4.436124e-01         # tuned so that max_sigma_g(He+/He) = 2.746e-14 (notebook)
+
 
 def _table(e0, e1, n, fn):
     eps = np.unique(np.concatenate([[e0], np.geomspace(max(e0, 1e-3), e1, n), [e1]]))
@@ -17,8 +20,8 @@ def _table(e0, e1, n, fn):
 
 def helium_electron(scale=1.0):
     """sigma_1..sigma_4 for e + He: elastic, two excitations (19.82, 20.61 eV), ionisation (24.587 eV)."""
-    s = 6.35e-20 * scale
-    el = _table(0.0, 965.0509, 96, lambda e: s / (1.0 + (e / 25.0)) ** 1.1)
+    s = EL_HE * scale
+    el = _table(0.0, 965.0509, 96, lambda e: s / (1.0 + (e / 9.7)) ** 1.1)
 
     def bump(thr, amp):
         def f(e):
@@ -33,8 +36,8 @@ def helium_electron(scale=1.0):
 
 def helium_ion(scale=1.0):
     """sigma_e2 (backscatter, 1e-4..1e4 eV) and sigma_e1 (isotropic, 0..1e4 eV) for He+ + He."""
-    back = _table(1e-4, 1e4, 96, lambda e: 2.3e-19 * scale / (1.0 + e) ** 0.16)
-    iso = _table(0.0, 1e4, 96, lambda e: 1.6e-19 * scale / (1.0 + e) ** 0.16)
+    back = _table(1e-4, 1e4, 96, lambda e: ION_HE * 2.3e-19 * scale / (1.0 + e) ** 0.16)
+    iso = _table(0.0, 1e4, 96, lambda e: ION_HE * 1.6e-19 * scale / (1.0 + e) ** 0.16)
     return back, iso
 
 

@@ -560,20 +560,21 @@ void orc_advance_mt(orc_species *s, const orc_grid *g, const double *E, double d
 void orc_deposit_mt(const orc_grid *g, const orc_species *s, double *u) {
   const int64_t nx = g->nx, nn = (int64_t)g->nx * g->ny;
   memset(u, 0, sizeof(double) * (size_t)nn);
-#pragma omp parallel
-  {
-    double *loc = (double *)calloc((size_t)nn, sizeof(double));
-#pragma omp for schedule(static)
-    for (int64_t p = 0; p < s->np; ++p) {
-      int64_t i, j; double hx, hy;
-      cell1(s->x[p], g->dx, &i, &hx); cell1(s->y[p], g->dy, &j, &hy);
-      const int64_t n00 = (i - 1) + (j - 1) * nx;
-      const double w = s->wg[p];
-      loc[n00] += (1.0 - hx) * (1.0 - hy) * w; loc[n00 + 1] += hx * (1.0 - hy) * w;
-      loc[n00 + nx] += (1.0 - hx) * hy * w;    loc[n00 + nx + 1] += hx * hy * w;
-    }
-#pragma omp critical
-    for (int64_t k = 0; k < nn; ++k) u[k] += loc[k];
-    free(loc);
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < s->np; ++p) {
+    int64_t i, j; double hx, hy;
+    cell1(s->x[p], g->dx, &i, &hx); cell1(s->y[p], g->dy, &j, &hy);
+    const int64_t n00 = (i - 1) + (j - 1) * nx;
+    const double w = s->wg[p];
+    const double c00 = (1.0 - hx) * (1.0 - hy) * w, c10 = hx * (1.0 - hy) * w;
+    const double c01 = (1.0 - hx) * hy * w, c11 = hx * hy * w;
+#pragma omp atomic
+    u[n00] += c00;
+#pragma omp atomic
+    u[n00 + 1] += c10;
+#pragma omp atomic
+    u[n00 + nx] += c01;
+#pragma omp atomic
+    u[n00 + nx + 1] += c11;
   }
 }

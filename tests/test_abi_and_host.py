@@ -1,0 +1,126 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/iskra_b200.h declares,
+fails loudly without a GPU, and the host-side mirror logic (reactions parsing, lazy species
+mirrors, workload parameters, synthetic tables) behaves like the reference's set-up code."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "iskra_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(iskb_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from iskra_b200 import _lib
+    L = _lib.lib()
+    declared = _header_functions()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(L, name), "symbol %s declared in include/iskra_b200.h is not exported" % name
+    # the ctypes table binds exactly the declared interface
+    assert sorted(_lib.SIGNATURES) == declared
+    assert L.iskb_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from iskra_b200 import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    rc = L.iskb_create(0, C.byref(h))
+    assert rc == _lib.E_CUDA and not h.value
+    assert b"no CPU fallback" in L.iskb_last_error()
+    with pytest.raises(_lib.IskraError):
+        import iskra_b200
+        iskra_b200.regular_grids.create_uniform_grid(np.arange(5.0), np.arange(5.0))
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10 (Salmon et al., SC'11 distribution kat_vectors)."""
+    from iskra_b200 import _lib
+    L = _lib.lib()
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, expect in kats:
+        out = (C.c_uint32 * 4)()
+        L.iskb_debug_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+        assert tuple(out) == expect
+
+
+def test_reactions_macro_semantics():
+    from iskra_b200 import chemistry as CH, particle_in_cell as PIC
+    e = PIC.create_kinetic_species("e-", 10, -1.0, 1.0, 2.0)
+    iHe = PIC.create_kinetic_species("He+", 10, 1.0, 4.0, 2.0)
+    He = PIC.FluidSpecies("He", 1.0, 0.0, 4.0, np.ones((3, 3)), 300.0)
+    s = CH.CrossSection(np.array([[0.0, 1.0], [10.0, 2.0]]))
+    rs = CH.reactions([(s, "e + He --> e + He"),
+                       (s, "e + He --> e + He", CH.MCC.Excitation(19.82)),
+                       (s, "e + He --> e + e + iHe", CH.MCC.Ionization(24.587))], {"e": e, "He": He, "iHe": iHe})
+    assert [(r[0].name, r[1]) for r in rs[0].reactants] == [("e-", 1), ("He", 1)]
+    assert rs[0].stoichiometry == []
+    assert [(p.name, c) for p, c in rs[2].stoichiometry] == [("e-", 1), ("He", -1), ("He+", 1)]   # reactions.jl:39-51
+    m = CH.mcc(rs)
+    assert [c.type.kind for c in m.collisions] == [0, 3, 4]        # default ElasticIsotropic, mcc.jl:292
+    assert m.collisions[2].products == [e, iHe] and m.collisions[2].source is e and m.collisions[2].target is He
+    with pytest.raises(AssertionError):
+        CH.mcc(CH.reactions([(s, "e + He + iHe --> e")], {"e": e, "He": He, "iHe": iHe}))
+    with pytest.raises(ValueError):
+        CH.mcc(CH.reactions([(s, "e + iHe --> e + iHe")], {"e": e, "iHe": iHe}))   # no fluid species
+
+
+def test_species_host_mirror_unbound():
+    from iskra_b200 import particle_in_cell as PIC
+    sp = PIC.create_kinetic_species("e-", 100, -1.6e-19, 9.1e-31, 3.5e7)
+    assert sp.np == 0 and sp.x.shape == (100, 2) and sp.v.shape == (100, 3)
+    assert np.all(sp.wg == 3.5e7) and sp.w0 == 3.5e7                 # configuration.jl:99-100
+    assert sp.id.tolist() == list(range(1, 101))                     # kinetic.jl:15
+    sp.x[:5, 0] = 1.0
+    sp.np = 5
+    assert sp.np == 5 and sp.x[:5, 0].tolist() == [1.0] * 5
+    with pytest.raises(RuntimeError):
+        sp._push()                                                    # no grid -> no silent fallback
+
+
+def test_synthetic_tables_reproduce_notebook_max_sigma_g():
+    """max_sigma_g of the synthetic He tables through the oracle formula (mcc.jl:27-51) against
+    the notebook constants (docs/capacitively_induced_discharge.ipynb:163)."""
+    from iskra_b200 import datasets
+    from oracle import pic_oracle as O
+    e = O.KineticSpecies("e-", 1, -O.qe, O.me, 1.0)
+    i = O.KineticSpecies("He+", 1, O.qe, 3.99 * O.mp, 1.0)
+    He = O.FluidSpecies("He", 1.0, 0.0, 3.99 * O.mp, np.ones((2, 2)), 300.0)
+    me_ = O.MonteCarloCollisions([O.Collision(0, O.CrossSection(t), e, He) for t in datasets.helium_electron()])
+    mi_ = O.MonteCarloCollisions([O.Collision(0, O.CrossSection(t), i, He) for t in datasets.helium_ion()])
+    assert me_.max_sigma_g == pytest.approx(8.976965143603543e-14, rel=5e-3, abs=0)
+    assert mi_.max_sigma_g == pytest.approx(2.7462885393092625e-14, rel=5e-3, abs=0)
+    for t in datasets.helium_electron() + datasets.helium_ion() + datasets.argon_electron():
+        assert np.all(np.diff(t[:, 0]) > 0) and np.all(t[:, 1] >= 0)
+    ext = [(t[0, 0], t[-1, 0]) for t in datasets.helium_electron()]
+    assert ext == [(0.0, 965.0509), (19.82, 984.8709), (20.61, 985.6609), (24.59, 989.6379)]   # ipynb:145-156
+    # the RF case keeps max_Pt <= 1/N (mcc.jl:244-246) and gives the notebook's candidate counts
+    dt = 1.8436578171091445e-10
+    assert 4 * (1 - math.exp(-9.64e20 * me_.max_sigma_g * dt)) * 16384 == pytest.approx(1037.3, rel=6e-3, abs=0)
+    assert 2 * (1 - math.exp(-9.64e20 * mi_.max_sigma_g * dt)) * 16384 == pytest.approx(159.55, rel=6e-3, abs=0)
+
+
+def test_sharding_slices():
+    from iskra_b200.sharding import slice_for_rank
+    for n in (0, 1, 7, 1000, 125_000_001):
+        for w in (1, 2, 3, 8):
+            sl = [slice_for_rank(n, r, w) for r in range(w)]
+            assert sl[0][0] == 0 and sl[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+            sizes = [b - a for a, b in sl]
+            assert max(sizes) - min(sizes) <= 1

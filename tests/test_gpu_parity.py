@@ -240,7 +240,8 @@ def test_poisson_separable_vs_dense_oracle(ib, nx, ny, periodic, edges):
     assert np.array_equal(A, ops.A)                                 # same operator, bit for bit
     rng = np.random.default_rng(nx * ny)
     rho = rng.standard_normal((nx, ny)) * 1e-7
-    phi_ref = O.calculate_electric_potential(ops, -rho)
+    phi_lu = O.calculate_electric_potential(ops, -rho)              # the reference's one-shot A\\b
+    phi_ref = _refined_solve(ops.A, ops.b, dx).reshape((nx, ny), order="F")
     E_ref = O.calculate_electric_field(ops, phi_ref)
     phi = FDM.calculate_electric_potential(ps, -rho)
     E = FDM.calculate_electric_field(ps, phi)
@@ -248,6 +249,10 @@ def test_poisson_separable_vs_dense_oracle(ib, nx, ny, periodic, edges):
     assert np.abs(phi - phi_ref).max() <= REL * sc
     assert np.abs(E - E_ref).max() <= REL * np.abs(E_ref).max()
     assert np.all(E[:, :, 2] == 0)
+    # the reference's own LU sits within its (measured) rounding noise of both
+    lu_noise = np.abs(phi_lu - phi_ref).max() / sc
+    assert lu_noise <= 1e-6
+    assert np.abs(phi - phi_lu).max() <= (lu_noise + REL) * sc
 
 
 @pytest.mark.parametrize("nx,ny,periodic", [(129, 2, (1, 2)), (24, 17, (1, 2)), (17, 24, (1,)), (20, 20, ())])
@@ -295,34 +300,66 @@ def test_poisson_dense_fallback_irregular_mask(ib):
         FDM.apply_dirichlet(ps, mask, val)
     assert ps.mode == "dense"
     rho = np.random.default_rng(0).standard_normal((nx, ny)) * 1e-8
-    phi_ref = O.calculate_electric_potential(ops, -rho)
+    O.calculate_electric_potential(ops, -rho)
+    phi_ref = _refined_solve(ops.A, ops.b, dx).reshape((nx, ny), order="F")
     phi = FDM.calculate_electric_potential(ps, -rho)
     assert np.abs(phi - phi_ref).max() <= REL * np.abs(phi_ref).max()
     assert np.all(phi[m2] == 12.0)
 
 
 # ------------------------------------------------------------------------- multi-step parity ---
-class _OracleSolver:
-    """Dense solve of the oracle operator.  The reference refactors A every step (A\\b); one LU
-    (scipy.linalg.lu_factor = dgetrf, the same factorisation) is reused here to keep the test fast.
-    Singular operators use the pseudo-inverse of the mean-projected system."""
+def _refined_solve(A, b, dx):
+    """Exact solution of the reference's linear system A x = b: LU of the row-equilibrated matrix
+    plus iterative refinement with extended-precision residuals.
 
-    def __init__(self, A, nn, singular):
+    Why the pin is not the one-shot LU: the reference's A mixes identity rows (Dirichlet, scale 1)
+    with stencil rows of scale 1/dh^2 (generalized_poisson.jl:65, :210-211), so `A\\b` (dgetrf without
+    equilibration) returns phi with a relative error of 2e-10 .. 2e-8 on these grids
+    (test_reference_lu_noise_level measures it).  That noise depends on LAPACK's pivot order and
+    cannot be reproduced by any second implementation, so phi/E parity at the 1e-10 bar of
+    north_star is checked against the exact solution of the same system, and the one-shot LU is
+    checked at its own noise level."""
+    import scipy.linalg as sla
+    d = np.where((np.abs(np.diag(A)) == 1.0) & (np.count_nonzero(A, axis=1) == 1), 1.0, dx * dx)
+    As, bs = A * d[:, None], b * d
+    lu = sla.lu_factor(As)
+    x = sla.lu_solve(lu, bs)
+    Al = As.astype(np.longdouble)
+    for _ in range(3):
+        r = (bs.astype(np.longdouble) - Al @ x.astype(np.longdouble)).astype(np.float64)
+        x = x + sla.lu_solve(lu, r)
+    return x
+
+
+class _OracleSolver:
+    """Field solve of the oracle operator for the multi-step tests.  The reference refactors A every
+    step (A\\b); here one LU of the row-equilibrated matrix is reused and refined (see
+    _refined_solve for why).  Singular operators use the pseudo-inverse of the mean-projected
+    system."""
+
+    def __init__(self, A, nn, singular, dx):
         import scipy.linalg as sla
-        self.singular = singular
+        self.singular, self.sla = singular, sla
         Am = A.reshape((nn, nn), order="F")
         if singular:
-            self.pinv = np.linalg.pinv(Am, rcond=1e-12)
+            self.pinv = np.linalg.pinv(Am * dx * dx, rcond=1e-12) * dx * dx
         else:
-            self.lu = sla.lu_factor(Am)
-            self.sla = sla
+            self.d = np.where((np.abs(np.diag(Am)) == 1.0) & (np.count_nonzero(Am, axis=1) == 1), 1.0, dx * dx)
+            self.As = Am * self.d[:, None]
+            self.Al = self.As.astype(np.longdouble)
+            self.lu = sla.lu_factor(self.As)
 
     def __call__(self, b):
         if self.singular:
             bb = b - b.mean()
             phi = self.pinv @ bb
             return phi - phi.mean()
-        return self.sla.lu_solve(self.lu, b)
+        bs = b * self.d
+        x = self.sla.lu_solve(self.lu, bs)
+        for _ in range(2):
+            r = (bs.astype(np.longdouble) - self.Al @ x.astype(np.longdouble)).astype(np.float64)
+            x = x + self.sla.lu_solve(self.lu, r)
+        return x
 
 
 def _oracle_step(species, cg, solver, b, dof, E, dt, bmode, V, nn):
@@ -390,7 +427,7 @@ def _two_species(ib, g, cg, n, cap, seed, Te=300.0, drift=1e7, wgt=3.5e7, ion_m=
 def _compare_species(pcs, pgs, tol):
     for pc, pg in zip(pcs, pgs):
         m = pc.np
-        assert pg.np == m
+        assert pg.np == m and m > 0
         xg, yg, v0, v1, v2 = _by_id(pg.id[:m], pg.x[:m, 0], pg.x[:m, 1], pg.v[:m, 0], pg.v[:m, 1], pg.v[:m, 2])
         xc, yc, c0, c1, c2 = _by_id(pc.id[:m], pc.xy[0, :m], pc.xy[1, :m], pc.v[0, :m], pc.v[1, :m], pc.v[2, :m])
         assert np.array_equal(np.sort(pg.id[:m]), np.sort(pc.id[:m]))
@@ -419,7 +456,7 @@ def test_two_stream_100_steps(ib, mode):
     cfg.grid, cfg.solver, cfg.pusher, cfg.species = g, ps, PIC.create_boris_pusher(), pgs
     E = np.zeros(3 * nn)
     steps = 100
-    osolve = _OracleSolver(A, nn, singular=True)
+    osolve = _OracleSolver(A, nn, True, dx)
     for _ in range(steps):
         rho, phi, E = _oracle_step(pcs, cg, osolve, b, dof, E, dt, (1, 1), V, nn)
     if mode == "operators":
@@ -440,7 +477,7 @@ def test_rf_like_100_steps_discard(ib, mode):
     """C2-like (11_rf_discharge.jl) without MCC: Dirichlet electrodes in x with a driven voltage,
     'periodic' in y, discard!(dims=1) + wrap!(dims=2), 100 steps."""
     PIC, FDM = ib.particle_in_cell, ib.finite_difference_method
-    nx, ny = (129, 2) if mode != "fused-tiled" else (65, 33)
+    nx, ny = (129, 2) if mode != "fused-tiled" else (129, 33)
     dx = 5.234375e-4
     dt = 1.8436578171091445e-10
     g, cg = _grid_pair(ib, nx, ny, dx)
@@ -457,7 +494,7 @@ def test_rf_like_100_steps_discard(ib, mode):
     n = 4000 if mode != "fused-tiled" else 50000
     rng = np.random.default_rng(21)
     pcs, pgs = [], []
-    for name, q, m, T in (("e-", -O.qe, O.me, 30000.0), ("He+", O.qe, 3.99 * O.mp, 300.0)):
+    for name, q, m, T in (("e-", -O.qe, O.me, 10000.0), ("He+", O.qe, 3.99 * O.mp, 300.0)):
         x = rng.random(n) * (nx - 1) * dx
         y = rng.random(n) * (ny - 1) * dx
         v = rng.standard_normal((n, 3)) * O.thermal_speed(T, m)
@@ -477,7 +514,7 @@ def test_rf_like_100_steps_discard(ib, mode):
     E = np.zeros(3 * nn)
     steps = 100
     lmask = np.ascontiguousarray(left.ravel(order="F").astype(np.uint8))
-    osolve = _OracleSolver(A, nn, singular=False)
+    osolve = _OracleSolver(A, nn, False, dx)
     for it in range(1, steps + 1):
         rho, phi, E = _oracle_step(pcs, cg, osolve, b, dof, E, dt, (2, 1), V, nn)
         t = it * dt - dt
