@@ -155,7 +155,7 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
   cudaStreamSynchronize(c->stream);
   comm_destroy(c);
   for (iskb_mcc *m : c->mccs) {
-    cudaFree(m->d_tn); cudaFree(m->d_eps); cudaFree(m->d_sig); cudaFree(m->d_stats); cudaFree(m->d_nu);
+    cudaFree(m->d_tn); cudaFree(m->d_eps); cudaFree(m->d_sig); cudaFree(m->d_stats); cudaFree(m->d_nu); cudaFree(m->d_cand); cudaFree(m->d_coll); cudaFree(m->d_lists_cnt);
     delete m;
   }
   for (iskb_species *s : c->species) free_species(s);

@@ -71,6 +71,7 @@ struct PoissonState {
   bool b_cyclic = false;
   bool singular = false;
   bool use_fft = false;         // DST-I by FFT (ma+1 power of two)
+  int fft_log2M = 0;
   double *d_V = nullptr;        // ma x ma orthonormal eigenvectors (column-major), V[p,k]
   double *d_Vt = nullptr;       // transpose of V
   double *d_lam = nullptr;      // ma eigenvalues of the a-axis operator
@@ -164,6 +165,9 @@ struct iskb_mcc {
   void *d_procs = nullptr;      // MccProcDev[N]
   unsigned long long *d_stats = nullptr;   // [0] candidates, [1] collisions, [2+k] per process
   float *d_nu = nullptr;        // nx*ny*N counters of the last perform (lazy)
+  uint32_t *d_cand = nullptr;   // candidate rows of the current call
+  uint2 *d_coll = nullptr;      // (row, process) of accepted collisions
+  unsigned int *d_lists_cnt = nullptr;
   int64_t totals[2 + 16] = {0};
 };
 

@@ -8,8 +8,13 @@
 // 1 - exp(-n sigma_k g dt) in both schemes; they differ at second order in P, so
 // parity for this step is statistical by construction.
 //
-// Only the candidate decision touches every row, and it needs no particle data: one Philox call
-// decides four rows.  Candidate rows (a few %) then read x, v and the sigma tables.
+// Three dense phases with warp-aggregated compaction between them (no divergent fat paths):
+//   k_mcc_select  : the candidate decision touches every row but needs no particle data -- one
+//                   Philox call decides four rows; candidate rows are appended to a list
+//                   (one atomic per warp via ballot/popc);
+//   k_mcc_test    : one thread per candidate: cell, density, process choice, sigma(eps), acceptance
+//                   (mcc.jl:252-281); accepted rows go to the collider list the same way;
+//   k_mcc_collide : one thread per collider: kinematics (mcc.jl:129-229), ionisation appends.
 #include <algorithm>
 #include <cmath>
 
@@ -185,56 +190,109 @@ __device__ void collide(const MccDev &m, const ProcDev &pc, int64_t p, Rng &g) {
       if (!append_row(m.prod[pc.prod], x, y, tv, m.status)) return;
 }
 
-__global__ void k_snapshot_begin(int64_t *cnt) { cnt[CNT_BEGIN] = cnt[CNT_NSLOTS]; }
+__global__ void k_snapshot_begin(int64_t *cnt, unsigned int *lists_cnt) {
+  cnt[CNT_BEGIN] = cnt[CNT_NSLOTS];
+  lists_cnt[0] = 0;   // candidates
+  lists_cnt[1] = 0;   // colliders
+}
 
-__global__ void k_mcc(MccDev m) {
+// warp-aggregated append: returns the slot of this lane's item (or -1 when pred is false)
+__device__ __forceinline__ int64_t warp_append(bool pred, unsigned int *counter) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (!m) return -1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return pred ? (int64_t)base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+__global__ void k_mcc_select(MccDev m, unsigned int *lists_cnt, uint32_t *cand, unsigned int cand_cap) {
   const int64_t n = m.src.cnt[CNT_BEGIN];   // rows that existed when the step started
-  unsigned long long my_cand = 0, my_coll = 0;
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q * 4 < n;
+  const int64_t nq = (n + 3) / 4;
+  const int64_t nq_pad = (nq + 31) / 32 * 32;   // whole warps stay in the loop (ballots)
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq_pad;
        q += (int64_t)gridDim.x * blockDim.x) {
-    // one Philox call decides candidacy of rows 4q..4q+3 (counter draw index 0 of row 4q)
+    // one Philox call decides candidacy of rows 4q..4q+3 (draw index 0 of row 4q)
     const Philox4 o = philox4x32_10((uint32_t)(q * 4), (uint32_t)((q * 4) >> 32), m.call, 0u, m.k0, m.k1);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const int64_t p = q * 4 + s;
-      if (p >= n || o.c[s] >= m.p_cand_u32) continue;
-      const double px = m.src.col[0][p];
-      if (is_dead(px)) continue;
-      ++my_cand;
-      int i, j;
-      double hx, hy;
-      cell1(px, m.g.dx, i, hx);
-      cell1(m.src.col[1][p], m.g.dy, j, hy);
-      if (!cell_in_grid(i, j, m.g.nx, m.g.ny)) { atomicOr(m.status, ISKB_ST_OOB); continue; }
-      const int64_t node = (int64_t)(i - 1) + (int64_t)(j - 1) * m.g.nx;   // lower-left node :252-253
-      const double dens = m.tn[node];
-      if (dens < 0) continue;                                               // :254-257
-      Rng g(p, m.call, m.k0, m.k1, 1u);
-      const double U = g.u01();                                             // :260
-      int k = (int)floor(m.N * U + 1.0);                                    // :261
-      if (k > m.N) k = m.N;
-      const ProcDev pc = m.proc[k - 1];
-      const double2 e = m.E2[node];
-      double d[3];
-      d[0] = (m.tqm * e.x) * m.dt - m.src.col[2][p];                        // :266-267
-      d[1] = (m.tqm * e.y) * m.dt - m.src.col[3][p];
-      d[2] = (m.tqm * 0.0) * m.dt - m.src.col[4][p];
-      const double gg = norm3(d);
-      const double eps = 0.5 * m.m_eV * (gg * gg);                          // :268
-      const double skg = xsec_eval(m.eps + pc.offset, m.sig + pc.offset, pc.len, eps) * gg;
-      double Pk = 1.0 - exp(-dens * skg * m.dt);                            // :271
-      Pk /= m.p_cand;                                                       // :272  N*max_Pt
-      if (Pk > 1.0) { atomicOr(m.status, ISKB_ST_PK); continue; }           // :273-279
-      if (U > (double)k / m.N - Pk) {                                       // :281
-        collide(m, pc, p, g);
-        ++my_coll;
-        atomicAdd(&m.stats[2 + (k - 1)], 1ull);
-        if (m.nu) atomicAdd(&m.nu[node + (int64_t)(k - 1) * m.g.nx * m.g.ny], 1.0f);   // :283
+      const bool is_cand = p < n && o.c[s] < m.p_cand_u32;
+      const int64_t slot = warp_append(is_cand, &lists_cnt[0]);
+      if (is_cand) {
+        if (slot < cand_cap) cand[slot] = (uint32_t)p;
+        else atomicOr(m.status, ISKB_ST_CAPACITY);
       }
     }
   }
+}
+
+__global__ void k_mcc_test(MccDev m, unsigned int *lists_cnt, const uint32_t *__restrict__ cand,
+                           unsigned int cand_cap, uint2 *coll) {
+  unsigned int nc = lists_cnt[0];
+  if (nc > cand_cap) nc = cand_cap;
+  const unsigned int nc_pad = (nc + 31u) / 32u * 32u;
+  unsigned long long my_cand = 0;
+  for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < nc_pad; t += gridDim.x * blockDim.x) {
+    bool hit = false;
+    int64_t p = 0;
+    int k = 0;
+    if (t < nc) {
+      p = cand[t];
+      const double px = m.src.col[0][p];
+      if (!is_dead(px)) {
+        ++my_cand;
+        int i, j;
+        double hx, hy;
+        cell1(px, m.g.dx, i, hx);
+        cell1(m.src.col[1][p], m.g.dy, j, hy);
+        if (!cell_in_grid(i, j, m.g.nx, m.g.ny)) {
+          atomicOr(m.status, ISKB_ST_OOB);
+        } else {
+          const int64_t node = (int64_t)(i - 1) + (int64_t)(j - 1) * m.g.nx;   // lower-left node :252-253
+          const double dens = m.tn[node];
+          if (dens >= 0) {                                                      // :254-257
+            Rng g(p, m.call, m.k0, m.k1, 1u);
+            const double U = g.u01();                                           // :260
+            k = (int)floor(m.N * U + 1.0);                                      // :261
+            if (k > m.N) k = m.N;
+            const ProcDev pc = m.proc[k - 1];
+            const double2 e = m.E2[node];
+            double d[3];
+            d[0] = (m.tqm * e.x) * m.dt - m.src.col[2][p];                      // :266-267
+            d[1] = (m.tqm * e.y) * m.dt - m.src.col[3][p];
+            d[2] = (m.tqm * 0.0) * m.dt - m.src.col[4][p];
+            const double gg = norm3(d);
+            const double eps = 0.5 * m.m_eV * (gg * gg);                        // :268
+            const double skg = xsec_eval(m.eps + pc.offset, m.sig + pc.offset, pc.len, eps) * gg;
+            double Pk = 1.0 - exp(-dens * skg * m.dt);                          // :271
+            Pk /= m.p_cand;                                                     // :272  N*max_Pt
+            if (Pk > 1.0) atomicOr(m.status, ISKB_ST_PK);                       // :273-279
+            else if (U > (double)k / m.N - Pk) {                                // :281
+              hit = true;
+              atomicAdd(&m.stats[2 + (k - 1)], 1ull);
+              if (m.nu) atomicAdd(&m.nu[node + (int64_t)(k - 1) * m.g.nx * m.g.ny], 1.0f);   // :283
+            }
+          }
+        }
+      }
+    }
+    const int64_t slot = warp_append(hit, &lists_cnt[1]);
+    if (hit) coll[slot] = make_uint2((uint32_t)p, (uint32_t)k);   // collider list has cand_cap entries
+  }
   if (my_cand) atomicAdd(&m.stats[0], my_cand);
-  if (my_coll) atomicAdd(&m.stats[1], my_coll);
+}
+
+__global__ void k_mcc_collide(MccDev m, const unsigned int *__restrict__ lists_cnt, const uint2 *__restrict__ coll) {
+  const unsigned int nc = lists_cnt[1];
+  for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < nc; t += gridDim.x * blockDim.x) {
+    const uint2 c = coll[t];
+    Rng g((int64_t)c.x, m.call, m.k0, m.k1, 2u);   // draw block 1 belonged to the acceptance test
+    collide(m, m.proc[c.y - 1], (int64_t)c.x, g);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nc) atomicAdd(&m.stats[1], (unsigned long long)nc);
 }
 
 SpDev spdev(const iskb_species *s) {
@@ -303,13 +361,31 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
     CU_TRY(cudaMemsetAsync(mc->d_nu, 0, nn * N * sizeof(float), c->stream));
     m.nu = mc->d_nu;
   }
-  k_snapshot_begin<<<1, 1, 0, c->stream>>>(src->d_cnt);
+  // candidate / collider lists (lazy; sized for the worst case of every row being a candidate)
+  if (!mc->d_cand) {
+    CU_TRY(cudaMalloc(&mc->d_cand, src->cap * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&mc->d_coll, src->cap * sizeof(uint2)));
+    CU_TRY(cudaMalloc(&mc->d_lists_cnt, 2 * sizeof(unsigned int)));
+  }
+  const unsigned int cand_cap = (unsigned int)src->cap;
+  k_snapshot_begin<<<1, 1, 0, c->stream>>>(src->d_cnt, mc->d_lists_cnt);
   LAUNCH_CHECK(c);
   const int64_t bound = src->counts_stale ? src->cap : src->h_nslots;
   int64_t blocks = (bound / 4 + TPB) / TPB;
   if (blocks > (int64_t)c->n_sm * 8) blocks = (int64_t)c->n_sm * 8;
   if (blocks < 1) blocks = 1;
-  k_mcc<<<(int)blocks, TPB, 0, c->stream>>>(m);
+  k_mcc_select<<<(int)blocks, TPB, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
+  LAUNCH_CHECK(c);
+  // the list lengths live on the device: size the dense phases from the expected candidate count
+  int64_t exp_cand = (int64_t)(m.p_cand * (double)bound) + 1024;
+  int64_t b2 = (exp_cand + 127) / 128;
+  if (b2 > (int64_t)c->n_sm * 16) b2 = (int64_t)c->n_sm * 16;
+  k_mcc_test<<<(int)b2, 128, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap, mc->d_coll);
+  LAUNCH_CHECK(c);
+  int64_t b3 = (exp_cand / 8 + 127) / 128;
+  if (b3 > (int64_t)c->n_sm * 4) b3 = (int64_t)c->n_sm * 4;
+  if (b3 < 1) b3 = 1;
+  k_mcc_collide<<<(int)b3, 128, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_coll);
   LAUNCH_CHECK(c);
   return ISKB_OK;
 }

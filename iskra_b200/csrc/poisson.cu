@@ -283,61 +283,171 @@ __global__ void __launch_bounds__(256) k_dgemm(int M, int N, int K, const double
     }
 }
 
-// One thread per mode k: Thomas along b with precomputed factors; cyclic via Sherman-Morrison.
-// W[k + q*ma] holds the transformed rhs on entry and the transformed solution on exit.
-__global__ void k_thomas(int ma, int mb, int cyclic, int singular_mode, const double *__restrict__ mt,
-                         const double *__restrict__ qt, const double *__restrict__ qden,
-                         const double *__restrict__ gam, const double *__restrict__ msing, double *W) {
+// Thomas solve along b, one thread per mode k (coalesced over k), split in three passes so that
+// every pass reads and writes different buffers (__restrict__): the loads do not depend on the
+// recurrence and the unrolled loops keep many of them in flight per thread.
+//   pass 1  y_q = (r_q - y_{q-1}) * m_q                      (forward elimination, m precomputed)
+//   pass 2  x_q = y_q - m_q * x_{q+1}                        (back substitution)
+//   pass 3  x_q -= qt_q * f, f = (x_0 + x_{n-1}/gamma)*qden  (Sherman-Morrison, cyclic systems only)
+// The singular mode (all-periodic / all-open operator) is pinned and mean-projected instead.
+constexpr int TH_UNROLL = 16;
+
+__global__ void k_thomas_fwd(int ma, int mb, int singular_mode, const double *__restrict__ mt,
+                             const double *__restrict__ msing, const double *__restrict__ in,
+                             double *__restrict__ out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= ma) return;
   if (k == singular_mode) {
-    // T x = r with T singular (null vector = const): project r, pin x_0 = 0, remove the mean
+    // T x = r, T singular (null vector = const): project r, pin x_0 = 0
     double mean = 0.0;
-    for (int q = 0; q < mb; ++q) mean += W[k + (int64_t)q * ma];
+    for (int q = 0; q < mb; ++q) mean += in[k + (int64_t)q * ma];
     mean /= mb;
     double y = 0.0;
+    out[k] = 0.0;
     for (int q = 1; q < mb; ++q) {
-      y = ((W[k + (int64_t)q * ma] - mean) - y) * msing[q];
-      W[k + (int64_t)q * ma] = y;
+      y = ((in[k + (int64_t)q * ma] - mean) - y) * msing[q];
+      out[k + (int64_t)q * ma] = y;
     }
-    double x = 0.0, sum = 0.0;
-    for (int q = mb - 1; q >= 1; --q) {
-      x = W[k + (int64_t)q * ma] - msing[q] * x;
-      W[k + (int64_t)q * ma] = x;
-      sum += x;
-    }
-    const double xm = sum / mb;
-    W[k] = -xm;
-    for (int q = 1; q < mb; ++q) W[k + (int64_t)q * ma] -= xm;
     return;
   }
   double y = 0.0;
-  for (int q = 0; q < mb; ++q) {
+  int q = 0;
+  for (; q + TH_UNROLL <= mb; q += TH_UNROLL) {
+    double r[TH_UNROLL], m[TH_UNROLL];
+#pragma unroll
+    for (int u = 0; u < TH_UNROLL; ++u) {
+      const int64_t o = k + (int64_t)(q + u) * ma;
+      r[u] = in[o];
+      m[u] = mt[o];
+    }
+#pragma unroll
+    for (int u = 0; u < TH_UNROLL; ++u) {
+      y = (r[u] - y) * m[u];
+      out[k + (int64_t)(q + u) * ma] = y;
+    }
+  }
+  for (; q < mb; ++q) {
     const int64_t o = k + (int64_t)q * ma;
-    y = (W[o] - y) * mt[o];
-    W[o] = y;
+    y = (in[o] - y) * mt[o];
+    out[o] = y;
+  }
+}
+
+__global__ void k_thomas_bwd(int ma, int mb, int singular_mode, const double *__restrict__ mt,
+                             const double *__restrict__ msing, const double *__restrict__ in,
+                             double *__restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ma) return;
+  if (k == singular_mode) {
+    double x = 0.0, sum = 0.0;
+    for (int q = mb - 1; q >= 1; --q) {
+      x = in[k + (int64_t)q * ma] - msing[q] * x;
+      out[k + (int64_t)q * ma] = x;
+      sum += x;
+    }
+    const double xm = sum / mb;          // x_0 = 0 is part of the mean
+    out[k] = -xm;
+    for (int q = 1; q < mb; ++q) out[k + (int64_t)q * ma] -= xm;
+    return;
   }
   double x = 0.0;
-  for (int q = mb - 1; q >= 0; --q) {
+  int q = mb - 1;
+  {   // last row: x = y
     const int64_t o = k + (int64_t)q * ma;
-    x = W[o] - (q == mb - 1 ? 0.0 : mt[o] * x);
-    W[o] = x;
+    x = in[o];
+    out[o] = x;
+    --q;
   }
-  if (cyclic) {
-    const double f = (W[k] + W[k + (int64_t)(mb - 1) * ma] / gam[k]) * qden[k];
-    for (int q = 0; q < mb; ++q) {
-      const int64_t o = k + (int64_t)q * ma;
-      W[o] -= qt[o] * f;
+  for (; q - TH_UNROLL + 1 >= 0; q -= TH_UNROLL) {
+    double yv[TH_UNROLL], m[TH_UNROLL];
+#pragma unroll
+    for (int u = 0; u < TH_UNROLL; ++u) {
+      const int64_t o = k + (int64_t)(q - u) * ma;
+      yv[u] = in[o];
+      m[u] = mt[o];
     }
+#pragma unroll
+    for (int u = 0; u < TH_UNROLL; ++u) {
+      x = yv[u] - m[u] * x;
+      out[k + (int64_t)(q - u) * ma] = x;
+    }
+  }
+  for (; q >= 0; --q) {
+    const int64_t o = k + (int64_t)q * ma;
+    x = in[o] - mt[o] * x;
+    out[o] = x;
+  }
+}
+
+__global__ void k_thomas_cyc(int ma, int mb, int singular_mode, const double *__restrict__ qt,
+                             const double *__restrict__ qden, const double *__restrict__ gam,
+                             const double *__restrict__ in, double *__restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ma) return;
+  const bool sing = k == singular_mode;
+  const double f = sing ? 0.0 : (in[k] + in[k + (int64_t)(mb - 1) * ma] / gam[k]) * qden[k];
+  for (int q = threadIdx.y; q < mb; q += blockDim.y) {
+    const int64_t o = k + (int64_t)q * ma;
+    out[o] = sing ? in[o] : in[o] - qt[o] * f;
+  }
+}
+
+// DST-I along the contiguous axis by a complex FFT of length M = 2(m+1) in shared memory.
+// Two real columns are packed into one complex sequence (odd extension): with
+// Z = FFT(z_a + i z_b), the sine sums are S_a[k] = -Im Z[k]/2 and S_b[k] = Re Z[k]/2.
+// out[k-1, col] = scale * S[k], scale = sqrt(2/(m+1)) (orthonormal, so forward == inverse).
+__global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, const double2 *__restrict__ tw,
+                                                 const double *__restrict__ in, double *__restrict__ out,
+                                                 double scale) {
+  extern __shared__ double2 zs[];
+  const int M = 1 << log2M;
+  const int ca = blockIdx.x * 2, cb = ca + 1;
+  const double *xa = in + (int64_t)ca * m;
+  const double *xb = cb < ncols ? in + (int64_t)cb * m : nullptr;
+  // load with bit-reversed addressing; z[0] = z[m+1] = 0, z[M-p] = -z[p]
+  for (int p = threadIdx.x; p <= m + 1; p += blockDim.x) {
+    double2 v = make_double2(0.0, 0.0);
+    if (p >= 1 && p <= m) {
+      v.x = xa[p - 1];
+      v.y = xb ? xb[p - 1] : 0.0;
+    }
+    const int r0 = (int)(__brev((unsigned)p) >> (32 - log2M));
+    zs[r0] = v;
+    if (p >= 1 && p <= m) {
+      const int r1 = (int)(__brev((unsigned)(M - p)) >> (32 - log2M));
+      zs[r1] = make_double2(-v.x, -v.y);
+    }
+  }
+  __syncthreads();
+  for (int s = 0; s < log2M; ++s) {
+    const int half = 1 << s;
+    for (int t = threadIdx.x; t < M / 2; t += blockDim.x) {
+      const int pos = t & (half - 1);
+      const int i0 = ((t >> s) << (s + 1)) + pos, i1 = i0 + half;
+      const double2 w = __ldg(&tw[pos << (log2M - 1 - s)]);
+      const double2 a = zs[i0], b = zs[i1];
+      const double br = fma(b.x, w.x, -(b.y * w.y)), bi = fma(b.x, w.y, b.y * w.x);
+      zs[i0] = make_double2(a.x + br, a.y + bi);
+      zs[i1] = make_double2(a.x - br, a.y - bi);
+    }
+    __syncthreads();
+  }
+  const double h = 0.5 * scale;
+  double *ya = out + (int64_t)ca * m;
+  double *yb = cb < ncols ? out + (int64_t)cb * m : nullptr;
+  for (int k = 1 + threadIdx.x; k <= m; k += blockDim.x) {
+    const double2 z = zs[k];
+    ya[k - 1] = -h * z.y;
+    if (yb) yb[k - 1] = h * z.x;
   }
 }
 
 // dense fallback: b = isdir ? dval : (-rho)/eps0 ; phi = Ainv * b
 __global__ void k_dense_rhs(const double *__restrict__ rho, const uint8_t *__restrict__ isdir,
-                            const double *__restrict__ dval, double eps0, int64_t nn, double *b) {
+                            const double *__restrict__ dval, double eps0, double d2, int64_t nn, double *b) {
   for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn;
        n += (int64_t)gridDim.x * blockDim.x)
-    b[n] = isdir[n] ? dval[n] : (-rho[n]) / eps0;
+    b[n] = isdir[n] ? dval[n] : ((-rho[n]) / eps0) * d2;   // rows of the inverse are equilibrated by dh^2
 }
 __global__ void k_dense_gemv(const double *__restrict__ Ainv, const double *__restrict__ b, int64_t nn,
                              double *phi) {
@@ -399,12 +509,14 @@ int32_t upload(T **dptr, const std::vector<T> &h, cudaStream_t st) {
 int32_t poisson_free(iskb_ctx *c) {
   PoissonState &ps = c->ps;
   double **ptrs[] = {&ps.d_dval, &ps.d_V, &ps.d_lam, &ps.d_cp, &ps.d_q, &ps.d_qden, &ps.d_w1, &ps.d_w2,
-                     &ps.d_w3, &ps.d_Ainv, &ps.d_Vt, &ps.d_gam, &ps.d_msing};
+                     &ps.d_Ainv, &ps.d_Vt, &ps.d_gam, &ps.d_msing};
   for (auto p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
   if (ps.d_isdir) { cudaFree(ps.d_isdir); ps.d_isdir = nullptr; }
   if (ps.d_tw) { cudaFree(ps.d_tw); ps.d_tw = nullptr; }
   return ISKB_OK;
 }
+
+static long double PIl() { return 3.141592653589793238462643383279502884L; }
 
 static bool classify_axis(bool periodic, bool dir_lo, bool dir_hi, int n, AxisInfo &ax) {
   ax.n = n;
@@ -426,6 +538,12 @@ static int32_t prepare_dense(iskb_ctx *c) {
                                   "for the dense fallback", (long long)nn);
   std::vector<double> A, b;
   assemble_dense(c, A, b);
+  // row equilibration: stencil rows carry 1/dh^2, Dirichlet rows 1 (generalized_poisson.jl:65,210-211);
+  // inverting D*A (and scaling the rhs in k_dense_rhs) keeps the inverse accurate to ~cond*eps
+  const double d2 = c->g.dx * c->g.dx;
+  for (int64_t r = 0; r < nn; ++r)
+    if (!ps.isdir[(size_t)r])
+      for (int64_t col = 0; col < nn; ++col) A[(size_t)(r + col * nn)] *= d2;
   if (!invert_dense(A, nn)) return iskb_fail(ISKB_E_SINGULAR, "dense Poisson operator is singular");
   ISKB_TRY(upload(&ps.d_Ainv, A, c->stream));
   ps.nn_dense = nn;
@@ -547,6 +665,26 @@ int32_t poisson_prepare(iskb_ctx *c) {
       ISKB_TRY(upload(&ps.d_qden, qden, c->stream));
       ISKB_TRY(upload(&ps.d_gam, gam, c->stream));
       ISKB_TRY(upload(&ps.d_msing, msing, c->stream));
+      // DST-I by FFT when the Dirichlet-Dirichlet interior length + 1 is a power of two
+      ps.use_fft = false;
+      ps.fft_log2M = 0;
+      if (A.kind == AX_DD && ma + 1 >= 16 && ((ma + 1) & ma) == 0 && 2 * (ma + 1) <= 8192) {
+        int lg = 0;
+        while ((1 << lg) < 2 * (ma + 1)) ++lg;
+        const int M = 1 << lg;
+        std::vector<double2> tw((size_t)M / 2);
+        for (int j = 0; j < M / 2; ++j) {
+          const long double th = -2.0L * PIl() * j / M;
+          tw[(size_t)j] = make_double2((double)cosl(th), (double)sinl(th));
+        }
+        if (ps.d_tw) { cudaFree(ps.d_tw); ps.d_tw = nullptr; }
+        CU_TRY(cudaMalloc(&ps.d_tw, tw.size() * sizeof(double2)));
+        CU_TRY(cudaMemcpyAsync(ps.d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        CU_TRY(cudaFuncSetAttribute(k_dst_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, M * (int)sizeof(double2)));
+        ps.use_fft = true;
+        ps.fft_log2M = lg;
+      }
       if (ps.d_w1) { cudaFree(ps.d_w1); ps.d_w1 = nullptr; }
       if (ps.d_w2) { cudaFree(ps.d_w2); ps.d_w2 = nullptr; }
       CU_TRY(cudaMalloc(&ps.d_w1, (size_t)ma * mb * sizeof(double)));
@@ -571,7 +709,8 @@ int32_t poisson_solve(iskb_ctx *c) {
   const int nx = c->g.nx, ny = c->g.ny;
   const int64_t nn = (int64_t)nx * ny;
   if (ps.mode == 2) {
-    k_dense_rhs<<<blocks_for(c, nn), TPB, 0, c->stream>>>(c->d_rho, ps.d_isdir, ps.d_dval, ps.eps0, nn, ps.d_w1);
+    k_dense_rhs<<<blocks_for(c, nn), TPB, 0, c->stream>>>(c->d_rho, ps.d_isdir, ps.d_dval, ps.eps0, c->g.dx * c->g.dx, nn,
+                                                          ps.d_w1);
     LAUNCH_CHECK(c);
     k_dense_gemv<<<(int)((nn + 127) / 128), 128, 0, c->stream>>>(ps.d_Ainv, ps.d_w1, nn, c->d_phi);
     LAUNCH_CHECK(c);
@@ -581,14 +720,38 @@ int32_t poisson_solve(iskb_ctx *c) {
     k_build_rhs<<<blocks_for(c, tot), TPB, 0, c->stream>>>(s, c->d_rho, ps.d_isdir, ps.d_dval, ps.d_w1);
     LAUNCH_CHECK(c);
     dim3 gg((ps.ma + 63) / 64, (ps.mb + 63) / 64);
-    k_dgemm<<<gg, 256, 0, c->stream>>>(ps.ma, ps.mb, ps.ma, ps.d_Vt, ps.ma, ps.d_w1, ps.ma, ps.d_w2, ps.ma);
+    const double dst_scale = sqrt(2.0 / (ps.ma + 1));
+    const int M = 1 << ps.fft_log2M;
+    // forward transform  w1 -> w2
+    if (ps.use_fft)
+      k_dst_fft<<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->stream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, ps.d_w1,
+                                                                         ps.d_w2, dst_scale);
+    else
+      k_dgemm<<<gg, 256, 0, c->stream>>>(ps.ma, ps.mb, ps.ma, ps.d_Vt, ps.ma, ps.d_w1, ps.ma, ps.d_w2, ps.ma);
     LAUNCH_CHECK(c);
-    k_thomas<<<(ps.ma + 63) / 64, 64, 0, c->stream>>>(ps.ma, ps.mb, ps.b_cyclic ? 1 : 0, ps.singular_mode, ps.d_cp,
-                                                     ps.d_q, ps.d_qden, ps.d_gam, ps.d_msing, ps.d_w2);
+    // tridiagonal solves along b:  w2 -> w1 -> w2 (-> w1 when cyclic)
+    const int tb = (ps.ma + 31) / 32;
+    k_thomas_fwd<<<tb, 32, 0, c->stream>>>(ps.ma, ps.mb, ps.singular_mode, ps.d_cp, ps.d_msing, ps.d_w2, ps.d_w1);
     LAUNCH_CHECK(c);
-    k_dgemm<<<gg, 256, 0, c->stream>>>(ps.ma, ps.mb, ps.ma, ps.d_V, ps.ma, ps.d_w2, ps.ma, ps.d_w1, ps.ma);
+    k_thomas_bwd<<<tb, 32, 0, c->stream>>>(ps.ma, ps.mb, ps.singular_mode, ps.d_cp, ps.d_msing, ps.d_w1, ps.d_w2);
     LAUNCH_CHECK(c);
-    k_store_phi<<<blocks_for(c, nn), TPB, 0, c->stream>>>(s, ps.d_w1, ps.d_isdir, ps.d_dval, c->d_phi);
+    double *cur = ps.d_w2, *other = ps.d_w1;
+    if (ps.b_cyclic) {
+      k_thomas_cyc<<<tb, dim3(32, 16), 0, c->stream>>>(ps.ma, ps.mb, ps.singular_mode, ps.d_q, ps.d_qden, ps.d_gam,
+                                                      ps.d_w2, ps.d_w1);
+      LAUNCH_CHECK(c);
+      cur = ps.d_w1;
+      other = ps.d_w2;
+    }
+    // inverse transform  cur -> other
+    if (ps.use_fft)
+      k_dst_fft<<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->stream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, cur, other,
+                                                                         dst_scale);
+    else
+      k_dgemm<<<gg, 256, 0, c->stream>>>(ps.ma, ps.mb, ps.ma, ps.d_V, ps.ma, cur, ps.ma, other, ps.ma);
+    LAUNCH_CHECK(c);
+    ps.d_w3 = other;   // (alias, not owned) result of the inverse transform
+    k_store_phi<<<blocks_for(c, nn), TPB, 0, c->stream>>>(s, ps.d_w3, ps.d_isdir, ps.d_dval, c->d_phi);
     LAUNCH_CHECK(c);
   }
   k_efield<<<blocks_for(c, nn), TPB, 0, c->stream>>>(nx, ny, c->g.dx, c->g.dy, c->d_phi, c->d_E2);

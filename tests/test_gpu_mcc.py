@@ -157,7 +157,7 @@ def test_mcc_kinematics_distributions_match_oracle(ib):
     the check is distribution-vs-oracle and not an energy identity."""
     PIC, CH = ib.particle_in_cell, ib.chemistry
     nx, ny, dx = 129, 2, 5.234375e-4
-    n = 200000
+    n = 1000000
     m_eV = O.me / O.QE_MCC
     en = lambda v: 0.5 * m_eV * np.sum(v * v, axis=-1)
     cases = (("iso", 0, 0.0), ("back", 1, 0.0), ("inel", 2, 0.0), ("exc", 3, 19.82), ("ion", 4, 24.587))
@@ -174,7 +174,7 @@ def test_mcc_kinematics_distributions_match_oracle(ib):
         e.v[:n] = v0
         e.np = n
         He = PIC.FluidSpecies("He", 1.0, 0.0, 3.99 * O.mp, NHE * np.ones((nx, ny)), 300.0)
-        table = np.array([[0.0, 2e-19], [1000.0, 2e-19]])
+        table = np.array([[0.0, 2.5e-20], [1000.0, 2.5e-20]])   # P ~ 1.8 %: second-order differences (H7) stay small
         typ = {"iso": None, "back": CH.MCC.ElasticBackward(), "inel": CH.MCC.InelasticBackward(),
                "exc": CH.MCC.Excitation(thr), "ion": CH.MCC.Ionization(thr)}[kind]
         eq = "e + He --> e + e + iHe" if kind == "ion" else "e + He --> e + He"
@@ -190,7 +190,7 @@ def test_mcc_kinematics_distributions_match_oracle(ib):
                      300.0, NHE * np.ones(nx * ny))
         rc, _, Nc_ref, coll_ref = cm.perform(CO.make_grid(nx, ny, dx, dx), np.zeros(nx * ny * 3), DT, CO.make_rng(3))
         assert rc == 0
-        p_coll = 1.0 - math.exp(-NHE * 2e-19 * speed * DT)
+        p_coll = 1.0 - math.exp(-NHE * 2.5e-20 * speed * DT)
         for c_ in (coll, coll_ref):
             assert abs(c_ - n * p_coll) <= 5 * math.sqrt(n * p_coll)
         vg, vc = e.v[:e.np], ce.v[:, :ce.np].T

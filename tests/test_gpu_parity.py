@@ -424,15 +424,17 @@ def _two_species(ib, g, cg, n, cap, seed, Te=300.0, drift=1e7, wgt=3.5e7, ion_m=
     return out_c, out_g
 
 
-def _compare_species(pcs, pgs, tol):
+def _compare_species(pcs, pgs, tol, lengths):
+    """State keyed by id; positions relative to the box size, velocities to max |v|."""
     for pc, pg in zip(pcs, pgs):
         m = pc.np
-        assert pg.np == m and m > 0
+        assert pg.np == m and m > 100
         xg, yg, v0, v1, v2 = _by_id(pg.id[:m], pg.x[:m, 0], pg.x[:m, 1], pg.v[:m, 0], pg.v[:m, 1], pg.v[:m, 2])
         xc, yc, c0, c1, c2 = _by_id(pc.id[:m], pc.xy[0, :m], pc.xy[1, :m], pc.v[0, :m], pc.v[1, :m], pc.v[2, :m])
         assert np.array_equal(np.sort(pg.id[:m]), np.sort(pc.id[:m]))
-        for a, r in ((xg, xc), (yg, yc), (v0, c0), (v1, c1), (v2, c2)):
-            assert np.abs(a - r).max() <= tol * max(np.abs(r).max(), 1e-300)
+        vmax = max(np.abs(c0).max(), np.abs(c1).max(), np.abs(c2).max())
+        for a, r, sc in ((xg, xc, lengths[0]), (yg, yc, lengths[1]), (v0, c0, vmax), (v1, c1, vmax), (v2, c2, vmax)):
+            assert np.abs(a - r).max() <= tol * sc
 
 
 @pytest.mark.parametrize("mode", ["operators", "fused", "fused-tiled"])
@@ -465,7 +467,7 @@ def test_two_stream_100_steps(ib, mode):
     else:
         PIC.solve(cfg, dt, steps, after_push=(1, 1), sort_interval=10 if mode == "fused-tiled" else 0)
     rho_g, phi_g, E_g = g._rt.fields()
-    _compare_species(pcs, pgs, REL)
+    _compare_species(pcs, pgs, REL, ((nx - 1) * dx, (ny - 1) * dx))
     assert np.abs(rho_g.ravel(order="F") - rho).max() <= REL * np.abs(rho).max()
     Eg = _colmajor3(E_g)
     assert np.abs(Eg - E).max() <= 1e-8 * np.abs(E).max()           # singular operator: gauge-free E
@@ -511,6 +513,7 @@ def test_rf_like_100_steps_discard(ib, mode):
     cfg = ib.configuration.Config()
     cfg.grid, cfg.solver, cfg.pusher, cfg.species = g, ps, PIC.create_boris_pusher(), pgs
     f = 13.56e6
+    VRF = 20.0   # reduced from the script's 450 V: the thin test plasma cannot shield the full drive
     E = np.zeros(3 * nn)
     steps = 100
     lmask = np.ascontiguousarray(left.ravel(order="F").astype(np.uint8))
@@ -520,8 +523,8 @@ def test_rf_like_100_steps_discard(ib, mode):
         t = it * dt - dt
         CO.lib().orc_poisson_apply_dirichlet(C.byref(cg), CO.dp(A), CO.dp(b), dof.ctypes.data_as(C.POINTER(C.c_uint8)),
                                              lmask.ctypes.data_as(C.POINTER(C.c_uint8)),
-                                             C.c_double(450 * math.sin(2 * math.pi * f * t)))   # 11_rf_discharge.jl:95
-    PIC.hooks.after_loop = lambda i, t, dt_: FDM.apply_dirichlet(ps, left, 450 * math.sin(2 * math.pi * f * t))
+                                             C.c_double(VRF * math.sin(2 * math.pi * f * t)))   # 11_rf_discharge.jl:95
+    PIC.hooks.after_loop = lambda i, t, dt_: FDM.apply_dirichlet(ps, left, VRF * math.sin(2 * math.pi * f * t))
 
     def after_push(part, grid):
         PIC.discard_(part, grid, dims=[1])
@@ -537,7 +540,7 @@ def test_rf_like_100_steps_discard(ib, mode):
         PIC.hooks.after_push = lambda part, grid: PIC.wrap_(part, grid)
     assert pcs[0].np < n                                            # electrons did reach the walls
     rho_g, phi_g, E_g = g._rt.fields()
-    _compare_species(pcs, pgs, REL)
+    _compare_species(pcs, pgs, REL, ((nx - 1) * dx, (ny - 1) * dx))
     assert np.abs(rho_g.ravel(order="F") - rho).max() <= REL * np.abs(rho).max()
     assert np.abs(phi_g.ravel(order="F") - phi).max() <= REL * np.abs(phi).max()
     assert np.abs(_colmajor3(E_g) - E).max() <= REL * np.abs(E).max()
