@@ -151,6 +151,10 @@ int32_t iskb_cell_index(iskb_species *sp, int32_t *i_out, int32_t *j_out, double
 /* Stable counting (radix) sort of the live particles by cell key; new, enables tiled deposition.
  * perm_out[k] (0-based) = previous row of the particle now in row k.  Key layout: DESIGN.md. */
 int32_t iskb_sort_by_cell(iskb_species *sp, uint32_t *perm_out);
+/* The layout the fused step keeps between re-sorts: the cell sort above followed by a
+ * deterministic round-robin over the cells inside every 8x8 tile (DESIGN.md "row order"), so
+ * that the 32 rows of a warp batch deposit into 32 different cells. */
+int32_t iskb_sort_for_deposit(iskb_species *sp, uint32_t *perm_out);
 /* grid_to_particle(grid, part, (i,j)->E[i,j,:])  cloud_in_cell.jl:20-36 ; out is np x 3, ld = np */
 int32_t iskb_gather(iskb_species *sp, double *partE_out);
 /* push_particles!(::BorisPusher{:xy}, part, E, B, dt)  pushers.jl:8-11,37-50 with B == 0.

@@ -59,6 +59,7 @@ SIGNATURES = {
     "iskb_species_density_download": [vp, vp],
     "iskb_cell_index": [vp, vp, vp, vp, vp],
     "iskb_sort_by_cell": [vp, vp],
+    "iskb_sort_for_deposit": [vp, vp],
     "iskb_gather": [vp, vp],
     "iskb_push": [vp, vp, f64],
     "iskb_boundary": [vp, i32, i32, C.POINTER(i64)],

@@ -248,6 +248,14 @@ extern "C" int32_t iskb_grid_set(iskb_ctx *c, int32_t nx, int32_t ny, double dx,
   c->g.nx = nx; c->g.ny = ny; c->g.dx = dx; c->g.dy = dy; c->g.ox = ox; c->g.oy = oy;
   c->g.Lx = (double)(nx - 1) * dx;   // wrap.jl:3-4  Lx = nx*dx with nx = grid.n[i]-1
   c->g.Ly = (double)(ny - 1) * dy;
+  c->g.rdx = 1.0 / dx;   // IEEE division: correctly rounded reciprocals
+  c->g.rdy = 1.0 / dy;
+  auto all_ones = [](double v) {
+    uint64_t b;
+    memcpy(&b, &v, sizeof(b));
+    return (b & 0xfffffffffffffull) == 0xfffffffffffffull;
+  };
+  c->g.fast_div = (all_ones(dx) || all_ones(dy)) ? 0 : 1;
   for (int k = 0; k < 4; ++k) c->bcs[k] = bcs ? bcs[k] : ISKB_BC_OPEN;
   const int64_t nn = (int64_t)nx * ny;
   CU_TRY(cudaMalloc(&c->d_V, nn * sizeof(double)));
@@ -469,7 +477,7 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
   for (int it = 0; it < n_steps; ++it) {
     const bool tiled = c->sort_interval > 0;
     if (tiled && (c->step_count % c->sort_interval) == 0)
-      for (iskb_species *s : c->species) ISKB_TRY(sp_sort(s, nullptr));
+      for (iskb_species *s : c->species) ISKB_TRY(sp_sort(s, nullptr, true));
     for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));       // :109-111
     for (iskb_species *s : c->species) {                                   // :113-115
       CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));

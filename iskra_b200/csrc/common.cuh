@@ -47,6 +47,8 @@ struct GridDev {
   double dx, dy;       // dh
   double ox, oy;       // origin (used by wrap!/discard! only, wrap.jl:5,24)
   double Lx, Ly;       // (n-1)*dh  (wrap.jl:3-4)
+  double rdx, rdy;     // RN(1/dx), RN(1/dy) for the exact fast division (pic_device.cuh)
+  int fast_div;        // 0: always use the IEEE divide instruction sequence
 };
 
 // Axis kinds of the separable operator (generalized_poisson.jl:34-68, 205-215, 286-324)
@@ -158,6 +160,8 @@ struct iskb_mcc {
   std::vector<MccProc> procs;
   double max_sigma_g = 0, m_eV = 0;
   double max_n0 = 0;
+  double eps_hi = 0;                 // largest tabulated energy
+  std::vector<double> sup_sigma_g;   // per process: sup of sigma_k*g on [0, eps_hi]
   uint64_t seed = 0;
   uint64_t calls = 0;
   double *d_tn = nullptr;       // target density on nodes
@@ -174,7 +178,7 @@ struct iskb_mcc {
 // ---- internal entry points across translation units ------------------------------------------
 int32_t sp_sync_counts(iskb_species *sp);
 int32_t sp_compact(iskb_species *sp);
-int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host);
+int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host, bool interleave);
 int32_t sp_ensure_alt(iskb_species *sp);
 int32_t ctx_check_status(iskb_ctx *ctx);
 int32_t poisson_prepare(iskb_ctx *ctx);

@@ -55,6 +55,8 @@ struct MccDev {
   double dt;
   double p_cand;     // N * max_Pt
   uint32_t p_cand_u32;
+  double pk_bound[8];   // sup over eps in [0, eps_hi] of P_k (with n = max density): exact pruning bound
+  double eps_hi;        // largest tabulated energy of all processes
   uint32_t k0, k1;   // Philox key
   uint32_t call;
   unsigned long long *stats;
@@ -208,25 +210,59 @@ __device__ __forceinline__ int64_t warp_append(bool pred, unsigned int *counter)
   return pred ? (int64_t)base + __popc(m & ((1u << lane) - 1u)) : -1;
 }
 
-__global__ void k_mcc_select(MccDev m, unsigned int *lists_cnt, uint32_t *cand, unsigned int cand_cap) {
+__global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *lists_cnt, uint32_t *cand,
+                                                    unsigned int cand_cap) {
+  __shared__ unsigned int s_warp[8];
+  __shared__ unsigned int s_base;
   const int64_t n = m.src.cnt[CNT_BEGIN];   // rows that existed when the step started
   const int64_t nq = (n + 3) / 4;
-  const int64_t nq_pad = (nq + 31) / 32 * 32;   // whole warps stay in the loop (ballots)
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq_pad;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    // one Philox call decides candidacy of rows 4q..4q+3 (draw index 0 of row 4q)
-    const Philox4 o = philox4x32_10((uint32_t)(q * 4), (uint32_t)((q * 4) >> 32), m.call, 0u, m.k0, m.k1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long my_cand = 0;
+  for (int64_t q0 = (int64_t)blockIdx.x * 256; q0 < nq; q0 += (int64_t)gridDim.x * 256) {
+    const int64_t q = q0 + threadIdx.x;
+    unsigned keep = 0;
+    if (q < nq) {
+      // one Philox call decides candidacy of rows 4q..4q+3 (draw index 0 of row 4q)
+      const Philox4 o = philox4x32_10((uint32_t)(q * 4), (uint32_t)((q * 4) >> 32), m.call, 0u, m.k0, m.k1);
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int64_t p = q * 4 + s;
-      const bool is_cand = p < n && o.c[s] < m.p_cand_u32;
-      const int64_t slot = warp_append(is_cand, &lists_cnt[0]);
-      if (is_cand) {
-        if (slot < cand_cap) cand[slot] = (uint32_t)p;
-        else atomicOr(m.status, ISKB_ST_CAPACITY);
-      }
+      for (int s = 0; s < 4; ++s)
+        if (q * 4 + s < n && o.c[s] < m.p_cand_u32) keep |= 1u << s;
     }
+    const unsigned cnt = __popc(keep);
+    my_cand += cnt;
+    // block-aggregated append: ONE global atomic per block iteration (1024 rows)
+    unsigned incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned tot = 0;
+      for (int w = 0; w < 8; ++w) {
+        const unsigned c = s_warp[w];
+        s_warp[w] = tot;
+        tot += c;
+      }
+      s_base = tot ? atomicAdd(&lists_cnt[0], tot) : 0u;
+    }
+    __syncthreads();
+    unsigned slot = s_base + s_warp[warp] + incl - cnt;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+      if (keep & (1u << s)) {
+        if (slot < cand_cap) cand[slot] = (uint32_t)(q * 4 + s);
+        else atomicOr(m.status, ISKB_ST_CAPACITY);
+        ++slot;
+      }
+    __syncthreads();
   }
+  // candidates statistic (rows drawn; includes the few discarded rows still parked in the columns)
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) my_cand += __shfl_down_sync(0xffffffffu, my_cand, d);
+  if (lane == 0 && my_cand) atomicAdd(&m.stats[0], my_cand);
 }
 
 __global__ void k_mcc_test(MccDev m, unsigned int *lists_cnt, const uint32_t *__restrict__ cand,
@@ -234,46 +270,54 @@ __global__ void k_mcc_test(MccDev m, unsigned int *lists_cnt, const uint32_t *__
   unsigned int nc = lists_cnt[0];
   if (nc > cand_cap) nc = cand_cap;
   const unsigned int nc_pad = (nc + 31u) / 32u * 32u;
-  unsigned long long my_cand = 0;
   for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < nc_pad; t += gridDim.x * blockDim.x) {
     bool hit = false;
     int64_t p = 0;
     int k = 0;
     if (t < nc) {
       p = cand[t];
-      const double px = m.src.col[0][p];
-      if (!is_dead(px)) {
-        ++my_cand;
-        int i, j;
-        double hx, hy;
-        cell1(px, m.g.dx, i, hx);
-        cell1(m.src.col[1][p], m.g.dy, j, hy);
-        if (!cell_in_grid(i, j, m.g.nx, m.g.ny)) {
-          atomicOr(m.status, ISKB_ST_OOB);
-        } else {
-          const int64_t node = (int64_t)(i - 1) + (int64_t)(j - 1) * m.g.nx;   // lower-left node :252-253
-          const double dens = m.tn[node];
-          if (dens >= 0) {                                                      // :254-257
-            Rng g(p, m.call, m.k0, m.k1, 1u);
-            const double U = g.u01();                                           // :260
-            k = (int)floor(m.N * U + 1.0);                                      // :261
-            if (k > m.N) k = m.N;
-            const ProcDev pc = m.proc[k - 1];
-            const double2 e = m.E2[node];
-            double d[3];
-            d[0] = (m.tqm * e.x) * m.dt - m.src.col[2][p];                      // :266-267
-            d[1] = (m.tqm * e.y) * m.dt - m.src.col[3][p];
-            d[2] = (m.tqm * 0.0) * m.dt - m.src.col[4][p];
-            const double gg = norm3(d);
-            const double eps = 0.5 * m.m_eV * (gg * gg);                        // :268
-            const double skg = xsec_eval(m.eps + pc.offset, m.sig + pc.offset, pc.len, eps) * gg;
-            double Pk = 1.0 - exp(-dens * skg * m.dt);                          // :271
-            Pk /= m.p_cand;                                                     // :272  N*max_Pt
-            if (Pk > 1.0) atomicOr(m.status, ISKB_ST_PK);                       // :273-279
-            else if (U > (double)k / m.N - Pk) {                                // :281
-              hit = true;
-              atomicAdd(&m.stats[2 + (k - 1)], 1ull);
-              if (m.nu) atomicAdd(&m.nu[node + (int64_t)(k - 1) * m.g.nx * m.g.ny], 1.0f);   // :283
+      Rng g(p, m.call, m.k0, m.k1, 1u);
+      const double U = g.u01();                                             // :260
+      k = (int)floor(m.N * U + 1.0);                                        // :261
+      if (k > m.N) k = m.N;
+      const double delta = (double)k / m.N - U;                             // collide iff delta < P_k (:281)
+      const double vx = m.src.col[2][p], vy = m.src.col[3][p], vz = m.src.col[4][p];
+      // exact early-out for a neutral target: g = |v| needs no field; P_k <= pk_bound[k] on the tables
+      bool maybe = true;
+      if (m.tqm == 0.0) {
+        const double g2 = (vx * vx + vy * vy) + vz * vz;
+        if (0.5 * m.m_eV * g2 <= m.eps_hi && delta >= m.pk_bound[k - 1]) maybe = false;
+      }
+      if (maybe) {
+        const double px = m.src.col[0][p];
+        if (!is_dead(px)) {
+          int i, j;
+          double hx, hy;
+          cell1(px, m.g.dx, m.g.rdx, m.g.fast_div, i, hx);
+          cell1(m.src.col[1][p], m.g.dy, m.g.rdy, m.g.fast_div, j, hy);
+          if (!cell_in_grid(i, j, m.g.nx, m.g.ny)) {
+            atomicOr(m.status, ISKB_ST_OOB);
+          } else {
+            const int64_t node = (int64_t)(i - 1) + (int64_t)(j - 1) * m.g.nx;   // lower-left node :252-253
+            const double dens = m.tn[node];
+            if (dens >= 0) {                                                      // :254-257
+              const ProcDev pc = m.proc[k - 1];
+              const double2 e = m.E2[node];
+              double d[3];
+              d[0] = (m.tqm * e.x) * m.dt - vx;                                   // :266-267
+              d[1] = (m.tqm * e.y) * m.dt - vy;
+              d[2] = (m.tqm * 0.0) * m.dt - vz;
+              const double gg = norm3(d);
+              const double eps = 0.5 * m.m_eV * (gg * gg);                        // :268
+              const double skg = xsec_eval(m.eps + pc.offset, m.sig + pc.offset, pc.len, eps) * gg;
+              double Pk = 1.0 - exp(-dens * skg * m.dt);                          // :271
+              Pk /= m.p_cand;                                                     // :272  N*max_Pt
+              if (Pk > 1.0) atomicOr(m.status, ISKB_ST_PK);                       // :273-279
+              else if (delta < Pk) {                                              // :281  U > k/N - P_k
+                hit = true;
+                atomicAdd(&m.stats[2 + (k - 1)], 1ull);
+                if (m.nu) atomicAdd(&m.nu[node + (int64_t)(k - 1) * m.g.nx * m.g.ny], 1.0f);   // :283
+              }
             }
           }
         }
@@ -282,7 +326,6 @@ __global__ void k_mcc_test(MccDev m, unsigned int *lists_cnt, const uint32_t *__
     const int64_t slot = warp_append(hit, &lists_cnt[1]);
     if (hit) coll[slot] = make_uint2((uint32_t)p, (uint32_t)k);   // collider list has cand_cap entries
   }
-  if (my_cand) atomicAdd(&m.stats[0], my_cand);
 }
 
 __global__ void k_mcc_collide(MccDev m, const unsigned int *__restrict__ lists_cnt, const uint2 *__restrict__ coll) {
@@ -349,6 +392,13 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
   m.p_cand = N * max_Pt;
   const double pc32 = m.p_cand * 4294967296.0;
   m.p_cand_u32 = pc32 >= 4294967295.0 ? 0xffffffffu : (uint32_t)pc32;
+  // exact pruning bounds: sup over [0, eps_hi] of sigma_k(eps)*g(eps) (interior maxima of the
+  // piecewise (a + b*eps)*sqrt(eps) included), at the largest target density
+  m.eps_hi = mc->eps_hi;
+  for (int k = 0; k < N; ++k) {
+    const double pk = (1.0 - exp(-mc->max_n0 * mc->sup_sigma_g[(size_t)k] * dt)) / m.p_cand;
+    m.pk_bound[k] = pk * (1.0 + 1e-9) + 1e-300;
+  }
   m.k0 = (uint32_t)mc->seed;
   m.k1 = (uint32_t)(mc->seed >> 32) ^ (0x9E3779B9u * (uint32_t)(c->rank + 1));
   m.call = (uint32_t)(mc->calls++);
@@ -431,6 +481,27 @@ extern "C" int32_t iskb_mcc_create(iskb_ctx *c, iskb_species *source, double tar
     best = std::fmax(best, sg);
   }
   mc->max_sigma_g = best;
+  // per-process supremum of sigma_k(eps)*alpha*sqrt(eps) on [0, eps_hi] (for the pruning bound)
+  mc->eps_hi = e.back();
+  mc->sup_sigma_g.assign((size_t)n_proc, 0.0);
+  for (int k = 0; k < n_proc; ++k) {
+    const MccProc &p = mc->procs[(size_t)k];
+    double sup = 0.0;
+    auto f = [&](double ee) { return xsec_eval_host(eps + p.offset, sigma + p.offset, p.len, ee) * alpha * sqrt(ee); };
+    for (size_t q = 0; q + 1 < e.size(); ++q) {
+      const double e0 = e[q], e1 = e[q + 1];
+      sup = std::fmax(sup, std::fmax(f(e0), f(e1)));
+      // sigma is linear on [e0,e1] (union grid contains every knot): s = a + b*eps
+      const double s0 = xsec_eval_host(eps + p.offset, sigma + p.offset, p.len, e0);
+      const double s1 = xsec_eval_host(eps + p.offset, sigma + p.offset, p.len, e1);
+      const double b = (s1 - s0) / (e1 - e0), a = s0 - b * e0;
+      if (b < 0.0 && a > 0.0) {
+        const double es = -a / (3.0 * b);
+        if (es > e0 && es < e1) sup = std::fmax(sup, f(es));
+      }
+    }
+    mc->sup_sigma_g[(size_t)k] = sup;
+  }
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   mc->max_n0 = -INFINITY;
   for (int64_t k = 0; k < nn; ++k) mc->max_n0 = std::fmax(mc->max_n0, target_n[k]);   // :242

@@ -27,8 +27,8 @@ __global__ void k_cell_index(const double *__restrict__ x, const double *__restr
        p += (int64_t)gridDim.x * blockDim.x) {
     int i, j;
     double fx, fy;
-    cell1(x[p], g.dx, i, fx);
-    cell1(y[p], g.dy, j, fy);
+    cell1(x[p], g.dx, g.rdx, g.fast_div, i, fx);
+    cell1(y[p], g.dy, g.rdy, g.fast_div, j, fy);
     ci[p] = i;
     cj[p] = j;
     if (hx) hx[p] = fx;
@@ -41,8 +41,8 @@ __device__ __forceinline__ bool gather_E(const double2 *__restrict__ E2, const G
                                          double y, double &ex, double &ey) {
   int i, j;
   double hx, hy;
-  cell1(x, g.dx, i, hx);
-  cell1(y, g.dy, j, hy);
+  cell1(x, g.dx, g.rdx, g.fast_div, i, hx);
+  cell1(y, g.dy, g.rdy, g.fast_div, j, hy);
   if (!cell_in_grid(i, j, g.nx, g.ny)) {
     ex = ey = 0.0;
     return false;
@@ -141,8 +141,8 @@ __global__ void k_deposit_atomic(const double *__restrict__ x, const double *__r
     if (is_dead(px)) continue;
     int i, j;
     double hx, hy;
-    cell1(px, g.dx, i, hx);
-    cell1(y[p], g.dy, j, hy);
+    cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
+    cell1(y[p], g.dy, g.rdy, g.fast_div, j, hy);
     if (!cell_in_grid(i, j, g.nx, g.ny)) {
       atomicOr(status, ISKB_ST_OOB);
       continue;
@@ -234,8 +234,8 @@ __global__ void k_advance_simple(double *x, double *y, double *vx, double *vy, d
           if (u) {
             int i, j;
             double hx, hy;
-            cell1(px, g.dx, i, hx);
-            cell1(py, g.dy, j, hy);
+            cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
+            cell1(py, g.dy, g.rdy, g.fast_div, j, hy);
             if (!cell_in_grid(i, j, g.nx, g.ny)) {
               atomicOr(status, ISKB_ST_OOB);
             } else {

@@ -6,7 +6,30 @@
 
 __device__ __forceinline__ bool is_dead(double x) { return x != x; }   // dead slots carry x = NaN
 
+// Correctly rounded x/d in three FP64 operations (Markstein 1990; Muller et al., Handbook of
+// Floating-Point Arithmetic, thm. "correction of a faithful quotient"): with r = RN(1/d),
+//   q0 = RN(x*r) ;  rem = x - q0*d  (exact in one FMA) ;  q = RN(q0 + rem*r) = RN(x/d).
+// Valid away from over/underflow (guarded: otherwise the IEEE divide is used) and not for a
+// divisor whose significand is all ones (the host clears fast_div then).  Exhaustively compared
+// with exact rational arithmetic on the host and with __ddiv_rn in the GPU tests.
+// __ddiv_rn costs 4.6 SM-cycles per warp on B200 (profiles/r1_microbench_warp_ops_b200.txt).
+__device__ __forceinline__ double div_exact(double x, double d, double r, int fast) {
+  const double ax = fabs(x);
+  if (fast && ((ax > 1e-250 && ax < 1e250) || x == 0.0)) {
+    const double q0 = __dmul_rn(x, r);
+    const double rem = __fma_rn(-q0, d, x);
+    return __fma_rn(rem, r, q0);
+  }
+  return __ddiv_rn(x, d);
+}
+
 // particle_cell(px, p, dh)  ParticleInCell.jl:28-35:  f = 1 + x/dh ; i = floor(f) ; h = f - i
+__device__ __forceinline__ void cell1(double x, double d, double rd, int fast, int &i, double &h) {
+  const double f = __dadd_rn(1.0, div_exact(x, d, rd, fast));
+  const double fl = floor(f);
+  i = (int)fl;
+  h = __dsub_rn(f, fl);
+}
 __device__ __forceinline__ void cell1(double x, double d, int &i, double &h) {
   const double f = __dadd_rn(1.0, __ddiv_rn(x, d));
   const double fl = floor(f);

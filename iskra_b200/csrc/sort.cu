@@ -28,8 +28,8 @@ __global__ void k_cell_keys(const double *__restrict__ x, const double *__restri
       key = key_max;
       int i, j;
       double hx, hy;
-      cell1(px, g.dx, i, hx);
-      cell1(y[p], g.dy, j, hy);
+      cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
+      cell1(y[p], g.dy, g.rdy, g.fast_div, j, hy);
       if (cell_in_grid(i, j, g.nx, g.ny)) {
         const uint32_t cx = (uint32_t)(i - 1), cy = (uint32_t)(j - 1);
         key = (((cy >> 3) * (uint32_t)tiles_x + (cx >> 3)) << 6) | ((cy & 7u) << 3) | (cx & 7u);
@@ -185,6 +185,72 @@ __global__ void k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint
   }
 }
 
+// ---- cell-interleaved order inside every 8x8 tile ----------------------------------------------
+// After the stable sort the rows of a tile are grouped by cell.  The fused advance kernel deposits
+// with shared-memory CAS adds whose cost is proportional to how many lanes of a 32-row batch hit
+// the same node, so the rows of a tile are re-ordered round-robin over its cells: first the
+// rank-0 row of every non-empty cell (cell order), then the rank-1 rows, ...  A batch of 32
+// consecutive rows then touches 32 different cells.  dest(c, r) = start + F[r] + #{c' < c : cnt[c'] > r},
+// F[r] = sum_c' min(cnt[c'], r); ranks >= IL_RMAX keep the sorted order behind the interleaved part.
+// Deterministic: a pure function of the sorted (cell, previous-row) order.
+constexpr int IL_RMAX = 512;
+
+__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t *__restrict__ a, int64_t lo, int64_t hi, uint32_t v) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(64) k_tile_interleave(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ idx_in,
+                                                        uint32_t *__restrict__ idx_out, int64_t n, uint32_t ntiles) {
+  __shared__ int64_t s_cs[65];            // start of every cell's run
+  __shared__ uint32_t s_cnt[64], s_over[65];
+  __shared__ unsigned long long s_mask[IL_RMAX];
+  __shared__ uint32_t s_F[IL_RMAX + 1];
+  __shared__ uint32_t s_maxcnt;
+  const uint32_t tile = blockIdx.x;
+  const int c = threadIdx.x;
+  if (tile == ntiles) {   // out-of-grid and dead rows: keep the sorted order
+    const int64_t s0 = lower_bound_u32(keys, 0, n, ntiles << 6);
+    for (int64_t p = s0 + c; p < n; p += 64) idx_out[p] = idx_in[p];
+    return;
+  }
+  s_cs[c] = lower_bound_u32(keys, 0, n, (tile << 6) | (uint32_t)c);
+  if (c == 0) s_cs[64] = lower_bound_u32(keys, 0, n, (tile + 1) << 6);
+  __syncthreads();
+  const int64_t start = s_cs[0], end = s_cs[64];
+  if (end == start) return;
+  const uint32_t cnt = (uint32_t)(s_cs[c + 1] - s_cs[c]);
+  s_cnt[c] = cnt;
+  if (c == 0) s_maxcnt = 0;
+  __syncthreads();
+  atomicMax(&s_maxcnt, cnt);
+  __syncthreads();
+  const uint32_t R = s_maxcnt < IL_RMAX ? s_maxcnt : IL_RMAX;
+  for (uint32_t r = 0; r < R; ++r) {      // mask_r: cells that still have a row of rank r
+    const unsigned b = __ballot_sync(0xffffffffu, cnt > r);
+    if ((c & 31) == 0) ((unsigned *)&s_mask[r])[c >> 5] = b;
+  }
+  __syncthreads();
+  if (c == 0) {
+    uint32_t f = 0, o = 0;
+    for (uint32_t r = 0; r < R; ++r) { s_F[r] = f; f += __popcll(s_mask[r]); }
+    s_F[R] = f;
+    for (int q = 0; q < 64; ++q) { s_over[q] = o; o += s_cnt[q] > R ? s_cnt[q] - R : 0; }
+  }
+  __syncthreads();
+  for (int64_t p = start + c; p < end; p += 64) {
+    const uint32_t cell = keys[p] & 63u;
+    const uint32_t r = (uint32_t)(p - s_cs[cell]);
+    int64_t dest;
+    if (r < R) dest = start + s_F[r] + __popcll(s_mask[r] & ((1ull << cell) - 1ull));
+    else dest = start + s_F[R] + s_over[cell] + (r - R);
+    idx_out[dest] = idx_in[p];
+  }
+}
+
 struct Cols {
   const double *in[6];
   double *out[6];
@@ -237,7 +303,7 @@ int32_t ensure_sort_scratch(iskb_species *sp) {
 }
 
 // keys already in d_key[0][0..n); runs `passes` 8-bit passes, permutes all columns, fixes counters
-int32_t sort_by_keys(iskb_species *sp, int64_t n, int passes, uint32_t *perm_out_host) {
+int32_t sort_by_keys(iskb_species *sp, int64_t n, int passes, uint32_t *perm_out_host, uint32_t interleave_tiles = 0) {
   iskb_ctx *c = sp->ctx;
   const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
   const int64_t hn = 256 * (int64_t)nblocks;
@@ -252,6 +318,12 @@ int32_t sort_by_keys(iskb_species *sp, int64_t n, int passes, uint32_t *perm_out
                                                     sp->d_hist, nblocks);
     LAUNCH_CHECK(c);
     cur ^= 1;
+  }
+  if (interleave_tiles) {
+    k_tile_interleave<<<interleave_tiles + 1, 64, 0, c->stream>>>(sp->d_key[cur], sp->d_idx[cur], sp->d_idx[cur ^ 1], n,
+                                                                interleave_tiles);
+    LAUNCH_CHECK(c);
+    std::swap(sp->d_idx[cur], sp->d_idx[cur ^ 1]);   // keys stay in d_key[cur]; idx now interleaved
   }
   Cols cols;
   for (int q = 0; q < 6; ++q) {
@@ -301,7 +373,7 @@ int32_t sp_compact(iskb_species *sp) {
   return sort_by_keys(sp, n, 1, nullptr);
 }
 
-int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host) {
+int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host, bool interleave) {
   iskb_ctx *c = sp->ctx;
   if (!c->has_grid) return iskb_fail(ISKB_E_INVALID, "iskb_grid_set must be called first");
   ISKB_TRY(sp_sync_counts(sp));
@@ -319,11 +391,17 @@ int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host) {
   if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
   k_cell_keys<<<blocks, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], n, c->g, tiles_x, key_max, sp->d_key[0]);
   LAUNCH_CHECK(c);
-  return sort_by_keys(sp, n, passes, perm_out_host);
+  return sort_by_keys(sp, n, passes, perm_out_host, interleave ? (uint32_t)(tiles_x * tiles_y) : 0u);
 }
 
 extern "C" int32_t iskb_sort_by_cell(iskb_species *sp, uint32_t *perm_out) {
   if (!sp) return iskb_fail(ISKB_E_INVALID, "null species");
   ISKB_TRY(sp_compact(sp));   // perm_out refers to the compacted (download) row order
-  return sp_sort(sp, perm_out);
+  return sp_sort(sp, perm_out, false);
+}
+
+extern "C" int32_t iskb_sort_for_deposit(iskb_species *sp, uint32_t *perm_out) {
+  if (!sp) return iskb_fail(ISKB_E_INVALID, "null species");
+  ISKB_TRY(sp_compact(sp));
+  return sp_sort(sp, perm_out, true);
 }

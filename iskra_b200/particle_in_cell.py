@@ -263,11 +263,14 @@ def discard_(part, grid, dims=None):
     return removed.value
 
 
-def sort_by_cell_(part, grid):
-    """New (no reference counterpart): stable sort of the rows by cell; returns the permutation."""
+def sort_by_cell_(part, grid, for_deposit=False):
+    """New (no reference counterpart): stable sort of the rows by cell; returns the permutation.
+    for_deposit=True additionally interleaves the rows of every 8x8 tile round-robin over its cells
+    (the layout the fused step keeps)."""
     part._push(grid)
     perm = np.zeros(part.np, dtype=np.uint32)
-    L.check(part._rt.lib.iskb_sort_by_cell(part._h, L.ptr(perm)))
+    fn = part._rt.lib.iskb_sort_for_deposit if for_deposit else part._rt.lib.iskb_sort_by_cell
+    L.check(fn(part._h, L.ptr(perm)))
     part._touched_on_device()
     return perm
 

@@ -173,6 +173,76 @@ def test_sort_permutation_bitexact(ib, nx, ny, n):
     assert np.all(np.diff(k2) >= 0)                                 # sortedness
 
 
+@pytest.mark.parametrize("nx,ny,n", [(65, 33, 100000), (257, 257, 1500000), (17, 17, 200000)])
+def test_deposit_layout_permutation_bitexact(ib, nx, ny, n):
+    """Row order kept by the fused step: cell sort, then round-robin over the cells of each 8x8
+    tile: order by (tile, rank-in-cell, cell) for ranks < 512, the rest behind in (cell, rank) order."""
+    PIC = ib.particle_in_cell
+    g, cg = _grid_pair(ib, nx, ny, 1e-3)
+    pc, pg = _species_pair(ib, g, n, n + 5, seed=n + 3)
+    if nx == 17:                                      # pile-up in one cell: exercises ranks >= 512
+        pg.x[:5000, 0] = 2.5e-3
+        pg.x[:5000, 1] = 3.5e-3
+        pc.xy[0, :5000], pc.xy[1, :5000] = 2.5e-3, 3.5e-3
+    i, j, _, _ = O.particle_cell(np.stack([pc.xy[0, :n], pc.xy[1, :n]], 1), g.dh)
+    key = _cell_key(i, j, nx, ny)
+    srt = np.argsort(key, kind="stable")
+    ks = key[srt]
+    first = np.r_[True, ks[1:] != ks[:-1]]
+    run_start = np.maximum.accumulate(np.where(first, np.arange(n), 0))
+    rank = np.arange(n) - run_start
+    tile, cell = ks >> 6, ks & 63
+    capped = np.minimum(rank, 512)
+    order = np.lexsort((np.where(capped < 512, 0, rank), cell, capped, tile)) if False else None
+    # rows with rank < 512: (tile, rank, cell); rows with rank >= 512: (tile, 512, cell, rank)
+    sec = np.where(rank < 512, rank, 512)
+    order = np.lexsort((np.where(rank < 512, 0, rank), cell, sec, tile))
+    expect = srt[order]
+    perm = PIC.sort_by_cell_(pg, g, for_deposit=True)
+    assert np.array_equal(perm.astype(np.int64), expect)
+    # property: the first rows of every populated tile hit distinct cells
+    i2, j2, _, _ = PIC.particle_cell(pg, g)
+    k2 = _cell_key(i2.astype(np.int64), j2.astype(np.int64), nx, ny)
+    assert np.all(np.diff(k2 >> 6) >= 0)
+    t0 = np.flatnonzero(np.r_[True, (k2[1:] >> 6) != (k2[:-1] >> 6)])
+    for s0 in t0[:200]:
+        t = k2[s0] >> 6
+        seg = k2[s0:s0 + 64]
+        seg = seg[(seg >> 6) == t]
+        ncells = len(np.unique(k2[(k2 >> 6) == t] & 63)) if len(t0) < 300 else None
+        head = seg[:min(len(seg), ncells)] if ncells else seg[:8]
+        assert len(np.unique(head & 63)) == len(head)
+
+
+def test_fast_division_matches_ieee_on_adversarial_positions(ib):
+    """cell1 uses q = RN(x*r); rem = fma(-q,d,x); q' = fma(rem,r,q): must equal IEEE x/d for every
+    input (bit-exact cell index contract).  Positions one/two ulps around 4096 cell edges."""
+    PIC = ib.particle_in_cell
+    for dx in (1.8743613985989574e-08, 5.234375e-4, 1.25e-3, 1.0 / 3.0):
+        nx = 4097
+        g = ib.regular_grids.create_uniform_grid(np.arange(nx) * dx, np.arange(17) * dx)
+        k = np.arange(1, nx - 1, dtype=np.float64)
+        edges = k * dx
+        xs = [edges]
+        lo, hi = edges.copy(), edges.copy()
+        for _ in range(3):
+            lo, hi = np.nextafter(lo, 0.0), np.nextafter(hi, 1e9)
+            xs += [lo.copy(), hi.copy()]
+        rng = np.random.default_rng(0)
+        xs.append(rng.random(200000) * (nx - 1) * dx)
+        x = np.concatenate(xs)
+        x = x[(x >= 0) & (x < (nx - 1) * dx)]
+        n = len(x)
+        pg = PIC.create_kinetic_species("s", n, -O.qe, O.me, 1.0)
+        pg.x[:n, 0] = x
+        pg.x[:n, 1] = rng.random(n) * 16 * dx
+        pg.np = n
+        i, j, hx, hy = PIC.particle_cell(pg, g)
+        f = 1.0 + x / dx
+        assert np.array_equal(i, np.floor(f).astype(np.int32))
+        assert np.array_equal(hx, f - np.floor(f))
+
+
 # ------------------------------------------------------------------------------ field solve ---
 def _oracle_poisson(nx, ny, dx, periodic, edges):
     grid = O.CartesianGrid2(np.arange(nx) * dx, np.arange(ny) * dx)
