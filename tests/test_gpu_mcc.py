@@ -207,7 +207,10 @@ def test_mcc_kinematics_distributions_match_oracle(ib):
             # |[s_chi c_eta, s_chi s_eta, c_chi] * T| <= sqrt(2): the non-orthogonal T can double the energy
             assert en(vg[:n][chg]).max() <= 2.0 * (50.0 - thr) * (1 + 1e-12)
         if kind == "ion":
-            assert e.np == n + coll and iHe.np == coll and ce.np == n + coll_ref and ci.np == coll_ref
+            assert e.np == n + coll and iHe.np == coll
+            # oracle (with replacement): a row hit twice can fail the threshold the second time; the
+            # collision is still counted (mcc.jl:179-182,282-283, H8) but nothing is appended
+            assert 0 < ce.np - n <= coll_ref and ci.np == ce.np - n
             a, r = en(vg[n:]), en(vc[n:])
             se = math.sqrt(a.var() / len(a) + r.var() / len(r))
             assert abs(a.mean() - r.mean()) <= 5 * se
