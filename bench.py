@@ -253,6 +253,8 @@ def run_b200(a):
     np_before = wl.n_particles()
     rt.profile(True)
     rt.profile_read()
+    for sp in wl.kinetic():
+        sp.window_stats()
     clocks = ClockSampler(local)
     clocks.start()
     l0 = rt.launch_count()
@@ -266,6 +268,7 @@ def run_b200(a):
     clk = clocks.stop()
     l1 = rt.launch_count()
     adv_ms, adv_launches = rt.profile_read()
+    wstats = {sp.name: [int(v) for v in sp.window_stats()] for sp in wl.kinetic()}
     rt.profile(False)
     np_after = wl.n_particles()
     rt.synchronize()
@@ -296,7 +299,8 @@ def run_b200(a):
         ach = ALGO_BYTES_PER_PARTICLE_STEP * per_launch_particles / per_launch_s / 1e9
         roof.update({"achieved": ach, "frac": ach / peak, "avg_launch_ms": 1e3 * per_launch_s,
                      "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PARTICLE_STEP * per_launch_particles,
-                     "kernel_share_of_step": adv_ms / ms})
+                     "kernel_share_of_step": adv_ms / ms,
+                     "window_stats(gather_miss,deposit_miss,moves,rounds)": wstats})
     tr = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tr):
         try:

@@ -134,6 +134,9 @@ int32_t iskb_species_upload(iskb_species *sp, const double *x, const double *v, 
 int32_t iskb_species_download(iskb_species *sp, double *x, double *v, double *wg, uint32_t *id,
                               int64_t ld);
 int32_t iskb_species_np(iskb_species *sp, int64_t *np_out);
+/* Diagnostics of the fused advance kernel since the last call (then reset): rows whose gather
+ * missed the shared window, rows whose deposit missed it, window moves, deposit rounds. */
+int32_t iskb_species_window_stats(iskb_species *sp, int64_t out[4]);
 /* sample!(src::MaxwellianSource, species, dt)  sources.jl:24-34 with n given: appends n
  * particles x = rand*wx + dx, v = randn*wv + dv  (device Philox stream, key = seed). */
 int32_t iskb_species_sample_maxwellian(iskb_species *sp, int64_t n, const double wx[2],

@@ -54,6 +54,7 @@ SIGNATURES = {
     "iskb_species_upload": [vp, vp, vp, vp, vp, i64, i64],
     "iskb_species_download": [vp, vp, vp, vp, vp, i64],
     "iskb_species_np": [vp, C.POINTER(i64)],
+    "iskb_species_window_stats": [vp, vp],
     "iskb_species_sample_maxwellian": [vp, i64, vp, vp, vp, vp, u64],
     "iskb_species_copy_positions": [vp, vp, vp],
     "iskb_species_density_download": [vp, vp],

@@ -415,6 +415,16 @@ extern "C" int32_t iskb_species_np(iskb_species *s, int64_t *np_out) {
   return ISKB_OK;
 }
 
+extern "C" int32_t iskb_species_window_stats(iskb_species *s, int64_t out[4]) {
+  if (!s || !out) return iskb_fail(ISKB_E_INVALID, "null");
+  iskb_ctx *c = s->ctx;
+  CU_TRY(cudaMemcpyAsync(c->h_scratch, s->d_cnt + 3, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemsetAsync(s->d_cnt + 3, 0, 4 * sizeof(int64_t), c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 4; ++k) out[k] = c->h_scratch[k];
+  return ISKB_OK;
+}
+
 extern "C" int32_t iskb_species_sample_maxwellian(iskb_species *s, int64_t n, const double wx[2], const double dx[2],
                                                   const double wv[3], const double dv[3], uint64_t seed) {
   if (!s || !wx || !wv) return iskb_fail(ISKB_E_INVALID, "null");

@@ -24,8 +24,18 @@ __device__ __forceinline__ double div_exact(double x, double d, double r, int fa
 }
 
 // particle_cell(px, p, dh)  ParticleInCell.jl:28-35:  f = 1 + x/dh ; i = floor(f) ; h = f - i
+// In cell1 the magnitude guards of div_exact are unnecessary: a quotient below 2^-53 cannot change
+// f = 1 + x/d (both ways f == 1 and h == 0), and for |x| so large that q0 overflows the cell is
+// out of the grid either way ((int) saturates identically).  So only the uniform `fast` flag is tested.
 __device__ __forceinline__ void cell1(double x, double d, double rd, int fast, int &i, double &h) {
-  const double f = __dadd_rn(1.0, div_exact(x, d, rd, fast));
+  double q;
+  if (fast) {
+    const double q0 = __dmul_rn(x, rd);
+    q = __fma_rn(__fma_rn(-q0, d, x), rd, q0);
+  } else {
+    q = __ddiv_rn(x, d);
+  }
+  const double f = __dadd_rn(1.0, q);
   const double fl = floor(f);
   i = (int)fl;
   h = __dsub_rn(f, fl);
@@ -82,16 +92,19 @@ __device__ __forceinline__ double jl_fld(double x, double y) {
 
 // One axis of discard!/wrap!  (wrap.jl:1-33).  Returns true when the particle is discarded.
 // Fast path: 0 <= x-o < L  <=>  fld(x-o, L) == 0 (DESIGN.md "boundary fast path").
-__device__ __forceinline__ bool boundary_axis(double &x, double o, double L, int mode) {
-  if (mode == ISKB_BND_NONE) return false;
-  const double xs = __dsub_rn(x, o);
-  if (xs >= 0.0 && xs < L) return false;
+static __device__ __noinline__ bool boundary_axis_slow(double &x, double xs, double L, int mode) {
   const double a = jl_fld(xs, L);
   if (a != 0.0) {
     if (mode == ISKB_BND_DISCARD) return true;
     x = __dsub_rn(x, __dmul_rn(a, L));
   }
   return false;
+}
+__device__ __forceinline__ bool boundary_axis(double &x, double o, double L, int mode) {
+  if (mode == ISKB_BND_NONE) return false;
+  const double xs = __dsub_rn(x, o);
+  if (xs >= 0.0 && xs < L) return false;
+  return boundary_axis_slow(x, xs, L, mode);   // rare: only rows that actually crossed an edge
 }
 
 __device__ __forceinline__ bool cell_in_grid(int i, int j, int nx, int ny) {

@@ -283,112 +283,103 @@ __global__ void __launch_bounds__(256) k_dgemm(int M, int N, int K, const double
     }
 }
 
-// Thomas solve along b, one thread per mode k (coalesced over k), split in three passes so that
-// every pass reads and writes different buffers (__restrict__): the loads do not depend on the
-// recurrence and the unrolled loops keep many of them in flight per thread.
-//   pass 1  y_q = (r_q - y_{q-1}) * m_q                      (forward elimination, m precomputed)
-//   pass 2  x_q = y_q - m_q * x_{q+1}                        (back substitution)
-//   pass 3  x_q -= qt_q * f, f = (x_0 + x_{n-1}/gamma)*qden  (Sherman-Morrison, cyclic systems only)
-// The singular mode (all-periodic / all-open operator) is pinned and mean-projected instead.
-constexpr int TH_UNROLL = 16;
-
-__global__ void k_thomas_fwd(int ma, int mb, int singular_mode, const double *__restrict__ mt,
-                             const double *__restrict__ msing, const double *__restrict__ in,
-                             double *__restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= ma) return;
-  if (k == singular_mode) {
-    // T x = r, T singular (null vector = const): project r, pin x_0 = 0
-    double mean = 0.0;
-    for (int q = 0; q < mb; ++q) mean += in[k + (int64_t)q * ma];
-    mean /= mb;
-    double y = 0.0;
-    out[k] = 0.0;
-    for (int q = 1; q < mb; ++q) {
-      y = ((in[k + (int64_t)q * ma] - mean) - y) * msing[q];
-      out[k + (int64_t)q * ma] = y;
-    }
-    return;
-  }
-  double y = 0.0;
-  int q = 0;
-  for (; q + TH_UNROLL <= mb; q += TH_UNROLL) {
-    double r[TH_UNROLL], m[TH_UNROLL];
+// Thomas solve along b, ONE WARP PER MODE k on mode-major data (W[q + k*mb], q contiguous).
+// Both sweeps are first-order linear recurrences, y_q = A_q*y_{q-1} + B_q, so a tile of 32
+// consecutive q is resolved with a 5-step warp scan over the composed affine maps
+// (A2,B2) o (A1,B1) = (A2*A1, A2*B1 + B2) and the tiles are chained through a carried value:
+//   forward   y_q = (r_q - y_{q-1}) * m_q          A = -m_q, B = r_q*m_q      (m precomputed)
+//   backward  x_q = y_q - m_q * x_{q+1}            A = -m_q, B = y_q
+//   cyclic    x_q -= qt_q * f, f = (x_0 + x_{n-1}/gamma)*qden   (Sherman-Morrison)
+// The singular mode (all-periodic / all-open operator) pins x_0 = 0 on the mean-projected rhs and
+// removes the mean of the result.  Depth per sweep: mb/32 tiles x ~60 cycles instead of mb steps.
+__device__ __forceinline__ void affine_scan_up(double &A, double &B, int lane) {
 #pragma unroll
-    for (int u = 0; u < TH_UNROLL; ++u) {
-      const int64_t o = k + (int64_t)(q + u) * ma;
-      r[u] = in[o];
-      m[u] = mt[o];
+  for (int d = 1; d < 32; d <<= 1) {
+    const double Ap = __shfl_up_sync(0xffffffffu, A, d), Bp = __shfl_up_sync(0xffffffffu, B, d);
+    if (lane >= d) {
+      B = fma(A, Bp, B);
+      A = A * Ap;
     }
-#pragma unroll
-    for (int u = 0; u < TH_UNROLL; ++u) {
-      y = (r[u] - y) * m[u];
-      out[k + (int64_t)(q + u) * ma] = y;
-    }
-  }
-  for (; q < mb; ++q) {
-    const int64_t o = k + (int64_t)q * ma;
-    y = (in[o] - y) * mt[o];
-    out[o] = y;
   }
 }
 
-__global__ void k_thomas_bwd(int ma, int mb, int singular_mode, const double *__restrict__ mt,
-                             const double *__restrict__ msing, const double *__restrict__ in,
-                             double *__restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_thomas_warp(int ma, int mb, int cyclic, int singular_mode,
+                                                     const double *__restrict__ mt, const double *__restrict__ msing,
+                                                     const double *__restrict__ qt, const double *__restrict__ qden,
+                                                     const double *__restrict__ gam, double *W) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (k >= ma) return;
-  if (k == singular_mode) {
-    double x = 0.0, sum = 0.0;
-    for (int q = mb - 1; q >= 1; --q) {
-      x = in[k + (int64_t)q * ma] - msing[q] * x;
-      out[k + (int64_t)q * ma] = x;
-      sum += x;
-    }
-    const double xm = sum / mb;          // x_0 = 0 is part of the mean
-    out[k] = -xm;
-    for (int q = 1; q < mb; ++q) out[k + (int64_t)q * ma] -= xm;
-    return;
-  }
-  double x = 0.0;
-  int q = mb - 1;
-  {   // last row: x = y
-    const int64_t o = k + (int64_t)q * ma;
-    x = in[o];
-    out[o] = x;
-    --q;
-  }
-  for (; q - TH_UNROLL + 1 >= 0; q -= TH_UNROLL) {
-    double yv[TH_UNROLL], m[TH_UNROLL];
-#pragma unroll
-    for (int u = 0; u < TH_UNROLL; ++u) {
-      const int64_t o = k + (int64_t)(q - u) * ma;
-      yv[u] = in[o];
-      m[u] = mt[o];
-    }
-#pragma unroll
-    for (int u = 0; u < TH_UNROLL; ++u) {
-      x = yv[u] - m[u] * x;
-      out[k + (int64_t)(q - u) * ma] = x;
-    }
-  }
-  for (; q >= 0; --q) {
-    const int64_t o = k + (int64_t)q * ma;
-    x = in[o] - mt[o] * x;
-    out[o] = x;
-  }
-}
-
-__global__ void k_thomas_cyc(int ma, int mb, int singular_mode, const double *__restrict__ qt,
-                             const double *__restrict__ qden, const double *__restrict__ gam,
-                             const double *__restrict__ in, double *__restrict__ out) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= ma) return;
+  double *w = W + (int64_t)k * mb;
   const bool sing = k == singular_mode;
-  const double f = sing ? 0.0 : (in[k] + in[k + (int64_t)(mb - 1) * ma] / gam[k]) * qden[k];
-  for (int q = threadIdx.y; q < mb; q += blockDim.y) {
-    const int64_t o = k + (int64_t)q * ma;
-    out[o] = sing ? in[o] : in[o] - qt[o] * f;
+  const double *m = sing ? msing : mt + (int64_t)k * mb;
+  double mean = 0.0;
+  if (sing) {
+    for (int q = lane; q < mb; q += 32) mean += w[q];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mean += __shfl_xor_sync(0xffffffffu, mean, d);
+    mean /= mb;
+  }
+  const int ntile = (mb + 31) / 32;
+  // forward sweep
+  double carry = 0.0;
+  for (int t = 0; t < ntile; ++t) {
+    const int q = t * 32 + lane;
+    double A = 1.0, B = 0.0;   // identity for padding lanes
+    if (q < mb) {
+      const double mq = m[q];
+      A = -mq;
+      B = (w[q] - mean) * mq;
+      if (sing && q == 0) { A = 0.0; B = 0.0; }   // pinned x_0 = 0
+    }
+    affine_scan_up(A, B, lane);
+    const double y = fma(A, carry, B);
+    if (q < mb) w[q] = y;
+    carry = __shfl_sync(0xffffffffu, y, 31);
+  }
+  // backward sweep (reversed index r = mb-1-q so that the recurrence runs upward in r)
+  carry = 0.0;
+  for (int t = 0; t < ntile; ++t) {
+    const int r = t * 32 + lane, q = mb - 1 - r;
+    double A = 1.0, B = 0.0;
+    if (r < mb) {
+      A = (r == 0) ? 0.0 : -m[q];
+      B = w[q];
+      if (sing && q == 0) { A = 0.0; B = 0.0; }
+    }
+    affine_scan_up(A, B, lane);
+    const double x = fma(A, carry, B);
+    if (r < mb) w[q] = x;
+    carry = __shfl_sync(0xffffffffu, x, 31);
+  }
+  __syncwarp();
+  if (sing) {
+    double sum = 0.0;
+    for (int q = lane; q < mb; q += 32) sum += w[q];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const double xm = sum / mb;
+    for (int q = lane; q < mb; q += 32) w[q] -= xm;
+  } else if (cyclic) {
+    const double f = (w[0] + w[mb - 1] / gam[k]) * qden[k];
+    __syncwarp();
+    const double *qk = qt + (int64_t)k * mb;
+    for (int q = lane; q < mb; q += 32) w[q] -= qk[q] * f;
+  }
+}
+
+// out[c + r*cols] = in[r + c*rows]  (tiled through shared memory, coalesced on both sides)
+__global__ void k_transpose(int rows, int cols, const double *__restrict__ in, double *__restrict__ out) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int dc = threadIdx.y; dc < 32; dc += blockDim.y) {
+    const int r = r0 + threadIdx.x, c = c0 + dc;
+    if (r < rows && c < cols) tile[dc][threadIdx.x] = in[(int64_t)r + (int64_t)c * rows];
+  }
+  __syncthreads();
+  for (int dr = threadIdx.y; dr < 32; dr += blockDim.y) {
+    const int r = r0 + dr, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) out[(int64_t)c + (int64_t)r * cols] = tile[threadIdx.x][dr];
   }
 }
 
@@ -613,7 +604,7 @@ int32_t poisson_prepare(iskb_ctx *c) {
       std::vector<double> d((size_t)mb), qv((size_t)mb);
       for (int k = 0; k < ma; ++k) {
         if (k == ps.singular_mode) {
-          for (int q = 0; q < mb; ++q) mt[(size_t)k + (size_t)q * ma] = 0.0;
+          for (int q = 0; q < mb; ++q) mt[(size_t)q + (size_t)k * mb] = 0.0;
           continue;
         }
         for (int q = 0; q < mb; ++q) d[(size_t)q] = db[(size_t)q] + lam[(size_t)k];
@@ -627,7 +618,7 @@ int32_t poisson_prepare(iskb_ctx *c) {
         double cprev = 0.0;
         for (int q = 0; q < mb; ++q) {
           const double mq = 1.0 / (d[(size_t)q] - cprev);
-          mt[(size_t)k + (size_t)q * ma] = mq;
+          mt[(size_t)q + (size_t)k * mb] = mq;
           cprev = mq;
         }
         if (ps.b_cyclic) {
@@ -635,15 +626,15 @@ int32_t poisson_prepare(iskb_ctx *c) {
           double y = 0.0;
           for (int q = 0; q < mb; ++q) {
             const double u = q == 0 ? g : (q == mb - 1 ? 1.0 : 0.0);
-            y = (u - y) * mt[(size_t)k + (size_t)q * ma];
+            y = (u - y) * mt[(size_t)q + (size_t)k * mb];
             qv[(size_t)q] = y;
           }
           double x = 0.0;
           for (int q = mb - 1; q >= 0; --q) {
-            x = qv[(size_t)q] - (q == mb - 1 ? 0.0 : mt[(size_t)k + (size_t)q * ma] * x);
+            x = qv[(size_t)q] - (q == mb - 1 ? 0.0 : mt[(size_t)q + (size_t)k * mb] * x);
             qv[(size_t)q] = x;
           }
-          for (int q = 0; q < mb; ++q) qt[(size_t)k + (size_t)q * ma] = qv[(size_t)q];
+          for (int q = 0; q < mb; ++q) qt[(size_t)q + (size_t)k * mb] = qv[(size_t)q];
           qden[(size_t)k] = 1.0 / (1.0 + qv[0] + qv[(size_t)mb - 1] / g);
         }
       }
@@ -729,20 +720,19 @@ int32_t poisson_solve(iskb_ctx *c) {
     else
       k_dgemm<<<gg, 256, 0, c->stream>>>(ps.ma, ps.mb, ps.ma, ps.d_Vt, ps.ma, ps.d_w1, ps.ma, ps.d_w2, ps.ma);
     LAUNCH_CHECK(c);
-    // tridiagonal solves along b:  w2 -> w1 -> w2 (-> w1 when cyclic)
-    const int tb = (ps.ma + 31) / 32;
-    k_thomas_fwd<<<tb, 32, 0, c->stream>>>(ps.ma, ps.mb, ps.singular_mode, ps.d_cp, ps.d_msing, ps.d_w2, ps.d_w1);
-    LAUNCH_CHECK(c);
-    k_thomas_bwd<<<tb, 32, 0, c->stream>>>(ps.ma, ps.mb, ps.singular_mode, ps.d_cp, ps.d_msing, ps.d_w1, ps.d_w2);
-    LAUNCH_CHECK(c);
-    double *cur = ps.d_w2, *other = ps.d_w1;
-    if (ps.b_cyclic) {
-      k_thomas_cyc<<<tb, dim3(32, 16), 0, c->stream>>>(ps.ma, ps.mb, ps.singular_mode, ps.d_q, ps.d_qden, ps.d_gam,
-                                                      ps.d_w2, ps.d_w1);
+    // tridiagonal solves along b on mode-major data:  w2 --T--> w1, in place, w1 --T--> w2
+    {
+      dim3 tg((ps.ma + 31) / 32, (ps.mb + 31) / 32), tb(32, 8);
+      k_transpose<<<tg, tb, 0, c->stream>>>(ps.ma, ps.mb, ps.d_w2, ps.d_w1);
       LAUNCH_CHECK(c);
-      cur = ps.d_w1;
-      other = ps.d_w2;
+      k_thomas_warp<<<(ps.ma + 3) / 4, 128, 0, c->stream>>>(ps.ma, ps.mb, ps.b_cyclic ? 1 : 0, ps.singular_mode, ps.d_cp,
+                                                            ps.d_msing, ps.d_q, ps.d_qden, ps.d_gam, ps.d_w1);
+      LAUNCH_CHECK(c);
+      dim3 tg2((ps.mb + 31) / 32, (ps.ma + 31) / 32);
+      k_transpose<<<tg2, tb, 0, c->stream>>>(ps.mb, ps.ma, ps.d_w1, ps.d_w2);
+      LAUNCH_CHECK(c);
     }
+    double *cur = ps.d_w2, *other = ps.d_w1;
     // inverse transform  cur -> other
     if (ps.use_fft)
       k_dst_fft<<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->stream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, cur, other,

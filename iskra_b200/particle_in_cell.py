@@ -78,6 +78,12 @@ class KineticSpecies:
         L.check(self._rt.lib.iskb_species_np(self._h, C.byref(v)))
         return v.value
 
+    def window_stats(self):
+        """(gather misses, deposit misses, window moves, deposit rounds) of the fused kernel since the last call."""
+        out = np.zeros(4, dtype=np.int64)
+        L.check(self._rt.lib.iskb_species_window_stats(self._h, L.ptr(out)))
+        return out
+
     def _touched_on_device(self):
         self._dev_newer = True
 
