@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restrict__ VX, double *__restrict__ VY,
                 double *__restrict__ VZ, const double *__restrict__ WG, int64_t *cnt, GridDev g,
                 const double2 *__restrict__ E2, double qm, double dt, int mode_x, int mode_y, double *u,
-                int *status) {
+                int *status, unsigned long long *vmax2) {
   extern __shared__ double2 s_dyn[];   // per warp: E window (double2), rho window (double), claim bytes
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2 *sE = s_dyn + warp * (WN * WN);
@@ -118,6 +118,7 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
   const int64_t rend = rbeg + per < n ? rbeg + per : n;
   Window w{0, 0, false};
   unsigned dead_total = 0;
+  double vm2 = 0.0;   // max |v|^2 of the rows of this lane (bound used by the MCC pruning)
 
   int64_t p = rbeg + lane;
   double px = 0, py = 0, vx = 0, vy = 0, vz = 0, wq = 0;
@@ -190,6 +191,7 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
       vz = push_v(vz, 0.0, c1, qm, dt);
       px = push_x(px, vx, dt);
       py = push_x(py, vy, dt);
+      vm2 = fmax(vm2, fma(vz, vz, fma(vy, vy, vx * vx)));
       // ---- after_push: discards first, then wraps ----
       bool dead = (mode_x == ISKB_BND_DISCARD) && boundary_axis(px, g.ox, g.Lx, mode_x);
       if (!dead) dead = (mode_y == ISKB_BND_DISCARD) && boundary_axis(py, g.oy, g.Ly, mode_y);
@@ -266,6 +268,9 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
   __syncwarp();
   if (w.anchored) flush_rho<WN>(rho, w, g, u, lane);
   if (lane == 0 && dead_total) atomicAdd((unsigned long long *)&cnt[CNT_NDEAD], (unsigned long long)dead_total);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) vm2 = fmax(vm2, __shfl_xor_sync(0xffffffffu, vm2, d));
+  if (lane == 0 && vm2 > 0.0) atomicMax(vmax2, (unsigned long long)__double_as_longlong(vm2));
   // window statistics (diagnostics): gather misses, deposit misses, anchors, deposit rounds
   n_dmiss = __reduce_add_sync(0xffffffffu, n_dmiss);
   if (lane == 0) {
@@ -295,10 +300,11 @@ static int32_t launch_variant(iskb_species *sp, double dt, int mode_x, int mode_
   const int64_t maxb = (int64_t)c->n_sm * MINB;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
+  ISKB_TRY(sp_vmax_reset(sp));
   ISKB_TRY(prof_begin(c));
   k_advance_tiled<DEP, WN, WARPS, MINB><<<(int)blocks, WARPS * 32, SMEM, c->stream>>>(
       sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->d_cnt, c->g, c->d_E2, qm, dt, mode_x,
-      mode_y, sp->d_u, c->d_status);
+      mode_y, sp->d_u, c->d_status, sp->d_vmax2);
   LAUNCH_CHECK(c);
   ISKB_TRY(prof_end(c));
   if (mode_x == ISKB_BND_DISCARD || mode_y == ISKB_BND_DISCARD) sp->counts_stale = true;

@@ -143,7 +143,7 @@ extern "C" int32_t iskb_create(int32_t device, iskb_ctx **out) {
 
 static void free_species(iskb_species *s) {
   for (int q = 0; q < 6; ++q) { cudaFree(s->col[q]); cudaFree(s->alt[q]); }
-  cudaFree(s->id); cudaFree(s->alt_id); cudaFree(s->d_cnt); cudaFree(s->d_u); cudaFree(s->d_n);
+  cudaFree(s->id); cudaFree(s->alt_id); cudaFree(s->d_cnt); cudaFree(s->d_vmax2); cudaFree(s->d_u); cudaFree(s->d_n);
   for (int k = 0; k < 2; ++k) { cudaFree(s->d_key[k]); cudaFree(s->d_idx[k]); }
   cudaFree(s->d_hist);
   delete s;
@@ -155,7 +155,7 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
   cudaStreamSynchronize(c->stream);
   comm_destroy(c);
   for (iskb_mcc *m : c->mccs) {
-    cudaFree(m->d_tn); cudaFree(m->d_eps); cudaFree(m->d_sig); cudaFree(m->d_stats); cudaFree(m->d_nu); cudaFree(m->d_cand); cudaFree(m->d_coll); cudaFree(m->d_lists_cnt);
+    cudaFree(m->d_tn); cudaFree(m->d_eps); cudaFree(m->d_sig); cudaFree(m->d_stats); cudaFree(m->d_nu); cudaFree(m->d_cand); cudaFree(m->d_coll); cudaFree(m->d_lists_cnt); cudaFree(m->d_pk);
     delete m;
   }
   for (iskb_species *s : c->species) free_species(s);
@@ -325,6 +325,7 @@ extern "C" int32_t iskb_species_create(iskb_ctx *c, int64_t capacity, double q, 
     if (k < 5) CU_TRY(cudaMemsetAsync(s->col[k], 0, capacity * sizeof(double), c->stream));   // zeros(N,D), zeros(N,V)
   }
   CU_TRY(cudaMalloc(&s->id, capacity * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&s->d_vmax2, sizeof(unsigned long long)));
   CU_TRY(cudaMalloc(&s->d_cnt, CNT_N * sizeof(int64_t)));
   CU_TRY(cudaMemsetAsync(s->d_cnt, 0, CNT_N * sizeof(int64_t), c->stream));
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
@@ -334,8 +335,20 @@ extern "C" int32_t iskb_species_create(iskb_ctx *c, int64_t capacity, double q, 
   CU_TRY(cudaMemsetAsync(s->d_n, 0, nn * sizeof(double), c->stream));
   k_init_species<<<blocks_for(c, capacity), TPB, 0, c->stream>>>(s->col[5], s->id, capacity, w0);
   LAUNCH_CHECK(c);
+  ISKB_TRY(sp_vmax_unknown(s));
   c->species.push_back(s);
   *out = s;
+  return ISKB_OK;
+}
+
+// |v|^2 bound bookkeeping (used by the MCC pruning): +inf = unknown, 0 = about to be recomputed
+int32_t sp_vmax_unknown(iskb_species *s) {
+  static const unsigned long long inf_bits = 0x7ff0000000000000ull;
+  CU_TRY(cudaMemcpyAsync(s->d_vmax2, &inf_bits, sizeof(inf_bits), cudaMemcpyHostToDevice, s->ctx->stream));
+  return ISKB_OK;
+}
+int32_t sp_vmax_reset(iskb_species *s) {
+  CU_TRY(cudaMemsetAsync(s->d_vmax2, 0, sizeof(unsigned long long), s->ctx->stream));
   return ISKB_OK;
 }
 
@@ -382,6 +395,7 @@ extern "C" int32_t iskb_species_upload(iskb_species *s, const double *x, const d
   if (wg) CU_TRY(cudaMemcpyAsync(s->col[5], wg, s->cap * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (id) CU_TRY(cudaMemcpyAsync(s->id, id, s->cap * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   ISKB_TRY(set_counts(s, np, 0));
+  ISKB_TRY(sp_vmax_unknown(s));
   CU_TRY(cudaStreamSynchronize(c->stream));
   return ISKB_OK;
 }
@@ -441,6 +455,7 @@ extern "C" int32_t iskb_species_sample_maxwellian(iskb_species *s, int64_t n, co
                                                    wx[0], wx[1], dx[0], dx[1], wv[0], wv[1], wv[2], dv[0], dv[1], dv[2],
                                                    k0, k1, (uint32_t)(s->sample_calls++));
   LAUNCH_CHECK(c);
+  ISKB_TRY(sp_vmax_unknown(s));
   return set_counts(s, s->h_nslots + n, 0);
 }
 
@@ -458,6 +473,7 @@ extern "C" int32_t iskb_species_copy_positions(iskb_species *dst, iskb_species *
     k_fill3<<<blocks_for(c, n), TPB, 0, c->stream>>>(dst->col[2], dst->col[3], dst->col[4], n, v_fill[0], v_fill[1], v_fill[2]);
     LAUNCH_CHECK(c);
   }
+  ISKB_TRY(sp_vmax_unknown(dst));
   return set_counts(dst, n, 0);
 }
 

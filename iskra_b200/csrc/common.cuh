@@ -136,6 +136,7 @@ struct iskb_species {
   int64_t *d_cnt = nullptr;     // CNT_*
   int64_t h_nslots = 0, h_ndead = 0;   // host mirror, valid when !counts_stale
   bool counts_stale = false;
+  unsigned long long *d_vmax2 = nullptr;   // bits of an upper bound of |v|^2 over the live rows (+inf = unknown)
   double *d_u = nullptr;        // deposited weights  (particle_to_grid, cloud_in_cell.jl:1-18)
   double *d_n = nullptr;        // density n = u ./ V (kinetic.jl:53)
   // sort scratch
@@ -162,6 +163,8 @@ struct iskb_mcc {
   double max_n0 = 0;
   double eps_hi = 0;                 // largest tabulated energy
   std::vector<double> sup_sigma_g;   // per process: sup of sigma_k*g on [0, eps_hi]
+  std::vector<double> sig_last;      // per process: sigma_k at its last knot
+  double *d_pk = nullptr;            // device pruning bounds of the current call
   uint64_t seed = 0;
   uint64_t calls = 0;
   double *d_tn = nullptr;       // target density on nodes
@@ -190,5 +193,7 @@ int32_t comm_destroy(iskb_ctx *ctx);
 int32_t launch_advance(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit,
                        int64_t first_slot_from_cnt_begin);
 int32_t launch_rho_finalize(iskb_ctx *ctx);
+int32_t sp_vmax_unknown(iskb_species *sp);
+int32_t sp_vmax_reset(iskb_species *sp);
 int32_t prof_begin(iskb_ctx *ctx);
 int32_t prof_end(iskb_ctx *ctx);

@@ -17,6 +17,8 @@
 //   k_mcc_collide : one thread per collider: kinematics (mcc.jl:129-229), ionisation appends.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "pic_device.cuh"
 
@@ -30,6 +32,7 @@ struct SpDev {
   double *col[6];
   int64_t *cnt;
   int64_t cap;
+  unsigned long long *vmax2;
 };
 
 struct ProcDev {
@@ -57,6 +60,12 @@ struct MccDev {
   uint32_t p_cand_u32;
   double pk_bound[8];   // sup over eps in [0, eps_hi] of P_k (with n = max density): exact pruning bound
   double eps_hi;        // largest tabulated energy of all processes
+  double sup_sg[8];     // sup of sigma_k*g on the tables; sig_last: sigma_k at its last knot (Flat() beyond)
+  double sig_last[8];
+  double n0max;
+  const unsigned long long *vmax2;   // bits of the species-wide bound of |v|^2 (+inf = unknown)
+  int debug;
+  double *pk_dev;       // [8] pruning bounds valid for EVERY live row, computed on the device per call
   uint32_t k0, k1;   // Philox key
   uint32_t call;
   unsigned long long *stats;
@@ -131,6 +140,11 @@ __device__ void diffuse_reflection(const double *v, Rng &g, double *out) {     /
   scatter3(v, sc, cc, se, ce, out);
 }
 
+__device__ __forceinline__ void raise_vmax(unsigned long long *vmax2, const double *v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+  if (b > *(volatile unsigned long long *)vmax2) atomicMax(vmax2, b);   // almost never taken: same-address atomics are slow
+}
+
 __device__ bool append_row(const SpDev &s, double x, double y, const double *v, int *status) {
   const int64_t slot = (int64_t)atomicAdd((unsigned long long *)&s.cnt[CNT_NSLOTS], 1ull);
   if (slot >= s.cap) {
@@ -140,6 +154,7 @@ __device__ bool append_row(const SpDev &s, double x, double y, const double *v, 
   }
   s.col[0][slot] = x; s.col[1][slot] = y;
   s.col[2][slot] = v[0]; s.col[3][slot] = v[1]; s.col[4][slot] = v[2];
+  raise_vmax(s.vmax2, v);
   // wg and id of the slot stay as parked there (kinetic.jl:29-37 "dst has already correct ID")
   return true;
 }
@@ -161,7 +176,9 @@ __device__ void collide(const MccDev &m, const ProcDev &pc, int64_t p, Rng &g) {
     if (pc.kind == ISKB_MCC_ELASTIC_ISOTROPIC) isotropic_scattering(vr, g, dir);
     else if (pc.kind == ISKB_MCC_ELASTIC_BACKWARD) diffuse_reflection(vr, g, dir);
     else { mag = g.u01() * mag; diffuse_reflection(vr, g, dir); }
-    for (int k = 0; k < 3; ++k) m.src.col[2 + k][p] = w[k] + m.mr2 * (mag * dir[k]);
+    double nv[3];
+    for (int k = 0; k < 3; ++k) { nv[k] = w[k] + m.mr2 * (mag * dir[k]); m.src.col[2 + k][p] = nv[k]; }
+    raise_vmax(m.src.vmax2, nv);
     return;
   }
   const double sE = 0.5 * m.m_eV * ((sv[0] * sv[0] + sv[1] * sv[1]) + sv[2] * sv[2]) - pc.threshold;
@@ -170,7 +187,9 @@ __device__ void collide(const MccDev &m, const ProcDev &pc, int64_t p, Rng &g) {
     const double ev = sqrt(2.0 / m.m_eV) * sqrt(sE);
     double dir[3];
     isotropic_scattering(sv, g, dir);
-    for (int k = 0; k < 3; ++k) m.src.col[2 + k][p] = ev * dir[k];
+    double nv[3];
+    for (int k = 0; k < 3; ++k) { nv[k] = ev * dir[k]; m.src.col[2 + k][p] = nv[k]; }
+    raise_vmax(m.src.vmax2, nv);
     return;
   }
   // ionization :184-212
@@ -179,6 +198,7 @@ __device__ void collide(const MccDev &m, const ProcDev &pc, int64_t p, Rng &g) {
   double d1[3], d2[3];
   diffuse_reflection(sv, g, d1);
   for (int k = 0; k < 3; ++k) { sv[k] = e1v * d1[k]; m.src.col[2 + k][p] = sv[k]; }
+  raise_vmax(m.src.vmax2, sv);
   diffuse_reflection(sv, g, d2);
   const double x = m.src.col[0][p], y = m.src.col[1][p];
   double nv[3] = {e2v * d2[0], e2v * d2[1], e2v * d2[2]};
@@ -192,10 +212,24 @@ __device__ void collide(const MccDev &m, const ProcDev &pc, int64_t p, Rng &g) {
       if (!append_row(m.prod[pc.prod], x, y, tv, m.status)) return;
 }
 
-__global__ void k_snapshot_begin(int64_t *cnt, unsigned int *lists_cnt) {
+__global__ void k_snapshot_begin(int64_t *cnt, unsigned int *lists_cnt, MccDev m) {
   cnt[CNT_BEGIN] = cnt[CNT_NSLOTS];
   lists_cnt[0] = 0;   // candidates
   lists_cnt[1] = 0;   // colliders
+  // Row-independent pruning bounds: P_k <= pk_dev[k] for every live row, from the species-wide
+  // |v|^2 bound kept by the advance kernels.  Neutral target only (g = |v|); beyond the last knot
+  // sigma is flat, so sigma*g <= sig_last*|v|max.  Unknown (+inf) speed bound => no pruning.
+  const double v2 = __longlong_as_double((long long)*m.vmax2);
+  for (int k = 0; k < m.N; ++k) {
+    double pk = 2.0;   // > any delta: never prunes
+    if (m.tqm == 0.0 && v2 < 1e300) {
+      const double sg = fmax(m.sup_sg[k], m.sig_last[k] * sqrt(v2));
+      pk = (1.0 - exp(-m.n0max * sg * m.dt)) / m.p_cand * (1.0 + 1e-9) + 1e-300;
+    }
+    m.pk_dev[k] = pk;
+    if (m.debug) printf("mcc bound k=%d v2=%g sup_sg=%g sig_last=%g n0=%g dt=%g p_cand=%g pk=%g (1/N=%g)\n", k, v2, m.sup_sg[k],
+                        m.sig_last[k], m.n0max, m.dt, m.p_cand, pk, 1.0 / m.N);
+  }
 }
 
 // warp-aggregated append: returns the slot of this lane's item (or -1 when pred is false)
@@ -265,32 +299,38 @@ __global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *list
   if (lane == 0 && my_cand) atomicAdd(&m.stats[0], my_cand);
 }
 
-__global__ void k_mcc_test(MccDev m, unsigned int *lists_cnt, const uint32_t *__restrict__ cand,
-                           unsigned int cand_cap, uint2 *coll) {
+constexpr int TEST_TPB = 128;
+constexpr int TEST_BUF = 512;
+
+__global__ void __launch_bounds__(TEST_TPB) k_mcc_test(MccDev m, unsigned int *lists_cnt, const uint32_t *__restrict__ cand,
+                                                       unsigned int cand_cap, uint2 *coll) {
+  __shared__ uint2 s_hit[TEST_BUF];
+  __shared__ unsigned int s_nhit, s_base;
+  __shared__ unsigned int s_proc[8];
+  if (threadIdx.x == 0) s_nhit = 0;
+  if (threadIdx.x < 8) s_proc[threadIdx.x] = 0;
+  __syncthreads();
   unsigned int nc = lists_cnt[0];
   if (nc > cand_cap) nc = cand_cap;
-  const unsigned int nc_pad = (nc + 31u) / 32u * 32u;
-  for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < nc_pad; t += gridDim.x * blockDim.x) {
-    bool hit = false;
-    int64_t p = 0;
-    int k = 0;
+  const unsigned int nc_pad = (nc + TEST_TPB - 1) / TEST_TPB * TEST_TPB;   // block-uniform trip count
+  for (unsigned int t = blockIdx.x * TEST_TPB + threadIdx.x; t < nc_pad; t += gridDim.x * TEST_TPB) {
     if (t < nc) {
-      p = cand[t];
+      const int64_t p = cand[t];
       Rng g(p, m.call, m.k0, m.k1, 1u);
       const double U = g.u01();                                             // :260
-      k = (int)floor(m.N * U + 1.0);                                        // :261
+      int k = (int)floor(m.N * U + 1.0);                                    // :261
       if (k > m.N) k = m.N;
       const double delta = (double)k / m.N - U;                             // collide iff delta < P_k (:281)
-      const double vx = m.src.col[2][p], vy = m.src.col[3][p], vz = m.src.col[4][p];
-      // exact early-out for a neutral target: g = |v| needs no field; P_k <= pk_bound[k] on the tables
-      bool maybe = true;
-      if (m.tqm == 0.0) {
-        const double g2 = (vx * vx + vy * vy) + vz * vz;
-        if (0.5 * m.m_eV * g2 <= m.eps_hi && delta >= m.pk_bound[k - 1]) maybe = false;
-      }
-      if (maybe) {
-        const double px = m.src.col[0][p];
-        if (!is_dead(px)) {
+      // exact early-out before touching the row: P_k <= pk_dev[k] for every live row of the species
+      if (delta < m.pk_dev[k - 1]) {
+        const double vx = m.src.col[2][p], vy = m.src.col[3][p], vz = m.src.col[4][p];
+        bool maybe = true;
+        if (m.tqm == 0.0) {   // second exact early-out with the row's own energy (target at rest: g = |v|)
+          const double g2 = (vx * vx + vy * vy) + vz * vz;
+          if (0.5 * m.m_eV * g2 <= m.eps_hi && delta >= m.pk_bound[k - 1]) maybe = false;
+        }
+        const double px = maybe ? m.src.col[0][p] : 0.0;
+        if (maybe && !is_dead(px)) {
           int i, j;
           double hx, hy;
           cell1(px, m.g.dx, m.g.rdx, m.g.fast_div, i, hx);
@@ -314,8 +354,9 @@ __global__ void k_mcc_test(MccDev m, unsigned int *lists_cnt, const uint32_t *__
               Pk /= m.p_cand;                                                     // :272  N*max_Pt
               if (Pk > 1.0) atomicOr(m.status, ISKB_ST_PK);                       // :273-279
               else if (delta < Pk) {                                              // :281  U > k/N - P_k
-                hit = true;
-                atomicAdd(&m.stats[2 + (k - 1)], 1ull);
+                const unsigned slot = atomicAdd(&s_nhit, 1u);                     // block-local staging
+                s_hit[slot] = make_uint2((uint32_t)p, (uint32_t)k);
+                atomicAdd(&s_proc[k - 1], 1u);
                 if (m.nu) atomicAdd(&m.nu[node + (int64_t)(k - 1) * m.g.nx * m.g.ny], 1.0f);   // :283
               }
             }
@@ -323,9 +364,23 @@ __global__ void k_mcc_test(MccDev m, unsigned int *lists_cnt, const uint32_t *__
         }
       }
     }
-    const int64_t slot = warp_append(hit, &lists_cnt[1]);
-    if (hit) coll[slot] = make_uint2((uint32_t)p, (uint32_t)k);   // collider list has cand_cap entries
+    __syncthreads();
+    if (s_nhit > TEST_BUF - TEST_TPB) {   // flush the staged colliders with ONE global atomic
+      if (threadIdx.x == 0) s_base = atomicAdd(&lists_cnt[1], s_nhit);
+      __syncthreads();
+      for (unsigned int q = threadIdx.x; q < s_nhit; q += TEST_TPB) coll[s_base + q] = s_hit[q];
+      __syncthreads();
+      if (threadIdx.x == 0) s_nhit = 0;
+      __syncthreads();
+    }
   }
+  __syncthreads();
+  if (s_nhit) {
+    if (threadIdx.x == 0) s_base = atomicAdd(&lists_cnt[1], s_nhit);
+    __syncthreads();
+    for (unsigned int q = threadIdx.x; q < s_nhit; q += TEST_TPB) coll[s_base + q] = s_hit[q];
+  }
+  if (threadIdx.x < 8 && s_proc[threadIdx.x]) atomicAdd(&m.stats[2 + threadIdx.x], (unsigned long long)s_proc[threadIdx.x]);
 }
 
 __global__ void k_mcc_collide(MccDev m, const unsigned int *__restrict__ lists_cnt, const uint2 *__restrict__ coll) {
@@ -343,6 +398,7 @@ SpDev spdev(const iskb_species *s) {
   for (int q = 0; q < 6; ++q) d.col[q] = s->col[q];
   d.cnt = s->d_cnt;
   d.cap = s->cap;
+  d.vmax2 = s->d_vmax2;
   return d;
 }
 
@@ -399,6 +455,15 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
     const double pk = (1.0 - exp(-mc->max_n0 * mc->sup_sigma_g[(size_t)k] * dt)) / m.p_cand;
     m.pk_bound[k] = pk * (1.0 + 1e-9) + 1e-300;
   }
+  for (int k = 0; k < N; ++k) {
+    m.sup_sg[k] = mc->sup_sigma_g[(size_t)k];
+    m.sig_last[k] = mc->sig_last[(size_t)k];
+  }
+  m.n0max = mc->max_n0;
+  m.vmax2 = src->d_vmax2;
+  if (!mc->d_pk) CU_TRY(cudaMalloc(&mc->d_pk, 8 * sizeof(double)));
+  m.pk_dev = mc->d_pk;
+  m.debug = getenv("ISKB_DEBUG") ? 1 : 0;
   m.k0 = (uint32_t)mc->seed;
   m.k1 = (uint32_t)(mc->seed >> 32) ^ (0x9E3779B9u * (uint32_t)(c->rank + 1));
   m.call = (uint32_t)(mc->calls++);
@@ -418,7 +483,7 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
     CU_TRY(cudaMalloc(&mc->d_lists_cnt, 2 * sizeof(unsigned int)));
   }
   const unsigned int cand_cap = (unsigned int)src->cap;
-  k_snapshot_begin<<<1, 1, 0, c->stream>>>(src->d_cnt, mc->d_lists_cnt);
+  k_snapshot_begin<<<1, 1, 0, c->stream>>>(src->d_cnt, mc->d_lists_cnt, m);
   LAUNCH_CHECK(c);
   const int64_t bound = src->counts_stale ? src->cap : src->h_nslots;
   int64_t blocks = (bound / 4 + TPB) / TPB;
@@ -428,9 +493,9 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
   LAUNCH_CHECK(c);
   // the list lengths live on the device: size the dense phases from the expected candidate count
   int64_t exp_cand = (int64_t)(m.p_cand * (double)bound) + 1024;
-  int64_t b2 = (exp_cand + 127) / 128;
-  if (b2 > (int64_t)c->n_sm * 16) b2 = (int64_t)c->n_sm * 16;
-  k_mcc_test<<<(int)b2, 128, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap, mc->d_coll);
+  int64_t b2 = (exp_cand + TEST_TPB - 1) / TEST_TPB;
+  if (b2 > (int64_t)c->n_sm * 8) b2 = (int64_t)c->n_sm * 8;
+  k_mcc_test<<<(int)b2, TEST_TPB, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap, mc->d_coll);
   LAUNCH_CHECK(c);
   int64_t b3 = (exp_cand / 8 + 127) / 128;
   if (b3 > (int64_t)c->n_sm * 4) b3 = (int64_t)c->n_sm * 4;
@@ -501,6 +566,7 @@ extern "C" int32_t iskb_mcc_create(iskb_ctx *c, iskb_species *source, double tar
       }
     }
     mc->sup_sigma_g[(size_t)k] = sup;
+    mc->sig_last.push_back(sigma[p.offset + p.len - 1]);   // sigma_k(last knot): Flat() beyond the table, so sigma*g <= sig_last*|v|max there
   }
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   mc->max_n0 = -INFINITY;

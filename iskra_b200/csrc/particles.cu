@@ -198,9 +198,10 @@ __global__ void k_rho_finalize(RhoFin f, const double *__restrict__ V, double *r
 __global__ void k_advance_simple(double *x, double *y, double *vx, double *vy, double *vz,
                                  const double *__restrict__ wg, int64_t *cnt, int first_from_begin,
                                  GridDev g, const double2 *__restrict__ E2, double qm, double dt,
-                                 int mode_x, int mode_y, double *u, int *status) {
+                                 int mode_x, int mode_y, double *u, int *status, unsigned long long *vmax2) {
   const int64_t n = cnt[CNT_NSLOTS];
   const int64_t first = first_from_begin ? cnt[CNT_BEGIN] : 0;
+  double vm2 = 0.0;
   const double c1 = __dmul_rn(__dmul_rn(0.5, dt), qm);
   for (int64_t p0 = first + blockIdx.x * (int64_t)blockDim.x; p0 < n;
        p0 += (int64_t)gridDim.x * blockDim.x) {
@@ -216,6 +217,7 @@ __global__ void k_advance_simple(double *x, double *y, double *vx, double *vy, d
         const double nvz = push_v(vz[p], 0.0, c1, qm, dt);
         px = push_x(px, nvx, dt);
         py = push_x(py, nvy, dt);
+        vm2 = fmax(vm2, (nvx * nvx + nvy * nvy) + nvz * nvz);
         bool dead = (mode_x == ISKB_BND_DISCARD) && boundary_axis(px, g.ox, g.Lx, mode_x);
         if (!dead) dead = (mode_y == ISKB_BND_DISCARD) && boundary_axis(py, g.oy, g.Ly, mode_y);
         if (!dead) {
@@ -254,6 +256,9 @@ __global__ void k_advance_simple(double *x, double *y, double *vx, double *vy, d
     const unsigned m = __ballot_sync(0xffffffffu, dead_now);
     if (m && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&cnt[CNT_NDEAD], (unsigned long long)__popc(m));
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) vm2 = fmax(vm2, __shfl_xor_sync(0xffffffffu, vm2, d));
+  if ((threadIdx.x & 31) == 0 && vm2 > 0.0) atomicMax(vmax2, (unsigned long long)__double_as_longlong(vm2));
 }
 
 }  // namespace
@@ -319,6 +324,7 @@ extern "C" int32_t iskb_push(iskb_species *sp, const double *partE, double dt) {
     CU_TRY(cudaMemcpyAsync(d, partE, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
   const double qm = sp->q / sp->m;   // pushers.jl:39
+  ISKB_TRY(sp_vmax_unknown(sp));
   k_push<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4],
                                               sp->d_cnt, c->g, c->d_E2, d, n, qm, dt, c->d_status);
   LAUNCH_CHECK(c);
@@ -422,9 +428,10 @@ int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_
   iskb_ctx *c = sp->ctx;
   const double qm = sp->q / sp->m;
   int blocks = from_begin ? c->n_sm : grid_for(sp);
+  if (!from_begin) ISKB_TRY(sp_vmax_reset(sp));
   k_advance_simple<<<blocks, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4],
                                                   sp->col[5], sp->d_cnt, from_begin ? 1 : 0, c->g, c->d_E2, qm,
-                                                  dt, mode_x, mode_y, deposit ? sp->d_u : nullptr, c->d_status);
+                                                  dt, mode_x, mode_y, deposit ? sp->d_u : nullptr, c->d_status, sp->d_vmax2);
   LAUNCH_CHECK(c);
   if (mode_x == ISKB_BND_DISCARD || mode_y == ISKB_BND_DISCARD) sp->counts_stale = true;
   return ISKB_OK;
