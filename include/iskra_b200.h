@@ -179,6 +179,11 @@ int32_t iskb_rho_allreduce(iskb_ctx *ctx);
 int32_t iskb_set_after_push(iskb_ctx *ctx, int32_t mode_x, int32_t mode_y);
 /* re-sort every `interval` steps (0 = never) */
 int32_t iskb_set_sort_interval(iskb_ctx *ctx, int32_t interval);
+/* Adaptive variant: a species is re-sorted when at least `interval` steps have passed since its
+ * last sort AND (the fraction of its rows that missed the shared window in the last measured step
+ * exceeds miss_threshold OR max_interval steps have passed).  miss_threshold = 0 restores the
+ * fixed interval.  Slow species (ions) are then sorted rarely, fast ones (electrons) often. */
+int32_t iskb_set_sort_policy(iskb_ctx *ctx, double miss_threshold, int32_t max_interval);
 /* n_steps iterations of: MCC (registered interactions, in order) -> advance! every species
  * (gather, push, after_push) -> density / rho -> all-reduce -> phi -> E. */
 int32_t iskb_step(iskb_ctx *ctx, double dt, int32_t n_steps);

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restrict__ VX, double *__restrict__ VY,
                 double *__restrict__ VZ, const double *__restrict__ WG, int64_t *cnt, GridDev g,
                 const double2 *__restrict__ E2, double qm, double dt, int mode_x, int mode_y, double *u,
-                int *status, unsigned long long *vmax2) {
+                int *status, unsigned long long *vmax2, int64_t n_sorted) {
   extern __shared__ double2 s_dyn[];   // per warp: E window (double2), rho window (double), claim bytes
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double2 *sE = s_dyn + warp * (WN * WN);
@@ -111,23 +111,36 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
   constexpr int MARGIN = (WN - 9) / 2;   // cells of slack below the 8x8 tile (the rest above)
   const int64_t n = cnt[CNT_NSLOTS];
   const double c1 = __dmul_rn(__dmul_rn(0.5, dt), qm);
-  // contiguous range of rows per warp (multiple of 32)
+  // Every warp walks one contiguous range of the SORTED rows [0, ns) (its window follows the tiles)
+  // plus one slice of the unsorted tail [ns, n) (rows appended by ionisation since the last sort;
+  // they take the global path and never move the window).  Both ranges are multiples of 32.
   const int64_t nwarps = (int64_t)gridDim.x * WARPS, gwarp = (int64_t)blockIdx.x * WARPS + warp;
-  const int64_t per = ((n + nwarps - 1) / nwarps + 31) / 32 * 32;
-  const int64_t rbeg = gwarp * per;
-  const int64_t rend = rbeg + per < n ? rbeg + per : n;
+  const int64_t ns = n_sorted < n ? n_sorted : n;
+  const int64_t per = ((ns + nwarps - 1) / nwarps + 31) / 32 * 32;
+  int64_t rbeg = gwarp * per;
+  if (rbeg > ns) rbeg = ns;
+  const int64_t rend = rbeg + per < ns ? rbeg + per : ns;
+  const int64_t tper = ((n - ns + nwarps - 1) / nwarps + 31) / 32 * 32;
+  int64_t tbeg = ns + gwarp * tper;
+  if (tbeg > n) tbeg = n;
+  const int64_t tend = tbeg + tper < n ? tbeg + tper : n;
+  const int64_t nbm = (rend - rbeg + 31) / 32, nbt = (tend - tbeg + 31) / 32;
   Window w{0, 0, false};
   unsigned dead_total = 0;
   double vm2 = 0.0;   // max |v|^2 of the rows of this lane (bound used by the MCC pruning)
 
-  int64_t p = rbeg + lane;
+  int64_t p = (nbm ? rbeg : tbeg) + lane;
+  int64_t lim = nbm ? rend : tend;
   double px = 0, py = 0, vx = 0, vy = 0, vz = 0, wq = 0;
-  if (p < rend) { px = X[p]; py = Y[p]; vx = VX[p]; vy = VY[p]; vz = VZ[p]; wq = WG[p]; }
-  for (int64_t b0 = rbeg; b0 < rend; b0 += 32) {
-    const bool in_range = p < rend;
-    const int64_t pn = p + 32;
+  if (p < lim) { px = X[p]; py = Y[p]; vx = VX[p]; vy = VY[p]; vz = VZ[p]; wq = WG[p]; }
+  for (int64_t kb = 0; kb < nbm + nbt; ++kb) {
+    const bool windowed = kb < nbm;
+    const bool in_range = p < lim;
+    // next batch: next of this range, or the first batch of the tail slice
+    const int64_t limn = kb + 1 < nbm ? rend : tend;
+    const int64_t pn = kb + 1 == nbm ? tbeg + lane : p + 32;
     double nx_ = 0, ny_ = 0, nvx_ = 0, nvy_ = 0, nvz_ = 0, nwq_ = 0;
-    if (pn < rend) { nx_ = X[pn]; ny_ = Y[pn]; nvx_ = VX[pn]; nvy_ = VY[pn]; nvz_ = VZ[pn]; nwq_ = WG[pn]; }
+    if (kb + 1 < nbm + nbt && pn < limn) { nx_ = X[pn]; ny_ = Y[pn]; nvx_ = VX[pn]; nvy_ = VY[pn]; nvz_ = VZ[pn]; nwq_ = WG[pn]; }
 
     const bool live = in_range && !is_dead(px);
     // ---- cell of the old position; window management on it ----
@@ -145,7 +158,7 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
     if (gm) {
       const unsigned fm = __ballot_sync(0xffffffffu, fit);
       const unsigned miss = gm & ~fm;
-      if (!w.anchored || __popc(miss) > MISS_LIMIT) {
+      if (windowed && (!w.anchored || __popc(miss) > MISS_LIMIT)) {
         ++n_anchor;
         if (w.anchored) flush_rho<WN>(rho, w, g, u, lane);
         const int src = __ffs(miss) - 1;
@@ -263,6 +276,7 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
     }
     __syncwarp();   // rho window updates of this batch are ordered before a possible flush
     p = pn;
+    lim = limn;
     px = nx_; py = ny_; vx = nvx_; vy = nvy_; vz = nvz_; wq = nwq_;
   }
   __syncwarp();
@@ -304,7 +318,7 @@ static int32_t launch_variant(iskb_species *sp, double dt, int mode_x, int mode_
   ISKB_TRY(prof_begin(c));
   k_advance_tiled<DEP, WN, WARPS, MINB><<<(int)blocks, WARPS * 32, SMEM, c->stream>>>(
       sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->d_cnt, c->g, c->d_E2, qm, dt, mode_x,
-      mode_y, sp->d_u, c->d_status, sp->d_vmax2);
+      mode_y, sp->d_u, c->d_status, sp->d_vmax2, sp->h_nsorted);
   LAUNCH_CHECK(c);
   ISKB_TRY(prof_end(c));
   if (mode_x == ISKB_BND_DISCARD || mode_y == ISKB_BND_DISCARD) sp->counts_stale = true;

@@ -145,6 +145,8 @@ static void free_species(iskb_species *s) {
   for (int q = 0; q < 6; ++q) { cudaFree(s->col[q]); cudaFree(s->alt[q]); }
   cudaFree(s->id); cudaFree(s->alt_id); cudaFree(s->d_cnt); cudaFree(s->d_vmax2); cudaFree(s->d_u); cudaFree(s->d_n);
   for (int k = 0; k < 2; ++k) { cudaFree(s->d_key[k]); cudaFree(s->d_idx[k]); }
+  if (s->h_wstats) cudaFreeHost(s->h_wstats);
+  for (int k = 0; k < 2; ++k) if (s->ev_wstats[k]) cudaEventDestroy(s->ev_wstats[k]);
   cudaFree(s->d_hist);
   delete s;
 }
@@ -375,6 +377,7 @@ static int32_t set_counts(iskb_species *s, int64_t nslots, int64_t ndead) {
   k_set_counts<<<1, 1, 0, c->stream>>>(s->d_cnt, nslots, ndead);
   LAUNCH_CHECK(c);
   s->h_nslots = nslots; s->h_ndead = ndead; s->counts_stale = false;
+  s->h_nsorted = 0;   // set_counts is only used by upload / sample / copy: the layout is unknown
   return ISKB_OK;
 }
 
@@ -489,6 +492,59 @@ extern "C" int32_t iskb_set_sort_interval(iskb_ctx *c, int32_t interval) {
   return ISKB_OK;
 }
 
+extern "C" int32_t iskb_set_sort_policy(iskb_ctx *c, double miss_threshold, int32_t max_interval) {
+  if (!c || miss_threshold < 0 || max_interval < 0) return iskb_fail(ISKB_E_INVALID, "bad sort policy");
+  c->sort_miss_threshold = miss_threshold;
+  c->sort_max_interval = max_interval;
+  return ISKB_OK;
+}
+
+// Decide whether species s is re-sorted before this step.  The window statistics travel through
+// an async copy + event; the host waits for the snapshot taken TWO steps ago, which keeps one whole
+// step of work queued on the GPU (no bubble) while bounding how far the host runs ahead.
+static int32_t maybe_sort(iskb_ctx *c, iskb_species *s) {
+  if (c->sort_miss_threshold > 0.0 && s->h_wstats) {
+    const int slot = (int)(s->wstats_step & 1);   // the older of the two snapshots
+    if (s->wstats_pending[slot]) {
+      CU_TRY(cudaEventSynchronize(s->ev_wstats[slot]));
+      const int64_t g = s->h_wstats[4 * slot];
+      const int64_t rows = s->h_nslots > 0 ? s->h_nslots : 1;
+      const int64_t d = g >= s->last_gmiss ? g - s->last_gmiss : g;   // counters may have been reset by the user
+      s->last_gmiss = g;
+      // this snapshot has index wstats_step-2; ignore it if it predates the last sort
+      if (s->wstats_step - 2 >= s->wstats_sort_mark) s->miss_rate = (double)d / (double)rows;
+      s->wstats_pending[slot] = false;
+    }
+  }
+  bool do_sort = s->steps_since_sort >= c->sort_interval;
+  if (do_sort && c->sort_miss_threshold > 0.0 && s->steps_since_sort < (1 << 29)) {
+    const bool too_old = c->sort_max_interval > 0 && s->steps_since_sort >= c->sort_max_interval;
+    do_sort = too_old || s->miss_rate > c->sort_miss_threshold;
+  }
+  if (do_sort) {
+    ISKB_TRY(sp_sort(s, nullptr, true));
+    s->steps_since_sort = 0;
+    s->miss_rate = 0.0;
+    s->wstats_sort_mark = s->wstats_step;
+  }
+  return ISKB_OK;
+}
+
+static int32_t post_advance_stats(iskb_ctx *c, iskb_species *s) {
+  if (c->sort_miss_threshold <= 0.0) return ISKB_OK;
+  if (!s->h_wstats) {
+    CU_TRY(cudaMallocHost(&s->h_wstats, 8 * sizeof(int64_t)));
+    CU_TRY(cudaEventCreateWithFlags(&s->ev_wstats[0], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&s->ev_wstats[1], cudaEventDisableTiming));
+  }
+  const int slot = (int)(s->wstats_step & 1);
+  CU_TRY(cudaMemcpyAsync(s->h_wstats + 4 * slot, s->d_cnt + 3, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaEventRecord(s->ev_wstats[slot], c->stream));
+  s->wstats_pending[slot] = true;
+  s->wstats_step++;
+  return ISKB_OK;
+}
+
 extern "C" int32_t iskb_rho_allreduce(iskb_ctx *c) {
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
   if (c->n_ranks == 1) return ISKB_OK;
@@ -502,13 +558,18 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
   ISKB_TRY(poisson_prepare(c));
   for (int it = 0; it < n_steps; ++it) {
     const bool tiled = c->sort_interval > 0;
-    if (tiled && (c->step_count % c->sort_interval) == 0)
-      for (iskb_species *s : c->species) ISKB_TRY(sp_sort(s, nullptr, true));
+    if (tiled)
+      for (iskb_species *s : c->species) ISKB_TRY(maybe_sort(c, s));
     for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));       // :109-111
     for (iskb_species *s : c->species) {                                   // :113-115
       CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
-      if (tiled) ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
-      else ISKB_TRY(launch_advance_simple(s, dt, c->after_push[0], c->after_push[1], true, false));
+      if (tiled) {
+        ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
+        ISKB_TRY(post_advance_stats(c, s));
+        s->steps_since_sort++;
+      } else {
+        ISKB_TRY(launch_advance_simple(s, dt, c->after_push[0], c->after_push[1], true, false));
+      }
     }
     ISKB_TRY(launch_rho_finalize(c));                                      // :118-124
     if (c->n_ranks > 1) ISKB_TRY(comm_allreduce_sum(c, c->d_rho, nn));

@@ -110,6 +110,8 @@ struct iskb_ctx {
   std::vector<iskb_mcc *> mccs;
   int after_push[2] = {ISKB_BND_WRAP, ISKB_BND_WRAP};   // default hook wrap!, ParticleInCell.jl:41
   int sort_interval = 0;
+  double sort_miss_threshold = 0.0;   // adaptive: sort a species only when its window-miss rate exceeds this
+  int sort_max_interval = 0;          //           ... or this many steps have passed
   int64_t step_count = 0;
   // optional per-kernel timing of the dominant (advance) kernel, CUDA events on the launch stream
   bool profile = false;
@@ -135,6 +137,7 @@ struct iskb_species {
   uint32_t *alt_id = nullptr;
   int64_t *d_cnt = nullptr;     // CNT_*
   int64_t h_nslots = 0, h_ndead = 0;   // host mirror, valid when !counts_stale
+  int64_t h_nsorted = 0;               // rows [0, h_nsorted) are in the sorted layout of the last re-sort
   bool counts_stale = false;
   unsigned long long *d_vmax2 = nullptr;   // bits of an upper bound of |v|^2 over the live rows (+inf = unknown)
   double *d_u = nullptr;        // deposited weights  (particle_to_grid, cloud_in_cell.jl:1-18)
@@ -144,6 +147,15 @@ struct iskb_species {
   uint32_t *d_hist = nullptr;
   int64_t hist_cap = 0;
   uint64_t sample_calls = 0;
+  // adaptive re-sort bookkeeping (iskb_step)
+  int64_t steps_since_sort = 1 << 30;   // never sorted yet
+  int64_t *h_wstats = nullptr;          // pinned ring (2 x 4) of cnt[3..6] snapshots taken after the advance
+  cudaEvent_t ev_wstats[2] = {nullptr, nullptr};
+  bool wstats_pending[2] = {false, false};
+  int64_t wstats_step = 0;              // number of snapshots issued
+  int64_t wstats_sort_mark = 0;         // snapshots with index < this were taken before the last sort
+  int64_t last_gmiss = 0;
+  double miss_rate = 1.0;               // gather-miss fraction of the last measured step
 };
 
 struct MccProc {

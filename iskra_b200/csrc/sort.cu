@@ -258,17 +258,23 @@ struct Cols {
   uint32_t *id_out;
 };
 
-__global__ void k_permute(Cols c, const uint32_t *__restrict__ idx, int64_t n) {
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
-       k += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t s = idx[k];
-    double v[6];
+// Each block moves a CONTIGUOUS range of destination rows: after a re-sort the sources of
+// neighbouring destination rows sit in the same few tiles, so the 32-byte sectors fetched for one
+// row are reused from L1 by the other rows of the block instead of being re-read through L2.
+constexpr int PERM_CHUNK = 4096;
+__global__ void __launch_bounds__(256) k_permute(Cols c, const uint32_t *__restrict__ idx, int64_t n) {
+  for (int64_t base = (int64_t)blockIdx.x * PERM_CHUNK; base < n; base += (int64_t)gridDim.x * PERM_CHUNK) {
+    const int64_t end = base + PERM_CHUNK < n ? base + PERM_CHUNK : n;
+    for (int64_t k = base + threadIdx.x; k < end; k += blockDim.x) {
+      const uint32_t s = idx[k];
+      double v[6];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) v[q] = c.in[q][s];
-    const uint32_t id = c.id_in[s];
+      for (int q = 0; q < 6; ++q) v[q] = c.in[q][s];
+      const uint32_t id = c.id_in[s];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) c.out[q][k] = v[q];
-    c.id_out[k] = id;
+      for (int q = 0; q < 6; ++q) c.out[q][k] = v[q];
+      c.id_out[k] = id;
+    }
   }
 }
 
@@ -332,8 +338,8 @@ int32_t sort_by_keys(iskb_species *sp, int64_t n, int passes, uint32_t *perm_out
   }
   cols.id_in = sp->id;
   cols.id_out = sp->alt_id;
-  int blocks = (int)((n + TPB - 1) / TPB);
-  if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
+  int blocks = (int)((n + PERM_CHUNK - 1) / PERM_CHUNK);
+  if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
   k_permute<<<blocks, TPB, 0, c->stream>>>(cols, sp->d_idx[cur], n);
   LAUNCH_CHECK(c);
   // rows >= n (parked ids / default weights) must survive the buffer swap
@@ -353,6 +359,7 @@ int32_t sort_by_keys(iskb_species *sp, int64_t n, int passes, uint32_t *perm_out
                            c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   sp->h_nslots = nlive;
+  sp->h_nsorted = nlive;
   sp->h_ndead = 0;
   sp->counts_stale = false;
   return ISKB_OK;

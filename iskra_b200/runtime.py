@@ -36,7 +36,13 @@ class Runtime:
         L.check(self.lib.iskb_set_stream(self.h, L.vp(cuda_stream_ptr)))
 
     def use_torch_stream(self):
+        """Run the library on torch's current stream so that torch.cuda.Event timings bracket its
+        work.  torch's default stream has handle 0, which iskb_set_stream reads as "private
+        stream": in that case a dedicated torch stream is created and made current first."""
         import torch
+        if torch.cuda.current_stream().cuda_stream == 0:
+            self._torch_stream = torch.cuda.Stream()
+            torch.cuda.set_stream(self._torch_stream)
         self.set_stream(torch.cuda.current_stream().cuda_stream)
 
     def synchronize(self):
@@ -95,3 +101,6 @@ class Runtime:
 
     def set_sort_interval(self, k):
         L.check(self.lib.iskb_set_sort_interval(self.h, int(k)))
+
+    def set_sort_policy(self, miss_threshold, max_interval):
+        L.check(self.lib.iskb_set_sort_policy(self.h, float(miss_threshold), int(max_interval)))

@@ -1,0 +1,223 @@
+# ParticleInCellB200.jl -- the reference-side binding of libiskra_b200.so.
+#
+# What a maintainer of bchaber/iskra adds to run the per-timestep particle hot path on a B200:
+# new types + methods on the reference's OWN generic functions (multiple dispatch is the
+# reference's plugin mechanism, ParticleInCell.jl:44-45), no edits to reference sources.
+# Every `ccall` below binds one entry point of include/iskra_b200.h.
+#
+# NOTE: Julia is not installed in the build image (no `julia` binary, no network), so this file
+# has been syntax-reviewed only.  The executed mirror of exactly these calls is the Python/ctypes
+# host code in iskra_b200/ (same entry points, same argument order), which the test-suite drives.
+module ParticleInCellB200
+
+import ParticleInCell
+import ParticleInCell: KineticSpecies, FluidSpecies
+import FiniteDifferenceMethod
+import RegularGrids: CartesianGrid
+import Chemistry
+
+const LIB = get(ENV, "ISKRA_B200_LIB", "libiskra_b200.so")
+
+struct IskraB200Error <: Exception
+  code :: Int32
+  msg :: String
+end
+
+function check(rc :: Int32)
+  rc == 0 && return
+  throw(IskraB200Error(rc, unsafe_string(ccall((:iskb_last_error, LIB), Cstring, ()))))
+end
+
+# ---- context = one GPU + one grid (replaces phi, rho, E, B = zeros(size(grid)...), ParticleInCell.jl:97-100)
+mutable struct Context
+  h :: Ptr{Cvoid}
+  grid :: CartesianGrid{2}
+end
+
+function Context(grid :: CartesianGrid{2}; device = parse(Int, get(ENV, "LOCAL_RANK", "0")))
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:iskb_create, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, h))
+  nx, ny = grid.n
+  bc(s) = s == :periodic ? Int32(1) : Int32(0)
+  (l, r), (b, t) = grid.bcs
+  bcs = Int32[bc(l), bc(r), bc(b), bc(t)]
+  check(ccall((:iskb_grid_set, LIB), Int32,
+              (Ptr{Cvoid}, Int32, Int32, Float64, Float64, Float64, Float64, Ptr{Int32}),
+              h[], nx, ny, grid.Δh[1], grid.Δh[2], grid.origin[1], grid.origin[2], bcs))
+  ctx = Context(h[], grid)
+  finalizer(c -> ccall((:iskb_destroy, LIB), Int32, (Ptr{Cvoid},), c.h), ctx)
+  ctx
+end
+
+# ---- species: device-backed KineticSpecies{2,3} with lazily synced host mirrors --------------------
+mutable struct B200Species
+  host :: KineticSpecies{2,3}      # e.np, e.x, e.v ... keep working through this mirror
+  h :: Ptr{Cvoid}
+  ctx :: Context
+  device_newer :: Bool
+end
+
+function B200Species(ctx :: Context, part :: KineticSpecies{2,3})
+  N = size(part.x, 1)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:iskb_species_create, LIB), Int32,
+              (Ptr{Cvoid}, Int64, Float64, Float64, Float64, Ref{Ptr{Cvoid}}),
+              ctx.h, N, part.q, part.m, part.w0, h))
+  sp = B200Species(part, h[], ctx, false)
+  upload!(sp)
+  sp
+end
+
+function upload!(sp :: B200Species)
+  p = sp.host
+  GC.@preserve p begin   # the library copies during the call and keeps no host pointer
+    check(ccall((:iskb_species_upload, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt32}, Int64, Int64),
+                sp.h, p.x, p.v, p.wg, p.id, p.np, size(p.x, 1)))
+  end
+  sp.device_newer = false
+end
+
+function download!(sp :: B200Species)
+  p = sp.host
+  np = Ref{Int64}(0)
+  GC.@preserve p begin
+    check(ccall((:iskb_species_download, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt32}, Int64),
+                sp.h, p.x, p.v, p.wg, p.id, size(p.x, 1)))
+  end
+  check(ccall((:iskb_species_np, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), sp.h, np))
+  p.np = np[]
+  sp.device_newer = false
+  p
+end
+
+Base.getproperty(sp :: B200Species, s :: Symbol) =
+  s in (:host, :h, :ctx, :device_newer) ? getfield(sp, s) :
+  (getfield(sp, :device_newer) && download!(sp); getproperty(getfield(sp, :host), s))
+
+# ---- operators: methods on the reference's generic functions --------------------------------------
+# grid_to_particle(grid, part, (i,j)->E[i,j,:])           cloud_in_cell.jl:20-36
+function ParticleInCell.grid_to_particle(grid :: CartesianGrid{2}, sp :: B200Species, u)
+  np = sp.np
+  pu = zeros(np, 3)
+  check(ccall((:iskb_gather, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), sp.h, pu))
+  pu
+end
+
+# push_particles!(pusher, part, E, B, dt)                  pushers.jl:8-11
+function ParticleInCell.push_particles!(:: ParticleInCell.BorisPusher{:xy}, sp :: B200Species, E, B, Δt)
+  check(ccall((:iskb_push, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64), sp.h, E === nothing ? C_NULL : E, Δt))
+  sp.device_newer = true
+end
+
+# wrap!(part, grid; dims) / discard!(part, grid; dims)     surfaces/wrap.jl:1-33
+modes(dims, m) = (1 in dims ? Int32(m) : Int32(0), 2 in dims ? Int32(m) : Int32(0))
+function ParticleInCell.wrap!(sp :: B200Species, grid; dims = 1:2)
+  mx, my = modes(dims, 1)
+  check(ccall((:iskb_boundary, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}), sp.h, mx, my, C_NULL))
+  sp.device_newer = true
+end
+function ParticleInCell.discard!(sp :: B200Species, grid; dims = 1:2)
+  mx, my = modes(dims, 2)
+  removed = Ref{Int64}(0)
+  check(ccall((:iskb_boundary, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ref{Int64}), sp.h, mx, my, removed))
+  sp.device_newer = true
+  removed[]
+end
+
+# density(species, grid)                                    kinetic.jl:53
+function ParticleInCell.density(sp :: B200Species, grid :: CartesianGrid{2})
+  n = zeros(grid.n...)
+  check(ccall((:iskb_density, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), sp.h, n))
+  n
+end
+
+# ---- field solve ------------------------------------------------------------------------------------
+struct B200Poisson
+  ctx :: Context
+end
+function B200Poisson(ctx :: Context, ε0 :: Float64)
+  check(ccall((:iskb_poisson_create, LIB), Int32, (Ptr{Cvoid}, Float64), ctx.h, ε0))
+  B200Poisson(ctx)
+end
+FiniteDifferenceMethod.apply_periodic(ps :: B200Poisson, axis) =
+  check(ccall((:iskb_poisson_apply_periodic, LIB), Int32, (Ptr{Cvoid}, Int32), ps.ctx.h, axis))
+function FiniteDifferenceMethod.apply_dirichlet(ps :: B200Poisson, nodes :: BitArray{2}, ϕ0)
+  mask = UInt8.(nodes)                       # nx*ny bytes, column-major like the BitArray
+  check(ccall((:iskb_poisson_apply_dirichlet, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Float64), ps.ctx.h, mask, ϕ0))
+end
+# phi = calculate_electric_potential(solver, -rho) ; E = calculate_electric_field(solver, phi)
+function FiniteDifferenceMethod.calculate_electric_potential(ps :: B200Poisson, f)
+  ρ = -f
+  check(ccall((:iskb_fields_upload, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), ps.ctx.h, ρ, C_NULL, C_NULL))
+  check(ccall((:iskb_field_solve, LIB), Int32, (Ptr{Cvoid},), ps.ctx.h))
+  ϕ = zeros(size(f))
+  check(ccall((:iskb_fields_download, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), ps.ctx.h, C_NULL, ϕ, C_NULL))
+  ϕ
+end
+function FiniteDifferenceMethod.calculate_electric_field(ps :: B200Poisson, ϕ)
+  E = zeros(size(ϕ)..., 3)
+  check(ccall((:iskb_fields_download, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), ps.ctx.h, C_NULL, C_NULL, E))
+  E
+end
+
+# ---- MCC: perform!(mcc, E, dt, config)                    Chemistry/src/mcc.jl:231-289 --------------
+kind(::Chemistry.MCC.ElasticIsotropic) = (Int32(0), 0.0)
+kind(::Chemistry.MCC.ElasticBackward) = (Int32(1), 0.0)
+kind(::Chemistry.MCC.InelasticBackward) = (Int32(2), 0.0)
+kind(t::Chemistry.MCC.Excitation) = (Int32(3), t.energy)
+kind(t::Chemistry.MCC.Ionization) = (Int32(4), t.energy)
+
+mutable struct B200MCC
+  h :: Ptr{Cvoid}
+  source :: B200Species
+  products :: Vector{B200Species}
+end
+
+function B200MCC(ctx :: Context, mcc :: Chemistry.MonteCarloCollisions, lookup; seed = UInt64(0))
+  cs = mcc.collisions
+  src, tgt = lookup(first(cs).source), first(cs).target
+  kinds = Int32[kind(c.type)[1] for c in cs]
+  thr = Float64[kind(c.type)[2] for c in cs]
+  lens = Int32[size(c.rate.nodes, 1) for c in cs]
+  eps = vcat([c.rate.nodes[:, 1] for c in cs]...)
+  sig = vcat([c.rate.nodes[:, 2] for c in cs]...)
+  prods = Ptr{Cvoid}[C_NULL for _ in cs]
+  used = B200Species[]
+  for (k, c) in enumerate(cs), p in c.products
+    if kinds[k] == 4 && p !== first(cs).source
+      bp = lookup(p); prods[k] = bp.h; push!(used, bp)
+    end
+  end
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:iskb_mcc_create, LIB), Int32,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Float64, Ptr{Float64}, Int32, Ptr{Int32}, Ptr{Float64},
+               Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}, UInt64, Ref{Ptr{Cvoid}}),
+              ctx.h, src.h, tgt.q, tgt.m, tgt.T, tgt.n, length(cs), kinds, thr, lens, eps, sig, prods, seed, h))
+  B200MCC(h[], src, used)
+end
+
+function ParticleInCell.perform!(m :: B200MCC, E, Δt, config)
+  nc, ncoll = Ref{Int64}(0), Ref{Int64}(0)
+  check(ccall((:iskb_mcc_perform, LIB), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+              m.h, Δt, C_NULL, nc, ncoll))
+  m.source.device_newer = true
+  foreach(p -> p.device_newer = true, m.products)
+end
+
+# ---- fused loop: drop-in for ParticleInCell.solve that still fires the hooks (ParticleInCell.jl:84-139)
+function solve(ctx :: Context, species :: Vector{B200Species}, Δt, timesteps; after_push = (1, 1), sort_interval = 8)
+  check(ccall((:iskb_set_after_push, LIB), Int32, (Ptr{Cvoid}, Int32, Int32), ctx.h, after_push...))
+  check(ccall((:iskb_set_sort_interval, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, sort_interval))
+  ParticleInCell.enter_loop()
+  for it in 1:timesteps
+    check(ccall((:iskb_step, LIB), Int32, (Ptr{Cvoid}, Float64, Int32), ctx.h, float(Δt), 1))
+    foreach(sp -> sp.device_newer = true, species)
+    ParticleInCell.after_loop(it, it*Δt - Δt, Δt)     # scripts' iteration(): diagnostics, RF apply_dirichlet
+  end
+  check(ccall((:iskb_synchronize, LIB), Int32, (Ptr{Cvoid},), ctx.h))
+  ParticleInCell.exit_loop()
+end
+
+end # module
