@@ -108,7 +108,8 @@ __device__ __forceinline__ bool boundary_axis(double &x, double o, double L, int
 }
 
 __device__ __forceinline__ bool cell_in_grid(int i, int j, int nx, int ny) {
-  return i >= 1 && i <= nx - 1 && j >= 1 && j <= ny - 1;
+  // 1 <= i <= nx-1 and 1 <= j <= ny-1 as two unsigned range checks
+  return (unsigned)(i - 1) < (unsigned)(nx - 1) && (unsigned)(j - 1) < (unsigned)(ny - 1);
 }
 
 // ---- Philox4x32-10 counter-based RNG (Salmon et al. 2011), written from the published spec ---

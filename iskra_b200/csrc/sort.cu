@@ -190,10 +190,18 @@ __global__ void k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint
 // with shared-memory CAS adds whose cost is proportional to how many lanes of a 32-row batch hit
 // the same node, so the rows of a tile are re-ordered round-robin over its cells: first the
 // rank-0 row of every non-empty cell (cell order), then the rank-1 rows, ...  A batch of 32
-// consecutive rows then touches 32 different cells.  dest(c, r) = start + F[r] + #{c' < c : cnt[c'] > r},
-// F[r] = sum_c' min(cnt[c'], r); ranks >= IL_RMAX keep the sorted order behind the interleaved part.
+// consecutive rows then touches 32 different cells.  The round-robin visits the cells in CHECKERBOARD
+// order pi(c) = (((cx+cy)&1) << 5) | (c >> 1): first the 32 "even" cells, then the 32 "odd" ones, so the
+// cells of one batch are never edge neighbours and stay distinct longer while the rows drift.
+// dest(c, r) = start + F[r] + #{c' : pi(c') < pi(c), cnt[c'] > r}, F[r] = sum_c' min(cnt[c'], r);
+// ranks >= IL_RMAX keep the sorted order behind the interleaved part.
 // Deterministic: a pure function of the sorted (cell, previous-row) order.
 constexpr int IL_RMAX = 512;
+__device__ __forceinline__ uint32_t il_pi(uint32_t c) { return ((((c & 7u) + (c >> 3)) & 1u) << 5) | (c >> 1); }
+__device__ __forceinline__ uint32_t il_pi_inv(uint32_t t) {   // cell whose checkerboard position is t
+  const uint32_t par = t >> 5, r = t & 31u, cy = r >> 2, cxh = r & 3u;
+  return (cy << 3) | (2u * cxh + ((cy & 1u) ^ par));
+}
 
 __device__ __forceinline__ int64_t lower_bound_u32(const uint32_t *__restrict__ a, int64_t lo, int64_t hi, uint32_t v) {
   while (lo < hi) {
@@ -229,8 +237,9 @@ __global__ void __launch_bounds__(64) k_tile_interleave(const uint32_t *__restri
   atomicMax(&s_maxcnt, cnt);
   __syncthreads();
   const uint32_t R = s_maxcnt < IL_RMAX ? s_maxcnt : IL_RMAX;
-  for (uint32_t r = 0; r < R; ++r) {      // mask_r: cells that still have a row of rank r
-    const unsigned b = __ballot_sync(0xffffffffu, cnt > r);
+  const uint32_t cnt_pi = s_cnt[il_pi_inv((uint32_t)c)];   // thread c owns checkerboard position c
+  for (uint32_t r = 0; r < R; ++r) {      // mask_r (bit = checkerboard position): cells that still have a row of rank r
+    const unsigned b = __ballot_sync(0xffffffffu, cnt_pi > r);
     if ((c & 31) == 0) ((unsigned *)&s_mask[r])[c >> 5] = b;
   }
   __syncthreads();
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(64) k_tile_interleave(const uint32_t *__restri
     const uint32_t cell = keys[p] & 63u;
     const uint32_t r = (uint32_t)(p - s_cs[cell]);
     int64_t dest;
-    if (r < R) dest = start + s_F[r] + __popcll(s_mask[r] & ((1ull << cell) - 1ull));
+    if (r < R) dest = start + s_F[r] + __popcll(s_mask[r] & ((1ull << il_pi(cell)) - 1ull));
     else dest = start + s_F[R] + s_over[cell] + (r - R);
     idx_out[dest] = idx_in[p];
   }

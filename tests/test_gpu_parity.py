@@ -176,7 +176,8 @@ def test_sort_permutation_bitexact(ib, nx, ny, n):
 @pytest.mark.parametrize("nx,ny,n", [(65, 33, 100000), (257, 257, 1500000), (17, 17, 200000)])
 def test_deposit_layout_permutation_bitexact(ib, nx, ny, n):
     """Row order kept by the fused step: cell sort, then round-robin over the cells of each 8x8
-    tile: order by (tile, rank-in-cell, cell) for ranks < 512, the rest behind in (cell, rank) order."""
+    tile in checkerboard order pi(c): order by (tile, rank-in-cell, pi(cell)) for ranks < 512, the
+    rest behind in (cell, rank) order."""
     PIC = ib.particle_in_cell
     g, cg = _grid_pair(ib, nx, ny, 1e-3)
     pc, pg = _species_pair(ib, g, n, n + 5, seed=n + 3)
@@ -196,7 +197,8 @@ def test_deposit_layout_permutation_bitexact(ib, nx, ny, n):
     order = np.lexsort((np.where(capped < 512, 0, rank), cell, capped, tile)) if False else None
     # rows with rank < 512: (tile, rank, cell); rows with rank >= 512: (tile, 512, cell, rank)
     sec = np.where(rank < 512, rank, 512)
-    order = np.lexsort((np.where(rank < 512, 0, rank), cell, sec, tile))
+    pi = ((((cell & 7) + (cell >> 3)) & 1) << 5) | (cell >> 1)
+    order = np.lexsort((np.where(rank < 512, 0, rank), np.where(rank < 512, pi, cell), sec, tile))
     expect = srt[order]
     perm = PIC.sort_by_cell_(pg, g, for_deposit=True)
     assert np.array_equal(perm.astype(np.int64), expect)
