@@ -28,14 +28,14 @@ METRIC = "particle-steps/sec (push+gather+deposit+MCC)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=["c5", "c4"])
     ap.add_argument("--particles-per-gpu", type=int, default=None)
     ap.add_argument("--cells", type=int, default=None)
-    ap.add_argument("--sort-interval", type=int, default=8)
-    ap.add_argument("--sort-miss", type=float, default=0.0, help="adaptive re-sort: window-miss fraction threshold (0 = fixed interval)")
+    ap.add_argument("--sort-interval", type=int, default=4)
+    ap.add_argument("--sort-miss", type=float, default=0.03, help="adaptive re-sort: window-miss fraction threshold (0 = fixed interval)")
     ap.add_argument("--sort-max", type=int, default=64)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
