@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--sort-interval", type=int, default=4)
     ap.add_argument("--sort-miss", type=float, default=0.03, help="adaptive re-sort: window-miss fraction threshold (0 = fixed interval)")
     ap.add_argument("--sort-max", type=int, default=64)
+    ap.add_argument("--sort-full", type=int, default=64, help="steps between FULL sorts; re-sorts in between only re-group by tile")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=4_000_000)
@@ -55,7 +56,7 @@ def config_dict(a, ppg, cells, n_gpus, extra=None):
              "c4": "C4: 2D XY two-stream (BASELINE configs[3]), %dx%d grid, %.3g particles per GPU, periodic"}
     d = {"workload": names[a.workload] % (cells, cells, ppg), "grid_cells": [cells, cells],
          "particles_per_gpu": ppg, "particles_total": ppg * n_gpus, "sort_interval": a.sort_interval,
-         "sort_policy": {"miss_threshold": a.sort_miss, "max_interval": a.sort_max},
+         "sort_policy": {"miss_threshold": a.sort_miss, "max_interval": a.sort_max, "full_interval": a.sort_full},
          "l2": "inputs (%.1f GB of particle columns per GPU) are far larger than the 126 MB L2" % (ppg * 52 / 1e9),
          "parallelism": "particle index slices x%d, fields replicated" % n_gpus}
     if extra:
@@ -241,7 +242,7 @@ def run_b200(a):
           else workloads.build_c4(ppg, cells, device=local))
     rt = wl.rt
     rt.use_torch_stream()
-    wl.prepare(a.sort_interval, a.sort_miss, a.sort_max)
+    wl.prepare(a.sort_interval, a.sort_miss, a.sort_max, a.sort_full)
     rt.synchronize()
     build_s = time.perf_counter() - t_build
 

@@ -184,6 +184,10 @@ int32_t iskb_set_sort_interval(iskb_ctx *ctx, int32_t interval);
  * exceeds miss_threshold OR max_interval steps have passed).  miss_threshold = 0 restores the
  * fixed interval.  Slow species (ions) are then sorted rarely, fast ones (electrons) often. */
 int32_t iskb_set_sort_policy(iskb_ctx *ctx, double miss_threshold, int32_t max_interval);
+/* full_interval > 0: a due re-sort is a FULL sort (cells + interleave) only when that many steps
+ * have passed since the last full one; otherwise rows are re-grouped by tile only (stable, about
+ * half the cost).  0 = every re-sort is full. */
+int32_t iskb_set_sort_full_interval(iskb_ctx *ctx, int32_t full_interval);
 /* n_steps iterations of: MCC (registered interactions, in order) -> advance! every species
  * (gather, push, after_push) -> density / rho -> all-reduce -> phi -> E. */
 int32_t iskb_step(iskb_ctx *ctx, double dt, int32_t n_steps);

@@ -499,6 +499,12 @@ extern "C" int32_t iskb_set_sort_policy(iskb_ctx *c, double miss_threshold, int3
   return ISKB_OK;
 }
 
+extern "C" int32_t iskb_set_sort_full_interval(iskb_ctx *c, int32_t full_interval) {
+  if (!c || full_interval < 0) return iskb_fail(ISKB_E_INVALID, "bad interval");
+  c->sort_full_interval = full_interval;
+  return ISKB_OK;
+}
+
 // Decide whether species s is re-sorted before this step.  The window statistics travel through
 // an async copy + event; the host waits for the snapshot taken TWO steps ago, which keeps one whole
 // step of work queued on the GPU (no bubble) while bounding how far the host runs ahead.
@@ -522,7 +528,15 @@ static int32_t maybe_sort(iskb_ctx *c, iskb_species *s) {
     do_sort = too_old || s->miss_rate > c->sort_miss_threshold;
   }
   if (do_sort) {
-    ISKB_TRY(sp_sort(s, nullptr, true));
+    // full sort (cells + checkerboard interleave) the first time and every sort_full_interval steps;
+    // in between a cheaper stable re-group by tile
+    const bool full = c->sort_full_interval <= 0 || s->steps_since_full >= c->sort_full_interval;
+    if (full) {
+      ISKB_TRY(sp_sort(s, nullptr, true));
+      s->steps_since_full = 0;
+    } else {
+      ISKB_TRY(sp_regroup(s));
+    }
     s->steps_since_sort = 0;
     s->miss_rate = 0.0;
     s->wstats_sort_mark = s->wstats_step;
@@ -567,6 +581,7 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
         ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
         ISKB_TRY(post_advance_stats(c, s));
         s->steps_since_sort++;
+        s->steps_since_full++;
       } else {
         ISKB_TRY(launch_advance_simple(s, dt, c->after_push[0], c->after_push[1], true, false));
       }

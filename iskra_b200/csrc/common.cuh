@@ -112,6 +112,7 @@ struct iskb_ctx {
   int sort_interval = 0;
   double sort_miss_threshold = 0.0;   // adaptive: sort a species only when its window-miss rate exceeds this
   int sort_max_interval = 0;          //           ... or this many steps have passed
+  int sort_full_interval = 0;         // > 0: between full sorts re-group by tile only (cheaper)
   int64_t step_count = 0;
   // optional per-kernel timing of the dominant (advance) kernel, CUDA events on the launch stream
   bool profile = false;
@@ -149,6 +150,7 @@ struct iskb_species {
   uint64_t sample_calls = 0;
   // adaptive re-sort bookkeeping (iskb_step)
   int64_t steps_since_sort = 1 << 30;   // never sorted yet
+  int64_t steps_since_full = 1 << 30;   // steps since the last FULL (cell + interleave) sort
   int64_t *h_wstats = nullptr;          // pinned ring (2 x 4) of cnt[3..6] snapshots taken after the advance
   cudaEvent_t ev_wstats[2] = {nullptr, nullptr};
   bool wstats_pending[2] = {false, false};
@@ -194,6 +196,7 @@ struct iskb_mcc {
 int32_t sp_sync_counts(iskb_species *sp);
 int32_t sp_compact(iskb_species *sp);
 int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host, bool interleave);
+int32_t sp_regroup(iskb_species *sp);
 int32_t sp_ensure_alt(iskb_species *sp);
 int32_t ctx_check_status(iskb_ctx *ctx);
 int32_t poisson_prepare(iskb_ctx *ctx);

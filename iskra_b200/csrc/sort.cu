@@ -4,9 +4,12 @@
 // invariant -- SURVEY.md H5).  New relative to the reference: sorting exists only to make the
 // tiled shared-memory deposition possible.
 //
-// Sort key (DESIGN.md "cell key"): cells are grouped in 8x8 tiles, tile-major, then row-major
-// inside the tile: key = ((ty*tiles_x + tx) << 6) | ((cy & 7) << 3) | (cx & 7) with
-// cx = i-1, cy = j-1 from particle_cell (ParticleInCell.jl:28-35).  Out-of-grid rows get key_max and
+// Sort key (DESIGN.md "cell key"): cells are grouped in 8x8 tiles, tiles in 16x16 meta-tiles:
+//   tile = (((ty>>4)*mtx + (tx>>4)) << 8) | ((ty&15) << 4) | (tx&15),   mtx = ceil(tiles_x/16)
+//   key  = (tile << 6) | ((cy & 7) << 3) | (cx & 7)
+// with cx = i-1, cy = j-1 from particle_cell (ParticleInCell.jl:28-35), tx = cx>>3, ty = cy>>3.
+// The meta-tile level keeps the rows of vertically adjacent tiles within ~16 tiles of each other in
+// memory, so the gather of a re-sort finds the rows that crossed a tile edge in L2.  Out-of-grid rows get key_max and
 // dead rows key_max+1, so they land at the end.  The sort is stable in the previous row order, so the resulting
 // permutation is a pure function of the cell indices (bit-exact contract of north_star).
 #include "pic_device.cuh"
@@ -18,8 +21,22 @@ constexpr int RS_ITEMS = 16;
 constexpr int RS_WARPS = TPB / 32;
 constexpr int RS_TILE = TPB * RS_ITEMS;   // 4096 keys per block
 
+__device__ __forceinline__ uint32_t tile_ordinal(uint32_t tx, uint32_t ty, uint32_t mtx) {
+  return (((ty >> 4) * mtx + (tx >> 4)) << 8) | ((ty & 15u) << 4) | (tx & 15u);
+}
+struct TileGeom {
+  uint32_t mtx, ntiles;   // meta-tiles per row, padded tile count (multiple of 256)
+};
+static TileGeom tile_geom(const GridDev &g) {
+  const uint32_t tiles_x = (uint32_t)(g.nx - 1 + 7) / 8, tiles_y = (uint32_t)(g.ny - 1 + 7) / 8;
+  TileGeom t;
+  t.mtx = (tiles_x + 15) / 16;
+  t.ntiles = t.mtx * ((tiles_y + 15) / 16) * 256u;
+  return t;
+}
+
 __global__ void k_cell_keys(const double *__restrict__ x, const double *__restrict__ y, int64_t n,
-                            GridDev g, int tiles_x, uint32_t key_max, uint32_t *keys) {
+                            GridDev g, uint32_t mtx, uint32_t key_max, uint32_t *keys) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
        p += (int64_t)gridDim.x * blockDim.x) {
     const double px = x[p];
@@ -32,8 +49,28 @@ __global__ void k_cell_keys(const double *__restrict__ x, const double *__restri
       cell1(y[p], g.dy, g.rdy, g.fast_div, j, hy);
       if (cell_in_grid(i, j, g.nx, g.ny)) {
         const uint32_t cx = (uint32_t)(i - 1), cy = (uint32_t)(j - 1);
-        key = (((cy >> 3) * (uint32_t)tiles_x + (cx >> 3)) << 6) | ((cy & 7u) << 3) | (cx & 7u);
+        key = (tile_ordinal(cx >> 3, cy >> 3, mtx) << 6) | ((cy & 7u) << 3) | (cx & 7u);
       }
+    }
+    keys[p] = key;
+  }
+}
+
+// Tile-only key (re-group between full sorts): rows keep their previous relative order inside the
+// tile (stable sort), which was the cell-interleaved order of the last full sort plus drift.
+__global__ void k_tile_keys(const double *__restrict__ x, const double *__restrict__ y, int64_t n,
+                            GridDev g, uint32_t mtx, uint32_t ntiles, uint32_t *keys) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const double px = x[p];
+    uint32_t key = ntiles + 1u;
+    if (!is_dead(px)) {
+      key = ntiles;
+      int i, j;
+      double hx, hy;
+      cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
+      cell1(y[p], g.dy, g.rdy, g.fast_div, j, hy);
+      if (cell_in_grid(i, j, g.nx, g.ny)) key = tile_ordinal((uint32_t)(i - 1) >> 3, (uint32_t)(j - 1) >> 3, mtx);
     }
     keys[p] = key;
   }
@@ -45,19 +82,22 @@ __global__ void k_dead_keys(const double *__restrict__ x, int64_t n, uint32_t *k
     keys[p] = is_dead(x[p]) ? 1u : 0u;
 }
 
+template <int BITS>
 __global__ void k_radix_hist(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t *hist,
                              int nblocks) {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
+  constexpr int BINS = 1 << BITS;
+  constexpr uint32_t MASK = BINS - 1;
+  __shared__ uint32_t h[BINS];
+  for (int d = threadIdx.x; d < BINS; d += TPB) h[d] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
 #pragma unroll 4
   for (int t = 0; t < RS_ITEMS; ++t) {
     const int64_t p = base + t * TPB + threadIdx.x;
-    if (p < n) atomicAdd(&h[(keys[p] >> shift) & 255u], 1u);
+    if (p < n) atomicAdd(&h[(keys[p] >> shift) & MASK], 1u);
   }
   __syncthreads();
-  hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+  for (int d = threadIdx.x; d < BINS; d += TPB) hist[(int64_t)d * nblocks + blockIdx.x] = h[d];
 }
 
 // ---- exclusive scan over uint32 (3 kernels) ----------------------------------------------------
@@ -127,32 +167,35 @@ __global__ void k_scan_down(uint32_t *data, int64_t n, const uint32_t *__restric
   }
 }
 
-// ---- stable scatter of one 8-bit digit ---------------------------------------------------------
-__global__ void k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ idx_in,
+// ---- stable scatter of one BITS-wide digit -----------------------------------------------------
+template <int BITS>
+__global__ void __launch_bounds__(TPB, 4) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ idx_in,
                                 uint32_t *keys_out, uint32_t *idx_out, int64_t n, int shift,
                                 const uint32_t *__restrict__ offs, int nblocks) {
-  __shared__ uint32_t wcnt[RS_WARPS][256];
+  constexpr int BINS = 1 << BITS;
+  constexpr uint32_t MASK = BINS - 1;
+  __shared__ uint32_t wcnt[RS_WARPS][BINS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
-  for (int k = threadIdx.x; k < RS_WARPS * 256; k += TPB) (&wcnt[0][0])[k] = 0;
+  for (int k = threadIdx.x; k < RS_WARPS * BINS; k += TPB) (&wcnt[0][0])[k] = 0;
   __syncthreads();
   const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (RS_ITEMS * 32);
-  uint32_t key[RS_ITEMS];
+  uint32_t key[RS_ITEMS], src[RS_ITEMS];
   // phase 1: per-warp digit counts (warp-private rows; one writer per digit and iteration)
 #pragma unroll
   for (int t = 0; t < RS_ITEMS; ++t) {
     const int64_t p = wbase + t * 32 + lane;
     const bool valid = p < n;
     key[t] = valid ? keys_in[p] : 0xffffffffu;
-    const uint32_t d = valid ? ((key[t] >> shift) & 255u) : 256u;
+    src[t] = (valid && idx_in) ? idx_in[p] : (uint32_t)p;
+    const uint32_t d = valid ? ((key[t] >> shift) & MASK) : (uint32_t)BINS;
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
     if (valid && (peers & lt) == 0) wcnt[warp][d] += __popc(peers);
     __syncwarp();
   }
   __syncthreads();
   // exclusive prefix across warps + global base of (digit, block)
-  {
-    const int d = threadIdx.x;
+  for (int d = threadIdx.x; d < BINS; d += TPB) {
     uint32_t run = offs[(int64_t)d * nblocks + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
@@ -167,7 +210,7 @@ __global__ void k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint
   for (int t = 0; t < RS_ITEMS; ++t) {
     const int64_t p = wbase + t * 32 + lane;
     const bool valid = p < n;
-    const uint32_t d = valid ? ((key[t] >> shift) & 255u) : 256u;
+    const uint32_t d = valid ? ((key[t] >> shift) & MASK) : (uint32_t)BINS;
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
     const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
@@ -179,7 +222,7 @@ __global__ void k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint
     if (valid) {
       const uint32_t dest = old + __popc(peers & lt);
       keys_out[dest] = key[t];
-      idx_out[dest] = idx_in ? idx_in[p] : (uint32_t)p;
+      idx_out[dest] = src[t];
     }
     __syncwarp();
   }
@@ -270,10 +313,18 @@ struct Cols {
 // Each block moves a CONTIGUOUS range of destination rows: after a re-sort the sources of
 // neighbouring destination rows sit in the same few tiles, so the 32-byte sectors fetched for one
 // row are reused from L1 by the other rows of the block instead of being re-read through L2.
-constexpr int PERM_CHUNK = 4096;
-__global__ void __launch_bounds__(256) k_permute(Cols c, const uint32_t *__restrict__ idx, int64_t n) {
-  for (int64_t base = (int64_t)blockIdx.x * PERM_CHUNK; base < n; base += (int64_t)gridDim.x * PERM_CHUNK) {
-    const int64_t end = base + PERM_CHUNK < n ? base + PERM_CHUNK : n;
+__global__ void __launch_bounds__(256) k_permute(Cols c, const uint32_t *__restrict__ idx, int64_t n, int chunk,
+                                                 uint32_t *ticket) {
+  // chunks are handed out in increasing order (ticket), so the rows in flight always form one
+  // compact range and the 64-byte lines shared between neighbouring chunks are found in L2
+  __shared__ uint32_t s_chunk;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_chunk = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t base = (int64_t)s_chunk * chunk;
+    if (base >= n) break;
+    const int64_t end = base + chunk < n ? base + chunk : n;
     for (int64_t k = base + threadIdx.x; k < end; k += blockDim.x) {
       const uint32_t s = idx[k];
       double v[6];
@@ -310,27 +361,35 @@ int32_t ensure_sort_scratch(iskb_species *sp) {
       CU_TRY(cudaMalloc(&sp->d_idx[k], sp->cap * sizeof(uint32_t)));
     }
     const int64_t nblocks = (sp->cap + RS_TILE - 1) / RS_TILE;
-    const int64_t hn = 256 * nblocks;
+    const int64_t hn = 512 * nblocks;
     sp->hist_cap = hn + (hn + SC_PER_BLOCK - 1) / SC_PER_BLOCK + 16;
     CU_TRY(cudaMalloc(&sp->d_hist, sp->hist_cap * sizeof(uint32_t)));
   }
   return sp_ensure_alt(sp);
 }
 
-// keys already in d_key[0][0..n); runs `passes` 8-bit passes, permutes all columns, fixes counters
-int32_t sort_by_keys(iskb_species *sp, int64_t n, int passes, uint32_t *perm_out_host, uint32_t interleave_tiles = 0) {
+// keys (of `bits` significant bits) already in d_key[0][0..n); runs the digit passes, permutes all
+// columns, fixes counters.  Digits are 8 bits wide, or 9 when that saves a whole pass (17-bit tile keys).
+int32_t sort_by_keys(iskb_species *sp, int64_t n, int bits, uint32_t *perm_out_host, uint32_t interleave_tiles = 0) {
   iskb_ctx *c = sp->ctx;
   const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
-  const int64_t hn = 256 * (int64_t)nblocks;
+  const int width = (bits + 8) / 9 < (bits + 7) / 8 ? 9 : 8;
+  const int passes = (bits + width - 1) / width;
+  const int64_t hn = ((int64_t)1 << width) * nblocks;
   int cur = 0;
   for (int pass = 0; pass < passes; ++pass) {
-    const int shift = 8 * pass;
-    k_radix_hist<<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], n, shift, sp->d_hist, nblocks);
+    const int shift = width * pass;
+    const uint32_t *idx_in = pass == 0 ? nullptr : sp->d_idx[cur];
+    if (width == 9) k_radix_hist<9><<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], n, shift, sp->d_hist, nblocks);
+    else k_radix_hist<8><<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], n, shift, sp->d_hist, nblocks);
     LAUNCH_CHECK(c);
     ISKB_TRY(exclusive_scan_u32(c, sp->d_hist, hn, sp->d_hist + hn));
-    k_radix_scatter<<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], pass == 0 ? nullptr : sp->d_idx[cur],
-                                                    sp->d_key[cur ^ 1], sp->d_idx[cur ^ 1], n, shift,
-                                                    sp->d_hist, nblocks);
+    if (width == 9)
+      k_radix_scatter<9><<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], idx_in, sp->d_key[cur ^ 1], sp->d_idx[cur ^ 1],
+                                                         n, shift, sp->d_hist, nblocks);
+    else
+      k_radix_scatter<8><<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], idx_in, sp->d_key[cur ^ 1], sp->d_idx[cur ^ 1],
+                                                         n, shift, sp->d_hist, nblocks);
     LAUNCH_CHECK(c);
     cur ^= 1;
   }
@@ -347,9 +406,26 @@ int32_t sort_by_keys(iskb_species *sp, int64_t n, int passes, uint32_t *perm_out
   }
   cols.id_in = sp->id;
   cols.id_out = sp->alt_id;
+  if (getenv("ISKB_DEBUG_SORT")) {
+    std::vector<uint32_t> h(n);
+    cudaMemcpy(h.data(), sp->d_idx[cur], n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    int64_t seq = 0, near1k = 0, near300k = 0, sect = 0;
+    for (int64_t k = 0; k + 1 < n; ++k) {
+      seq += h[k + 1] == h[k] + 1;
+      sect += (h[k + 1] >> 3) == (h[k] >> 3);
+      const int64_t d = (int64_t)h[k] - k;
+      near1k += d > -4096 && d < 4096;
+      near300k += d > -300000 && d < 300000;
+    }
+    fprintf(stderr, "[sort] n=%lld bits=%d il=%u seq=%.3f same64B=%.3f |d|<4096=%.3f |d|<3e5=%.3f\n", (long long)n, bits,
+            interleave_tiles, (double)seq / n, (double)sect / n, (double)near1k / n, (double)near300k / n);
+  }
+  static const int PERM_CHUNK = getenv("ISKB_PERM_CHUNK") ? atoi(getenv("ISKB_PERM_CHUNK")) : 512;
   int blocks = (int)((n + PERM_CHUNK - 1) / PERM_CHUNK);
   if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
-  k_permute<<<blocks, TPB, 0, c->stream>>>(cols, sp->d_idx[cur], n);
+  uint32_t *ticket = sp->d_hist + sp->hist_cap - 1;   // last scratch word (hist_cap has 16 words of slack)
+  CU_TRY(cudaMemsetAsync(ticket, 0, sizeof(uint32_t), c->stream));
+  k_permute<<<blocks, TPB, 0, c->stream>>>(cols, sp->d_idx[cur], n, PERM_CHUNK, ticket);
   LAUNCH_CHECK(c);
   // rows >= n (parked ids / default weights) must survive the buffer swap
   if (sp->cap > n) {
@@ -386,7 +462,25 @@ int32_t sp_compact(iskb_species *sp) {
   if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
   k_dead_keys<<<blocks, TPB, 0, c->stream>>>(sp->col[0], n, sp->d_key[0]);
   LAUNCH_CHECK(c);
-  return sort_by_keys(sp, n, 1, nullptr);
+  return sort_by_keys(sp, n, 1, nullptr);   // 1-bit key
+}
+
+// Re-group by tile only (2 radix passes for <= 65535 tiles, no interleave pass): about half the
+// cost of the full sort, and the gather of the permutation stays nearly sequential.
+int32_t sp_regroup(iskb_species *sp) {
+  iskb_ctx *c = sp->ctx;
+  ISKB_TRY(sp_sync_counts(sp));
+  const int64_t n = sp->h_nslots;
+  if (n == 0) return ISKB_OK;
+  ISKB_TRY(ensure_sort_scratch(sp));
+  const TileGeom tg = tile_geom(c->g);
+  int bits = 1;
+  while ((1ull << bits) <= (uint64_t)tg.ntiles + 1u) ++bits;
+  int blocks = (int)((n + TPB - 1) / TPB);
+  if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
+  k_tile_keys<<<blocks, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], n, c->g, tg.mtx, tg.ntiles, sp->d_key[0]);
+  LAUNCH_CHECK(c);
+  return sort_by_keys(sp, n, bits, nullptr, 0);
 }
 
 int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host, bool interleave) {
@@ -396,18 +490,18 @@ int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host, bool interleave) {
   const int64_t n = sp->h_nslots;
   if (n == 0) return ISKB_OK;
   ISKB_TRY(ensure_sort_scratch(sp));
-  const int tiles_x = (c->g.nx - 1 + 7) / 8, tiles_y = (c->g.ny - 1 + 7) / 8;
-  const uint64_t kmax64 = (uint64_t)tiles_x * tiles_y * 64u;
-  if (kmax64 >= 0xffffffffull) return iskb_fail(ISKB_E_UNSUPPORTED, "grid too large for 32-bit cell keys");
+  const TileGeom tg = tile_geom(c->g);
+  const uint64_t kmax64 = (uint64_t)tg.ntiles * 64u;
+  if (kmax64 >= 0xffffffffull)
+    return iskb_fail(ISKB_E_UNSUPPORTED, "grid too large for 32-bit cell keys");
   const uint32_t key_max = (uint32_t)kmax64;
   int bits = 1;
   while ((1ull << bits) <= (uint64_t)key_max + 1u) ++bits;
-  const int passes = (bits + 7) / 8;
   int blocks = (int)((n + TPB - 1) / TPB);
   if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
-  k_cell_keys<<<blocks, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], n, c->g, tiles_x, key_max, sp->d_key[0]);
+  k_cell_keys<<<blocks, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], n, c->g, tg.mtx, key_max, sp->d_key[0]);
   LAUNCH_CHECK(c);
-  return sort_by_keys(sp, n, passes, perm_out_host, interleave ? (uint32_t)(tiles_x * tiles_y) : 0u);
+  return sort_by_keys(sp, n, bits, perm_out_host, interleave ? tg.ntiles : 0u);
 }
 
 extern "C" int32_t iskb_sort_by_cell(iskb_species *sp, uint32_t *perm_out) {

@@ -102,5 +102,6 @@ class Runtime:
     def set_sort_interval(self, k):
         L.check(self.lib.iskb_set_sort_interval(self.h, int(k)))
 
-    def set_sort_policy(self, miss_threshold, max_interval):
+    def set_sort_policy(self, miss_threshold, max_interval, full_interval=0):
         L.check(self.lib.iskb_set_sort_policy(self.h, float(miss_threshold), int(max_interval)))
+        L.check(self.lib.iskb_set_sort_full_interval(self.h, int(full_interval)))

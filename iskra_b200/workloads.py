@@ -38,9 +38,9 @@ class Workload:
     def n_particles(self):
         return sum(s.np for s in self.kinetic())
 
-    def prepare(self, sort_interval, miss_threshold=0.0, max_interval=0):
+    def prepare(self, sort_interval, miss_threshold=0.0, max_interval=0, full_interval=0):
         rt = self.rt
-        rt.set_sort_policy(miss_threshold, max_interval)
+        rt.set_sort_policy(miss_threshold, max_interval, full_interval)
         for s in self.kinetic():
             s._push(self.config.grid)
         for m in self.config.interactions:

@@ -148,10 +148,13 @@ def test_density_matches_oracle(ib, nx, ny, n):
 
 
 def _cell_key(i, j, nx, ny):
-    """The sort key documented in DESIGN.md / sort.cu (8x8 tiles, tile-major)."""
+    """The sort key documented in DESIGN.md / sort.cu (8x8-cell tiles inside 16x16-tile meta-tiles)."""
     cx, cy = i - 1, j - 1
     tiles_x = (nx - 1 + 7) // 8
-    return (((cy >> 3) * tiles_x + (cx >> 3)) << 6) | ((cy & 7) << 3) | (cx & 7)
+    mtx = (tiles_x + 15) // 16
+    tx, ty = cx >> 3, cy >> 3
+    tile = (((ty >> 4) * mtx + (tx >> 4)) << 8) | ((ty & 15) << 4) | (tx & 15)
+    return (tile << 6) | ((cy & 7) << 3) | (cx & 7)
 
 
 @pytest.mark.parametrize("nx,ny,n", [(129, 2, 3000), (65, 33, 100000), (257, 257, 1000000)])
