@@ -13,8 +13,11 @@
 //     (a CAS loop on sm_100a: 6 SM-cycles per warp instruction x conflict degree, and the
 //     interleaved row order keeps the conflict degree near 1) -- no lane sort, no scan;
 //   * the window is flushed with one red.global.add.f64 per non-zero node when the warp moves to
-//     another patch or finishes its rows; rows outside the window (fast particles between sorts)
-//     use the global field / global REDs directly;
+//     another patch or finishes its rows;
+//   * rows whose cell is outside the E window (fast particles between sorts, rows appended by
+//     ionisation) are NOT handled in line -- one such lane would stall the whole warp on an L2 round
+//     trip in about half of all batches -- but queued (row index, 64 per warp in shared memory) and
+//     advanced 32 at a time by drain_rows() with global gathers / global REDs;
 //   * every warp walks one contiguous range of rows, so its window moves tile by tile;
 //   * cell indices use the exact three-instruction division (pic_device.cuh).
 // The particle arithmetic (gather, push, boundary, cell index) is bit-identical to the oracle;
@@ -33,33 +36,28 @@ constexpr int MISS_LIMIT = 8;   // re-anchor when more rows of a batch miss the 
 // The E window is the larger one: a gather miss stalls the whole warp on an L2 round trip,
 // a deposit miss only issues fire-and-forget global REDs.
 // The rho window is the central WR x WR part of the E window (origin + (WE-WR)/2).
-struct Window {
-  int ei0, ej0;     // node coordinates of the E window's lower-left corner
-  bool anchored;
-};
-
 template <int WR>
-__device__ __forceinline__ void flush_rho(double *rho, const Window &w, int off, const GridDev &g, double *u, int lane) {
+__device__ __forceinline__ void flush_rho(double *rho, int ri0, int rj0, const GridDev &g, double *u, int lane) {
 #pragma unroll
   for (int k = 0; k < (WR * WR + 31) / 32; ++k) {
     const int e = k * 32 + lane;
     if (e >= WR * WR) break;
     const double v = rho[e];
     if (v != 0.0) {
-      atomicAdd(&u[(int64_t)(w.ei0 + off + (e % WR)) + (int64_t)(w.ej0 + off + (e / WR)) * g.nx], v);
+      atomicAdd(&u[(int64_t)(ri0 + (e % WR)) + (int64_t)(rj0 + (e / WR)) * g.nx], v);
       rho[e] = 0.0;
     }
   }
 }
 
 template <int WE>
-__device__ __forceinline__ void load_E(double2 *sE, const Window &w, const GridDev &g, const double2 *__restrict__ E2,
+__device__ __forceinline__ void load_E(double2 *sE, int ei0, int ej0, const GridDev &g, const double2 *__restrict__ E2,
                                        int lane) {
 #pragma unroll
   for (int k = 0; k < (WE * WE + 31) / 32; ++k) {
     const int e = k * 32 + lane;
     if (e >= WE * WE) break;
-    sE[e] = __ldg(&E2[(int64_t)(w.ei0 + (e % WE)) + (int64_t)(w.ej0 + (e / WE)) * g.nx]);
+    sE[e] = __ldg(&E2[(int64_t)(ei0 + (e % WE)) + (int64_t)(ej0 + (e / WE)) * g.nx]);
   }
 }
 
@@ -68,57 +66,148 @@ __device__ __forceinline__ int clamp_origin(int o, int n, int wn) {
   return o < 0 ? 0 : o;
 }
 
-template <int WE, int WR, int WARPS, int MINB, int MX, int MY>
+struct DrainOut {
+  double vm2;
+  unsigned dead;
+};
+
+// Advance `count` (<= 32) queued rows straight from / to global memory: same arithmetic as the
+// windowed path, E from the global field, deposit with global REDs.  Not inlined so that its
+// registers do not count against the main loop.
+template <int MX, int MY>
+__device__ __forceinline__ DrainOut drain_rows(const uint32_t *q, int count, int lane, double *__restrict__ X,
+                                            double *__restrict__ Y, double *__restrict__ VX, double *__restrict__ VY,
+                                            double *__restrict__ VZ, const double *__restrict__ WG, const GridDev &g,
+                                            const double2 *__restrict__ E2, double qm, double dt, double c1, double *u,
+                                            int *status) {
+  DrainOut out{0.0, 0u};
+  bool dead_now = false;
+  if (lane < count) {
+    const uint32_t p = q[lane];
+    double px = X[p], py = Y[p], vx = VX[p], vy = VY[p], vz = VZ[p];
+    const double wq = WG[p];
+    int i, j;
+    double hx, hy;
+    cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
+    cell1(py, g.dy, g.rdy, g.fast_div, j, hy);   // in the grid: checked before the row was queued
+    {
+      const CicW gw = cic_weights(hx, hy);
+      const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * g.nx;
+      const double2 e00 = __ldg(&E2[n00]), e10 = __ldg(&E2[n00 + 1]);
+      const double2 e01 = __ldg(&E2[n00 + g.nx]), e11 = __ldg(&E2[n00 + g.nx + 1]);
+      const double ex = cic_gather(gw, e00.x, e10.x, e01.x, e11.x);
+      const double ey = cic_gather(gw, e00.y, e10.y, e01.y, e11.y);
+      vx = push_v(vx, ex, c1, qm, dt);
+      vy = push_v(vy, ey, c1, qm, dt);
+      vz = push_v(vz, 0.0, c1, qm, dt);
+    }
+    px = push_x(px, vx, dt);
+    py = push_x(py, vy, dt);
+    out.vm2 = fma(vz, vz, fma(vy, vy, vx * vx));
+    bool dead = (MX == ISKB_BND_DISCARD) && boundary_axis(px, g.ox, g.Lx, MX);
+    if (!dead) dead = (MY == ISKB_BND_DISCARD) && boundary_axis(py, g.oy, g.Ly, MY);
+    if (!dead) {
+      if (MX == ISKB_BND_WRAP) boundary_axis(px, g.ox, g.Lx, MX);
+      if (MY == ISKB_BND_WRAP) boundary_axis(py, g.oy, g.Ly, MY);
+    }
+    VX[p] = vx; VY[p] = vy; VZ[p] = vz; Y[p] = py;
+    if (dead) {
+      X[p] = __longlong_as_double(0x7ff8000000000000LL);
+      dead_now = true;
+    } else {
+      X[p] = px;
+      cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
+      cell1(py, g.dy, g.rdy, g.fast_div, j, hy);
+      if (cell_in_grid(i, j, g.nx, g.ny)) {
+        const CicW cw = cic_weights(hx, hy);
+        const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * g.nx;
+        atomicAdd(&u[n00], __dmul_rn(cw.w00, wq));
+        atomicAdd(&u[n00 + 1], __dmul_rn(cw.w10, wq));
+        atomicAdd(&u[n00 + g.nx], __dmul_rn(cw.w01, wq));
+        atomicAdd(&u[n00 + g.nx + 1], __dmul_rn(cw.w11, wq));
+      } else {
+        atomicOr(status, ISKB_ST_OOB);
+      }
+    }
+  }
+  if (MX == ISKB_BND_DISCARD || MY == ISKB_BND_DISCARD) out.dead = __popc(__ballot_sync(0xffffffffu, dead_now));
+  return out;
+}
+
+constexpr int QCAP = 64;   // queued rows per warp: at most 31 left over + 32 new ones
+
+// Per-warp shared memory, one contiguous block per warp so that a single base register addresses
+// all of it: E window | rho window | miss queue | claim bytes | statistics.
+template <int WE, int WR>
+struct WarpSmem {
+  double2 E[WE * WE];
+  double rho[WR * WR];
+  uint32_t queue[QCAP];
+  unsigned char claim[WR * WR];
+  unsigned stats[4];   // gather misses, deposit misses, window moves, discards (lane 0 updates them)
+};
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+constexpr int NOT_ANCHORED = -(1 << 20);   // window origin that no cell can fit
+
+template <int WE, int WR, int WARPS, int MINB, int MX, int MY, bool CLAIM>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restrict__ VX, double *__restrict__ VY,
                 double *__restrict__ VZ, const double *__restrict__ WG, int64_t *cnt, GridDev g,
-                const double2 *__restrict__ E2, double qm, double dt, double *u, int *status,
+                const double2 *__restrict__ E2, double qm, double dt, double c1, double *u, int *status,
                 unsigned long long *vmax2, int64_t n_sorted) {
   constexpr int mode_x = MX, mode_y = MY;   // after_push modes are compile-time: no mode branches per row
-  extern __shared__ double2 s_dyn[];        // per warp: E window (double2), then the rho windows (double)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double2 *sE = s_dyn + warp * (WE * WE);
-  double *rho = (double *)(s_dyn + WARPS * (WE * WE)) + warp * (WR * WR);
-  unsigned n_gmiss = 0, n_dmiss = 0, n_anchor = 0;
-  for (int e = lane; e < WR * WR; e += 32) rho[e] = 0.0;
+  constexpr int OFF = (WE - WR) / 2;        // the rho window is the central part of the E window
+  extern __shared__ double2 s_dyn[];
+  const int lane = threadIdx.x & 31;
+  WarpSmem<WE, WR> &sm = ((WarpSmem<WE, WR> *)s_dyn)[threadIdx.x >> 5];
+  if (lane < 4) sm.stats[lane] = 0;
+  for (int e = lane; e < WR * WR; e += 32) sm.rho[e] = 0.0;
   __syncwarp();
-  const int64_t n = cnt[CNT_NSLOTS];
-  const double c1 = __dmul_rn(__dmul_rn(0.5, dt), qm);
-  // Every warp walks one contiguous range of the SORTED rows [0, ns) (its window follows the tiles)
-  // plus one slice of the unsorted tail [ns, n) (rows appended by ionisation since the last sort;
-  // they take the global path and never move the window).  Both ranges are multiples of 32.
-  const int64_t nwarps = (int64_t)gridDim.x * WARPS, gwarp = (int64_t)blockIdx.x * WARPS + warp;
-  const int64_t ns = n_sorted < n ? n_sorted : n;
-  const int64_t per = ((ns + nwarps - 1) / nwarps + 31) / 32 * 32;
-  int64_t rbeg = gwarp * per;
-  if (rbeg > ns) rbeg = ns;
-  const int64_t rend = rbeg + per < ns ? rbeg + per : ns;
-  const int64_t tper = ((n - ns + nwarps - 1) / nwarps + 31) / 32 * 32;
-  int64_t tbeg = ns + gwarp * tper;
-  if (tbeg > n) tbeg = n;
-  const int64_t tend = tbeg + tper < n ? tbeg + tper : n;
-  Window w{0, 0, false};
-  unsigned dead_total = 0;
-  double vm2 = 0.0;   // max |v|^2 of the rows of this lane (bound used by the MCC pruning)
+  // The loop-carried state is kept deliberately small (32-bit row index, packed window, float
+  // velocity bound, statistics in shared memory): the body must fit 80 registers WITHOUT spills,
+  // because a spill reload in the body shares its scoreboard with the row prefetch and makes its
+  // consumer wait for the prefetch as well (profiles/r1h_ncu_advance_tiled.md).
+  int qn = 0;                        // rows waiting in the queue (warp-uniform)
+  int ei0 = NOT_ANCHORED, ej0 = 0;   // node coordinates of the E window's lower-left corner
+  float vm2 = 0.0f;                  // upper bound of max |v|^2 of this lane's rows (MCC pruning)
 
-  // two passes over the same loop body: rg = 0 the sorted range (windowed), rg = 1 the tail slice.
-  // Inside a range rows are addressed with 32-bit offsets from per-range base pointers.
+  // Every warp walks one contiguous range of the SORTED rows [0, ns) (its window follows the tiles)
+  // and then one slice of the unsorted tail [ns, n) (rows appended by ionisation since the last sort;
+  // they never move the window).  Range starts are multiples of 32 rows; rows are addressed by their
+  // 32-bit global index.
   for (int rg = 0; rg < 2; ++rg) {
     const bool windowed = rg == 0;
-    const int64_t gbeg = windowed ? rbeg : tbeg;
-    const int cntr = (int)((windowed ? rend : tend) - gbeg);   // rows of this range (< 2^31 by construction)
-    if (cntr <= 0) continue;
-    double *__restrict__ Xr = X + gbeg, *__restrict__ Yr = Y + gbeg, *__restrict__ VXr = VX + gbeg;
-    double *__restrict__ VYr = VY + gbeg, *__restrict__ VZr = VZ + gbeg;
-    const double *__restrict__ WGr = WG + gbeg;
-    int p = lane;
-    double px = 0, py = 0, vx = 0, vy = 0, vz = 0, wq = 0;
-    if (p < cntr) { px = Xr[p]; py = Yr[p]; vx = VXr[p]; vy = VYr[p]; vz = VZr[p]; wq = WGr[p]; }
-    for (int b0 = 0; b0 < cntr; b0 += 32) {
-      const bool in_range = p < cntr;
-      const int pn = p + 32;
-      double nx_ = 0, ny_ = 0, nvx_ = 0, nvy_ = 0, nvz_ = 0, nwq_ = 0;
-      if (pn < cntr) { nx_ = Xr[pn]; ny_ = Yr[pn]; nvx_ = VXr[pn]; nvy_ = VYr[pn]; nvz_ = VZr[pn]; nwq_ = WGr[pn]; }
+    unsigned row, rend;
+    {
+      const int64_t n = cnt[CNT_NSLOTS];
+      const int64_t ns = n_sorted < n ? n_sorted : n;
+      const int64_t nwarps = (int64_t)gridDim.x * WARPS, gwarp = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+      const int64_t lo = windowed ? 0 : ns, hi = windowed ? ns : n;
+      const int64_t per = ((hi - lo + nwarps - 1) / nwarps + 31) / 32 * 32;
+      int64_t beg = lo + gwarp * per;
+      if (beg > hi) beg = hi;
+      const int64_t end = beg + per < hi ? beg + per : hi;
+      if (end <= beg) continue;
+      row = (unsigned)beg + lane;
+      rend = (unsigned)end;
+    }
+    const unsigned rlast = rend - 1;
+    double px, py, vx, vy, vz, wq;
+    {
+      const unsigned r = row < rlast ? row : rlast;
+      px = X[r]; py = Y[r]; vx = VX[r]; vy = VY[r]; vz = VZ[r]; wq = WG[r];
+    }
+    for (; row - lane < rend; row += 32) {
+      const bool in_range = row < rend;
+      // register prefetch of the next batch (index clamped instead of branching)
+      const unsigned rn = row + 32 < rlast ? row + 32 : rlast;
+      const double nx_ = X[rn], ny_ = Y[rn], nvx_ = VX[rn], nvy_ = VY[rn], nvz_ = VZ[rn], nwq_ = WG[rn];
 
       const bool live = in_range && !is_dead(px);
       // ---- cell of the old position; window management on it ----
@@ -132,43 +221,41 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
         if (!ing) atomicOr(status, ISKB_ST_OOB);
       }
       const unsigned gm = __ballot_sync(0xffffffffu, ing);
-      bool fit = ing && w.anchored && (unsigned)(i - 1 - w.ei0) < (unsigned)(WE - 1) &&
-                 (unsigned)(j - 1 - w.ej0) < (unsigned)(WE - 1);
+      bool fit = ing && (unsigned)(i - 1 - ei0) < (unsigned)(WE - 1) && (unsigned)(j - 1 - ej0) < (unsigned)(WE - 1);
       if (gm) {
-        const unsigned miss = gm & ~__ballot_sync(0xffffffffu, fit);
-        if (windowed && (!w.anchored || __popc(miss) > MISS_LIMIT)) {
+        unsigned dm = gm & ~__ballot_sync(0xffffffffu, fit);
+        if (windowed && (ei0 == NOT_ANCHORED || __popc(dm) > MISS_LIMIT)) {
           // move the window to the tile of the first row that missed
-          ++n_anchor;
-          if (w.anchored) flush_rho<WR>(rho, w, (WE - WR) / 2, g, u, lane);
-          const int src = __ffs(miss) - 1;
+          if (ei0 != NOT_ANCHORED) flush_rho<WR>(sm.rho, ei0 + OFF, ej0 + OFF, g, u, lane);
+          const int src = __ffs(dm) - 1;
           const int ti = (__shfl_sync(0xffffffffu, i, src) - 1) >> 3, tj = (__shfl_sync(0xffffffffu, j, src) - 1) >> 3;
-          w.ei0 = clamp_origin(ti * 8 - (WE - 9) / 2, g.nx, WE);
-          w.ej0 = clamp_origin(tj * 8 - (WE - 9) / 2, g.ny, WE);
-          w.anchored = true;
+          ei0 = clamp_origin(ti * 8 - (WE - 9) / 2, g.nx, WE);
+          ej0 = clamp_origin(tj * 8 - (WE - 9) / 2, g.ny, WE);
+          if (lane == 0) sm.stats[2] += 1;
           __syncwarp();
-          load_E<WE>(sE, w, g, E2, lane);
+          load_E<WE>(sm.E, ei0, ej0, g, E2, lane);
           __syncwarp();
-          fit = ing && (unsigned)(i - 1 - w.ei0) < (unsigned)(WE - 1) && (unsigned)(j - 1 - w.ej0) < (unsigned)(WE - 1);
-          n_gmiss += __popc(gm & ~__ballot_sync(0xffffffffu, fit));
-        } else {
-          n_gmiss += __popc(miss);
+          fit = ing && (unsigned)(i - 1 - ei0) < (unsigned)(WE - 1) && (unsigned)(j - 1 - ej0) < (unsigned)(WE - 1);
+          dm = gm & ~__ballot_sync(0xffffffffu, fit);
+        }
+        // rows outside the window are queued and advanced later, 32 at a time (drain_rows)
+        if (dm) {
+          if (ing && !fit) sm.queue[qn + __popc(dm & lanemask_lt())] = row;
+          qn += __popc(dm);
+          if (lane == 0) sm.stats[0] += __popc(dm);
         }
       }
       bool dead_now = false;
-      if (live) {
+      bool dep_win = false;            // CLAIM: this lane still has a deposit for the shared window
+      double d00 = 0, d10 = 0, d01 = 0, d11 = 0;
+      int ci = 0;
+      if (live && (fit || !ing)) {
         // ---- gather ----
         double ex = 0.0, ey = 0.0;
         if (ing) {
           const CicW gw = cic_weights(hx, hy);
-          double2 e00, e10, e01, e11;
-          if (fit) {
-            const int o = (j - 1 - w.ej0) * WE + (i - 1 - w.ei0);
-            e00 = sE[o]; e10 = sE[o + 1]; e01 = sE[o + WE]; e11 = sE[o + WE + 1];
-          } else {
-            const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * g.nx;
-            e00 = __ldg(&E2[n00]); e10 = __ldg(&E2[n00 + 1]);
-            e01 = __ldg(&E2[n00 + g.nx]); e11 = __ldg(&E2[n00 + g.nx + 1]);
-          }
+          const int o = (j - 1 - ej0) * WE + (i - 1 - ei0);
+          const double2 e00 = sm.E[o], e10 = sm.E[o + 1], e01 = sm.E[o + WE], e11 = sm.E[o + WE + 1];
           ex = cic_gather(gw, e00.x, e10.x, e01.x, e11.x);
           ey = cic_gather(gw, e00.y, e10.y, e01.y, e11.y);
         }
@@ -178,7 +265,7 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
         vz = push_v(vz, 0.0, c1, qm, dt);
         px = push_x(px, vx, dt);
         py = push_x(py, vy, dt);
-        vm2 = fmax(vm2, fma(vz, vz, fma(vy, vy, vx * vx)));
+        vm2 = fmaxf(vm2, __double2float_ru(fma(vz, vz, fma(vy, vy, vx * vx))));
         // ---- after_push: discards first, then wraps ----
         bool dead = (mode_x == ISKB_BND_DISCARD) && boundary_axis(px, g.ox, g.Lx, mode_x);
         if (!dead) dead = (mode_y == ISKB_BND_DISCARD) && boundary_axis(py, g.oy, g.Ly, mode_y);
@@ -186,60 +273,104 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
           if (mode_x == ISKB_BND_WRAP) boundary_axis(px, g.ox, g.Lx, mode_x);
           if (mode_y == ISKB_BND_WRAP) boundary_axis(py, g.oy, g.Ly, mode_y);
         }
-        VXr[p] = vx; VYr[p] = vy; VZr[p] = vz; Yr[p] = py;
+        VX[row] = vx; VY[row] = vy; VZ[row] = vz; Y[row] = py;
         if (dead) {
-          Xr[p] = __longlong_as_double(0x7ff8000000000000LL);
+          X[row] = __longlong_as_double(0x7ff8000000000000LL);
           dead_now = true;
         } else {
-          Xr[p] = px;
+          X[row] = px;
           // ---- deposit (new position) ----
           cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
           cell1(py, g.dy, g.rdy, g.fast_div, j, hy);
           if (cell_in_grid(i, j, g.nx, g.ny)) {
             const CicW cw = cic_weights(hx, hy);
-            const double d00 = __dmul_rn(cw.w00, wq), d10 = __dmul_rn(cw.w10, wq);
-            const double d01 = __dmul_rn(cw.w01, wq), d11 = __dmul_rn(cw.w11, wq);
-            const int ri = i - 1 - w.ei0 - (WE - WR) / 2, rj = j - 1 - w.ej0 - (WE - WR) / 2;
-            if (w.anchored && (unsigned)ri < (unsigned)(WR - 1) && (unsigned)rj < (unsigned)(WR - 1)) {
-              // shared CAS adds: 6 SM-cycles per warp instruction x conflict degree (about 1 here)
-              double *r0 = rho + rj * WR + ri;
-              // (hand-interleaved CAS sequences and claim/retry rounds were both measured slower than
-              //  the compiler's ATOMS.CAST.SPIN loops: 1.62 / 1.58 ms vs 1.47 ms per 62.5 M rows)
-              atomicAdd(r0, d00);
-              atomicAdd(r0 + 1, d10);
-              atomicAdd(r0 + WR, d01);
-              atomicAdd(r0 + WR + 1, d11);
+            d00 = __dmul_rn(cw.w00, wq); d10 = __dmul_rn(cw.w10, wq);
+            d01 = __dmul_rn(cw.w01, wq); d11 = __dmul_rn(cw.w11, wq);
+            const int ri = i - 1 - ei0 - OFF, rj = j - 1 - ej0 - OFF;   // fails for NOT_ANCHORED as well
+            if ((unsigned)ri < (unsigned)(WR - 1) && (unsigned)rj < (unsigned)(WR - 1)) {
+              ci = rj * WR + ri;
+              if (CLAIM) {
+                dep_win = true;
+              } else {
+                // shared CAS adds (ATOMS.CAST.SPIN loops)
+                double *r0 = sm.rho + ci;
+                atomicAdd(r0, d00);
+                atomicAdd(r0 + 1, d10);
+                atomicAdd(r0 + WR, d01);
+                atomicAdd(r0 + WR + 1, d11);
+              }
             } else {
               const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * g.nx;
               atomicAdd(&u[n00], d00);
               atomicAdd(&u[n00 + 1], d10);
               atomicAdd(&u[n00 + g.nx], d01);
               atomicAdd(&u[n00 + g.nx + 1], d11);
-              ++n_dmiss;
+              atomicAdd(&sm.stats[1], 1u);
             }
           } else {
             atomicOr(status, ISKB_ST_OOB);
           }
         }
       }
-      if (MX == ISKB_BND_DISCARD || MY == ISKB_BND_DISCARD) dead_total += __popc(__ballot_sync(0xffffffffu, dead_now));
+      if (CLAIM) {
+        // Deposit rounds without atomics.  Each round the lanes write their lane number into the claim
+        // byte of their CELL; the lanes that read their own number back sit in pairwise different
+        // cells, so for each of the four corners their nodes are pairwise different and a plain
+        // load-add-store is safe.  The rest retry.  (The shared CAS loops this replaces kept the
+        // LSU data pipe at 85 % of its wavefront peak: profiles/r1e_ncu_advance_tiled.md.)
+        unsigned pend = __ballot_sync(0xffffffffu, dep_win);
+        double *r0 = sm.rho + ci;
+        while (pend) {
+          if (dep_win) sm.claim[ci] = (unsigned char)lane;
+          __syncwarp();
+          const bool win = dep_win && sm.claim[ci] == (unsigned char)lane;
+          if (win) r0[0] = __dadd_rn(r0[0], d00);
+          __syncwarp();
+          if (win) r0[1] = __dadd_rn(r0[1], d10);
+          __syncwarp();
+          if (win) r0[WR] = __dadd_rn(r0[WR], d01);
+          __syncwarp();
+          if (win) r0[WR + 1] = __dadd_rn(r0[WR + 1], d11);
+          __syncwarp();
+          if (win) dep_win = false;
+          pend = __ballot_sync(0xffffffffu, dep_win);
+        }
+      }
+      if (MX == ISKB_BND_DISCARD || MY == ISKB_BND_DISCARD) {
+        const unsigned dmask = __ballot_sync(0xffffffffu, dead_now);
+        if (dmask && lane == 0) sm.stats[3] += __popc(dmask);
+      }
       __syncwarp();   // rho window updates of this batch are ordered before a possible flush
-      p = pn;
+      if (qn >= 32) {
+        const DrainOut o = drain_rows<MX, MY>(sm.queue, 32, lane, X, Y, VX, VY, VZ, WG, g, E2, qm, dt, c1, u, status);
+        vm2 = fmaxf(vm2, __double2float_ru(o.vm2));
+        if (lane == 0) { sm.stats[3] += o.dead; sm.stats[1] += 32; }
+        qn -= 32;
+        __syncwarp();
+        if (lane < qn) sm.queue[lane] = sm.queue[lane + 32];
+        __syncwarp();
+      }
       px = nx_; py = ny_; vx = nvx_; vy = nvy_; vz = nvz_; wq = nwq_;
     }
   }
   __syncwarp();
-  if (w.anchored) flush_rho<WR>(rho, w, (WE - WR) / 2, g, u, lane);
-  if (lane == 0 && dead_total) atomicAdd((unsigned long long *)&cnt[CNT_NDEAD], (unsigned long long)dead_total);
+  if (qn > 0) {
+    const DrainOut o = drain_rows<MX, MY>(sm.queue, qn, lane, X, Y, VX, VY, VZ, WG, g, E2, qm, dt, c1, u, status);
+    vm2 = fmaxf(vm2, __double2float_ru(o.vm2));
+    if (lane == 0) { sm.stats[3] += o.dead; sm.stats[1] += qn; }
+  }
+  __syncwarp();
+  if (ei0 != NOT_ANCHORED) flush_rho<WR>(sm.rho, ei0 + OFF, ej0 + OFF, g, u, lane);
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) vm2 = fmax(vm2, __shfl_xor_sync(0xffffffffu, vm2, d));
-  if (lane == 0 && vm2 > 0.0) atomicMax(vmax2, (unsigned long long)__double_as_longlong(vm2));
-  // window statistics (diagnostics + adaptive re-sort): gather misses, deposit misses, window moves
-  n_dmiss = __reduce_add_sync(0xffffffffu, n_dmiss);
+  for (int d = 16; d > 0; d >>= 1) vm2 = fmaxf(vm2, __shfl_xor_sync(0xffffffffu, vm2, d));
   if (lane == 0) {
-    atomicAdd((unsigned long long *)&cnt[3], (unsigned long long)n_gmiss);
-    atomicAdd((unsigned long long *)&cnt[4], (unsigned long long)n_dmiss);
-    atomicAdd((unsigned long long *)&cnt[5], (unsigned long long)n_anchor);
+    // float -> double is exact, and the float was rounded up, so this stays an upper bound
+    if (vm2 > 0.0f) atomicMax(vmax2, (unsigned long long)__double_as_longlong((double)vm2));
+    if (sm.stats[3]) atomicAdd((unsigned long long *)&cnt[CNT_NDEAD], (unsigned long long)sm.stats[3]);
+    // window statistics (diagnostics + adaptive re-sort): gather misses, deposit misses, window moves
+    atomicAdd((unsigned long long *)&cnt[3], (unsigned long long)sm.stats[0]);
+    atomicAdd((unsigned long long *)&cnt[4], (unsigned long long)sm.stats[1]);
+    atomicAdd((unsigned long long *)&cnt[5], (unsigned long long)sm.stats[2]);
   }
 }
 
@@ -247,13 +378,13 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
 
 int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit, bool from_begin);
 
-template <int WE, int WR, int WARPS, int MINB, int MX, int MY>
+template <int WE, int WR, int WARPS, int MINB, int MX, int MY, bool CLAIM>
 static int32_t launch_modes(iskb_species *sp, double dt) {
   iskb_ctx *c = sp->ctx;
-  constexpr int SMEM = WARPS * (WE * WE * 16 + WR * WR * 8);
+  constexpr int SMEM = WARPS * (int)sizeof(WarpSmem<WE, WR>);
   static bool attr_set = false;
   if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(k_advance_tiled<WE, WR, WARPS, MINB, MX, MY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    CU_TRY(cudaFuncSetAttribute(k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   const double qm = sp->q / sp->m;
@@ -264,27 +395,27 @@ static int32_t launch_modes(iskb_species *sp, double dt) {
   if (blocks < 1) blocks = 1;
   ISKB_TRY(sp_vmax_reset(sp));
   ISKB_TRY(prof_begin(c));
-  k_advance_tiled<WE, WR, WARPS, MINB, MX, MY><<<(int)blocks, WARPS * 32, SMEM, c->stream>>>(
+  k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM><<<(int)blocks, WARPS * 32, SMEM, c->stream>>>(
       sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->d_cnt, c->g, c->d_E2, qm, dt,
-      sp->d_u, c->d_status, sp->d_vmax2, sp->h_nsorted);
+      0.5 * dt * qm, sp->d_u, c->d_status, sp->d_vmax2, sp->h_nsorted);
   LAUNCH_CHECK(c);
   ISKB_TRY(prof_end(c));
   if (MX == ISKB_BND_DISCARD || MY == ISKB_BND_DISCARD) sp->counts_stale = true;
   return ISKB_OK;
 }
 
-template <int WE, int WR, int WARPS, int MINB>
+template <int WE, int WR, int WARPS, int MINB, bool CLAIM>
 static int32_t launch_variant(iskb_species *sp, double dt, int mode_x, int mode_y) {
   switch (mode_x * 3 + mode_y) {
-    case 0: return launch_modes<WE, WR, WARPS, MINB, 0, 0>(sp, dt);
-    case 1: return launch_modes<WE, WR, WARPS, MINB, 0, 1>(sp, dt);
-    case 2: return launch_modes<WE, WR, WARPS, MINB, 0, 2>(sp, dt);
-    case 3: return launch_modes<WE, WR, WARPS, MINB, 1, 0>(sp, dt);
-    case 4: return launch_modes<WE, WR, WARPS, MINB, 1, 1>(sp, dt);
-    case 5: return launch_modes<WE, WR, WARPS, MINB, 1, 2>(sp, dt);
-    case 6: return launch_modes<WE, WR, WARPS, MINB, 2, 0>(sp, dt);
-    case 7: return launch_modes<WE, WR, WARPS, MINB, 2, 1>(sp, dt);
-    default: return launch_modes<WE, WR, WARPS, MINB, 2, 2>(sp, dt);
+    case 0: return launch_modes<WE, WR, WARPS, MINB, 0, 0, CLAIM>(sp, dt);
+    case 1: return launch_modes<WE, WR, WARPS, MINB, 0, 1, CLAIM>(sp, dt);
+    case 2: return launch_modes<WE, WR, WARPS, MINB, 0, 2, CLAIM>(sp, dt);
+    case 3: return launch_modes<WE, WR, WARPS, MINB, 1, 0, CLAIM>(sp, dt);
+    case 4: return launch_modes<WE, WR, WARPS, MINB, 1, 1, CLAIM>(sp, dt);
+    case 5: return launch_modes<WE, WR, WARPS, MINB, 1, 2, CLAIM>(sp, dt);
+    case 6: return launch_modes<WE, WR, WARPS, MINB, 2, 0, CLAIM>(sp, dt);
+    case 7: return launch_modes<WE, WR, WARPS, MINB, 2, 1, CLAIM>(sp, dt);
+    default: return launch_modes<WE, WR, WARPS, MINB, 2, 2, CLAIM>(sp, dt);
   }
 }
 
@@ -292,5 +423,9 @@ int32_t launch_advance_tiled(iskb_species *sp, double dt, int mode_x, int mode_y
   iskb_ctx *c = sp->ctx;
   if (c->g.nx < 20 || c->g.ny < 20)   // windows do not fit small / quasi-1D grids: use the simple kernel
     return launch_advance_simple(sp, dt, mode_x, mode_y, true, false);
-  return launch_variant<16, 16, 8, 3>(sp, dt, mode_x, mode_y);
+  static const int variant = getenv("ISKB_ADV_VARIANT") ? atoi(getenv("ISKB_ADV_VARIANT")) : 1;
+  if (variant == 0) return launch_variant<16, 16, 8, 3, false>(sp, dt, mode_x, mode_y);
+  if (variant == 2) return launch_variant<16, 16, 7, 3, true>(sp, dt, mode_x, mode_y);
+  if (variant == 3) return launch_variant<16, 16, 6, 4, true>(sp, dt, mode_x, mode_y);
+  return launch_variant<16, 16, 8, 3, true>(sp, dt, mode_x, mode_y);
 }

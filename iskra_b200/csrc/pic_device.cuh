@@ -92,19 +92,26 @@ __device__ __forceinline__ double jl_fld(double x, double y) {
 
 // One axis of discard!/wrap!  (wrap.jl:1-33).  Returns true when the particle is discarded.
 // Fast path: 0 <= x-o < L  <=>  fld(x-o, L) == 0 (DESIGN.md "boundary fast path").
-static __device__ __noinline__ bool boundary_axis_slow(double &x, double xs, double L, int mode) {
+// Everything is passed and returned BY VALUE: a reference parameter of a non-inlined function would
+// pin the caller's x to a local-memory slot, and a local load in the hot loop shares its scoreboard
+// with the row prefetch.  Returns the wrapped coordinate, or NaN when the particle is discarded
+// (a live particle never has a NaN coordinate).
+static __device__ __noinline__ double boundary_axis_slow(double x, double xs, double L, int mode) {
   const double a = jl_fld(xs, L);
   if (a != 0.0) {
-    if (mode == ISKB_BND_DISCARD) return true;
+    if (mode == ISKB_BND_DISCARD) return __longlong_as_double(0x7ff8000000000000LL);
     x = __dsub_rn(x, __dmul_rn(a, L));
   }
-  return false;
+  return x;
 }
 __device__ __forceinline__ bool boundary_axis(double &x, double o, double L, int mode) {
   if (mode == ISKB_BND_NONE) return false;
   const double xs = __dsub_rn(x, o);
   if (xs >= 0.0 && xs < L) return false;
-  return boundary_axis_slow(x, xs, L, mode);   // rare: only rows that actually crossed an edge
+  const double r = boundary_axis_slow(x, xs, L, mode);   // rare: only rows that actually crossed an edge
+  if (r != r) return true;
+  x = r;
+  return false;
 }
 
 __device__ __forceinline__ bool cell_in_grid(int i, int j, int nx, int ny) {
