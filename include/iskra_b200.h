@@ -191,6 +191,11 @@ int32_t iskb_set_sort_full_interval(iskb_ctx *ctx, int32_t full_interval);
 /* n_steps iterations of: MCC (registered interactions, in order) -> advance! every species
  * (gather, push, after_push) -> density / rho -> all-reduce -> phi -> E. */
 int32_t iskb_step(iskb_ctx *ctx, double dt, int32_t n_steps);
+/* The field solve of a step runs on a private stream so that the next step's re-sort and MCC overlap
+ * it.  Every entry point that touches rho / phi / E joins it automatically; call this to make the
+ * ctx stream wait for it explicitly (stream-ordered, no host sync), e.g. before recording a timing
+ * event on the ctx stream. */
+int32_t iskb_stream_join(iskb_ctx *ctx);
 
 /* ---- MCC: Chemistry/src/mcc.jl ----------------------------------------------------------- */
 /* mcc(reactions) -> MonteCarloCollisions(collisions)  mcc.jl:313-320, :27-51.

@@ -73,6 +73,7 @@ SIGNATURES = {
     "iskb_set_sort_policy": [vp, f64, i32],
     "iskb_set_sort_full_interval": [vp, i32],
     "iskb_step": [vp, f64, i32],
+    "iskb_stream_join": [vp],
     "iskb_mcc_create": [vp, vp, f64, f64, f64, vp, i32, vp, vp, vp, vp, vp, vp, u64, C.POINTER(vp)],
     "iskb_mcc_constants": [vp, C.POINTER(f64), C.POINTER(f64)],
     "iskb_mcc_perform": [vp, f64, vp, C.POINTER(i64), C.POINTER(i64)],

@@ -421,6 +421,7 @@ static int32_t launch_variant(iskb_species *sp, double dt, int mode_x, int mode_
 
 int32_t launch_advance_tiled(iskb_species *sp, double dt, int mode_x, int mode_y) {
   iskb_ctx *c = sp->ctx;
+  ISKB_TRY(fields_join(c));
   if (c->g.nx < 20 || c->g.ny < 20)   // windows do not fit small / quasi-1D grids: use the simple kernel
     return launch_advance_simple(sp, dt, mode_x, mode_y, true, false);
   static const int variant = getenv("ISKB_ADV_VARIANT") ? atoi(getenv("ISKB_ADV_VARIANT")) : 1;

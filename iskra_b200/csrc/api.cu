@@ -133,6 +133,15 @@ extern "C" int32_t iskb_create(int32_t device, iskb_ctx **out) {
   c->n_sm = prop.multiProcessorCount;
   CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  {
+    // high priority: the solve is a chain of small latency-bound kernels; its blocks should get SM slots
+    // ahead of the bandwidth-bound particle kernels it overlaps with
+    int lo = 0, hi = 0;
+    CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU_TRY(cudaStreamCreateWithPriority(&c->fstream, cudaStreamNonBlocking, hi));
+  }
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_rho, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_E, cudaEventDisableTiming));
   CU_TRY(cudaMalloc(&c->d_status, sizeof(int)));
   CU_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
   CU_TRY(cudaMallocHost(&c->h_status, sizeof(int)));
@@ -154,6 +163,7 @@ static void free_species(iskb_species *s) {
 extern "C" int32_t iskb_destroy(iskb_ctx *c) {
   if (!c) return ISKB_OK;
   cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->fstream);
   cudaStreamSynchronize(c->stream);
   comm_destroy(c);
   for (iskb_mcc *m : c->mccs) {
@@ -165,6 +175,9 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
   cudaFree(c->d_V); cudaFree(c->d_rho); cudaFree(c->d_phi); cudaFree(c->d_E2); cudaFree(c->d_status);
   cudaFreeHost(c->h_status); cudaFreeHost(c->h_scratch);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_rho);
+  cudaEventDestroy(c->ev_E);
+  cudaStreamDestroy(c->fstream);
   cudaStreamDestroy(c->own_stream);
   delete c;
   return ISKB_OK;
@@ -172,13 +185,29 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
 
 extern "C" int32_t iskb_set_stream(iskb_ctx *c, void *s) {
   if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  CU_TRY(cudaStreamSynchronize(c->fstream));
   CU_TRY(cudaStreamSynchronize(c->stream));
+  c->fields_pending = false;
   c->stream = s ? (cudaStream_t)s : c->own_stream;
   return ISKB_OK;
 }
 
+int32_t fields_join(iskb_ctx *c) {
+  if (c->fields_pending) {
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_E, 0));
+    c->fields_pending = false;
+  }
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_stream_join(iskb_ctx *c) {
+  if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  return fields_join(c);
+}
+
 extern "C" int32_t iskb_synchronize(iskb_ctx *c) {
   if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  ISKB_TRY(fields_join(c));
   CU_TRY(cudaStreamSynchronize(c->stream));
   return ctx_check_status(c);
 }
@@ -281,6 +310,7 @@ extern "C" int32_t iskb_cell_volume(iskb_ctx *c, double *V_out) {
 }
 
 extern "C" int32_t iskb_fields_download(iskb_ctx *c, double *rho, double *phi, double *E) {
+  if (c) ISKB_TRY(fields_join(c));
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   double *tmp = nullptr;
@@ -298,6 +328,7 @@ extern "C" int32_t iskb_fields_download(iskb_ctx *c, double *rho, double *phi, d
 }
 
 extern "C" int32_t iskb_fields_upload(iskb_ctx *c, const double *rho, const double *phi, const double *E) {
+  if (c) ISKB_TRY(fields_join(c));
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   double *tmp = nullptr;
@@ -575,6 +606,7 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
     if (tiled)
       for (iskb_species *s : c->species) ISKB_TRY(maybe_sort(c, s));
     for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));       // :109-111
+    ISKB_TRY(fields_join(c));   // E of the previous step (the re-sort and MCC above did not need it)
     for (iskb_species *s : c->species) {                                   // :113-115
       CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
       if (tiled) {

@@ -93,6 +93,11 @@ struct PoissonState {
 struct iskb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  // The field solve (rho -> phi -> E) runs on its own stream so that the next step's re-sort and MCC,
+  // which do not read E, overlap it.  ev_rho: rho is final (main stream); ev_E: E is final (field stream).
+  cudaStream_t fstream = nullptr;
+  cudaEvent_t ev_rho = nullptr, ev_E = nullptr;
+  bool fields_pending = false;   // a solve is in flight on fstream; main-stream users of rho/phi/E must join first
   int64_t launches = 0;
   int n_sm = 148;
   // grid + fields
@@ -197,6 +202,7 @@ int32_t sp_sync_counts(iskb_species *sp);
 int32_t sp_compact(iskb_species *sp);
 int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host, bool interleave);
 int32_t sp_regroup(iskb_species *sp);
+int32_t fields_join(iskb_ctx *c);   // main stream waits for a field solve in flight (stream-ordered, no host sync)
 int32_t sp_ensure_alt(iskb_species *sp);
 int32_t ctx_check_status(iskb_ctx *ctx);
 int32_t poisson_prepare(iskb_ctx *ctx);

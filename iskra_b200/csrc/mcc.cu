@@ -244,6 +244,7 @@ __device__ __forceinline__ int64_t warp_append(bool pred, unsigned int *counter)
   return pred ? (int64_t)base + __popc(m & ((1u << lane) - 1u)) : -1;
 }
 
+constexpr int SEL_CALLS = 4;   // Philox calls (groups of 4 rows) per thread and block iteration: 4096 rows per block iteration
 __global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *lists_cnt, uint32_t *cand,
                                                     unsigned int cand_cap) {
   __shared__ unsigned int s_warp[8];
@@ -252,19 +253,25 @@ __global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *list
   const int64_t nq = (n + 3) / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long my_cand = 0;
-  for (int64_t q0 = (int64_t)blockIdx.x * 256; q0 < nq; q0 += (int64_t)gridDim.x * 256) {
-    const int64_t q = q0 + threadIdx.x;
+  for (int64_t q0 = (int64_t)blockIdx.x * (256 * SEL_CALLS); q0 < nq; q0 += (int64_t)gridDim.x * (256 * SEL_CALLS)) {
+    // thread t owns the groups q0 + SEL_CALLS*t .. +SEL_CALLS-1, i.e. 4*SEL_CALLS consecutive rows: the
+    // candidate list stays in increasing row order within a block iteration
+    const int64_t qb = q0 + (int64_t)threadIdx.x * SEL_CALLS;
     unsigned keep = 0;
-    if (q < nq) {
-      // one Philox call decides candidacy of rows 4q..4q+3 (draw index 0 of row 4q)
-      const Philox4 o = philox4x32_10((uint32_t)(q * 4), (uint32_t)((q * 4) >> 32), m.call, 0u, m.k0, m.k1);
 #pragma unroll
-      for (int s = 0; s < 4; ++s)
-        if (q * 4 + s < n && o.c[s] < m.p_cand_u32) keep |= 1u << s;
+    for (int u = 0; u < SEL_CALLS; ++u) {
+      const int64_t q = qb + u;
+      if (q < nq) {
+        // one Philox call decides candidacy of rows 4q..4q+3 (draw index 0 of row 4q)
+        const Philox4 o = philox4x32_10((uint32_t)(q * 4), (uint32_t)((q * 4) >> 32), m.call, 0u, m.k0, m.k1);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (q * 4 + s < n && o.c[s] < m.p_cand_u32) keep |= 1u << (4 * u + s);
+      }
     }
     const unsigned cnt = __popc(keep);
     my_cand += cnt;
-    // block-aggregated append: ONE global atomic per block iteration (1024 rows)
+    // block-aggregated append: ONE global atomic per block iteration
     unsigned incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -284,13 +291,13 @@ __global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *list
     }
     __syncthreads();
     unsigned slot = s_base + s_warp[warp] + incl - cnt;
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-      if (keep & (1u << s)) {
-        if (slot < cand_cap) cand[slot] = (uint32_t)(q * 4 + s);
-        else atomicOr(m.status, ISKB_ST_CAPACITY);
-        ++slot;
-      }
+    while (keep) {
+      const int b = __ffs(keep) - 1;
+      keep &= keep - 1;
+      if (slot < cand_cap) cand[slot] = (uint32_t)(qb * 4 + b);
+      else atomicOr(m.status, ISKB_ST_CAPACITY);
+      ++slot;
+    }
     __syncthreads();
   }
   // candidates statistic (rows drawn; includes the few discarded rows still parked in the columns)
@@ -342,7 +349,9 @@ __global__ void __launch_bounds__(TEST_TPB) k_mcc_test(MccDev m, unsigned int *l
             const double dens = m.tn[node];
             if (dens >= 0) {                                                      // :254-257
               const ProcDev pc = m.proc[k - 1];
-              const double2 e = m.E2[node];
+              // neutral target (tqm == 0): (0*E)*dt contributes exactly +0 for any finite E, so E is not
+              // read -- the field solve of the previous step may still be writing it on the field stream
+              const double2 e = m.tqm == 0.0 ? make_double2(0.0, 0.0) : m.E2[node];
               double d[3];
               d[0] = (m.tqm * e.x) * m.dt - vx;                                   // :266-267
               d[1] = (m.tqm * e.y) * m.dt - vy;
@@ -422,6 +431,7 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
     return iskb_fail(ISKB_E_PMAX, "Maximum probability (%g) is greater than 1/%d", max_Pt, N);   // :244-246
   MccDev m;
   m.src = spdev(src);
+  if (mc->tq != 0.0) ISKB_TRY(fields_join(c));   // charged target: the test kernel reads E (mcc.jl:266-267)
   int nprod = 0;
   for (int k = 0; k < N; ++k) {
     const MccProc &p = mc->procs[(size_t)k];

@@ -295,6 +295,7 @@ extern "C" int32_t iskb_cell_index(iskb_species *sp, int32_t *i_out, int32_t *j_
 }
 
 extern "C" int32_t iskb_gather(iskb_species *sp, double *partE_out) {
+  if (sp) ISKB_TRY(fields_join(sp->ctx));
   ISKB_TRY(need_grid(sp));
   iskb_ctx *c = sp->ctx;
   if (!partE_out) return iskb_fail(ISKB_E_INVALID, "partE_out is NULL");
@@ -390,12 +391,14 @@ extern "C" int32_t iskb_species_density_download(iskb_species *sp, double *n_out
 }
 
 extern "C" int32_t iskb_rho_zero(iskb_ctx *c) {
+  if (c) ISKB_TRY(fields_join(c));
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
   CU_TRY(cudaMemsetAsync(c->d_rho, 0, (int64_t)c->g.nx * c->g.ny * sizeof(double), c->stream));
   return ISKB_OK;
 }
 
 extern "C" int32_t iskb_rho_accumulate(iskb_ctx *c, iskb_species *sp) {
+  if (c) ISKB_TRY(fields_join(c));
   ISKB_TRY(need_grid(sp));
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   int blocks = (int)((nn + TPB - 1) / TPB);
@@ -406,6 +409,7 @@ extern "C" int32_t iskb_rho_accumulate(iskb_ctx *c, iskb_species *sp) {
 }
 
 int32_t launch_rho_finalize(iskb_ctx *c) {
+  if (c) ISKB_TRY(fields_join(c));
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   if (c->species.size() > 8) return iskb_fail(ISKB_E_UNSUPPORTED, "more than 8 kinetic species");
   RhoFin f;
@@ -425,6 +429,7 @@ int32_t launch_rho_finalize(iskb_ctx *c) {
 // advance! for one species, simple kernel (see advance_fused.cu for the tiled one)
 int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit,
                               bool from_begin) {
+  ISKB_TRY(fields_join(sp->ctx));
   iskb_ctx *c = sp->ctx;
   const double qm = sp->q / sp->m;
   int blocks = from_begin ? c->n_sm : grid_for(sp);

@@ -548,6 +548,7 @@ int32_t poisson_prepare(iskb_ctx *c) {
   if (!ps.created) return iskb_fail(ISKB_E_INVALID, "iskb_poisson_create must be called first");
   const int nx = c->g.nx, ny = c->g.ny;
   const int64_t nn = (int64_t)nx * ny;
+  if (ps.structure_dirty || ps.values_dirty) CU_TRY(cudaStreamSynchronize(c->fstream));   // a solve in flight reads these buffers
   if (ps.structure_dirty) {
     {
       std::vector<uint8_t> &m = ps.isdir;
@@ -694,58 +695,64 @@ int32_t poisson_prepare(iskb_ctx *c) {
   return ISKB_OK;
 }
 
+// Asynchronous: the solve is ordered after everything issued so far on the main stream (rho) and runs
+// on the field stream; main-stream users of phi / E call fields_join() first.
 int32_t poisson_solve(iskb_ctx *c) {
   ISKB_TRY(poisson_prepare(c));
+  CU_TRY(cudaEventRecord(c->ev_rho, c->stream));
+  CU_TRY(cudaStreamWaitEvent(c->fstream, c->ev_rho, 0));
   PoissonState &ps = c->ps;
   const int nx = c->g.nx, ny = c->g.ny;
   const int64_t nn = (int64_t)nx * ny;
   if (ps.mode == 2) {
-    k_dense_rhs<<<blocks_for(c, nn), TPB, 0, c->stream>>>(c->d_rho, ps.d_isdir, ps.d_dval, ps.eps0, c->g.dx * c->g.dx, nn,
+    k_dense_rhs<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(c->d_rho, ps.d_isdir, ps.d_dval, ps.eps0, c->g.dx * c->g.dx, nn,
                                                           ps.d_w1);
     LAUNCH_CHECK(c);
-    k_dense_gemv<<<(int)((nn + 127) / 128), 128, 0, c->stream>>>(ps.d_Ainv, ps.d_w1, nn, c->d_phi);
+    k_dense_gemv<<<(int)((nn + 127) / 128), 128, 0, c->fstream>>>(ps.d_Ainv, ps.d_w1, nn, c->d_phi);
     LAUNCH_CHECK(c);
   } else {
     SolveDims s{nx, ny, ps.transposed ? 1 : 0, ps.a0, ps.ma, ps.b0, ps.mb, c->g.dx * c->g.dx / ps.eps0};
     const int64_t tot = (int64_t)ps.ma * ps.mb;
-    k_build_rhs<<<blocks_for(c, tot), TPB, 0, c->stream>>>(s, c->d_rho, ps.d_isdir, ps.d_dval, ps.d_w1);
+    k_build_rhs<<<blocks_for(c, tot), TPB, 0, c->fstream>>>(s, c->d_rho, ps.d_isdir, ps.d_dval, ps.d_w1);
     LAUNCH_CHECK(c);
     dim3 gg((ps.ma + 63) / 64, (ps.mb + 63) / 64);
     const double dst_scale = sqrt(2.0 / (ps.ma + 1));
     const int M = 1 << ps.fft_log2M;
     // forward transform  w1 -> w2
     if (ps.use_fft)
-      k_dst_fft<<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->stream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, ps.d_w1,
+      k_dst_fft<<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, ps.d_w1,
                                                                          ps.d_w2, dst_scale);
     else
-      k_dgemm<<<gg, 256, 0, c->stream>>>(ps.ma, ps.mb, ps.ma, ps.d_Vt, ps.ma, ps.d_w1, ps.ma, ps.d_w2, ps.ma);
+      k_dgemm<<<gg, 256, 0, c->fstream>>>(ps.ma, ps.mb, ps.ma, ps.d_Vt, ps.ma, ps.d_w1, ps.ma, ps.d_w2, ps.ma);
     LAUNCH_CHECK(c);
     // tridiagonal solves along b on mode-major data:  w2 --T--> w1, in place, w1 --T--> w2
     {
       dim3 tg((ps.ma + 31) / 32, (ps.mb + 31) / 32), tb(32, 8);
-      k_transpose<<<tg, tb, 0, c->stream>>>(ps.ma, ps.mb, ps.d_w2, ps.d_w1);
+      k_transpose<<<tg, tb, 0, c->fstream>>>(ps.ma, ps.mb, ps.d_w2, ps.d_w1);
       LAUNCH_CHECK(c);
-      k_thomas_warp<<<(ps.ma + 3) / 4, 128, 0, c->stream>>>(ps.ma, ps.mb, ps.b_cyclic ? 1 : 0, ps.singular_mode, ps.d_cp,
+      k_thomas_warp<<<(ps.ma + 3) / 4, 128, 0, c->fstream>>>(ps.ma, ps.mb, ps.b_cyclic ? 1 : 0, ps.singular_mode, ps.d_cp,
                                                             ps.d_msing, ps.d_q, ps.d_qden, ps.d_gam, ps.d_w1);
       LAUNCH_CHECK(c);
       dim3 tg2((ps.mb + 31) / 32, (ps.ma + 31) / 32);
-      k_transpose<<<tg2, tb, 0, c->stream>>>(ps.mb, ps.ma, ps.d_w1, ps.d_w2);
+      k_transpose<<<tg2, tb, 0, c->fstream>>>(ps.mb, ps.ma, ps.d_w1, ps.d_w2);
       LAUNCH_CHECK(c);
     }
     double *cur = ps.d_w2, *other = ps.d_w1;
     // inverse transform  cur -> other
     if (ps.use_fft)
-      k_dst_fft<<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->stream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, cur, other,
+      k_dst_fft<<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, cur, other,
                                                                          dst_scale);
     else
-      k_dgemm<<<gg, 256, 0, c->stream>>>(ps.ma, ps.mb, ps.ma, ps.d_V, ps.ma, cur, ps.ma, other, ps.ma);
+      k_dgemm<<<gg, 256, 0, c->fstream>>>(ps.ma, ps.mb, ps.ma, ps.d_V, ps.ma, cur, ps.ma, other, ps.ma);
     LAUNCH_CHECK(c);
     ps.d_w3 = other;   // (alias, not owned) result of the inverse transform
-    k_store_phi<<<blocks_for(c, nn), TPB, 0, c->stream>>>(s, ps.d_w3, ps.d_isdir, ps.d_dval, c->d_phi);
+    k_store_phi<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(s, ps.d_w3, ps.d_isdir, ps.d_dval, c->d_phi);
     LAUNCH_CHECK(c);
   }
-  k_efield<<<blocks_for(c, nn), TPB, 0, c->stream>>>(nx, ny, c->g.dx, c->g.dy, c->d_phi, c->d_E2);
+  k_efield<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(nx, ny, c->g.dx, c->g.dy, c->d_phi, c->d_E2);
   LAUNCH_CHECK(c);
+  CU_TRY(cudaEventRecord(c->ev_E, c->fstream));
+  c->fields_pending = true;
   return ISKB_OK;
 }
 
@@ -803,7 +810,8 @@ extern "C" int32_t iskb_poisson_apply_dirichlet_edge(iskb_ctx *c, int32_t edge, 
   if (!ps.structure_dirty && !ps.values_dirty && ps.d_dval) {
     // solver already built and only this edge's value changed: patch the device copy in place
     const int len = edge < 2 ? ny : nx;
-    k_set_edge<<<(len + 255) / 256, 256, 0, c->stream>>>(nx, ny, edge, phi0, ps.d_dval);
+    // on the field stream: ordered after a solve still in flight (it reads d_dval) and before the next one
+    k_set_edge<<<(len + 255) / 256, 256, 0, c->fstream>>>(nx, ny, edge, phi0, ps.d_dval);
     LAUNCH_CHECK(c);
     return ISKB_OK;
   }
@@ -829,5 +837,6 @@ extern "C" int32_t iskb_poisson_mode(iskb_ctx *c, int32_t *mode_out) {
 
 extern "C" int32_t iskb_field_solve(iskb_ctx *c) {
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
-  return poisson_solve(c);
+  ISKB_TRY(poisson_solve(c));
+  return fields_join(c);
 }

@@ -102,6 +102,10 @@ class Runtime:
     def set_sort_interval(self, k):
         L.check(self.lib.iskb_set_sort_interval(self.h, int(k)))
 
+    def join(self):
+        """Make the context stream wait for a field solve still in flight on the field stream."""
+        L.check(self.lib.iskb_stream_join(self.h))
+
     def set_sort_policy(self, miss_threshold, max_interval, full_interval=0):
         L.check(self.lib.iskb_set_sort_policy(self.h, float(miss_threshold), int(max_interval)))
         L.check(self.lib.iskb_set_sort_full_interval(self.h, int(full_interval)))

@@ -60,6 +60,7 @@ class Workload:
                 L.check(rt.lib.iskb_poisson_apply_dirichlet_edge(rt.h, edge, v))
             rt.step(self.dt, 1)
             self.step_index += 1
+        rt.join()   # the last field solve runs on the field stream; order it before whatever follows
         for s in self.kinetic():
             s._touched_on_device()
 
