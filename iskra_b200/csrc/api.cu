@@ -1,6 +1,7 @@
 // C-ABI entry points: context, grid, fields, species storage, and the fused step.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "pic_device.cuh"
@@ -620,7 +621,8 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
     }
     ISKB_TRY(launch_rho_finalize(c));                                      // :118-124
     if (c->n_ranks > 1) ISKB_TRY(comm_allreduce_sum(c, c->d_rho, nn));
-    ISKB_TRY(poisson_solve(c));                                            // :126-128
+    static const bool skip_solve = getenv("ISKB_DEBUG_SKIP_SOLVE") != nullptr;   // timing experiments only
+    if (!skip_solve) ISKB_TRY(poisson_solve(c));                           // :126-128
     c->step_count++;
   }
   return ISKB_OK;
