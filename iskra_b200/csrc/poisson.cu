@@ -321,15 +321,19 @@ __global__ void __launch_bounds__(128) k_thomas_warp(int ma, int mb, int cyclic,
     mean /= mb;
   }
   const int ntile = (mb + 31) / 32;
-  // forward sweep
+  // forward sweep.  The recurrence is serial through `carry`, the loads are not: the operands of tile
+  // t+1 are fetched before the scan of tile t so that their latency hides behind it.
   double carry = 0.0;
+  double mq_n = 0.0, wq_n = 0.0;
+  if (lane < mb) { mq_n = m[lane]; wq_n = w[lane]; }
   for (int t = 0; t < ntile; ++t) {
     const int q = t * 32 + lane;
+    const double mq = mq_n, wq = wq_n;
+    if (q + 32 < mb) { mq_n = m[q + 32]; wq_n = w[q + 32]; }
     double A = 1.0, B = 0.0;   // identity for padding lanes
     if (q < mb) {
-      const double mq = m[q];
       A = -mq;
-      B = (w[q] - mean) * mq;
+      B = (wq - mean) * mq;
       if (sing && q == 0) { A = 0.0; B = 0.0; }   // pinned x_0 = 0
     }
     affine_scan_up(A, B, lane);
@@ -337,14 +341,18 @@ __global__ void __launch_bounds__(128) k_thomas_warp(int ma, int mb, int cyclic,
     if (q < mb) w[q] = y;
     carry = __shfl_sync(0xffffffffu, y, 31);
   }
+  __syncwarp();
   // backward sweep (reversed index r = mb-1-q so that the recurrence runs upward in r)
   carry = 0.0;
+  if (lane < mb) { mq_n = m[mb - 1 - lane]; wq_n = w[mb - 1 - lane]; }
   for (int t = 0; t < ntile; ++t) {
     const int r = t * 32 + lane, q = mb - 1 - r;
+    const double mq = mq_n, wq = wq_n;
+    if (r + 32 < mb) { mq_n = m[q - 32]; wq_n = w[q - 32]; }
     double A = 1.0, B = 0.0;
     if (r < mb) {
-      A = (r == 0) ? 0.0 : -m[q];
-      B = w[q];
+      A = (r == 0) ? 0.0 : -mq;
+      B = wq;
       if (sing && q == 0) { A = 0.0; B = 0.0; }
     }
     affine_scan_up(A, B, lane);
@@ -410,7 +418,38 @@ __global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, co
     }
   }
   __syncthreads();
-  for (int s = 0; s < log2M; ++s) {
+  // radix-2 stages fused in pairs (stage s on (a0,a1),(a2,a3), stage s+1 on (a0,a2),(a1,a3) of the same
+  // four elements): half the shared-memory passes and barriers of a plain radix-2 loop
+  int s = 0;
+  for (; s + 1 < log2M; s += 2) {
+    const int half = 1 << s;
+    for (int t = threadIdx.x; t < M / 4; t += blockDim.x) {
+      const int pos = t & (half - 1);
+      const int i0 = ((t >> s) << (s + 2)) + pos;
+      const double2 w1 = __ldg(&tw[pos << (log2M - 1 - s)]);
+      const double2 w2a = __ldg(&tw[pos << (log2M - 2 - s)]);
+      const double2 w2b = __ldg(&tw[(pos + half) << (log2M - 2 - s)]);
+      double2 a0 = zs[i0], a1 = zs[i0 + half], a2 = zs[i0 + 2 * half], a3 = zs[i0 + 3 * half];
+      {
+        const double br = fma(a1.x, w1.x, -(a1.y * w1.y)), bi = fma(a1.x, w1.y, a1.y * w1.x);
+        a1 = make_double2(a0.x - br, a0.y - bi);
+        a0 = make_double2(a0.x + br, a0.y + bi);
+        const double cr = fma(a3.x, w1.x, -(a3.y * w1.y)), ci = fma(a3.x, w1.y, a3.y * w1.x);
+        a3 = make_double2(a2.x - cr, a2.y - ci);
+        a2 = make_double2(a2.x + cr, a2.y + ci);
+      }
+      {
+        const double br = fma(a2.x, w2a.x, -(a2.y * w2a.y)), bi = fma(a2.x, w2a.y, a2.y * w2a.x);
+        zs[i0] = make_double2(a0.x + br, a0.y + bi);
+        zs[i0 + 2 * half] = make_double2(a0.x - br, a0.y - bi);
+        const double cr = fma(a3.x, w2b.x, -(a3.y * w2b.y)), ci = fma(a3.x, w2b.y, a3.y * w2b.x);
+        zs[i0 + half] = make_double2(a1.x + cr, a1.y + ci);
+        zs[i0 + 3 * half] = make_double2(a1.x - cr, a1.y - ci);
+      }
+    }
+    __syncthreads();
+  }
+  for (; s < log2M; ++s) {   // odd log2M: one plain radix-2 stage left
     const int half = 1 << s;
     for (int t = threadIdx.x; t < M / 2; t += blockDim.x) {
       const int pos = t & (half - 1);
