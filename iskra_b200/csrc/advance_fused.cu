@@ -316,7 +316,9 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
         // Deposit rounds without atomics.  Each round the lanes write their lane number into the claim
         // byte of their CELL; the lanes that read their own number back sit in pairwise different
         // cells, so for each of the four corners their nodes are pairwise different and a plain
-        // load-add-store is safe.  The rest retry.  (The shared CAS loops this replaces kept the
+        // load-add-store is safe.  The rest retry.  (compute-sanitizer racecheck reports the claim
+        // bytes as write-after-write hazards: several lanes storing to one byte is the point, any one
+        // of them may win; it reports no read-after-write or write-after-read hazard on the windows.)  (The shared CAS loops this replaces kept the
         // LSU data pipe at 85 % of its wavefront peak: profiles/r1e_ncu_advance_tiled.md.)
         unsigned pend = __ballot_sync(0xffffffffu, dep_win);
         double *r0 = sm.rho + ci;
