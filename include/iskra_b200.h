@@ -33,6 +33,7 @@ extern "C" {
 typedef struct iskb_ctx iskb_ctx;
 typedef struct iskb_species iskb_species;
 typedef struct iskb_mcc iskb_mcc;
+typedef struct iskb_tracker iskb_tracker;
 
 /* status codes */
 #define ISKB_OK 0
@@ -67,6 +68,13 @@ typedef struct iskb_mcc iskb_mcc;
 #define ISKB_MCC_INELASTIC_BACKWARD 2
 #define ISKB_MCC_EXCITATION 3
 #define ISKB_MCC_IONIZATION 4
+
+/* surface kinds (ParticleInCell/src/pic/surfaces/build.jl:8-11, circuit_coupling.jl:5-16) */
+#define ISKB_SURF_PERIODIC 0            /* PeriodicSurface: generic no-op hit!, hit.jl:26-31 */
+#define ISKB_SURF_ABSORBING 1           /* AbsorbingSurface            hit.jl:32-38 */
+#define ISKB_SURF_REFLECTIVE 2          /* ReflectiveSurface (specular) hit.jl:39-56 */
+#define ISKB_SURF_ELECTRODE_FIXED 3     /* FixedPotentialElectrode     circuit_coupling.jl:55-61 */
+#define ISKB_SURF_ELECTRODE_FLOATING 4  /* FloatingPotentialElectrode  circuit_coupling.jl:44-53 */
 
 /* ---- lifecycle -------------------------------------------------------------------------- */
 int32_t iskb_version(void);
@@ -189,13 +197,61 @@ int32_t iskb_set_sort_policy(iskb_ctx *ctx, double miss_threshold, int32_t max_i
  * half the cost).  0 = every re-sort is full. */
 int32_t iskb_set_sort_full_interval(iskb_ctx *ctx, int32_t full_interval);
 /* n_steps iterations of: MCC (registered interactions, in order) -> advance! every species
- * (gather, push, after_push) -> density / rho -> all-reduce -> phi -> E. */
+ * (gather, push, after_push) -> density / rho -> all-reduce -> phi -> E.  With a surface tracker on
+ * the context advance! is track! -> gather -> push -> check! -> after_push (ParticleInCell.jl:56-61);
+ * the circuit (advance!(circuit, ...), :116) stays on the host between steps: call iskb_step(ctx, dt, 1)
+ * and iskb_poisson_sigma_add from the after_loop hook's side. */
 int32_t iskb_step(iskb_ctx *ctx, double dt, int32_t n_steps);
 /* The field solve of a step runs on a private stream so that the next step's re-sort and MCC overlap
  * it.  Every entry point that touches rho / phi / E joins it automatically; call this to make the
  * ctx stream wait for it explicitly (stream-ordered, no host sync), e.g. before recording a timing
  * event on the ctx stream. */
 int32_t iskb_stream_join(iskb_ctx *ctx);
+
+/* ---- surfaces, electrodes, circuit coupling --------------------------- */
+/* add_new_dof(ps, :sigma)  generalized_poisson.jl:217-230 -> 1-based index of the new sigma dof.
+ * Systems with sigma dofs are solved by the dense path (grids up to 8192 nodes). */
+int32_t iskb_poisson_add_dof(iskb_ctx *ctx, int32_t *dof_out);
+/* apply_neumann(ps, nodes, dof)  :235-269 (eps_r == 1); mask is nx*ny bytes, column-major.  Rows of
+ * nodes on a vertical strip and at its ends are replaced, others are left alone like the reference. */
+int32_t iskb_poisson_apply_neumann(iskb_ctx *ctx, const uint8_t *mask, int32_t dof);
+/* get_rhs(ps, :sigma, dof) .= v / .+= dv / read   :367-370 (circuit_coupling.jl:41-42) */
+int32_t iskb_poisson_sigma_set(iskb_ctx *ctx, int32_t dof, double value);
+int32_t iskb_poisson_sigma_add(iskb_ctx *ctx, int32_t dof, double delta);
+int32_t iskb_poisson_sigma_get(iskb_ctx *ctx, int32_t dof, double *out);
+/* number of unknowns of the dense system (nx*ny + sigma dofs); iskb_poisson_get_dense returns that size */
+int32_t iskb_poisson_dense_size(iskb_ctx *ctx, int64_t *n_out);
+/* get_solution(ps, :phi, i, j)  :363-364 ; 1-based node */
+int32_t iskb_phi_at(iskb_ctx *ctx, int32_t i, int32_t j, double *out);
+
+/* create_surface_tracker(grid, ds)  build.jl:95-100 -> :76-87: default surface `default_kind` on the
+ * four domain faces, from the inside out.  One tracker per context (config.tracker). */
+int32_t iskb_tracker_create(iskb_ctx *ctx, int32_t default_kind, iskb_tracker **out);
+/* track_surface!(st, nodes, surface)  build.jl:109-111 -> :46-60.  For electrodes: sigma_dof (1-based,
+ * 0 for a fixed one) and area (create_electrode, problem/configuration.jl:45-53).  Returns a surface id. */
+int32_t iskb_tracker_track_surface(iskb_tracker *st, const uint8_t *node_mask, int32_t kind,
+                                   int32_t sigma_dof, double area, int32_t *surface_id_out);
+/* face lookup get(st, ((i,j),(k,l)), nothing)  build.jl:113-117: kind of the surface or -1 */
+int32_t iskb_tracker_lookup(iskb_tracker *st, int32_t i, int32_t j, int32_t k, int32_t l, int32_t *kind_out);
+/* track!(st, part, dt)  track.jl:42-52: remembers cell and fractions of every particle in a cell next
+ * to a surface.  Must be followed by iskb_push and iskb_tracker_check on the same species with no
+ * other call in between.  n_tracked may be NULL. */
+int32_t iskb_tracker_track(iskb_tracker *st, iskb_species *sp, double dt, int64_t *n_tracked);
+/* check!(st, part, dt)  check.jl:39-68: walks every tracked particle through the cell faces it
+ * crossed (check, :17-36), applies hit! (hit.jl:26-56, circuit_coupling.jl:44-61), removes the
+ * absorbed ones.  too_fast: the reference's "particle is too fast" message condition (:41-46). */
+int32_t iskb_tracker_check(iskb_tracker *st, iskb_species *sp, double dt, int64_t *n_absorbed,
+                           int32_t *too_fast);
+/* Sticky flag: some particle exceeded dh/dt per step since the last call (the reference prints
+ * "ERROR: ... particle is too fast", check.jl:41-46, and carries on); reading clears it. */
+int32_t iskb_warning_too_fast(iskb_ctx *ctx, int32_t *out);
+/* electrode.dq: charge collected by the surface so far (circuit_coupling.jl:49-50); reset != 0 zeroes it
+ * (foo!, :30) */
+int32_t iskb_surface_charge(iskb_tracker *st, int32_t surface_id, double *dq_out, int32_t reset);
+/* The reference builds its floating electrodes with sigma and phi swapped (problem/configuration.jl:69-70
+ * vs circuit_coupling.jl:11-16), so collected charge never reaches the sigma right-hand side.  on != 0
+ * routes dq/area into it (the evident intent); default 0 = the reference's behaviour. */
+int32_t iskb_tracker_route_hits_to_sigma(iskb_tracker *st, int32_t on);
 
 /* ---- MCC: Chemistry/src/mcc.jl ----------------------------------------------------------- */
 /* mcc(reactions) -> MonteCarloCollisions(collisions)  mcc.jl:313-320, :27-51.

@@ -13,6 +13,7 @@ E_INVALID, E_CUDA, E_CAPACITY, E_PMAX, E_PK, E_OOB, E_NCCL, E_UNSUPPORTED, E_SIN
 BND_NONE, BND_WRAP, BND_DISCARD = 0, 1, 2
 BC_OPEN, BC_PERIODIC = 0, 1
 EDGE_LEFT, EDGE_RIGHT, EDGE_BOTTOM, EDGE_TOP = 0, 1, 2, 3
+SURF_PERIODIC, SURF_ABSORBING, SURF_REFLECTIVE, SURF_ELECTRODE_FIXED, SURF_ELECTRODE_FLOATING = range(5)
 MCC_ELASTIC_ISOTROPIC, MCC_ELASTIC_BACKWARD, MCC_INELASTIC_BACKWARD, MCC_EXCITATION, MCC_IONIZATION = range(5)
 
 
@@ -78,6 +79,21 @@ SIGNATURES = {
     "iskb_mcc_constants": [vp, C.POINTER(f64), C.POINTER(f64)],
     "iskb_mcc_perform": [vp, f64, vp, C.POINTER(i64), C.POINTER(i64)],
     "iskb_mcc_totals": [vp, vp],
+    "iskb_poisson_add_dof": [vp, C.POINTER(i32)],
+    "iskb_poisson_apply_neumann": [vp, vp, i32],
+    "iskb_poisson_sigma_set": [vp, i32, f64],
+    "iskb_poisson_sigma_add": [vp, i32, f64],
+    "iskb_poisson_sigma_get": [vp, i32, C.POINTER(f64)],
+    "iskb_poisson_dense_size": [vp, C.POINTER(i64)],
+    "iskb_phi_at": [vp, i32, i32, C.POINTER(f64)],
+    "iskb_tracker_create": [vp, i32, C.POINTER(vp)],
+    "iskb_tracker_track_surface": [vp, vp, i32, i32, f64, C.POINTER(i32)],
+    "iskb_tracker_lookup": [vp, i32, i32, i32, i32, C.POINTER(i32)],
+    "iskb_tracker_track": [vp, vp, f64, C.POINTER(i64)],
+    "iskb_tracker_check": [vp, vp, f64, C.POINTER(i64), C.POINTER(i32)],
+    "iskb_surface_charge": [vp, i32, C.POINTER(f64), i32],
+    "iskb_tracker_route_hits_to_sigma": [vp, i32],
+    "iskb_warning_too_fast": [vp, C.POINTER(i32)],
 }
 _RESTYPES = {"iskb_last_error": C.c_char_p}
 

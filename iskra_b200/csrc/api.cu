@@ -172,6 +172,7 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
     delete m;
   }
   for (iskb_species *s : c->species) free_species(s);
+  tracker_free(c->tracker);
   poisson_free(c);
   cudaFree(c->d_V); cudaFree(c->d_rho); cudaFree(c->d_phi); cudaFree(c->d_E2); cudaFree(c->d_status);
   cudaFreeHost(c->h_status); cudaFreeHost(c->h_scratch);
@@ -211,6 +212,13 @@ extern "C" int32_t iskb_synchronize(iskb_ctx *c) {
   ISKB_TRY(fields_join(c));
   CU_TRY(cudaStreamSynchronize(c->stream));
   return ctx_check_status(c);
+}
+
+extern "C" int32_t iskb_warning_too_fast(iskb_ctx *c, int32_t *out) {
+  if (!c || !out) return iskb_fail(ISKB_E_INVALID, "null");
+  *out = c->warn_too_fast ? 1 : 0;
+  c->warn_too_fast = false;
+  return ISKB_OK;
 }
 
 extern "C" int32_t iskb_launch_count(iskb_ctx *c, int64_t *out) {
@@ -262,9 +270,13 @@ extern "C" int32_t iskb_profile_read(iskb_ctx *c, double *ms, int64_t *launches)
 int32_t ctx_check_status(iskb_ctx *c) {
   CU_TRY(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
-  const int st = *c->h_status;
+  int st = *c->h_status;
   if (!st) return ISKB_OK;
   CU_TRY(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
+  if (st & ISKB_ST_TOO_FAST) c->warn_too_fast = true;   // the reference only prints a message (check.jl:44-46)
+  st &= ~ISKB_ST_TOO_FAST;
+  if (!st) return ISKB_OK;
+  if (st & ISKB_ST_WALK) return iskb_fail(ISKB_E_UNSUPPORTED, "a tracked particle crossed more than 65536 cell faces in one step");
   if (st & ISKB_ST_CAPACITY) return iskb_fail(ISKB_E_CAPACITY, "species capacity exceeded while appending particles");
   if (st & ISKB_ST_PK) return iskb_fail(ISKB_E_PK, "collision probability P_k > 1 (energy outside of the range)");
   return iskb_fail(ISKB_E_OOB, "a live particle lies outside the grid (reference would raise BoundsError)");
@@ -603,14 +615,17 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   ISKB_TRY(poisson_prepare(c));
   for (int it = 0; it < n_steps; ++it) {
-    const bool tiled = c->sort_interval > 0;
+    const bool tiled = c->sort_interval > 0 && !c->tracker;
     if (tiled)
       for (iskb_species *s : c->species) ISKB_TRY(maybe_sort(c, s));
     for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));       // :109-111
     ISKB_TRY(fields_join(c));   // E of the previous step (the re-sort and MCC above did not need it)
     for (iskb_species *s : c->species) {                                   // :113-115
       CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
-      if (tiled) {
+      if (c->tracker) {
+        // config.tracker != nothing: track! -> gather -> push -> check! -> after_push  (:56-61), one pass
+        ISKB_TRY(launch_advance_tracked(s, dt, c->after_push[0], c->after_push[1], true));
+      } else if (tiled) {
         ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
         ISKB_TRY(post_advance_stats(c, s));
         s->steps_since_sort++;

@@ -14,6 +14,8 @@
 #define ISKB_ST_OOB 1
 #define ISKB_ST_CAPACITY 2
 #define ISKB_ST_PK 4
+#define ISKB_ST_TOO_FAST 8   // check!'s "particle is too fast" condition (check.jl:41-46): a warning, not an error
+#define ISKB_ST_WALK 16      // a tracked particle did not finish its cell walk within the iteration cap
 
 void iskb_set_error(const char *fmt, ...);
 int32_t iskb_fail(int32_t code, const char *fmt, ...);
@@ -88,7 +90,18 @@ struct PoissonState {
   // --- dense solver ---
   double *d_Ainv = nullptr;
   int64_t nn_dense = 0;
+  double *d_rowscale = nullptr;   // row equilibration of the dense system (dh^2 / 1 / Neumann row scale)
+  // --- sigma dofs and Neumann rows (add_new_dof / apply_neumann, generalized_poisson.jl:217-269) ---
+  int n_sigma = 0;
+  std::vector<double> sigma;        // host copy of b[sigma dofs], authoritative while sigma_host_newer
+  bool sigma_host_newer = false;
+  double *d_sigma = nullptr;        // device copy (electrode hits may add to it), capacity MAX_SIGMA
+  std::vector<uint8_t> neu_kind;    // per node: 0 none, 1 strip row (:248-255), 2 strip-end row (:256-267)
+  std::vector<int32_t> neu_i2, neu_j2, neu_dof;   // neighbour nodes i', j' (0-based) and sigma dof (0-based)
+  double *d_neu_coef = nullptr;     // per node: A[row, sigma dof] (0 where no Neumann row)
+  int32_t *d_neu_dof = nullptr;
 };
+constexpr int ISKB_MAX_SIGMA = 64;
 
 struct iskb_ctx {
   int device = 0;
@@ -113,12 +126,14 @@ struct iskb_ctx {
   PoissonState ps;
   std::vector<iskb_species *> species;
   std::vector<iskb_mcc *> mccs;
+  iskb_tracker *tracker = nullptr;   // config.tracker (create_surface_tracker); nullptr == `nothing`
   int after_push[2] = {ISKB_BND_WRAP, ISKB_BND_WRAP};   // default hook wrap!, ParticleInCell.jl:41
   int sort_interval = 0;
   double sort_miss_threshold = 0.0;   // adaptive: sort a species only when its window-miss rate exceeds this
   int sort_max_interval = 0;          //           ... or this many steps have passed
   int sort_full_interval = 0;         // > 0: between full sorts re-group by tile only (cheaper)
   int64_t step_count = 0;
+  bool warn_too_fast = false;        // check!'s "particle is too fast" message condition was seen (sticky until read)
   // optional per-kernel timing of the dominant (advance) kernel, CUDA events on the launch stream
   bool profile = false;
   std::vector<cudaEvent_t> prof_ev;     // pairs (start, stop)
@@ -197,6 +212,42 @@ struct iskb_mcc {
   int64_t totals[2 + 16] = {0};
 };
 
+// SurfaceTracker{2}  ParticleInCell/src/pic/surfaces/build.jl:13-18, flattened for the device:
+// cells (i,j) with 0 <= i <= nx, 0 <= j <= ny (ghost ring included, build.jl:33-44); per cell four
+// directed faces  0:(i,j-1)  1:(i+1,j)  2:(i,j+1)  3:(i-1,j)  holding a surface id (0 = no entry).
+struct TrackerDev {
+  int nx, ny;                 // nodes
+  double dh;                  // st.dh = grid.dh[1]  (build.jl:97)
+  const uint8_t *face;        // 4 * (nx+1) * (ny+1)
+  const uint8_t *tracked;     // (nx+1) * (ny+1): cell is on either side of some key (build.jl:86-93)
+  const int32_t *s_kind;      // per surface id
+  const int32_t *s_dof;       // sigma dof (0-based) of a floating electrode, -1 otherwise
+  const double *s_area;
+  double *s_dq;               // collected charge per surface
+  double *sigma;              // device sigma right-hand side (only touched when route_hits != 0)
+  int route_hits;
+};
+
+struct iskb_tracker {
+  iskb_ctx *ctx = nullptr;
+  int default_kind = ISKB_SURF_ABSORBING;
+  std::vector<uint8_t> h_face, h_tracked;
+  std::vector<int32_t> h_kind, h_dof;
+  std::vector<double> h_area;
+  bool dirty = true;
+  uint8_t *d_face = nullptr, *d_tracked = nullptr;
+  int32_t *d_kind = nullptr, *d_dof = nullptr;
+  double *d_area = nullptr, *d_dq = nullptr;
+  int route_hits = 0;
+  // track! -> check! hand-over of the operator-level API (one species at a time)
+  iskb_species *trk_sp = nullptr;
+  int64_t trk_rows = 0, trk_cap = 0;
+  int32_t *d_ti = nullptr, *d_tj = nullptr;
+  double *d_thx = nullptr, *d_thy = nullptr;
+  unsigned long long *d_counts = nullptr;   // [0] tracked, [1] absorbed
+};
+constexpr int ISKB_MAX_SURFACES = 250;
+
 // ---- internal entry points across translation units ------------------------------------------
 int32_t sp_sync_counts(iskb_species *sp);
 int32_t sp_compact(iskb_species *sp);
@@ -216,5 +267,9 @@ int32_t launch_advance(iskb_species *sp, double dt, int mode_x, int mode_y, bool
 int32_t launch_rho_finalize(iskb_ctx *ctx);
 int32_t sp_vmax_unknown(iskb_species *sp);
 int32_t sp_vmax_reset(iskb_species *sp);
+int32_t tracker_prepare(iskb_tracker *st, TrackerDev *out);
+int32_t tracker_free(iskb_tracker *st);
+int32_t launch_advance_tracked(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit);
+int32_t poisson_sigma_device(iskb_ctx *ctx, double **d_sigma_out);
 int32_t prof_begin(iskb_ctx *ctx);
 int32_t prof_end(iskb_ctx *ctx);

@@ -36,26 +36,7 @@ __global__ void k_cell_index(const double *__restrict__ x, const double *__restr
   }
 }
 
-// ---- grid_to_particle  cloud_in_cell.jl:20-36 --------------------------------------------------
-__device__ __forceinline__ bool gather_E(const double2 *__restrict__ E2, const GridDev &g, double x,
-                                         double y, double &ex, double &ey) {
-  int i, j;
-  double hx, hy;
-  cell1(x, g.dx, g.rdx, g.fast_div, i, hx);
-  cell1(y, g.dy, g.rdy, g.fast_div, j, hy);
-  if (!cell_in_grid(i, j, g.nx, g.ny)) {
-    ex = ey = 0.0;
-    return false;
-  }
-  const CicW w = cic_weights(hx, hy);
-  const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * g.nx;
-  const double2 e00 = __ldg(&E2[n00]), e10 = __ldg(&E2[n00 + 1]);
-  const double2 e01 = __ldg(&E2[n00 + g.nx]), e11 = __ldg(&E2[n00 + g.nx + 1]);
-  ex = cic_gather(w, e00.x, e10.x, e01.x, e11.x);
-  ey = cic_gather(w, e00.y, e10.y, e01.y, e11.y);
-  return true;
-}
-
+// ---- grid_to_particle  cloud_in_cell.jl:20-36 : gather_E lives in pic_device.cuh -----------------
 __global__ void k_gather(const double *__restrict__ x, const double *__restrict__ y,
                          const int64_t *__restrict__ cnt, GridDev g, const double2 *__restrict__ E2,
                          double *pE, int64_t ld, int *status) {

@@ -36,7 +36,8 @@ struct AxisInfo {
 void assemble_dense(const iskb_ctx *c, std::vector<double> &A, std::vector<double> &b) {
   const PoissonState &ps = c->ps;
   const int nx = c->g.nx, ny = c->g.ny;
-  const int64_t nn = (int64_t)nx * ny;
+  const int64_t nnodes = (int64_t)nx * ny;
+  const int64_t nn = nnodes + ps.n_sigma;                // add_new_dof appends one row/column per sigma dof :217-230
   A.assign((size_t)(nn * nn), 0.0);
   b.assign((size_t)nn, 0.0);
   auto at = [&](int64_t r, int64_t col) -> double & { return A[(size_t)(r + col * nn)]; };
@@ -50,6 +51,10 @@ void assemble_dense(const iskb_ctx *c, std::vector<double> &A, std::vector<doubl
     }
   const double d2 = c->g.dx * c->g.dx;                   // :65
   for (auto &v : A) v /= d2;
+  for (int k = 0; k < ps.n_sigma; ++k) {                 // :227-228
+    at(nnodes + k, nnodes + k) = 1.0;
+    b[(size_t)(nnodes + k)] = ps.sigma[(size_t)k];
+  }
   if (ps.periodic_j) {                                   // apply_periodic(ps, 1) :291-306
     const double cc = (0.5 + 0.5) / (c->g.dx * c->g.dx);
     for (int jj = 0; jj < 2; ++jj) {
@@ -71,7 +76,29 @@ void assemble_dense(const iskb_ctx *c, std::vector<double> &A, std::vector<doubl
         if (i == 0) { at(r, r) -= cc; at(r, (nx - 1) + (int64_t)j * nx) += cc; }
       }
   }
-  for (int64_t r = 0; r < nn; ++r)
+  if (!ps.neu_kind.empty()) {                            // apply_neumann :235-269 (eps_r == 1)
+    const double dx = c->g.dx, dy = c->g.dy;
+    for (int64_t r = 0; r < nnodes; ++r) {
+      const int kind = ps.neu_kind[(size_t)r];
+      if (!kind) continue;
+      const int i = (int)(r % nx), j = (int)(r / nx);
+      const int64_t ri = ps.neu_i2[(size_t)r] + (int64_t)j * nx, s = nnodes + ps.neu_dof[(size_t)r];
+      for (int64_t col = 0; col < nn; ++col) at(r, col) = 0.0;
+      if (kind == 1) {                                   // :248-255
+        at(r, r) -= 2 * 1.0 / dx;
+        at(r, ri) += 2 * 1.0 / dx;
+        at(r, s) += 2;
+      } else {                                           // :256-267
+        const int64_t rj = i + (int64_t)ps.neu_j2[(size_t)r] * nx;
+        at(r, r) -= 4 * 1.0 / (3 * (dx * dx));
+        at(r, r) -= 4 * 1.0 / (3 * (dy * dy));
+        at(r, ri) += 4 * 1.0 / (3 * (dx * dx));
+        at(r, rj) += 4 * 1.0 / (3 * (dy * dy));
+        at(r, s) += (2.0 / 3.0) * (dx + dy) / (dx * dy);
+      }
+    }
+  }
+  for (int64_t r = 0; r < nnodes; ++r)
     if (ps.isdir[(size_t)r]) {                           // apply_dirichlet :205-215
       for (int64_t col = 0; col < nn; ++col) at(r, col) = 0.0;
       at(r, r) = 1.0;
@@ -479,6 +506,30 @@ __global__ void k_dense_rhs(const double *__restrict__ rho, const uint8_t *__res
        n += (int64_t)gridDim.x * blockDim.x)
     b[n] = isdir[n] ? dval[n] : ((-rho[n]) / eps0) * d2;   // rows of the inverse are equilibrated by dh^2
 }
+// Same with Neumann rows: the sigma unknowns are identity rows (x[sigma] = b[sigma], :227-228), so they
+// move to the right-hand side of the phi block:  b[r] = -rho/eps0 - A[r,sigma_k] * sigma_k.
+__global__ void k_dense_rhs_sigma(const double *__restrict__ rho, const uint8_t *__restrict__ isdir,
+                                  const double *__restrict__ dval, double eps0,
+                                  const double *__restrict__ rowscale, const double *__restrict__ neu_coef,
+                                  const int32_t *__restrict__ neu_dof, const double *__restrict__ sigma,
+                                  int64_t nn, double *b) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn;
+       n += (int64_t)gridDim.x * blockDim.x) {
+    double r;
+    if (isdir[n]) r = dval[n];
+    else {
+      r = (-rho[n]) / eps0;
+      const double cf = neu_coef[n];
+      if (cf != 0.0) r -= cf * sigma[neu_dof[n]];
+      r *= rowscale[n];
+    }
+    b[n] = r;
+  }
+}
+__global__ void k_sigma_add(double *sigma, int dof, double delta, int set) {
+  if (set) sigma[dof] = delta;
+  else atomicAdd(&sigma[dof], delta);   // electrode hits on the main stream add to the same word
+}
 __global__ void k_dense_gemv(const double *__restrict__ Ainv, const double *__restrict__ b, int64_t nn,
                              double *phi) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -539,7 +590,8 @@ int32_t upload(T **dptr, const std::vector<T> &h, cudaStream_t st) {
 int32_t poisson_free(iskb_ctx *c) {
   PoissonState &ps = c->ps;
   double **ptrs[] = {&ps.d_dval, &ps.d_V, &ps.d_lam, &ps.d_cp, &ps.d_q, &ps.d_qden, &ps.d_w1, &ps.d_w2,
-                     &ps.d_Ainv, &ps.d_Vt, &ps.d_gam, &ps.d_msing};
+                     &ps.d_Ainv, &ps.d_Vt, &ps.d_gam, &ps.d_msing, &ps.d_rowscale, &ps.d_sigma, &ps.d_neu_coef};
+  if (ps.d_neu_dof) { cudaFree(ps.d_neu_dof); ps.d_neu_dof = nullptr; }
   for (auto p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
   if (ps.d_isdir) { cudaFree(ps.d_isdir); ps.d_isdir = nullptr; }
   if (ps.d_tw) { cudaFree(ps.d_tw); ps.d_tw = nullptr; }
@@ -568,14 +620,44 @@ static int32_t prepare_dense(iskb_ctx *c) {
                                   "for the dense fallback", (long long)nn);
   std::vector<double> A, b;
   assemble_dense(c, A, b);
-  // row equilibration: stencil rows carry 1/dh^2, Dirichlet rows 1 (generalized_poisson.jl:65,210-211);
-  // inverting D*A (and scaling the rhs in k_dense_rhs) keeps the inverse accurate to ~cond*eps
   const double d2 = c->g.dx * c->g.dx;
-  for (int64_t r = 0; r < nn; ++r)
-    if (!ps.isdir[(size_t)r])
-      for (int64_t col = 0; col < nn; ++col) A[(size_t)(r + col * nn)] *= d2;
+  std::vector<double> rowscale((size_t)nn, 1.0);
+  if (ps.n_sigma > 0 || !ps.neu_kind.empty()) {
+    // keep the phi block; the sigma columns go to the right-hand side (k_dense_rhs_sigma)
+    const int64_t nt = nn + ps.n_sigma;
+    std::vector<double> P((size_t)(nn * nn)), coef((size_t)nn, 0.0);
+    std::vector<int32_t> dof((size_t)nn, 0);
+    for (int64_t col = 0; col < nn; ++col)
+      for (int64_t r = 0; r < nn; ++r) P[(size_t)(r + col * nn)] = A[(size_t)(r + col * nt)];
+    for (int64_t r = 0; r < nn; ++r)
+      if (!ps.neu_kind.empty() && ps.neu_kind[(size_t)r] && !ps.isdir[(size_t)r]) {
+        dof[(size_t)r] = ps.neu_dof[(size_t)r];
+        coef[(size_t)r] = A[(size_t)(r + (nn + dof[(size_t)r]) * nt)];
+      }
+    A.swap(P);
+    ISKB_TRY(upload(&ps.d_neu_coef, coef, c->stream));
+    if (ps.d_neu_dof) { cudaFree(ps.d_neu_dof); ps.d_neu_dof = nullptr; }
+    CU_TRY(cudaMalloc(&ps.d_neu_dof, nn * sizeof(int32_t)));
+    CU_TRY(cudaMemcpyAsync(ps.d_neu_dof, dof.data(), nn * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+  }
+  // row equilibration: stencil rows carry 1/dh^2, Dirichlet rows 1 (generalized_poisson.jl:65,210-211),
+  // Neumann rows 2/dx or 4/(3 dh^2) (:252-253,:262-265); inverting D*A (and scaling the rhs in
+  // k_dense_rhs) keeps the inverse accurate to ~cond*eps
+  for (int64_t r = 0; r < nn; ++r) {
+    if (ps.isdir[(size_t)r]) continue;
+    double sc = d2;
+    if (!ps.neu_kind.empty() && ps.neu_kind[(size_t)r]) {
+      double mx = 0.0;
+      for (int64_t col = 0; col < nn; ++col) mx = std::fmax(mx, std::fabs(A[(size_t)(r + col * nn)]));
+      sc = mx > 0.0 ? 1.0 / mx : 1.0;
+    }
+    rowscale[(size_t)r] = sc;
+    for (int64_t col = 0; col < nn; ++col) A[(size_t)(r + col * nn)] *= sc;
+  }
   if (!invert_dense(A, nn)) return iskb_fail(ISKB_E_SINGULAR, "dense Poisson operator is singular");
   ISKB_TRY(upload(&ps.d_Ainv, A, c->stream));
+  ISKB_TRY(upload(&ps.d_rowscale, rowscale, c->stream));
   ps.nn_dense = nn;
   if (!ps.d_w1) CU_TRY(cudaMalloc(&ps.d_w1, nn * sizeof(double)));
   ps.mode = 2;
@@ -607,7 +689,9 @@ int32_t poisson_prepare(iskb_ctx *c) {
           if (!cov) { whole = false; break; }
         }
     AxisInfo axi{}, axj{};
-    bool sep = whole && c->g.dx == c->g.dy;
+    bool has_neumann = ps.n_sigma > 0;
+    for (uint8_t k : ps.neu_kind) has_neumann |= k != 0;
+    bool sep = whole && c->g.dx == c->g.dy && !has_neumann;
     sep = sep && classify_axis(ps.periodic_i, eL, eR, nx, axi) && classify_axis(ps.periodic_j, eB, eT, ny, axj);
     // choose the transform axis: the solve axis needs >= 3 unknowns when cyclic, >= 1 otherwise
     auto ok_solve = [](const AxisInfo &b) { return b.kind == AX_RING ? b.m >= 3 : b.m >= 1; };
@@ -725,6 +809,13 @@ int32_t poisson_prepare(iskb_ctx *c) {
     ps.structure_dirty = false;
     ps.values_dirty = true;
   }
+  if (ps.sigma_host_newer && ps.n_sigma > 0) {
+    if (!ps.d_sigma) CU_TRY(cudaMalloc(&ps.d_sigma, ISKB_MAX_SIGMA * sizeof(double)));
+    CU_TRY(cudaStreamSynchronize(c->fstream));
+    CU_TRY(cudaMemcpyAsync(ps.d_sigma, ps.sigma.data(), ps.n_sigma * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    ps.sigma_host_newer = false;
+  }
   if (ps.values_dirty) {
     if (!ps.d_dval) CU_TRY(cudaMalloc(&ps.d_dval, nn * sizeof(double)));
     CU_TRY(cudaMemcpyAsync(ps.d_dval, ps.dval.data(), nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -744,8 +835,12 @@ int32_t poisson_solve(iskb_ctx *c) {
   const int nx = c->g.nx, ny = c->g.ny;
   const int64_t nn = (int64_t)nx * ny;
   if (ps.mode == 2) {
-    k_dense_rhs<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(c->d_rho, ps.d_isdir, ps.d_dval, ps.eps0, c->g.dx * c->g.dx, nn,
-                                                          ps.d_w1);
+    if (ps.d_neu_coef && ps.n_sigma > 0)
+      k_dense_rhs_sigma<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(c->d_rho, ps.d_isdir, ps.d_dval, ps.eps0, ps.d_rowscale,
+                                                                  ps.d_neu_coef, ps.d_neu_dof, ps.d_sigma, nn, ps.d_w1);
+    else
+      k_dense_rhs<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(c->d_rho, ps.d_isdir, ps.d_dval, ps.eps0, c->g.dx * c->g.dx, nn,
+                                                            ps.d_w1);
     LAUNCH_CHECK(c);
     k_dense_gemv<<<(int)((nn + 127) / 128), 128, 0, c->fstream>>>(ps.d_Ainv, ps.d_w1, nn, c->d_phi);
     LAUNCH_CHECK(c);
@@ -796,6 +891,7 @@ int32_t poisson_solve(iskb_ctx *c) {
 }
 
 // ---- C ABI ------------------------------------------------------------------------------------
+static int32_t sigma_pull(iskb_ctx *c);
 extern "C" int32_t iskb_poisson_create(iskb_ctx *c, double eps0) {
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "iskb_grid_set must be called first");
   PoissonState &ps = c->ps;
@@ -805,6 +901,9 @@ extern "C" int32_t iskb_poisson_create(iskb_ctx *c, double eps0) {
   ps.periodic_i = ps.periodic_j = false;
   ps.isdir.assign((size_t)nn, 0);
   ps.dval.assign((size_t)nn, 0.0);
+  ps.n_sigma = 0;
+  ps.sigma.clear();
+  ps.neu_kind.clear(); ps.neu_i2.clear(); ps.neu_j2.clear(); ps.neu_dof.clear();
   ps.structure_dirty = ps.values_dirty = true;
   return ISKB_OK;
 }
@@ -824,6 +923,8 @@ extern "C" int32_t iskb_poisson_apply_dirichlet(iskb_ctx *c, const uint8_t *mask
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   for (int64_t n = 0; n < nn; ++n)
     if (mask[n]) {
+      if (!ps.neu_kind.empty() && ps.neu_kind[(size_t)n])
+        return iskb_fail(ISKB_E_UNSUPPORTED, "node %lld carries a Neumann row; overlapping electrodes are not supported", (long long)n);
       if (!ps.isdir[(size_t)n]) { ps.isdir[(size_t)n] = 1; ps.structure_dirty = true; }
       ps.dval[(size_t)n] = phi0;
       ps.values_dirty = true;
@@ -860,10 +961,122 @@ extern "C" int32_t iskb_poisson_apply_dirichlet_edge(iskb_ctx *c, int32_t edge, 
 
 extern "C" int32_t iskb_poisson_get_dense(iskb_ctx *c, double *A_out, double *b_out) {
   if (!c || !c->ps.created) return iskb_fail(ISKB_E_INVALID, "no Poisson solver");
+  ISKB_TRY(sigma_pull(c));
   std::vector<double> A, b;
   assemble_dense(c, A, b);
   if (A_out) memcpy(A_out, A.data(), A.size() * sizeof(double));
   if (b_out) memcpy(b_out, b.data(), b.size() * sizeof(double));
+  return ISKB_OK;
+}
+
+// ---- sigma dofs / Neumann rows / electrodes -----------------------------------
+// sigma lives on the device once the solver is built (electrode hits may add to it); before that, and
+// after host-side edits, the host vector is authoritative.
+static int32_t sigma_pull(iskb_ctx *c) {
+  PoissonState &ps = c->ps;
+  if (ps.sigma_host_newer || !ps.d_sigma || ps.n_sigma == 0) return ISKB_OK;
+  ISKB_TRY(fields_join(c));
+  CU_TRY(cudaStreamSynchronize(c->fstream));
+  CU_TRY(cudaMemcpyAsync(ps.sigma.data(), ps.d_sigma, ps.n_sigma * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  return ISKB_OK;
+}
+
+int32_t poisson_sigma_device(iskb_ctx *c, double **out) {
+  ISKB_TRY(poisson_prepare(c));
+  *out = c->ps.d_sigma;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_poisson_add_dof(iskb_ctx *c, int32_t *dof_out) {
+  if (!c || !c->ps.created) return iskb_fail(ISKB_E_INVALID, "no Poisson solver");
+  PoissonState &ps = c->ps;
+  if (ps.n_sigma >= ISKB_MAX_SIGMA) return iskb_fail(ISKB_E_UNSUPPORTED, "more than %d sigma dofs", ISKB_MAX_SIGMA);
+  ISKB_TRY(sigma_pull(c));
+  ps.sigma.push_back(0.0);                       // :228  b[s] = 0
+  ps.n_sigma++;
+  ps.sigma_host_newer = true;
+  ps.structure_dirty = true;
+  if (dof_out) *dof_out = ps.n_sigma;            // :229 length(s)
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_poisson_apply_neumann(iskb_ctx *c, const uint8_t *mask, int32_t dof) {
+  if (!c || !c->ps.created || !mask) return iskb_fail(ISKB_E_INVALID, "no Poisson solver / mask");
+  PoissonState &ps = c->ps;
+  if (dof < 1 || dof > ps.n_sigma) return iskb_fail(ISKB_E_INVALID, "sigma dof %d does not exist", dof);
+  const int nx = c->g.nx, ny = c->g.ny;
+  const int64_t nn = (int64_t)nx * ny;
+  if (ps.neu_kind.empty()) {
+    ps.neu_kind.assign((size_t)nn, 0);
+    ps.neu_i2.assign((size_t)nn, 0);
+    ps.neu_j2.assign((size_t)nn, 0);
+    ps.neu_dof.assign((size_t)nn, 0);
+  }
+  auto nd = [&](int i, int j) { return mask[(size_t)(i + (int64_t)j * nx)] != 0; };
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i < nx; ++i) {
+      if (!nd(i, j)) continue;
+      const int64_t r = i + (int64_t)j * nx;
+      const bool a = i > 0 ? nd(i - 1, j) : false;          // :241-244
+      const bool b = i < nx - 1 ? nd(i + 1, j) : false;
+      const bool cc = j > 0 ? nd(i, j - 1) : true;
+      const bool d = j < ny - 1 ? nd(i, j + 1) : true;
+      int kind = 0;
+      if (cc && d && !a && !b) kind = 1;                    // :246-247
+      if (cc != d) kind = 2;                                // :256
+      if (!kind) continue;
+      if (ps.isdir[(size_t)r])
+        return iskb_fail(ISKB_E_UNSUPPORTED, "node (%d,%d) is already a Dirichlet node; overlapping electrodes are not supported",
+                         i + 1, j + 1);
+      ps.neu_kind[(size_t)r] = (uint8_t)kind;
+      ps.neu_i2[(size_t)r] = i == 0 ? i + 1 : i - 1;        // :249,:257
+      ps.neu_j2[(size_t)r] = cc ? j + 1 : j - 1;            // :258
+      ps.neu_dof[(size_t)r] = dof - 1;
+      if (kind == 2 && (ps.neu_j2[(size_t)r] < 0 || ps.neu_j2[(size_t)r] >= ny))
+        return iskb_fail(ISKB_E_INVALID, "Neumann strip end at (%d,%d) points outside the grid (reference: BoundsError)", i + 1, j + 1);
+    }
+  ps.structure_dirty = true;
+  return ISKB_OK;
+}
+
+static int32_t sigma_edit(iskb_ctx *c, int32_t dof, double v, int set) {
+  if (!c || !c->ps.created) return iskb_fail(ISKB_E_INVALID, "no Poisson solver");
+  PoissonState &ps = c->ps;
+  if (dof < 1 || dof > ps.n_sigma) return iskb_fail(ISKB_E_INVALID, "sigma dof %d does not exist", dof);
+  if (ps.sigma_host_newer || !ps.d_sigma) {
+    ps.sigma[(size_t)(dof - 1)] = set ? v : ps.sigma[(size_t)(dof - 1)] + v;
+    ps.sigma_host_newer = true;
+    return ISKB_OK;
+  }
+  // device copy is authoritative: edit it in stream order after a solve still in flight
+  k_sigma_add<<<1, 1, 0, c->fstream>>>(ps.d_sigma, dof - 1, v, set);
+  LAUNCH_CHECK(c);
+  return ISKB_OK;
+}
+extern "C" int32_t iskb_poisson_sigma_set(iskb_ctx *c, int32_t dof, double value) { return sigma_edit(c, dof, value, 1); }
+extern "C" int32_t iskb_poisson_sigma_add(iskb_ctx *c, int32_t dof, double delta) { return sigma_edit(c, dof, delta, 0); }
+extern "C" int32_t iskb_poisson_sigma_get(iskb_ctx *c, int32_t dof, double *out) {
+  if (!c || !c->ps.created || !out) return iskb_fail(ISKB_E_INVALID, "no Poisson solver");
+  if (dof < 1 || dof > c->ps.n_sigma) return iskb_fail(ISKB_E_INVALID, "sigma dof %d does not exist", dof);
+  ISKB_TRY(sigma_pull(c));
+  *out = c->ps.sigma[(size_t)(dof - 1)];
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_poisson_dense_size(iskb_ctx *c, int64_t *n_out) {
+  if (!c || !c->ps.created || !n_out) return iskb_fail(ISKB_E_INVALID, "no Poisson solver");
+  *n_out = (int64_t)c->g.nx * c->g.ny + c->ps.n_sigma;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_phi_at(iskb_ctx *c, int32_t i, int32_t j, double *out) {
+  if (!c || !c->has_grid || !out) return iskb_fail(ISKB_E_INVALID, "no grid");
+  if (i < 1 || i > c->g.nx || j < 1 || j > c->g.ny) return iskb_fail(ISKB_E_INVALID, "node (%d,%d) outside the grid", i, j);
+  ISKB_TRY(fields_join(c));
+  CU_TRY(cudaMemcpyAsync(c->h_scratch, c->d_phi + (i - 1) + (int64_t)(j - 1) * c->g.nx, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
+  memcpy(out, c->h_scratch, sizeof(double));
   return ISKB_OK;
 }
 

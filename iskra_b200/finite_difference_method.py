@@ -23,8 +23,10 @@ class PoissonSolver:
         return {1: "separable", 2: "dense"}[m.value]
 
     def dense(self):
-        """(A, b) exactly as the reference assembles them (debug / parity)."""
-        nn = len(self.grid)
+        """(A, b) exactly as the reference assembles them (debug / parity); sigma dofs come last."""
+        v = L.i64()
+        L.check(self._rt.lib.iskb_poisson_dense_size(self._rt.h, C.byref(v)))
+        nn = v.value
         A = np.zeros((nn, nn), order="F")
         b = np.zeros(nn)
         L.check(self._rt.lib.iskb_poisson_get_dense(self._rt.h, L.ptr(A), L.ptr(b)))
@@ -73,3 +75,70 @@ def calculate_magnetic_field(ps):
     """calculate_magnetic_field  :412-419: identically zero."""
     nx, ny = ps.grid.n
     return np.zeros((nx, ny, 3), order="F")
+
+
+def add_new_dof(ps, symbol="sigma"):
+    """add_new_dof(ps, :sigma)  :217-230 -> 1-based index of the new dof"""
+    if symbol not in ("sigma", "σ"):
+        raise NotImplementedError("only sigma dofs exist in the reference")
+    d = L.i32()
+    L.check(ps._rt.lib.iskb_poisson_add_dof(ps._rt.h, C.byref(d)))
+    return d.value
+
+
+def apply_neumann(ps, nodes, dof):
+    """apply_neumann(ps, nodes, dof)  :235-269"""
+    mask = np.asfortranarray(np.asarray(nodes, dtype=bool).astype(np.uint8))
+    L.check(ps._rt.lib.iskb_poisson_apply_neumann(ps._rt.h, L.ptr(mask), int(dof)))
+
+
+class SigmaRhs:
+    """get_rhs(ps, :sigma, dof)  :367-370 -- a handle on the device value: `.value`, `+=` via add()."""
+
+    def __init__(self, ps, dof):
+        self.ps, self.dof = ps, int(dof)
+
+    @property
+    def value(self):
+        v = L.f64()
+        L.check(self.ps._rt.lib.iskb_poisson_sigma_get(self.ps._rt.h, self.dof, C.byref(v)))
+        return v.value
+
+    @value.setter
+    def value(self, x):
+        L.check(self.ps._rt.lib.iskb_poisson_sigma_set(self.ps._rt.h, self.dof, float(x)))
+
+    def add(self, dx):
+        L.check(self.ps._rt.lib.iskb_poisson_sigma_add(self.ps._rt.h, self.dof, float(dx)))
+
+
+class DirichletRhs:
+    """get_rhs(ps, :phi, i, j) of a Dirichlet node: the value last given to apply_dirichlet (host side)."""
+
+    def __init__(self, value):
+        self.value = float(value)
+
+
+class PhiSolution:
+    """get_solution(ps, :phi, i, j)  :363-364 ; 1-based node"""
+
+    def __init__(self, ps, i, j):
+        self.ps, self.i, self.j = ps, int(i), int(j)
+
+    @property
+    def value(self):
+        v = L.f64()
+        L.check(self.ps._rt.lib.iskb_phi_at(self.ps._rt.h, self.i, self.j, C.byref(v)))
+        return v.value
+
+
+def get_rhs(ps, symbol, *idx):
+    if symbol in ("sigma", "σ"):
+        return SigmaRhs(ps, idx[0])
+    raise NotImplementedError("get_rhs(:phi) is only meaningful for Dirichlet nodes; see create_electrode")
+
+
+def get_solution(ps, symbol, i, j):
+    if symbol in ("phi", "ϕ", "φ"):
+        return PhiSolution(ps, i, j)
+    raise NotImplementedError(symbol)

@@ -281,6 +281,164 @@ def sort_by_cell_(part, grid, for_deposit=False):
     return perm
 
 
+# ---- surfaces: pic/surfaces/{build,track,check,hit}.jl, pic/circuit_coupling.jl ----
+class Surface:
+    """abstract type Surface  build.jl:8"""
+    kind = None
+    _sid = None
+
+
+class PeriodicSurface(Surface):
+    kind = L.SURF_PERIODIC
+
+
+class AbsorbingSurface(Surface):
+    kind = L.SURF_ABSORBING
+
+
+class ReflectiveSurface(Surface):
+    kind = L.SURF_REFLECTIVE
+
+
+def create_periodic_surface():
+    return PeriodicSurface()
+
+
+def create_absorbing_surface():
+    return AbsorbingSurface()
+
+
+def create_reflective_surface():
+    return ReflectiveSurface()
+
+
+class FixedPotentialElectrode(Surface):
+    """FixedPotentialElectrode  circuit_coupling.jl:5-9 (phi, dq, area)"""
+    kind = L.SURF_ELECTRODE_FIXED
+
+    def __init__(self, phi, dq, area):
+        self.phi, self._dq, self.area = phi, float(dq), float(area)
+        self._st = None
+
+    @property
+    def dq(self):
+        return self._dq
+
+
+class FloatingPotentialElectrode(Surface):
+    """FloatingPotentialElectrode  circuit_coupling.jl:11-16: fields (sigma, phi, dq, area) IN THIS ORDER.
+    problem/configuration.jl:70 passes (phi0, sigma0, ...), so `.sigma` is the potential of the reference
+    node and `.phi` the sigma right-hand side (quirk S1); kept as is."""
+    kind = L.SURF_ELECTRODE_FLOATING
+
+    def __init__(self, sigma, phi, dq, area):
+        self.sigma, self.phi, self._dq0, self.area = sigma, phi, float(dq), float(area)
+        self._st = None
+        self._dof = 0
+
+    @property
+    def dq(self):
+        """s.dq: charge collected on the device since the last reset"""
+        if self._st is None or self._sid is None:
+            return self._dq0
+        v = L.f64()
+        L.check(self._st._rt.lib.iskb_surface_charge(self._st._h, self._sid, C.byref(v), 0))
+        return self._dq0 + v.value
+
+    @dq.setter
+    def dq(self, value):
+        self._dq0 = float(value)
+        if self._st is not None and self._sid is not None:
+            L.check(self._st._rt.lib.iskb_surface_charge(self._st._h, self._sid, None, 1))
+
+
+class SurfaceTracker:
+    """SurfaceTracker{2}  build.jl:13-18 -- the Dict lives on the device as a per-cell face table."""
+
+    def __init__(self, grid, ds=None):
+        ds = AbsorbingSurface() if ds is None else ds
+        self._rt = grid._rt
+        self.dh = grid.dh[0]                                   # build.jl:96-97
+        h = L.vp()
+        L.check(self._rt.lib.iskb_tracker_create(self._rt.h, ds.kind, C.byref(h)))
+        self._h = h
+        self.surfaces = [ds]
+
+    def get(self, bc, default=None):
+        """get(st, ((i,j),(k,l)), nothing)  build.jl:113-117 -> surface kind or default"""
+        (i, j), (k, l) = bc
+        v = L.i32()
+        L.check(self._rt.lib.iskb_tracker_lookup(self._h, i, j, k, l, C.byref(v)))
+        return default if v.value < 0 else v.value
+
+    def route_hits_to_sigma(self, on=True):
+        L.check(self._rt.lib.iskb_tracker_route_hits_to_sigma(self._h, 1 if on else 0))
+
+
+def create_surface_tracker(grid, ds=None):
+    """create_surface_tracker(grid::CartesianGrid{2}, ds=AbsorbingSurface())  build.jl:95-100"""
+    return SurfaceTracker(grid, ds)
+
+
+def track_surface_(st, bcs, ss):
+    """track_surface!(st, bcs::BitArray{2}, ss)  build.jl:109-111"""
+    mask = np.asfortranarray(np.asarray(bcs, dtype=bool).astype(np.uint8))
+    sid = L.i32()
+    dof = getattr(ss, "_dof", 0) if ss.kind == L.SURF_ELECTRODE_FLOATING else 0
+    area = getattr(ss, "area", 0.0)
+    L.check(st._rt.lib.iskb_tracker_track_surface(st._h, L.ptr(mask), ss.kind, dof, area, C.byref(sid)))
+    ss._sid, ss._st = sid.value, st
+    st.surfaces.append(ss)
+
+
+def track_(st, part, dt, grid=None):
+    """track!(st, part, dt)  track.jl:41-52 -> number of tracked particles"""
+    if st is None:
+        return 0
+    part._push(grid)
+    n = L.i64()
+    L.check(st._rt.lib.iskb_tracker_track(st._h, part._h, float(dt), C.byref(n)))
+    return n.value
+
+
+def check_(st, part, dt):
+    """check!(st, part, dt)  check.jl:38-68 -> (too_fast, n_absorbed)"""
+    if st is None:
+        return False, 0
+    n, tf = L.i64(), L.i32()
+    L.check(st._rt.lib.iskb_tracker_check(st._h, part._h, float(dt), C.byref(n), C.byref(tf)))
+    part._touched_on_device()
+    if tf.value:
+        print("ERROR: %s particle is too fast" % part)          # check.jl:44-46
+    return bool(tf.value), n.value
+
+
+class PlasmaDevice:
+    """PlasmaDevice <: Circuit.CircuitDevice  circuit_coupling.jl:18-25"""
+
+    def __init__(self, positive, negative):
+        self.positive, self.negative = positive, negative
+
+    def voltage(self):
+        return self.positive.phi.value - self.negative.phi.value   # :23-25
+
+
+def advance_circuit_coupling_(circuit, phi, dt, config):
+    """advance!(circuit, phi, dt, config)  circuit_coupling.jl:33-43 (foo! :26-32 inlined)"""
+    if circuit is None:
+        return 0.0
+    from . import circuit as CIR
+    from . import finite_difference_method as FDM
+    CIR.advance_circuit_(circuit, 0, dt)
+    if isinstance(circuit.ext, PlasmaDevice):
+        circuit.ext.positive.dq = 0.0
+        dsig = -dt * circuit.i / circuit.ext.positive.area
+    else:
+        dsig = 0.0
+    FDM.get_rhs(config.solver, "sigma", 1).add(dsig)            # :41-42
+    return dsig
+
+
 # ---- hooks and loop (ParticleInCell.jl:37-45, 51-72, 84-139) --------------------------------------
 class Hooks:
     def __init__(self):
@@ -298,7 +456,9 @@ def advance_(part, E, B, dt, config):
     grid = config.grid
     if E is not None:
         grid._rt.set_fields(E=E)
+    track_(config.tracker, part, dt, grid)                          # :56
     push_particles_(config.pusher, part, None, None, dt, grid)     # gather :57 + push :59 fused
+    check_(config.tracker, part, dt)                                # :60
     hooks.after_push(part, grid)                                    # :61
 
 
@@ -326,6 +486,8 @@ def solve(config, dt=1e-5, timesteps=200, after_push=None, sort_interval=0, fuse
         rt.set_after_push(mx, my)
         rt.set_sort_interval(sort_interval)
     for it in range(1, timesteps + 1):
+        if fused and config.circuit is not None:
+            raise NotImplementedError("the circuit advances between advance! and density (:116); use fused=False")
         if fused:
             rt.step(dt, 1)
             for s in kinetic:
@@ -335,6 +497,7 @@ def solve(config, dt=1e-5, timesteps=200, after_push=None, sort_interval=0, fuse
                 inter.perform_(None, dt, config)
             for part in kinetic:                                              # :113-115
                 advance_(part, None, None, dt, config)
+            advance_circuit_coupling_(config.circuit, None, dt, config)       # :116
             L.check(rt.lib.iskb_rho_zero(rt.h))                               # :118
             for part in kinetic:                                              # :119-124
                 part._push(grid)

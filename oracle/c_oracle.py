@@ -147,3 +147,56 @@ class CMcc:
         rc = lib().orc_mcc_perform(C.byref(self.c), C.byref(grid), dp(E), C.c_double(dt),
                                    dp(nu) if want_nu else None, out, C.byref(rng))
         return rc, nu, int(out[0]), int(out[1])
+
+
+# ---- surface tracker ---------------------------------------------------------
+class Tracker(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("dh", C.c_double), ("face", C.POINTER(C.c_uint8)),
+                ("tracked", C.POINTER(C.c_uint8)), ("kind", C.POINTER(C.c_int32)), ("area", c_dp), ("dq", c_dp)]
+
+
+class TrackedParticle(C.Structure):
+    _fields_ = [("dt", C.c_double), ("p", C.c_int64), ("i", C.c_int32), ("j", C.c_int32),
+                ("hx", C.c_double), ("hy", C.c_double)]
+
+
+_DIRS = {(0, -1): 0, (1, 0): 1, (0, 1): 2, (-1, 0): 3}
+
+
+class CTracker:
+    """Flattens the Dict of an oracle.surfaces_oracle.SurfaceTracker into the C table."""
+
+    def __init__(self, st, nx, ny):
+        self.nx, self.ny = nx, ny
+        self.face = np.zeros(4 * (nx + 1) * (ny + 1), dtype=np.uint8)
+        self.tracked = np.zeros((nx + 1) * (ny + 1), dtype=np.uint8)
+        self.surfaces = [None]
+        ids = {}
+        for ((i, j), (k, l)), s in st.surface.items():
+            if id(s) not in ids:
+                ids[id(s)] = len(self.surfaces)
+                self.surfaces.append(s)
+            self.face[4 * (i + j * (nx + 1)) + _DIRS[(k - i, l - j)]] = ids[id(s)]
+            for (a, b) in ((i, j), (k, l)):
+                if 0 <= a <= nx and 0 <= b <= ny:
+                    self.tracked[a + b * (nx + 1)] = 1
+        self.kind = np.array([-1] + [s.kind for s in self.surfaces[1:]], dtype=np.int32)
+        self.area = np.array([0.0] + [getattr(s, "area", 0.0) for s in self.surfaces[1:]])
+        self.dq = np.zeros(len(self.surfaces))
+        self.c = Tracker(nx, ny, st.dh, self.face.ctypes.data_as(C.POINTER(C.c_uint8)),
+                         self.tracked.ctypes.data_as(C.POINTER(C.c_uint8)),
+                         self.kind.ctypes.data_as(C.POINTER(C.c_int32)), dp(self.area), dp(self.dq))
+        self.queue = None
+
+    def advance(self, sp, grid, E, dt, bmode=(0, 0)):
+        """advance! with the tracker -> (n_absorbed, too_fast)"""
+        L = lib()
+        L.orc_advance_tracked.restype = C.c_int64
+        qcap = max(sp.cap, 1)
+        if self.queue is None or len(self.queue) < qcap:
+            self.queue = (TrackedParticle * qcap)()
+        tf = C.c_int32(0)
+        E = np.ascontiguousarray(E)
+        n = L.orc_advance_tracked(sp.ref(), C.byref(grid), C.byref(self.c), dp(E), C.c_double(dt),
+                                  (C.c_int32 * 2)(*bmode), self.queue, C.c_int64(qcap), C.byref(tf))
+        return int(n), bool(tf.value)

@@ -578,3 +578,136 @@ void orc_deposit_mt(const orc_grid *g, const orc_species *s, double *u) {
     u[n00 + nx + 1] += c11;
   }
 }
+
+/* ==== SURVEY.md 8f row N1: surface tracker (ParticleInCell/src/pic/surfaces/{build,track,check,hit}.jl) ==================
+ * The reference's Dict{(cell,cell) -> Surface} is flattened into a table over the cells
+ * 0..nx x 0..ny with four directed faces per cell  0:(i,j-1) 1:(i+1,j) 2:(i,j+1) 3:(i-1,j)
+ * holding a surface id (0 = no key).  Kinds: 0 periodic (no-op hit!), 1 absorbing, 2 reflective,
+ * 3 fixed electrode, 4 floating electrode.  The FIFO of check! (check.jl:48-62) is kept literally:
+ * a ring buffer of tuples, popfirst!/push!, so electrode charge sums run in the reference's order. */
+typedef struct {
+  int32_t nx, ny;          /* nodes */
+  double dh;               /* st.dh  build.jl:17 */
+  uint8_t *face;           /* 4*(nx+1)*(ny+1) */
+  uint8_t *tracked;        /* (nx+1)*(ny+1): Base.in(::BoundaryCell, st)  build.jl:86-93 */
+  int32_t *kind;           /* per surface id */
+  double *area;
+  double *dq;              /* s.dq  circuit_coupling.jl:49-50 */
+} orc_tracker;
+
+typedef struct { double dt; int64_t p; int32_t i, j; double hx, hy; } orc_tp;   /* TrackedParticle{2}  build.jl:5 */
+
+static inline int trk_dir(int32_t i, int32_t j, int32_t k, int32_t l) {
+  if (k == i && l == j - 1) return 0;
+  if (k == i + 1 && l == j) return 1;
+  if (k == i && l == j + 1) return 2;
+  return 3;
+}
+
+/* check(pt::TrackedParticle{2}, pv, dh)  check.jl:17-36 */
+static orc_tp trk_check1(orc_tp pt, const orc_species *s, double dh) {
+  double vx = s->vx[pt.p], vy = s->vy[pt.p];
+  double dx = (vx > 0) ? dh * (1 - pt.hx) : dh * pt.hx;
+  double dy = (vy > 0) ? dh * (1 - pt.hy) : dh * pt.hy;
+  double dtx = dx / fabs(vx), dty = dy / fabs(vy);
+  if (pt.dt < dtx && pt.dt < dty) return pt;
+  orc_tp o = pt;
+  if (dtx < dty) {
+    o.dt = pt.dt - dtx;
+    o.hy = pt.hy + vy * dtx / dh;
+    if (vx > 0) { o.i = pt.i + 1; o.hx = 0.; } else { o.i = pt.i - 1; o.hx = 1.; }
+  } else {
+    o.dt = pt.dt - dty;
+    o.hx = pt.hx + vx * dty / dh;
+    if (vy > 0) { o.j = pt.j + 1; o.hy = 0.; } else { o.j = pt.j - 1; o.hy = 1.; }
+  }
+  return o;
+}
+
+static int cmp_i64_desc(const void *a, const void *b) {
+  int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
+  return (x < y) - (x > y);
+}
+
+/* track! (track.jl:42-52) -> push (caller) -> check! (check.jl:39-68).  orc_track fills `queue`
+ * (capacity >= np) and returns the number of tracked particles; orc_check consumes it and returns the
+ * number absorbed; *too_fast is the condition of the printed message (:41-46). */
+int64_t orc_track(const orc_tracker *t, const orc_species *s, double dt, orc_tp *queue) {
+  int64_t n = 0;
+  for (int64_t p = 0; p < s->np; ++p) {
+    int64_t i, j;
+    double hx, hy;
+    cell1(s->x[p], t->dh, &i, &hx);      /* particle_cell(px, p, st.dh): scalar dh for both axes */
+    cell1(s->y[p], t->dh, &j, &hy);
+    if (i < 0 || i > t->nx || j < 0 || j > t->ny) continue;
+    if (!t->tracked[i + j * (t->nx + 1)]) continue;
+    orc_tp pt = {dt, p, (int32_t)i, (int32_t)j, hx, hy};
+    queue[n++] = pt;
+  }
+  return n;
+}
+
+int64_t orc_check(orc_tracker *t, orc_species *s, double dt, orc_tp *queue, int64_t n_tracked, int64_t qcap,
+                  int32_t *too_fast) {
+  double vmax = t->dh / dt;
+  int tf = 0;
+  for (int64_t p = 0; p < s->np; ++p)
+    if (fabs(s->vx[p]) > vmax || fabs(s->vy[p]) > vmax || fabs(s->vz[p]) > vmax) tf = 1;
+  if (too_fast) *too_fast = tf;
+  int64_t *absorbed = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_tracked > 0 ? n_tracked : 1));
+  int64_t nabs = 0, head = 0, tail = n_tracked % qcap, count = n_tracked;
+  while (count > 0) {
+    orc_tp pt = queue[head];                         /* popfirst! */
+    head = (head + 1) % qcap;
+    --count;
+    orc_tp p2 = trk_check1(pt, s, t->dh);
+    if (p2.i == pt.i && p2.j == pt.j) continue;
+    int sid = 0;
+    if (pt.i >= 0 && pt.i <= t->nx && pt.j >= 0 && pt.j <= t->ny)
+      sid = t->face[4 * (pt.i + pt.j * (t->nx + 1)) + trk_dir(pt.i, pt.j, p2.i, p2.j)];
+    if (!sid) {                                      /* track!(st, pt') */
+      queue[tail] = p2; tail = (tail + 1) % qcap; ++count;
+      continue;
+    }
+    int kind = t->kind[sid];
+    if (kind == 1 || kind == 3) {                    /* absorbed! */
+      absorbed[nabs++] = pt.p;
+    } else if (kind == 4) {                          /* circuit_coupling.jl:44-53 (sigma update: quirk S1, no effect) */
+      t->dq[sid] += s->q * s->wg[pt.p];
+      absorbed[nabs++] = pt.p;
+    } else if (kind == 2) {                          /* hit.jl:39-56 */
+      int64_t p = pt.p;
+      s->x[p] -= s->vx[p] * p2.dt;
+      s->y[p] -= s->vy[p] * p2.dt;
+      if (p2.i != pt.i) s->vx[p] *= -1;
+      if (p2.j != pt.j) s->vy[p] *= -1;
+      s->x[p] += s->vx[p] * p2.dt;
+      s->y[p] += s->vy[p] * p2.dt;
+      orc_tp p3 = p2;                                /* scattered!  hit.jl:12-20 */
+      if (p2.hx == 0.) { p3.i = p2.i - 1; p3.hx = 1.; }
+      if (p2.hx == 1.) { p3.i = p2.i + 1; p3.hx = 0.; }
+      if (p2.hy == 0.) { p3.j = p2.j - 1; p3.hy = 1.; }
+      if (p2.hy == 1.) { p3.j = p2.j + 1; p3.hy = 0.; }
+      queue[tail] = p3; tail = (tail + 1) % qcap; ++count;
+    }                                                /* kind 0: generic no-op hit! */
+  }
+  qsort(absorbed, (size_t)nabs, sizeof(int64_t), cmp_i64_desc);   /* SortedSet(Reverse) */
+  for (int64_t k = 0; k < nabs; ++k)
+    if (k == 0 || absorbed[k] != absorbed[k - 1]) remove1(s, absorbed[k]);
+  free(absorbed);
+  return nabs;
+}
+
+/* advance!(part, E, B, dt, config) with config.tracker  ParticleInCell.jl:51-61 */
+int64_t orc_advance_tracked(orc_species *s, const orc_grid *g, orc_tracker *t, const double *E, double dt,
+                            const int32_t *bmode, orc_tp *queue, int64_t qcap, int32_t *too_fast) {
+  int64_t n = orc_track(t, s, dt, queue);
+  double *pE = (double *)malloc(sizeof(double) * 3 * (size_t)(s->np > 0 ? s->np : 1));
+  orc_gather(g, s, E, pE);
+  orc_push(s, pE, dt);
+  free(pE);
+  int64_t nabs = orc_check(t, s, dt, queue, n, qcap, too_fast);
+  for (int d = 0; d < 2; ++d) if (bmode[d] == 2) orc_discard(s, g, d + 1);
+  for (int d = 0; d < 2; ++d) if (bmode[d] == 1) orc_wrap(s, g, d + 1);
+  return nabs;
+}
