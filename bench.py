@@ -31,7 +31,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c4"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c4", "walls"])
     ap.add_argument("--particles-per-gpu", type=int, default=None)
     ap.add_argument("--cells", type=int, default=None)
     ap.add_argument("--sort-interval", type=int, default=4)
@@ -50,10 +50,16 @@ def workload_defaults(a):
     return a.particles_per_gpu or 100_000_000, a.cells or 1024
 
 
+def algo_kernel(a):
+    return "k_advance_tracked" if a.workload == "walls" else "k_advance_tiled"
+
+
 def config_dict(a, ppg, cells, n_gpus, extra=None):
     names = {"c5": "C5 shard: 2D XY RF discharge + MCC (BASELINE configs[4]), %dx%d grid, %.3g particles per GPU "
                    "(1e9 over 8 GPUs), index-slice sharding, rho all-reduce, replicated field solve",
-             "c4": "C4: 2D XY two-stream (BASELINE configs[3]), %dx%d grid, %.3g particles per GPU, periodic"}
+             "c4": "C4: 2D XY two-stream (BASELINE configs[3]), %dx%d grid, %.3g particles per GPU, periodic",
+             "walls": "N1 (SURVEY 8f): bounded RF cell with surface tracker -- %dx%d grid, %.3g particles per GPU, "
+                      "2 fixed electrodes, absorbing walls, reflective block, no MCC"}
     d = {"workload": names[a.workload] % (cells, cells, ppg), "grid_cells": [cells, cells],
          "particles_per_gpu": ppg, "particles_total": ppg * n_gpus, "sort_interval": a.sort_interval,
          "sort_policy": {"miss_threshold": a.sort_miss, "max_interval": a.sort_max, "full_interval": a.sort_full},
@@ -81,10 +87,10 @@ def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
     cores = Lc.orc_num_threads()
     rng = np.random.default_rng(0)
     n_each = n_particles // 2
-    if a.workload == "c5":
+    if a.workload in ("c5", "walls"):
         dh, dt = 6.7 * 0.01 / 128, 1 / (400 * 13.56e6)
         spec = [("e-", -O.qe, O.me, 30000.0, 0.0), ("He+", O.qe, 3.99 * O.mp, 300.0, 0.0)]
-        bmode = (2, 1)
+        bmode = (2, 1) if a.workload == "c5" else (2, 2)
     else:
         w = 2 * math.pi * 9e3 * math.sqrt(2e-6 * 1e24)
         dh = 5e-3 * O.c0 / w
@@ -129,18 +135,39 @@ def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
         t0 = time.perf_counter()
         fn(probe.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), (C.c_int32 * 2)(1, 1))
         tt.append(time.perf_counter() - t0)
-    use_mt = cores > 1 and tt[1] < 0.8 * tt[0]
+    use_mt = cores > 1 and tt[1] < 0.8 * tt[0] and a.workload != "walls"
     adv = Lc.orc_advance_mt if use_mt else Lc.orc_advance
     dep = Lc.orc_deposit_mt if use_mt else Lc.orc_deposit
     if not use_mt:
         cores = 1
+
+    ctr = None
+    if a.workload == "walls":
+        # the reference's advance! with config.tracker (track! / check!, FIFO walk): single thread like the reference
+        from oracle import surfaces_oracle as SO
+        og = O.CartesianGrid2(np.arange(nx) * dh, np.arange(ny) * dh)
+        ost = SO.create_surface_tracker(og)
+        m1 = np.zeros((nx, ny), dtype=bool)
+        m1[0, :] = True
+        m2 = np.zeros((nx, ny), dtype=bool)
+        m2[nx - 1, :] = True
+        m3 = np.zeros((nx, ny), dtype=bool)
+        b0, b1 = (3 * cells) // 8, (5 * cells) // 8
+        m3[b0:b1 + 1, b0:b1 + 1] = True
+        SO.track_surface_(ost, m1, SO.FixedPotentialElectrode(None, 0.0))
+        SO.track_surface_(ost, m2, SO.FixedPotentialElectrode(None, 0.0))
+        SO.track_surface_(ost, m3, SO.create_reflective_surface())
+        ctr = CO.CTracker(ost, nx, ny)
 
     def one_step():
         cnt = sum(s.np for s in sp)
         for m in mccs:
             m.perform(cg, E, dt, rngc, want_nu=False)
         for s in sp:
-            adv(s.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), bm)
+            if ctr is not None:
+                ctr.advance(s, cg, E, dt, bmode=bmode)
+            else:
+                adv(s.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), bm)
         for s in sp:
             dep(C.byref(cg), s.ref(), CO.dp(u))
         return cnt
@@ -153,9 +180,9 @@ def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
         done += one_step()
     el_s = time.perf_counter() - t0
     return {"value": done / el_s, "unit": "particle-steps/s", "cores": int(cores), "kind": "port",
-            "sample": "C oracle (%d thread(s); OpenMP used only when faster on this host): MCC + gather + push + boundary + deposit on %d particles, "
-                      "%dx%d grid, %d steps; field solve excluded (reference dense LU impossible at this size)"
-                      % (cores, n_particles, cells, cells, steps),
+            "sample": ("C oracle (%d thread(s); OpenMP used only when faster on this host): MCC + " + ("track!/check! + " if ctr is not None else "")
+                       + "gather + push + boundary + deposit on %d particles, %dx%d grid, %d steps; field solve excluded "
+                       "(reference dense LU impossible at this size)") % (cores, n_particles, cells, cells, steps),
             "seconds": el_s, "steps": steps}
 
 
@@ -239,6 +266,7 @@ def run_b200(a):
     ppg, cells = workload_defaults(a)
     t_build = time.perf_counter()
     wl = (workloads.build_c5(ppg, cells, n_gpus_total=8, device=local) if a.workload == "c5"
+          else workloads.build_walls(ppg, cells, device=local) if a.workload == "walls"
           else workloads.build_c4(ppg, cells, device=local))
     rt = wl.rt
     rt.use_torch_stream()
@@ -296,7 +324,7 @@ def run_b200(a):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-            "kernel": "k_advance_tiled", "peak_source": peak_src}
+            "kernel": algo_kernel(a), "peak_source": peak_src}
     if adv_launches > 0 and adv_ms > 0:
         per_launch_particles = psteps_local / adv_launches
         per_launch_s = adv_ms * 1e-3 / adv_launches

@@ -451,11 +451,13 @@ int32_t launch_advance_tracked(iskb_species *sp, double dt, int mode_x, int mode
   ISKB_TRY(tracker_prepare(c->tracker, &t));
   const double qm = sp->q / sp->m;
   ISKB_TRY(sp_vmax_reset(sp));
+  ISKB_TRY(prof_begin(c));
   k_advance_tracked<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5],
                                                          sp->d_cnt, c->g, t, c->d_E2, sp->q, qm, dt, mode_x, mode_y,
                                                          deposit ? sp->d_u : nullptr, c->d_status, sp->d_vmax2,
                                                          c->tracker->d_counts);
   LAUNCH_CHECK(c);
+  ISKB_TRY(prof_end(c));
   sp->counts_stale = true;
   return ISKB_OK;
 }

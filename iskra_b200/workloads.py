@@ -5,6 +5,10 @@
        i=nx (0 V), "periodic" in j, discard! dim 1 / wrap! dim 2, e- at 30 000 K + He+ at 300 K
        loaded uniformly, He background 9.64e20 m^-3 at 300 K, 4 + 2 MCC processes (synthetic
        tables, datasets.py).  1e9 particles over 8 GPUs = 1.25e8 per GPU (index-slice sharding).
+  walls : SURVEY.md 8f row N1 at scale -- a bounded RF cell: 1025x1025 nodes, the RF-driven electrode
+       (i = 1) and the grounded one (i = nx) registered as FixedPotentialElectrode surfaces, default
+       AbsorbingSurface on the other two faces, a ReflectiveSurface block inside, e- + He+ loaded
+       uniformly outside the block, no MCC.  advance! runs with config.tracker (track! / check!).
   c4 : 2-D XY two-stream (configs[3]) -- 1025x1025 nodes, dh and CFL of problem/10_two_streams.jl,
        fully "periodic", two +-1e7 m/s electron beams at 300 K + co-located ions, wrap! both axes.
 """
@@ -148,3 +152,44 @@ def build_c4(particles_per_gpu=100_000_000, cells=1024, seed=1, capacity_factor=
     cfg.species, cfg.interactions = [e, iHe], []
     meta = {"grid_nodes": [nx, ny], "dh": dh, "dt": dt, "particles_per_gpu": 2 * n_each, "mcc_processes": []}
     return Workload("c4", cfg, dt, (L.BND_WRAP, L.BND_WRAP), meta=meta)
+
+
+def build_walls(particles_per_gpu=100_000_000, cells=1024, seed=3, device=None):
+    """N1 at scale: electrodes, absorbing walls and a reflecting block (see the module docstring)."""
+    from . import configuration as CFG
+    dh = 6.7 * 0.01 / 128
+    f = 13.56e6
+    dt = 1 / (400 * f)
+    ne = 2.56e14
+    n_each = particles_per_gpu // 2
+    grid = RG.create_uniform_grid(np.arange(cells + 1) * dh, np.arange(cells + 1) * dh, device=device)
+    grid._rt.comm_init_torch()
+    nx, ny = grid.n
+    wgt = ne * (cells * dh) ** 2 / n_each
+    cap = n_each + 1024
+    e = PIC.create_kinetic_species("e-", cap, -qe, me, wgt)
+    iHe = PIC.create_kinetic_species("He+", cap, +qe, 3.99 * mp, wgt)
+    cfg = Config()
+    cfg.grid, cfg.solver, cfg.pusher = grid, FDM.create_poisson_solver(grid, eps0), PIC.create_boris_pusher()
+    left = np.zeros((nx, ny), dtype=bool)
+    left[0, :] = True
+    right = np.zeros((nx, ny), dtype=bool)
+    right[nx - 1, :] = True
+    block = np.zeros((nx, ny), dtype=bool)
+    b0, b1 = (3 * cells) // 8, (5 * cells) // 8
+    block[b0:b1 + 1, b0:b1 + 1] = True
+    CFG.create_electrode(left, cfg, fixed=True, phi=0.0)
+    CFG.create_electrode(right, cfg, fixed=True, phi=0.0)
+    PIC.track_surface_(cfg.tracker, block, PIC.create_reflective_surface())
+    _load_uniform(e, grid, n_each, 30000.0, [0.0, 0.0, 0.0], seed * 1000 + 1)
+    _load_uniform(iHe, grid, n_each, 300.0, [0.0, 0.0, 0.0], seed * 1000 + 2)
+    # empty the block: particles loaded inside it are mirrored to the strip left of it
+    for s in (e, iHe):
+        x = s.x
+        n = s.np
+        inside = (x[:n, 0] >= b0 * dh) & (x[:n, 0] <= b1 * dh) & (x[:n, 1] >= b0 * dh) & (x[:n, 1] <= b1 * dh)
+        x[:n, 0][inside] -= (b1 - b0 + 1) * dh
+    cfg.species, cfg.interactions = [e, iHe], []
+    meta = {"grid_nodes": [nx, ny], "dh": dh, "dt": dt, "particles_per_gpu": 2 * n_each, "mcc_processes": [],
+            "surfaces": "2 fixed electrodes (whole edges), default absorbing, reflective block %d..%d" % (b0, b1)}
+    return Workload("walls", cfg, dt, (L.BND_DISCARD, L.BND_DISCARD), rf=(L.EDGE_LEFT, 450.0, f), meta=meta)
