@@ -23,8 +23,9 @@
 // The particle arithmetic (gather, push, boundary, cell index) is bit-identical to the oracle;
 // the deposit differs from the reference's sequential sum only in summation order.
 #include <cstdlib>
+#include <cstring>
 
-#include "pic_device.cuh"
+#include "surfaces_device.cuh"
 
 namespace {
 
@@ -69,18 +70,24 @@ __device__ __forceinline__ int clamp_origin(int o, int n, int wn) {
 struct DrainOut {
   double vm2;
   unsigned dead;
+  bool too_fast;   // TRACK: check!'s message condition seen on one of this lane's rows
 };
 
 // Advance `count` (<= 32) queued rows straight from / to global memory: same arithmetic as the
 // windowed path, E from the global field, deposit with global REDs.  Not inlined so that its
 // registers do not count against the main loop.
-template <int MX, int MY>
+// TRACK: rows in cells next to a surface (track!, track.jl:42-52) are not advanced here either: their row
+// index goes to the species' tracked list, and k_advance_tracked (surfaces.cu) advances exactly those rows
+// with the cell walk of check! right after this kernel.  An out-of-line walk inside this kernel would cost
+// the hot loop its spill-free register allocation (measured: 100 B of spills, 1.67 vs 1.31 ms per launch).
+template <int MX, int MY, bool TRACK>
 __device__ __forceinline__ DrainOut drain_rows(const uint32_t *q, int count, int lane, double *__restrict__ X,
                                             double *__restrict__ Y, double *__restrict__ VX, double *__restrict__ VY,
                                             double *__restrict__ VZ, const double *__restrict__ WG, const GridDev &g,
                                             const double2 *__restrict__ E2, double qm, double dt, double c1, double *u,
-                                            int *status) {
-  DrainOut out{0.0, 0u};
+                                            int *status, const uint8_t *__restrict__ trk_cells, uint32_t *trk_list,
+                                            unsigned *trk_n, double v_too_fast) {
+  DrainOut out{0.0, 0u, false};
   bool dead_now = false;
   if (lane < count) {
     const uint32_t p = q[lane];
@@ -90,6 +97,12 @@ __device__ __forceinline__ DrainOut drain_rows(const uint32_t *q, int count, int
     double hx, hy;
     cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
     cell1(py, g.dy, g.rdy, g.fast_div, j, hy);   // in the grid: checked before the row was queued
+    // track!: dx == dy on this path, so (i, j) is the cell particle_cell(px, p, st.dh) gives
+    bool trk = false;
+    if (TRACK) trk = trk_cells[i + j * (g.nx + 1)] != 0;
+    if (trk) {
+      trk_list[atomicAdd(trk_n, 1u)] = p;
+    } else {
     {
       const CicW gw = cic_weights(hx, hy);
       const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * g.nx;
@@ -103,6 +116,7 @@ __device__ __forceinline__ DrainOut drain_rows(const uint32_t *q, int count, int
     }
     px = push_x(px, vx, dt);
     py = push_x(py, vy, dt);
+    if (TRACK) out.too_fast = fmax(fmax(fabs(vx), fabs(vy)), fabs(vz)) > v_too_fast;   // check.jl:41-46
     out.vm2 = fma(vz, vz, fma(vy, vy, vx * vx));
     bool dead = (MX == ISKB_BND_DISCARD) && boundary_axis(px, g.ox, g.Lx, MX);
     if (!dead) dead = (MY == ISKB_BND_DISCARD) && boundary_axis(py, g.oy, g.Ly, MY);
@@ -129,6 +143,7 @@ __device__ __forceinline__ DrainOut drain_rows(const uint32_t *q, int count, int
         atomicOr(status, ISKB_ST_OOB);
       }
     }
+    }   // !trk
   }
   if (MX == ISKB_BND_DISCARD || MY == ISKB_BND_DISCARD) out.dead = __popc(__ballot_sync(0xffffffffu, dead_now));
   return out;
@@ -146,6 +161,17 @@ struct WarpSmem {
   unsigned char claim[WR * WR];
   unsigned stats[4];   // gather misses, deposit misses, window moves, discards (lane 0 updates them)
 };
+// TRACK adds one flag per cell of the E window: the cell is next to a surface (st.cells, build.jl:86-93)
+template <int WE, int WR>
+struct WarpSmemTrk : WarpSmem<WE, WR> {
+  unsigned char trk[WE * WE];
+  uint32_t tq[64];     // tracked rows waiting to be appended to the global list, 32 at a time
+  unsigned tcnt;       // (one global atomic per 32 rows: same-address atomics cost ~2 ns each on B200)
+};
+template <int WE, int WR, bool TRACK>
+struct SmemOf { typedef WarpSmem<WE, WR> type; };
+template <int WE, int WR>
+struct SmemOf<WE, WR, true> { typedef WarpSmemTrk<WE, WR> type; };
 
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
@@ -155,17 +181,19 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 
 constexpr int NOT_ANCHORED = -(1 << 20);   // window origin that no cell can fit
 
-template <int WE, int WR, int WARPS, int MINB, int MX, int MY, bool CLAIM>
+template <int WE, int WR, int WARPS, int MINB, int MX, int MY, bool CLAIM, bool TRACK>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restrict__ VX, double *__restrict__ VY,
                 double *__restrict__ VZ, const double *__restrict__ WG, int64_t *cnt, GridDev g,
                 const double2 *__restrict__ E2, double qm, double dt, double c1, double *u, int *status,
-                unsigned long long *vmax2, int64_t n_sorted) {
+                unsigned long long *vmax2, int64_t n_sorted, const uint8_t *__restrict__ trk_cells, uint32_t *trk_list,
+                unsigned *trk_n, double v_too_fast, int dbg) {
+  typedef typename SmemOf<WE, WR, TRACK>::type Smem;
   constexpr int mode_x = MX, mode_y = MY;   // after_push modes are compile-time: no mode branches per row
   constexpr int OFF = (WE - WR) / 2;        // the rho window is the central part of the E window
   extern __shared__ double2 s_dyn[];
   const int lane = threadIdx.x & 31;
-  WarpSmem<WE, WR> &sm = ((WarpSmem<WE, WR> *)s_dyn)[threadIdx.x >> 5];
+  Smem &sm = ((Smem *)s_dyn)[threadIdx.x >> 5];
   if (lane < 4) sm.stats[lane] = 0;
   for (int e = lane; e < WR * WR; e += 32) sm.rho[e] = 0.0;
   __syncwarp();
@@ -173,6 +201,11 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
   // velocity bound, statistics in shared memory): the body must fit 80 registers WITHOUT spills,
   // because a spill reload in the body shares its scoreboard with the row prefetch and makes its
   // consumer wait for the prefetch as well (profiles/r1h_ncu_advance_tiled.md).
+  bool too_fast = false;             // TRACK: check!'s message condition (check.jl:41-46), reported once per warp
+  if constexpr (TRACK) {
+    if (lane == 0) sm.tcnt = 0;
+    __syncwarp();
+  }
   int qn = 0;                        // rows waiting in the queue (warp-uniform)
   int ei0 = NOT_ANCHORED, ej0 = 0;   // node coordinates of the E window's lower-left corner
   float vm2 = 0.0f;                  // upper bound of max |v|^2 of this lane's rows (MCC pruning)
@@ -234,15 +267,50 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
           if (lane == 0) sm.stats[2] += 1;
           __syncwarp();
           load_E<WE>(sm.E, ei0, ej0, g, E2, lane);
+          if constexpr (TRACK) {
+            // cell (ei0+1+a, ej0+1+b) <-> window offset b*WE + a (same offset as its lower-left node)
+#pragma unroll
+            for (int k = 0; k < (WE * WE + 31) / 32; ++k) {
+              const int e = k * 32 + lane;
+              if (e < WE * WE) sm.trk[e] = trk_cells[(ei0 + 1 + (e % WE)) + (ej0 + 1 + (e / WE)) * (g.nx + 1)];
+            }
+          }
           __syncwarp();
           fit = ing && (unsigned)(i - 1 - ei0) < (unsigned)(WE - 1) && (unsigned)(j - 1 - ej0) < (unsigned)(WE - 1);
           dm = gm & ~__ballot_sync(0xffffffffu, fit);
         }
+        bool trkrow = false;
+        if constexpr (TRACK) {
+          // track!: rows in cells next to a surface go to the tracked list (warp-aggregated append) and are
+          // advanced by k_advance_tracked after this kernel
+          trkrow = fit && !(dbg & 2) && sm.trk[(j - 1 - ej0) * WE + (i - 1 - ei0)] != 0;
+          const unsigned tm = __ballot_sync(0xffffffffu, trkrow);
+          if (tm) {
+            unsigned nt = sm.tcnt;
+            if (trkrow) {
+              sm.tq[nt + __popc(tm & lanemask_lt())] = row;
+              fit = false;
+            }
+            nt += __popc(tm);
+            __syncwarp();
+            if (nt >= 32) {
+              unsigned g0 = 0;
+              if (lane == 0) g0 = atomicAdd(trk_n, 32u);
+              g0 = __shfl_sync(0xffffffffu, g0, 0);
+              trk_list[g0 + lane] = sm.tq[lane];
+              nt -= 32;
+              __syncwarp();
+              if (lane < (int)nt) sm.tq[lane] = sm.tq[lane + 32];
+            }
+            if (lane == 0) sm.tcnt = nt;
+            __syncwarp();
+          }
+        }
         // rows outside the window are queued and advanced later, 32 at a time (drain_rows)
         if (dm) {
-          if (ing && !fit) sm.queue[qn + __popc(dm & lanemask_lt())] = row;
+          if (ing && !fit && !trkrow) sm.queue[qn + __popc(dm & lanemask_lt())] = row;
           qn += __popc(dm);
-          if (lane == 0) sm.stats[0] += __popc(dm);
+          if (lane == 0) sm.stats[0] += __popc(dm);   // (tracked rows had fit == true when dm was formed: not in dm)
         }
       }
       bool dead_now = false;
@@ -266,6 +334,9 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
         px = push_x(px, vx, dt);
         py = push_x(py, vy, dt);
         vm2 = fmaxf(vm2, __double2float_ru(fma(vz, vz, fma(vy, vy, vx * vx))));
+        if constexpr (TRACK) {   // check!'s message condition, check.jl:41-46 (queued rows: in drain_rows)
+          if (!(dbg & 1)) too_fast |= fmax(fmax(fabs(vx), fabs(vy)), fabs(vz)) > v_too_fast;
+        }
         // ---- after_push: discards first, then wraps ----
         bool dead = (mode_x == ISKB_BND_DISCARD) && boundary_axis(px, g.ox, g.Lx, mode_x);
         if (!dead) dead = (mode_y == ISKB_BND_DISCARD) && boundary_axis(py, g.oy, g.Ly, mode_y);
@@ -344,8 +415,10 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
       }
       __syncwarp();   // rho window updates of this batch are ordered before a possible flush
       if (qn >= 32) {
-        const DrainOut o = drain_rows<MX, MY>(sm.queue, 32, lane, X, Y, VX, VY, VZ, WG, g, E2, qm, dt, c1, u, status);
+        const DrainOut o = drain_rows<MX, MY, TRACK>(sm.queue, 32, lane, X, Y, VX, VY, VZ, WG, g, E2, qm, dt, c1, u, status,
+                                                     trk_cells, trk_list, trk_n, v_too_fast);
         vm2 = fmaxf(vm2, __double2float_ru(o.vm2));
+        if constexpr (TRACK) too_fast |= o.too_fast;
         if (lane == 0) { sm.stats[3] += o.dead; sm.stats[1] += 32; }
         qn -= 32;
         __syncwarp();
@@ -357,11 +430,23 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
   }
   __syncwarp();
   if (qn > 0) {
-    const DrainOut o = drain_rows<MX, MY>(sm.queue, qn, lane, X, Y, VX, VY, VZ, WG, g, E2, qm, dt, c1, u, status);
+    const DrainOut o = drain_rows<MX, MY, TRACK>(sm.queue, qn, lane, X, Y, VX, VY, VZ, WG, g, E2, qm, dt, c1, u, status,
+                                                 trk_cells, trk_list, trk_n, v_too_fast);
     vm2 = fmaxf(vm2, __double2float_ru(o.vm2));
+    if constexpr (TRACK) too_fast |= o.too_fast;
     if (lane == 0) { sm.stats[3] += o.dead; sm.stats[1] += qn; }
   }
   __syncwarp();
+  if constexpr (TRACK) {
+    const unsigned nt = sm.tcnt;
+    if (nt) {
+      unsigned g0 = 0;
+      if (lane == 0) g0 = atomicAdd(trk_n, nt);
+      g0 = __shfl_sync(0xffffffffu, g0, 0);
+      if (lane < (int)nt) trk_list[g0 + lane] = sm.tq[lane];
+    }
+    if (__any_sync(0xffffffffu, too_fast) && lane == 0) atomicOr(status, ISKB_ST_TOO_FAST);
+  }
   if (ei0 != NOT_ANCHORED) flush_rho<WR>(sm.rho, ei0 + OFF, ej0 + OFF, g, u, lane);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) vm2 = fmaxf(vm2, __shfl_xor_sync(0xffffffffu, vm2, d));
@@ -380,14 +465,29 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
 
 int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit, bool from_begin);
 
-template <int WE, int WR, int WARPS, int MINB, int MX, int MY, bool CLAIM>
+template <int WE, int WR, int WARPS, int MINB, int MX, int MY, bool CLAIM, bool TRACK = false>
 static int32_t launch_modes(iskb_species *sp, double dt) {
   iskb_ctx *c = sp->ctx;
-  constexpr int SMEM = WARPS * (int)sizeof(WarpSmem<WE, WR>);
+  constexpr int SMEM = WARPS * (int)sizeof(typename SmemOf<WE, WR, TRACK>::type);
   static bool attr_set = false;
   if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    CU_TRY(cudaFuncSetAttribute(k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM, TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
+  }
+  const uint8_t *trk_cells = nullptr;
+  double v_too_fast = 0.0;
+  static const int dbg = getenv("ISKB_DEBUG_TRK") ? atoi(getenv("ISKB_DEBUG_TRK")) : 0;   // timing experiments only
+  if (TRACK) {
+    TrackerDev t;
+    memset(&t, 0, sizeof(t));
+    ISKB_TRY(tracker_prepare(c->tracker, &t));
+    trk_cells = t.tracked;
+    v_too_fast = t.dh / dt;
+    if (!sp->d_trk_list) {
+      CU_TRY(cudaMalloc(&sp->d_trk_list, sp->cap * sizeof(uint32_t)));
+      CU_TRY(cudaMalloc(&sp->d_trk_n, sizeof(unsigned)));
+    }
+    CU_TRY(cudaMemsetAsync(sp->d_trk_n, 0, sizeof(unsigned), c->stream));
   }
   const double qm = sp->q / sp->m;
   const int64_t bound = sp->counts_stale ? sp->cap : sp->h_nslots;
@@ -397,12 +497,13 @@ static int32_t launch_modes(iskb_species *sp, double dt) {
   if (blocks < 1) blocks = 1;
   ISKB_TRY(sp_vmax_reset(sp));
   ISKB_TRY(prof_begin(c));
-  k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM><<<(int)blocks, WARPS * 32, SMEM, c->stream>>>(
+  k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM, TRACK><<<(int)blocks, WARPS * 32, SMEM, c->stream>>>(
       sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->d_cnt, c->g, c->d_E2, qm, dt,
-      0.5 * dt * qm, sp->d_u, c->d_status, sp->d_vmax2, sp->h_nsorted);
+      0.5 * dt * qm, sp->d_u, c->d_status, sp->d_vmax2, sp->h_nsorted, trk_cells, sp->d_trk_list, sp->d_trk_n, v_too_fast, dbg);
   LAUNCH_CHECK(c);
+  if (TRACK && !(dbg & 4)) ISKB_TRY(launch_advance_tracked_list(sp, dt, MX, MY));   // the rows this kernel left to track! / check!
   ISKB_TRY(prof_end(c));
-  if (MX == ISKB_BND_DISCARD || MY == ISKB_BND_DISCARD) sp->counts_stale = true;
+  if (MX == ISKB_BND_DISCARD || MY == ISKB_BND_DISCARD || TRACK) sp->counts_stale = true;
   return ISKB_OK;
 }
 
@@ -418,6 +519,24 @@ static int32_t launch_variant(iskb_species *sp, double dt, int mode_x, int mode_
     case 6: return launch_modes<WE, WR, WARPS, MINB, 2, 0, CLAIM>(sp, dt);
     case 7: return launch_modes<WE, WR, WARPS, MINB, 2, 1, CLAIM>(sp, dt);
     default: return launch_modes<WE, WR, WARPS, MINB, 2, 2, CLAIM>(sp, dt);
+  }
+}
+
+// advance! with config.tracker on the tiled path (dx == dy, grid large enough for the windows)
+int32_t launch_advance_tiled_tracked(iskb_species *sp, double dt, int mode_x, int mode_y) {
+  iskb_ctx *c = sp->ctx;
+  ISKB_TRY(fields_join(c));
+  if (c->g.nx < 20 || c->g.ny < 20 || c->g.dx != c->g.dy) return launch_advance_tracked(sp, dt, mode_x, mode_y, true);
+  switch (mode_x * 3 + mode_y) {
+    case 0: return launch_modes<16, 16, 8, 3, 0, 0, true, true>(sp, dt);
+    case 1: return launch_modes<16, 16, 8, 3, 0, 1, true, true>(sp, dt);
+    case 2: return launch_modes<16, 16, 8, 3, 0, 2, true, true>(sp, dt);
+    case 3: return launch_modes<16, 16, 8, 3, 1, 0, true, true>(sp, dt);
+    case 4: return launch_modes<16, 16, 8, 3, 1, 1, true, true>(sp, dt);
+    case 5: return launch_modes<16, 16, 8, 3, 1, 2, true, true>(sp, dt);
+    case 6: return launch_modes<16, 16, 8, 3, 2, 0, true, true>(sp, dt);
+    case 7: return launch_modes<16, 16, 8, 3, 2, 1, true, true>(sp, dt);
+    default: return launch_modes<16, 16, 8, 3, 2, 2, true, true>(sp, dt);
   }
 }
 

@@ -157,7 +157,7 @@ static void free_species(iskb_species *s) {
   for (int k = 0; k < 2; ++k) { cudaFree(s->d_key[k]); cudaFree(s->d_idx[k]); }
   if (s->h_wstats) cudaFreeHost(s->h_wstats);
   for (int k = 0; k < 2; ++k) if (s->ev_wstats[k]) cudaEventDestroy(s->ev_wstats[k]);
-  cudaFree(s->d_hist);
+  cudaFree(s->d_hist); cudaFree(s->d_trk_list); cudaFree(s->d_trk_n);
   delete s;
 }
 
@@ -615,18 +615,20 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   ISKB_TRY(poisson_prepare(c));
   for (int it = 0; it < n_steps; ++it) {
-    const bool tiled = c->sort_interval > 0 && !c->tracker;
+    const bool tiled = c->sort_interval > 0;
     if (tiled)
       for (iskb_species *s : c->species) ISKB_TRY(maybe_sort(c, s));
     for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));       // :109-111
     ISKB_TRY(fields_join(c));   // E of the previous step (the re-sort and MCC above did not need it)
     for (iskb_species *s : c->species) {                                   // :113-115
       CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
-      if (c->tracker) {
+      if (c->tracker && !tiled) {
         // config.tracker != nothing: track! -> gather -> push -> check! -> after_push  (:56-61), one pass
         ISKB_TRY(launch_advance_tracked(s, dt, c->after_push[0], c->after_push[1], true));
       } else if (tiled) {
-        ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
+        static const bool ignore_tracker = getenv("ISKB_DEBUG_IGNORE_TRACKER") != nullptr;   // timing experiments only
+        if (c->tracker && !ignore_tracker) ISKB_TRY(launch_advance_tiled_tracked(s, dt, c->after_push[0], c->after_push[1]));
+        else ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
         ISKB_TRY(post_advance_stats(c, s));
         s->steps_since_sort++;
         s->steps_since_full++;

@@ -178,6 +178,9 @@ struct iskb_species {
   int64_t wstats_sort_mark = 0;         // snapshots with index < this were taken before the last sort
   int64_t last_gmiss = 0;
   double miss_rate = 1.0;               // gather-miss fraction of the last measured step
+  // rows the tiled advance leaves to the surface tracker (cells next to a surface), filled per launch
+  uint32_t *d_trk_list = nullptr;
+  unsigned *d_trk_n = nullptr;
 };
 
 struct MccProc {
@@ -270,6 +273,8 @@ int32_t sp_vmax_reset(iskb_species *sp);
 int32_t tracker_prepare(iskb_tracker *st, TrackerDev *out);
 int32_t tracker_free(iskb_tracker *st);
 int32_t launch_advance_tracked(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit);
+int32_t launch_advance_tiled_tracked(iskb_species *sp, double dt, int mode_x, int mode_y);
+int32_t launch_advance_tracked_list(iskb_species *sp, double dt, int mode_x, int mode_y);
 int32_t poisson_sigma_device(iskb_ctx *ctx, double **d_sigma_out);
 int32_t prof_begin(iskb_ctx *ctx);
 int32_t prof_end(iskb_ctx *ctx);

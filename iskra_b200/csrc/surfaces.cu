@@ -10,81 +10,11 @@
 #include <climits>
 #include <cstring>
 
-#include "pic_device.cuh"
+#include "surfaces_device.cuh"
 
 namespace {
 
 constexpr int TPB = 256;
-constexpr int WALK_CAP = 1 << 16;
-
-__device__ __forceinline__ double nan_dead() { return __longlong_as_double(0x7ff8000000000000LL); }
-
-// particle_cell(px, p, st.dh)  track.jl:47 -- BOTH coordinates are divided by the scalar st.dh (quirk S2)
-__device__ __forceinline__ bool tracked_cell(const TrackerDev &t, double x, double y, int &i, int &j, double &hx,
-                                             double &hy) {
-  cell1(x, t.dh, i, hx);
-  cell1(y, t.dh, j, hy);
-  if ((unsigned)i > (unsigned)t.nx || (unsigned)j > (unsigned)t.ny) return false;   // not a key of the Dict
-  return t.tracked[i + j * (t.nx + 1)] != 0;                                       // (i,j) in st, build.jl:86-93
-}
-
-// check! loop body for one particle, check.jl:48-62 with check :17-36 and hit! inlined.
-// Returns true when the particle was absorbed.  x, y, vx, vy are updated by reflections.
-__device__ bool walk_tracked(const TrackerDev &t, double dt, int i, int j, double hx, double hy, double &x, double &y,
-                             double &vx, double &vy, double qw, int *status) {
-  const double dh = t.dh;
-  for (int it = 0; it < WALK_CAP; ++it) {
-    const double dx = vx > 0 ? __dmul_rn(dh, __dsub_rn(1.0, hx)) : __dmul_rn(dh, hx);   // :20
-    const double dy = vy > 0 ? __dmul_rn(dh, __dsub_rn(1.0, hy)) : __dmul_rn(dh, hy);   // :21
-    const double dtx = __ddiv_rn(dx, fabs(vx)), dty = __ddiv_rn(dy, fabs(vy));          // :23
-    if (dt < dtx && dt < dty) return false;                                              // :24-26 stayed in the cell
-    int i2 = i, j2 = j, dir;
-    double hx2, hy2, dt2;
-    if (dtx < dty) {                                                                      // :28-31
-      dt2 = __dsub_rn(dt, dtx);
-      hy2 = __dadd_rn(hy, __ddiv_rn(__dmul_rn(vy, dtx), dh));
-      if (vx > 0) { i2 = i + 1; hx2 = 0.0; dir = 1; } else { i2 = i - 1; hx2 = 1.0; dir = 3; }
-    } else {                                                                              // :32-35
-      dt2 = __dsub_rn(dt, dty);
-      hx2 = __dadd_rn(hx, __ddiv_rn(__dmul_rn(vx, dty), dh));
-      if (vy > 0) { j2 = j + 1; hy2 = 0.0; dir = 2; } else { j2 = j - 1; hy2 = 1.0; dir = 0; }
-    }
-    int sid = 0;                                                                          // get(st, (ij, ij'), nothing) :55
-    if ((unsigned)i <= (unsigned)t.nx && (unsigned)j <= (unsigned)t.ny) sid = t.face[4 * (i + j * (t.nx + 1)) + dir];
-    if (sid == 0) {                                                                       // :59 track!(st, pt')
-      i = i2; j = j2; hx = hx2; hy = hy2; dt = dt2;
-      continue;
-    }
-    const int kind = t.s_kind[sid];
-    if (kind == ISKB_SURF_ABSORBING || kind == ISKB_SURF_ELECTRODE_FIXED) return true;    // hit.jl:32-38, circuit_coupling.jl:55-61
-    if (kind == ISKB_SURF_ELECTRODE_FLOATING) {                                           // circuit_coupling.jl:44-53
-      atomicAdd(&t.s_dq[sid], qw);                                                        // s.dq += q*wg[p]
-      // s.sigma .+= dq/s.area lands in the solution vector in the reference (quirk S1) and is overwritten by
-      // the next solve; it reaches the sigma right-hand side only when the caller asks for it
-      if (t.route_hits && t.s_dof[sid] >= 0) atomicAdd(&t.sigma[t.s_dof[sid]], __ddiv_rn(qw, t.s_area[sid]));
-      return true;
-    }
-    if (kind == ISKB_SURF_REFLECTIVE) {                                                   // hit.jl:39-56
-      x = __dsub_rn(x, __dmul_rn(vx, dt2));                                               // :47 px .-= pv*dt'
-      y = __dsub_rn(y, __dmul_rn(vy, dt2));
-      if (i2 != i) vx = -vx;                                                              // :48-52 n = [i'-i, j'-j, 0]
-      if (j2 != j) vy = -vy;
-      x = __dadd_rn(x, __dmul_rn(vx, dt2));                                               // :53 px .+= pv*dt'
-      y = __dadd_rn(y, __dmul_rn(vy, dt2));
-      int i3 = i2, j3 = j2;                                                               // scattered!  hit.jl:12-20
-      double hx3 = hx2, hy3 = hy2;
-      if (hx2 == 0.0) { i3 = i2 - 1; hx3 = 1.0; }
-      if (hx2 == 1.0) { i3 = i2 + 1; hx3 = 0.0; }
-      if (hy2 == 0.0) { j3 = j2 - 1; hy3 = 1.0; }
-      if (hy2 == 1.0) { j3 = j2 + 1; hy3 = 0.0; }
-      i = i3; j = j3; hx = hx3; hy = hy3; dt = dt2;
-      continue;
-    }
-    return false;                                                                          // PeriodicSurface: no-op hit!, hit.jl:26-31
-  }
-  atomicOr(status, ISKB_ST_WALK);
-  return false;
-}
 
 // ---- track!  track.jl:42-52 (operator-level API) ---------------------------------------------------
 __global__ void k_track(const double *__restrict__ x, const double *__restrict__ y, const int64_t *__restrict__ cnt,
@@ -113,6 +43,7 @@ __global__ void k_check(double *x, double *y, double *vx, double *vy, const doub
                         const double *__restrict__ thy, unsigned long long *counts, int *status) {
   const int64_t n = cnt[CNT_NSLOTS];
   const double vmax = __ddiv_rn(t.dh, dt);                                                 // :42
+  bool too_fast = false;
   for (int64_t p0 = blockIdx.x * (int64_t)blockDim.x; p0 < n; p0 += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = p0 + threadIdx.x;
     bool dead_now = false;
@@ -120,7 +51,7 @@ __global__ void k_check(double *x, double *y, double *vx, double *vy, const doub
       double px = x[p];
       if (!is_dead(px)) {
         double pvx = vx[p], pvy = vy[p];
-        if (fabs(pvx) > vmax || fabs(pvy) > vmax || fabs(vz[p]) > vmax) atomicOr(status, ISKB_ST_TOO_FAST);   // :43-46
+        too_fast |= fabs(pvx) > vmax || fabs(pvy) > vmax || fabs(vz[p]) > vmax;            // :43-46
         const int i = ti[p];
         if (i != INT_MIN) {
           double py = y[p];
@@ -140,6 +71,7 @@ __global__ void k_check(double *x, double *y, double *vx, double *vy, const doub
       atomicAdd(&counts[1], (unsigned long long)__popc(m));
     }
   }
+  if (__any_sync(0xffffffffu, too_fast) && (threadIdx.x & 31) == 0) atomicOr(status, ISKB_ST_TOO_FAST);
 }
 
 // ---- advance!(part, E, B, dt, config) with a tracker, one pass  ParticleInCell.jl:51-61 -------------
@@ -147,15 +79,20 @@ __global__ void k_check(double *x, double *y, double *vx, double *vy, const doub
 __global__ void k_advance_tracked(double *x, double *y, double *vx, double *vy, double *vz, const double *__restrict__ wg,
                                   int64_t *cnt, GridDev g, TrackerDev t, const double2 *__restrict__ E2, double q, double qm,
                                   double dt, int mode_x, int mode_y, double *u, int *status, unsigned long long *vmax2,
-                                  unsigned long long *counts) {
-  const int64_t n = cnt[CNT_NSLOTS];
+                                  unsigned long long *counts, const uint32_t *__restrict__ list,
+                                  const unsigned *__restrict__ n_list) {
+  // list == nullptr: every row; otherwise exactly the rows the tiled advance left to the tracker
+  const int64_t n = list ? (int64_t)*n_list : cnt[CNT_NSLOTS];
   double vm2 = 0.0;
   const double c1 = __dmul_rn(__dmul_rn(0.5, dt), qm);
   const double vmax = __ddiv_rn(t.dh, dt);
+  bool too_fast = false;
+  unsigned n_abs = 0;
   for (int64_t p0 = blockIdx.x * (int64_t)blockDim.x; p0 < n; p0 += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = p0 + threadIdx.x;
+    const int64_t k = p0 + threadIdx.x;
     bool dead_now = false;
-    if (p < n) {
+    if (k < n) {
+      const int64_t p = list ? (int64_t)list[k] : k;
       double px = x[p], py = y[p];
       if (!is_dead(px)) {
         int ti, tj;
@@ -168,10 +105,10 @@ __global__ void k_advance_tracked(double *x, double *y, double *vx, double *vy, 
         const double nvz = push_v(vz[p], 0.0, c1, qm, dt);
         px = push_x(px, nvx, dt);
         py = push_x(py, nvy, dt);
-        if (fabs(nvx) > vmax || fabs(nvy) > vmax || fabs(nvz) > vmax) atomicOr(status, ISKB_ST_TOO_FAST);
+        too_fast |= fabs(nvx) > vmax || fabs(nvy) > vmax || fabs(nvz) > vmax;
         bool dead = false;
         if (trk) dead = walk_tracked(t, dt, ti, tj, thx, thy, px, py, nvx, nvy, __dmul_rn(q, wg[p]), status);   // :60 check!
-        if (dead) atomicAdd(&counts[1], 1ull);
+        if (dead) ++n_abs;
         vm2 = fmax(vm2, (nvx * nvx + nvy * nvy) + nvz * nvz);
         if (!dead) {                                                                       // :61 after_push
           dead = (mode_x == ISKB_BND_DISCARD) && boundary_axis(px, g.ox, g.Lx, mode_x);
@@ -216,6 +153,10 @@ __global__ void k_advance_tracked(double *x, double *y, double *vx, double *vy, 
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) vm2 = fmax(vm2, __shfl_xor_sync(0xffffffffu, vm2, d));
   if ((threadIdx.x & 31) == 0 && vm2 > 0.0) atomicMax(vmax2, (unsigned long long)__double_as_longlong(vm2));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) n_abs += __shfl_xor_sync(0xffffffffu, n_abs, d);
+  if ((threadIdx.x & 31) == 0 && n_abs) atomicAdd(&counts[1], (unsigned long long)n_abs);
+  if (__any_sync(0xffffffffu, too_fast) && (threadIdx.x & 31) == 0) atomicOr(status, ISKB_ST_TOO_FAST);
 }
 
 inline int grid_for(const iskb_species *sp) {
@@ -388,6 +329,7 @@ extern "C" int32_t iskb_tracker_track(iskb_tracker *st, iskb_species *sp, double
   iskb_ctx *c = st->ctx;
   ISKB_TRY(sp_compact(sp));
   TrackerDev t;
+  memset(&t, 0, sizeof(t));
   ISKB_TRY(tracker_prepare(st, &t));
   if (st->trk_cap < sp->cap) {
     cudaFree(st->d_ti); cudaFree(st->d_tj); cudaFree(st->d_thx); cudaFree(st->d_thy);
@@ -417,6 +359,7 @@ extern "C" int32_t iskb_tracker_check(iskb_tracker *st, iskb_species *sp, double
   if (st->trk_sp != sp || sp->counts_stale || sp->h_nslots != st->trk_rows)
     return iskb_fail(ISKB_E_INVALID, "iskb_tracker_check must follow iskb_tracker_track + iskb_push on the same species");
   TrackerDev t;
+  memset(&t, 0, sizeof(t));
   ISKB_TRY(tracker_prepare(st, &t));
   k_check<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->d_cnt,
                                                t, dt, sp->q, st->d_ti, st->d_tj, st->d_thx, st->d_thy, st->d_counts, c->d_status);
@@ -448,6 +391,7 @@ int32_t launch_advance_tracked(iskb_species *sp, double dt, int mode_x, int mode
   iskb_ctx *c = sp->ctx;
   ISKB_TRY(fields_join(c));
   TrackerDev t;
+  memset(&t, 0, sizeof(t));
   ISKB_TRY(tracker_prepare(c->tracker, &t));
   const double qm = sp->q / sp->m;
   ISKB_TRY(sp_vmax_reset(sp));
@@ -455,9 +399,26 @@ int32_t launch_advance_tracked(iskb_species *sp, double dt, int mode_x, int mode
   k_advance_tracked<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5],
                                                          sp->d_cnt, c->g, t, c->d_E2, sp->q, qm, dt, mode_x, mode_y,
                                                          deposit ? sp->d_u : nullptr, c->d_status, sp->d_vmax2,
-                                                         c->tracker->d_counts);
+                                                         c->tracker->d_counts, nullptr, nullptr);
   LAUNCH_CHECK(c);
   ISKB_TRY(prof_end(c));
+  sp->counts_stale = true;
+  return ISKB_OK;
+}
+
+// Second half of the tiled advance with a tracker: the rows it appended to the species' tracked list.
+int32_t launch_advance_tracked_list(iskb_species *sp, double dt, int mode_x, int mode_y) {
+  iskb_ctx *c = sp->ctx;
+  TrackerDev t;
+  memset(&t, 0, sizeof(t));
+  ISKB_TRY(tracker_prepare(c->tracker, &t));
+  const double qm = sp->q / sp->m;
+  // the list length is only known on the device; a few blocks per SM cover the usual <1 % of the rows
+  k_advance_tracked<<<c->n_sm * 2, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5],
+                                                      sp->d_cnt, c->g, t, c->d_E2, sp->q, qm, dt, mode_x, mode_y, sp->d_u,
+                                                      c->d_status, sp->d_vmax2, c->tracker->d_counts, sp->d_trk_list,
+                                                      sp->d_trk_n);
+  LAUNCH_CHECK(c);
   sp->counts_stale = true;
   return ISKB_OK;
 }

@@ -28,7 +28,7 @@ def ib():
 
 def _by_id(ids, *cols):
     o = np.argsort(ids, kind="stable")
-    return [np.asarray(c)[o] for c in cols]
+    return [np.asarray(ids)[o]] + [np.asarray(c)[o] for c in cols]
 
 
 def _boundaries(ib, n=20000, seed=3, nx=11, ny=11, dh=0.1, vfrac=0.3, dt=1e-8, electrodes=True):
@@ -309,9 +309,11 @@ def test_too_fast_flag_and_reflective_box(ib):
     assert x[1, 0] == pytest.approx(0.04, rel=1e-12) and x[1, 1] == pytest.approx(0.04, rel=1e-12)
 
 
-def test_large_grid_tracked_advance_vs_c_oracle(ib):
+@pytest.mark.parametrize("sort_interval", [0, 1])
+def test_large_grid_tracked_advance_vs_c_oracle(ib, sort_interval):
     """513^2 nodes, 2e6 particles: fixed electrodes on two whole edges (separable solver), a reflecting
-    block, default absorbing walls; three fused steps against the C oracle, keyed by id."""
+    block, default absorbing walls; fused steps against the C oracle, keyed by id.  sort_interval = 0 runs
+    the simple tracked kernel, 1 the tiled one (rows sorted by cell, tracked rows through the drain path)."""
     PIC, FDM, CFG = ib.particle_in_cell, ib.finite_difference_method, ib.configuration
     Lc = CO.lib()
     nx = ny = 513
@@ -355,10 +357,11 @@ def test_large_grid_tracked_advance_vs_c_oracle(ib):
     V = np.zeros(nx * ny)
     Lc.orc_cell_volume(C.byref(cg), CO.dp(V))
     tot = 0
-    for it in range(3):
+    for it in range(4):
         nabs, _ = ct.advance(cs, cg, E, dt, bmode=(2, 2))
         tot += nabs
-        PIC.solve(cfg, dt, 1, after_push=(ib._lib.BND_DISCARD, ib._lib.BND_DISCARD), fused=True)
+        PIC.solve(cfg, dt, 1, after_push=(ib._lib.BND_DISCARD, ib._lib.BND_DISCARD), fused=True,
+                  sort_interval=sort_interval)
         _, _, gE = g._rt.fields(rho=False, phi=False)
         E = np.ascontiguousarray(gE.reshape(-1, order="F"))       # the device field drives both sides
         assert gsp.np == cs.np, it
