@@ -206,6 +206,94 @@ function ParticleInCell.perform!(m :: B200MCC, E, Δt, config)
   foreach(p -> p.device_newer = true, m.products)
 end
 
+# ---- surfaces, electrodes, circuit (SURVEY.md 8f row N1) ------------------------------------------------
+# ParticleInCell/src/pic/surfaces/{build,track,check,hit}.jl and pic/circuit_coupling.jl.  The tracker's
+# Dict{(cell,cell) => Surface} lives on the device as a per-cell face table; the reference's own Surface
+# values stay the host-side handles (their kind decides hit!, electrodes also carry dq / area).
+const SURF_PERIODIC, SURF_ABSORBING, SURF_REFLECTIVE, SURF_FIXED, SURF_FLOATING = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
+
+surface_kind(:: ParticleInCell.PeriodicSurface)            = SURF_PERIODIC
+surface_kind(:: ParticleInCell.AbsorbingSurface)           = SURF_ABSORBING
+surface_kind(:: ParticleInCell.ReflectiveSurface)          = SURF_REFLECTIVE
+surface_kind(:: ParticleInCell.FixedPotentialElectrode)    = SURF_FIXED
+surface_kind(:: ParticleInCell.FloatingPotentialElectrode) = SURF_FLOATING
+
+mutable struct B200SurfaceTracker
+  h :: Ptr{Cvoid}
+  ctx :: Context
+  ids :: IdDict{Any,Int32}         # Surface => surface id on the device
+end
+
+# create_surface_tracker(grid, ds)  build.jl:95-100
+function B200SurfaceTracker(ctx :: Context, ds :: ParticleInCell.Surface = ParticleInCell.AbsorbingSurface())
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:iskb_tracker_create, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), ctx.h, surface_kind(ds), h))
+  B200SurfaceTracker(h[], ctx, IdDict{Any,Int32}())
+end
+
+# track_surface!(st, bcs::BitArray{2}, ss)  build.jl:109-111 ; sigma_dof: the electrode's dof from add_new_dof
+function ParticleInCell.track_surface!(st :: B200SurfaceTracker, bcs :: BitArray{2}, ss :: ParticleInCell.Surface;
+                                       sigma_dof :: Integer = 0)
+  mask = UInt8.(bcs)
+  sid = Ref{Int32}(0)
+  area = hasproperty(ss, :area) ? Float64(ss.area) : 0.0
+  GC.@preserve mask check(ccall((:iskb_tracker_track_surface, LIB), Int32,
+                                (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32, Float64, Ref{Int32}),
+                                st.h, mask, surface_kind(ss), Int32(sigma_dof), area, sid))
+  st.ids[ss] = sid[]
+end
+
+# track!(st, part, dt)  track.jl:42-52  /  check!(st, part, dt)  check.jl:39-68
+function ParticleInCell.track!(st :: B200SurfaceTracker, sp :: B200Species, Δt)
+  upload!(sp)
+  check(ccall((:iskb_tracker_track, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Ptr{Int64}), st.h, sp.h, Δt, C_NULL))
+end
+function ParticleInCell.check!(st :: B200SurfaceTracker, sp :: B200Species, Δt)
+  nabs, fast = Ref{Int64}(0), Ref{Int32}(0)
+  check(ccall((:iskb_tracker_check, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Ref{Int64}, Ref{Int32}),
+              st.h, sp.h, Δt, nabs, fast))
+  sp.device_newer = true
+  fast[] != 0 && println("ERROR: $(sp.host) particle is too fast")     # check.jl:44-46
+  nabs[]
+end
+
+# electrode.dq (circuit_coupling.jl:49-50) accumulates on the device
+function collected_charge(st :: B200SurfaceTracker, ss; reset = false)
+  dq = Ref{Float64}(0.0)
+  check(ccall((:iskb_surface_charge, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Float64}, Int32), st.h, st.ids[ss], dq, reset ? 1 : 0))
+  dq[]
+end
+
+# add_new_dof / apply_neumann / get_rhs(ps, :σ, dof)  generalized_poisson.jl:217-269, 367-370
+function FiniteDifferenceMethod.add_new_dof(ps :: B200Poisson, symbol :: Symbol)
+  symbol == :σ || error("only σ dofs exist")
+  dof = Ref{Int32}(0)
+  check(ccall((:iskb_poisson_add_dof, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}), ps.ctx.h, dof))
+  Int(dof[])
+end
+function FiniteDifferenceMethod.apply_neumann(ps :: B200Poisson, nodes :: BitArray{2}, dof)
+  mask = UInt8.(nodes)
+  GC.@preserve mask check(ccall((:iskb_poisson_apply_neumann, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32), ps.ctx.h, mask, Int32(dof)))
+end
+sigma_rhs(ps :: B200Poisson, dof) = (v = Ref{Float64}(0.0);
+  check(ccall((:iskb_poisson_sigma_get, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Float64}), ps.ctx.h, Int32(dof), v)); v[])
+sigma_rhs!(ps :: B200Poisson, dof, value) =
+  check(ccall((:iskb_poisson_sigma_set, LIB), Int32, (Ptr{Cvoid}, Int32, Float64), ps.ctx.h, Int32(dof), Float64(value)))
+sigma_rhs_add!(ps :: B200Poisson, dof, delta) =
+  check(ccall((:iskb_poisson_sigma_add, LIB), Int32, (Ptr{Cvoid}, Int32, Float64), ps.ctx.h, Int32(dof), Float64(delta)))
+phi_at(ps :: B200Poisson, i, j) = (v = Ref{Float64}(0.0);
+  check(ccall((:iskb_phi_at, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ref{Float64}), ps.ctx.h, Int32(i), Int32(j), v)); v[])
+
+# advance!(circuit::CircuitRLC, ϕ, Δt, config)  circuit_coupling.jl:33-43: the RLC recurrence (Circuit.jl:117-136)
+# stays Julia; only `σ .+= dσ` crosses the boundary (8 bytes).
+function advance_circuit!(circuit, ps :: B200Poisson, Δt)
+  circuit === nothing && return 0.0
+  ParticleInCell.Circuit.advance_circuit!(circuit, 0, Δt)
+  dσ = ParticleInCell.foo!(circuit.ext, circuit.i, Δt)
+  sigma_rhs_add!(ps, 1, dσ)
+  dσ
+end
+
 # ---- fused loop: drop-in for ParticleInCell.solve that still fires the hooks (ParticleInCell.jl:84-139)
 function solve(ctx :: Context, species :: Vector{B200Species}, Δt, timesteps; after_push = (1, 1), sort_interval = 8)
   check(ccall((:iskb_set_after_push, LIB), Int32, (Ptr{Cvoid}, Int32, Int32), ctx.h, after_push...))
