@@ -152,6 +152,16 @@ int32_t iskb_species_sample_maxwellian(iskb_species *sp, int64_t n, const double
                                        uint64_t seed);
 /* iHe.x .= e.x ; iHe.np = e.np   (problem/10_two_streams.jl:66-68); v filled with v_fill */
 int32_t iskb_species_copy_positions(iskb_species *dst, iskb_species *src, const double v_fill[3]);
+/* remove!(sp, i)  kinetic.jl:20-27 ; i is the 1-based row of the download order.  Exactly the reference's
+ * swap with the last row: x, v of row np move to row i, wg[i] = wg[np], wg[np] = w0, id[i] <-> id[np], np -= 1. */
+int32_t iskb_species_remove(iskb_species *sp, int64_t i);
+/* add!(src, dst)  kinetic.jl:29-37: appends x, v of src's live rows to dst (wg and id of dst stay, like the
+ * reference); ISKB_E_CAPACITY where the reference would raise BoundsError. */
+int32_t iskb_species_add(iskb_species *src, iskb_species *dst);
+/* remove_particles!(part, dh, matches)  kinetic.jl:39-50 with matches(i,j) given as a byte mask over the
+ * cells (nx*ny, column-major, entry (i-1) + (j-1)*nx for the 1-based lower-left node (i,j)).  Survivors keep
+ * their ids; row order differs from the reference's swap sequence (compare keyed by id). */
+int32_t iskb_species_remove_in_cells(iskb_species *sp, const uint8_t *cell_mask, int64_t *n_removed);
 /* density field n of the last iskb_density()/iskb_step() (part.n, kinetic.jl:4) */
 int32_t iskb_species_density_download(iskb_species *sp, double *n_out);
 

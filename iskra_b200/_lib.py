@@ -59,6 +59,9 @@ SIGNATURES = {
     "iskb_species_sample_maxwellian": [vp, i64, vp, vp, vp, vp, u64],
     "iskb_species_copy_positions": [vp, vp, vp],
     "iskb_species_density_download": [vp, vp],
+    "iskb_species_remove": [vp, i64],
+    "iskb_species_add": [vp, vp],
+    "iskb_species_remove_in_cells": [vp, vp, C.POINTER(i64)],
     "iskb_cell_index": [vp, vp, vp, vp, vp],
     "iskb_sort_by_cell": [vp, vp],
     "iskb_sort_for_deposit": [vp, vp],

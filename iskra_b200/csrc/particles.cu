@@ -242,6 +242,50 @@ __global__ void k_advance_simple(double *x, double *y, double *vx, double *vy, d
   if ((threadIdx.x & 31) == 0 && vm2 > 0.0) atomicMax(vmax2, (unsigned long long)__double_as_longlong(vm2));
 }
 
+// remove!(sp, i)  kinetic.jl:20-27 (one thread: an API-level operation)
+__global__ void k_remove_one(double *x, double *y, double *vx, double *vy, double *vz, double *wg, uint32_t *id,
+                             int64_t *cnt, int64_t i, double w0) {
+  const int64_t l = cnt[CNT_NSLOTS] - 1;
+  x[i] = x[l]; y[i] = y[l];                 // :22
+  vx[i] = vx[l]; vy[i] = vy[l]; vz[i] = vz[l];   // :23
+  wg[i] = wg[l]; wg[l] = w0;                // :24
+  const uint32_t t = id[i]; id[i] = id[l]; id[l] = t;   // :25
+  cnt[CNT_NSLOTS] = l;                      // :26
+  cnt[CNT_BEGIN] = l;
+}
+
+__global__ void k_set_np(int64_t *cnt, int64_t np) {
+  cnt[CNT_NSLOTS] = np;
+  cnt[CNT_NDEAD] = 0;
+  cnt[CNT_BEGIN] = np;
+}
+
+// remove_particles!(part, dh, matches)  kinetic.jl:39-50: rows whose cell matches are marked dead
+__global__ void k_remove_in_cells(double *x, const double *__restrict__ y, int64_t *cnt, GridDev g,
+                                  const uint8_t *__restrict__ mask) {
+  const int64_t n = cnt[CNT_NSLOTS];
+  for (int64_t p0 = blockIdx.x * (int64_t)blockDim.x; p0 < n; p0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = p0 + threadIdx.x;
+    bool dead_now = false;
+    if (p < n) {
+      const double px = x[p];
+      if (!is_dead(px)) {
+        int i, j;
+        double hx, hy;
+        cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
+        cell1(y[p], g.dy, g.rdy, g.fast_div, j, hy);
+        if ((unsigned)(i - 1) < (unsigned)g.nx && (unsigned)(j - 1) < (unsigned)g.ny &&
+            mask[(i - 1) + (int64_t)(j - 1) * g.nx]) {
+          x[p] = __longlong_as_double(0x7ff8000000000000LL);
+          dead_now = true;
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, dead_now);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)&cnt[CNT_NDEAD], (unsigned long long)__popc(m));
+  }
+}
+
 }  // namespace
 
 // ================================ host side ====================================================
@@ -420,5 +464,57 @@ int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_
                                                   dt, mode_x, mode_y, deposit ? sp->d_u : nullptr, c->d_status, sp->d_vmax2);
   LAUNCH_CHECK(c);
   if (mode_x == ISKB_BND_DISCARD || mode_y == ISKB_BND_DISCARD) sp->counts_stale = true;
+  return ISKB_OK;
+}
+
+// ---- kinetic.jl:20-50 remove! / add! / remove_particles! ------------------------------------------
+extern "C" int32_t iskb_species_remove(iskb_species *sp, int64_t i) {
+  if (!sp) return iskb_fail(ISKB_E_INVALID, "null species");
+  iskb_ctx *c = sp->ctx;
+  ISKB_TRY(sp_compact(sp));
+  if (i < 1 || i > sp->h_nslots) return iskb_fail(ISKB_E_INVALID, "remove!: row %lld outside 1..np = %lld", (long long)i, (long long)sp->h_nslots);
+  k_remove_one<<<1, 1, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->id, sp->d_cnt,
+                                       i - 1, sp->w0);
+  LAUNCH_CHECK(c);
+  sp->h_nslots -= 1;
+  sp->h_nsorted = 0;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_species_add(iskb_species *src, iskb_species *dst) {
+  if (!src || !dst || src->ctx != dst->ctx || src == dst) return iskb_fail(ISKB_E_INVALID, "bad species");
+  iskb_ctx *c = dst->ctx;
+  ISKB_TRY(sp_compact(src));
+  ISKB_TRY(sp_compact(dst));
+  const int64_t n = src->h_nslots, at = dst->h_nslots;
+  if (n == 0) return ISKB_OK;                       // :30
+  if (at + n > dst->cap) return iskb_fail(ISKB_E_CAPACITY, "add!: %lld + %lld rows exceed the capacity %lld", (long long)at, (long long)n, (long long)dst->cap);
+  for (int k = 0; k < 5; ++k)                       // :32-33 (wg and id of dst stay)
+    CU_TRY(cudaMemcpyAsync(dst->col[k] + at, src->col[k], n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  const int64_t newn = at + n;                      // :35
+  k_set_np<<<1, 1, 0, c->stream>>>(dst->d_cnt, newn);
+  LAUNCH_CHECK(c);
+  dst->h_nslots = newn; dst->h_ndead = 0; dst->counts_stale = false;
+  dst->h_nsorted = dst->h_nsorted < at ? dst->h_nsorted : at;
+  ISKB_TRY(sp_vmax_unknown(dst));
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_species_remove_in_cells(iskb_species *sp, const uint8_t *cell_mask, int64_t *n_removed) {
+  ISKB_TRY(need_grid(sp));
+  if (!cell_mask) return iskb_fail(ISKB_E_INVALID, "cell_mask is NULL");
+  iskb_ctx *c = sp->ctx;
+  ISKB_TRY(sp_sync_counts(sp));
+  const int64_t before = sp->h_nslots - sp->h_ndead;
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  uint8_t *d = nullptr;
+  CU_TRY(cudaMalloc(&d, nn));
+  CU_TRY(cudaMemcpyAsync(d, cell_mask, nn, cudaMemcpyHostToDevice, c->stream));
+  k_remove_in_cells<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->d_cnt, c->g, d);
+  LAUNCH_CHECK(c);
+  sp->counts_stale = true;
+  ISKB_TRY(sp_sync_counts(sp));
+  cudaFree(d);
+  if (n_removed) *n_removed = before - (sp->h_nslots - sp->h_ndead);
   return ISKB_OK;
 }

@@ -141,6 +141,36 @@ def create_kinetic_species(name, N, q, m, weight, D=2, V=3):
     return sp
 
 
+def remove_(sp, i):
+    """remove!(sp, i)  kinetic.jl:20-27 ; i is 1-based"""
+    sp._push()
+    L.check(sp._rt.lib.iskb_species_remove(sp._h, int(i)))
+    sp._touched_on_device()
+
+
+def add_(src, dst):
+    """add!(src, dst)  kinetic.jl:29-37"""
+    src._push()
+    dst._push()
+    L.check(dst._rt.lib.iskb_species_add(src._h, dst._h))
+    dst._touched_on_device()
+
+
+def remove_particles_(part, grid, matches):
+    """remove_particles!(part, dh, matches)  kinetic.jl:39-50.  `matches(i, j)` (1-based cell) is evaluated on
+    the host once per cell and shipped as a mask; returns the number of particles removed."""
+    part._push(grid)
+    nx, ny = grid.n
+    mask = np.zeros((nx, ny), dtype=np.uint8, order="F")
+    for j in range(1, ny + 1):
+        for i in range(1, nx + 1):
+            mask[i - 1, j - 1] = 1 if matches(i, j) else 0
+    n = L.i64()
+    L.check(part._rt.lib.iskb_species_remove_in_cells(part._h, L.ptr(mask), C.byref(n)))
+    part._touched_on_device()
+    return n.value
+
+
 # ---- sources ------------------------------------------------------------------------------------
 class MaxwellianSource:
     """MaxwellianSource{D,V}  pic/sources.jl:8-22"""

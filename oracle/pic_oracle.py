@@ -121,6 +121,28 @@ def remove_(sp, i):
     sp.np = np_ - 1
 
 
+def add_(src, dst):
+    """kinetic.jl:29-37 add!(src, dst): x, v appended; wg and id of dst stay."""
+    if src.np > 0:
+        a, b = dst.np, dst.np + src.np
+        dst.x[a:b, :] = src.x[: src.np]
+        dst.v[a:b, :] = src.v[: src.np]
+        dst.np += src.np
+
+
+def remove_particles_(part, dh, matches):
+    """kinetic.jl:39-50 remove_particles!(part, dh, matches): sequential scan, re-testing the row that was
+    swapped in."""
+    p = 1
+    while p <= part.np:
+        fx = 1.0 + part.x[p - 1, 0] / dh[0]
+        fy = 1.0 + part.x[p - 1, 1] / dh[1]
+        if matches(int(math.floor(fx)), int(math.floor(fy))):
+            remove_(part, p)
+            continue
+        p += 1
+
+
 # ---------------------------------------------------------------------------------
 # ParticleInCell/src/ParticleInCell.jl:28-35
 # ---------------------------------------------------------------------------------

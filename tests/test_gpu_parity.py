@@ -639,3 +639,55 @@ def test_tiled_deposit_matches_simple_when_particles_leave_window(ib):
     assert np.allclose(res[0][0], res[1][0], rtol=1e-12, atol=1e-12 * res[0][0].max())
     assert np.allclose(res[0][1], res[1][1], rtol=1e-11, atol=1e-11 * np.abs(res[0][1]).max())
     assert np.allclose(res[0][2], res[1][2], rtol=1e-12, atol=1e-12 * nx * dx)
+
+
+# ------------------------------------------------------- kinetic.jl:20-50 remove! / add! / remove_particles! ---
+def test_remove_add_remove_particles_vs_oracle(ib):
+    PIC = ib.particle_in_cell
+    nx, ny, dx = 17, 9, 0.25
+    g, cg = _grid_pair(ib, nx, ny, dx)
+    og = O.CartesianGrid2(np.arange(nx) * dx, np.arange(ny) * dx)
+    n, cap = 500, 1200
+    rng = np.random.default_rng(21)
+    x = rng.random((n, 2)) * np.array([(nx - 1) * dx, (ny - 1) * dx])
+    v = rng.standard_normal((n, 3))
+    wg = 2.0 + rng.random(n)
+
+    def make():
+        o = O.KineticSpecies("a", cap, -O.qe, O.me, 7.0)
+        o.x[:n], o.v[:n], o.wg[:n], o.np = x, v, wg, n
+        s = PIC.create_kinetic_species("a", cap, -O.qe, O.me, 7.0)
+        s.x[:n] = x
+        s.v[:n] = v
+        s.wg[:n] = wg
+        s.np = n
+        s._push(g)
+        return o, s
+    o1, s1 = make()
+    # remove!: exactly the reference's swap with the last row, repeated; whole arrays bit-identical
+    for i in (1, 250, 498, 3, 3):
+        O.remove_(o1, i)
+        PIC.remove_(s1, i)
+    assert s1.np == o1.np == n - 5
+    assert np.array_equal(s1.x[: o1.np], o1.x[: o1.np]) and np.array_equal(s1.v[: o1.np], o1.v[: o1.np])
+    assert np.array_equal(s1.wg, o1.wg) and np.array_equal(s1.id, o1.id)
+    # add!: rows appended, wg and id of the destination untouched
+    o2, s2 = make()
+    O.add_(o1, o2)
+    PIC.add_(s1, s2)
+    assert s2.np == o2.np == 2 * n - 5
+    assert np.array_equal(s2.x[: o2.np], o2.x[: o2.np]) and np.array_equal(s2.v[: o2.np], o2.v[: o2.np])
+    assert np.array_equal(s2.wg, o2.wg) and np.array_equal(s2.id, o2.id)
+    with pytest.raises(ib.IskraError):
+        PIC.add_(s2, s1)                                            # 995 + 495 rows > capacity 1200 (reference: BoundsError)
+    # remove_particles!: same survivors (keyed by id), ids stay a permutation
+    matches = lambda i, j: (i + j) % 3 == 0 or i == 5
+    O.remove_particles_(o2, og.dh, matches)
+    removed = PIC.remove_particles_(s2, g, matches)
+    assert removed == 2 * n - 5 - o2.np and s2.np == o2.np and removed > 100
+    m = o2.np
+    gx, gy, gw = _by_id(s2.id[:m], s2.x[:m, 0], s2.x[:m, 1], s2.wg[:m])
+    ox, oy, ow = _by_id(o2.id[:m], o2.x[:m, 0], o2.x[:m, 1], o2.wg[:m])
+    assert np.array_equal(np.sort(s2.id[:m]), np.sort(o2.id[:m]))
+    assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gw, ow)
+    assert np.array_equal(np.sort(s2.id), np.arange(1, cap + 1))

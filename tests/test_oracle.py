@@ -294,3 +294,23 @@ def test_cross_section_interpolation():
         assert c == got[k]
         if e is not None:
             assert got[k] == e
+
+
+def test_add_and_remove_particles_restatement():
+    """kinetic.jl:29-50: add! appends x, v only; remove_particles! re-tests the row swapped in, keeps id a permutation."""
+    g = O.CartesianGrid2(np.arange(5) * 1.0, np.arange(4) * 1.0)
+    a = O.KineticSpecies("a", 10, -1.0, 1.0, 3.0)
+    b = O.KineticSpecies("b", 10, -1.0, 1.0, 5.0)
+    a.x[:3] = [[0.5, 0.5], [1.5, 0.5], [3.5, 2.5]]
+    a.v[:3] = [[1, 0, 0], [2, 0, 0], [3, 0, 0]]
+    a.np = 3
+    b.x[:2] = [[2.5, 1.5], [3.5, 2.6]]
+    b.np = 2
+    O.add_(a, b)
+    assert b.np == 5 and np.array_equal(b.x[2:5], a.x[:3]) and np.array_equal(b.v[2:5, 0], [1, 2, 3])
+    assert np.all(b.wg == 5.0) and np.array_equal(b.id, np.arange(1, 11))
+    # remove everything in cell (4,3): rows 2 and 5 (1-based) -- row 5 is swapped into row 2 first and re-tested
+    O.remove_particles_(b, g.dh, lambda i, j: (i, j) == (4, 3))
+    assert b.np == 3
+    assert sorted(map(tuple, b.x[:3].tolist())) == [(0.5, 0.5), (1.5, 0.5), (2.5, 1.5)]
+    assert sorted(b.id.tolist()) == list(range(1, 11))
