@@ -58,6 +58,7 @@ struct MccDev {
   double dt;
   double p_cand;     // N * max_Pt
   uint32_t p_cand_u32;
+  double inv_log1mp;   // 1 / log(1 - p_cand): gaps between candidates are geometric (k_mcc_select_skip)
   double pk_bound[8];   // sup over eps in [0, eps_hi] of P_k (with n = max density): exact pruning bound
   double eps_hi;        // largest tabulated energy of all processes
   double sup_sg[8];     // sup of sigma_k*g on the tables; sig_last: sigma_k at its last knot (Flat() beyond)
@@ -306,6 +307,80 @@ __global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *list
   if (lane == 0 && my_cand) atomicAdd(&m.stats[0], my_cand);
 }
 
+// Same decision, drawn the other way round: with independent Bernoulli(p) trials per row the gap between
+// two consecutive candidates is geometric, gap = floor(log U / log(1-p)), and because the geometric law is
+// memoryless the sequence may restart at every chunk boundary.  Each thread owns 64 consecutive rows and
+// draws gaps until it leaves them: the work is proportional to the candidates (6 % / 1 % of the rows at
+// C5) instead of the rows (one Philox call per 4 rows before: 2 x 120 us per step under ncu).  Measured on
+// the C5 step: 3.82 -> 3.77 ms -- most of the selection was already hidden behind the field solve on the
+// side stream.  ISKB_MCC_SELECT_PER_ROW=1 restores the per-row kernel.  One Philox call yields four gaps;
+// counter = (first row of the chunk, call, 0x40000000 + k), disjoint from the per-row streams (draws 0, 1, ...).
+constexpr int SKIP_ROWS = 64;
+__global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int *lists_cnt, uint32_t *cand,
+                                                         unsigned int cand_cap) {
+  __shared__ unsigned int s_warp[8];
+  __shared__ unsigned int s_base;
+  const int64_t n = m.src.cnt[CNT_BEGIN];   // rows that existed when the step started
+  const int64_t nchunk = (n + SKIP_ROWS - 1) / SKIP_ROWS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long my_cand = 0;
+  for (int64_t c0 = (int64_t)blockIdx.x * 256; c0 < nchunk; c0 += (int64_t)gridDim.x * 256) {
+    const int64_t ch = c0 + threadIdx.x;
+    const int64_t row0 = ch * SKIP_ROWS;
+    unsigned long long keep = 0;
+    if (ch < nchunk) {
+      const int lim = n - row0 < SKIP_ROWS ? (int)(n - row0) : SKIP_ROWS;
+      int pos = -1;
+      for (uint32_t k = 0; pos < lim; ++k) {
+        const Philox4 o = philox4x32_10((uint32_t)row0, (uint32_t)(row0 >> 32), m.call, 0x40000000u + k, m.k0, m.k1);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          // U uniform on (0,1): 32 bits are ample, the law is cut off at (1-p)^gap = 2^-33
+          const double u = ((double)o.c[s] + 0.5) * (1.0 / 4294967296.0);
+          const double gq = log(u) * m.inv_log1mp;
+          const int gap = gq < 1048576.0 ? (int)gq : 1048576;
+          if (pos < lim) {
+            pos += gap + 1;
+            if (pos < lim) keep |= 1ull << pos;
+          }
+        }
+      }
+    }
+    const unsigned cnt = __popcll(keep);
+    my_cand += cnt;
+    unsigned incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned tot = 0;
+      for (int w = 0; w < 8; ++w) {
+        const unsigned c = s_warp[w];
+        s_warp[w] = tot;
+        tot += c;
+      }
+      s_base = tot ? atomicAdd(&lists_cnt[0], tot) : 0u;
+    }
+    __syncthreads();
+    unsigned slot = s_base + s_warp[warp] + incl - cnt;
+    while (keep) {
+      const int b = __ffsll((long long)keep) - 1;
+      keep &= keep - 1;
+      if (slot < cand_cap) cand[slot] = (uint32_t)(row0 + b);
+      else atomicOr(m.status, ISKB_ST_CAPACITY);
+      ++slot;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) my_cand += __shfl_down_sync(0xffffffffu, my_cand, d);
+  if (lane == 0 && my_cand) atomicAdd(&m.stats[0], my_cand);
+}
+
 constexpr int TEST_TPB = 128;
 constexpr int TEST_BUF = 512;
 
@@ -458,6 +533,7 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
   m.p_cand = N * max_Pt;
   const double pc32 = m.p_cand * 4294967296.0;
   m.p_cand_u32 = pc32 >= 4294967295.0 ? 0xffffffffu : (uint32_t)pc32;
+  m.inv_log1mp = m.p_cand < 1.0 ? 1.0 / log1p(-m.p_cand) : 0.0;   // p = 1: every gap is 0
   // exact pruning bounds: sup over [0, eps_hi] of sigma_k(eps)*g(eps) (interior maxima of the
   // piecewise (a + b*eps)*sqrt(eps) included), at the largest target density
   m.eps_hi = mc->eps_hi;
@@ -499,7 +575,15 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
   int64_t blocks = (bound / 4 + TPB) / TPB;
   if (blocks > (int64_t)c->n_sm * 8) blocks = (int64_t)c->n_sm * 8;
   if (blocks < 1) blocks = 1;
-  k_mcc_select<<<(int)blocks, TPB, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
+  static const bool per_row = getenv("ISKB_MCC_SELECT_PER_ROW") != nullptr;   // the earlier one-draw-per-row kernel (A/B)
+  if (per_row || !(m.p_cand > 0.0)) {
+    k_mcc_select<<<(int)blocks, TPB, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
+  } else {
+    int64_t bs = (bound / SKIP_ROWS + TPB) / TPB;
+    if (bs > (int64_t)c->n_sm * 8) bs = (int64_t)c->n_sm * 8;
+    if (bs < 1) bs = 1;
+    k_mcc_select_skip<<<(int)bs, TPB, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
+  }
   LAUNCH_CHECK(c);
   // the list lengths live on the device: size the dense phases from the expected candidate count
   int64_t exp_cand = (int64_t)(m.p_cand * (double)bound) + 1024;
