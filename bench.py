@@ -31,7 +31,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c5", "c4", "walls"])
+    ap.add_argument("--workload", default="c5", choices=["c5", "c4", "walls", "seed"])
     ap.add_argument("--particles-per-gpu", type=int, default=None)
     ap.add_argument("--cells", type=int, default=None)
     ap.add_argument("--sort-interval", type=int, default=4)
@@ -47,17 +47,21 @@ def parse():
 def workload_defaults(a):
     if a.workload == "c5":
         return a.particles_per_gpu or 125_000_000, a.cells or 2048
+    if a.workload == "seed":
+        return a.particles_per_gpu or 40_000_000, 64
     return a.particles_per_gpu or 100_000_000, a.cells or 1024
 
 
 def algo_kernel(a):
-    return "k_advance_tracked" if a.workload == "walls" else "k_advance_tiled"
+    return {"walls": "k_advance_tiled<TRACK> + k_advance_tracked", "seed": "k_advance_simple (r-z)"}.get(a.workload, "k_advance_tiled")
 
 
 def config_dict(a, ppg, cells, n_gpus, extra=None):
     names = {"c5": "C5 shard: 2D XY RF discharge + MCC (BASELINE configs[4]), %dx%d grid, %.3g particles per GPU "
                    "(1e9 over 8 GPUs), index-slice sharding, rho all-reduce, replicated field solve",
              "c4": "C4: 2D XY two-stream (BASELINE configs[3]), %dx%d grid, %.3g particles per GPU, periodic",
+             "seed": "N3 (SURVEY 8f): axisymmetric r-z column, problem/13_seed.jl geometry -- %dx%d-cell-class axial grid (65x125 nodes), "
+                     "%.3g particles per GPU, axial Boris pusher, plates in z, discard dim 2, no MCC",
              "walls": "N1 (SURVEY 8f): bounded RF cell with surface tracker -- %dx%d grid, %.3g particles per GPU, "
                       "2 fixed electrodes, absorbing walls, reflective block, no MCC"}
     d = {"workload": names[a.workload] % (cells, cells, ppg), "grid_cells": [cells, cells],
@@ -91,6 +95,11 @@ def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
         dh, dt = 6.7 * 0.01 / 128, 1 / (400 * 13.56e6)
         spec = [("e-", -O.qe, O.me, 30000.0, 0.0), ("He+", O.qe, 3.99 * O.mp, 300.0, 0.0)]
         bmode = (2, 1) if a.workload == "c5" else (2, 2)
+    elif a.workload == "seed":
+        dh, dt = 0.08 / 32, 0.075e-9
+        spec = [("e-", -O.qe, O.me, 11600.0, 0.0), ("Ar+", O.qe, 3.99 * O.mp, 300.0, 0.0)]
+        bmode = (0, 2)
+        cells = 64
     else:
         w = 2 * math.pi * 9e3 * math.sqrt(2e-6 * 1e24)
         dh = 5e-3 * O.c0 / w
@@ -98,6 +107,8 @@ def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
         spec = [("e-", -O.qe, O.me, 300.0, 1e7), ("He+", O.qe, 4.002602 * O.me / 5.48579903e-04, 300.0, 0.0)]
         bmode = (1, 1)
     nx = ny = cells + 1
+    if a.workload == "seed":
+        nx, ny = 65, 125
     cg = CO.make_grid(nx, ny, dh, dh)
     sp = []
     for name, q, m, T, drift in spec:
@@ -106,7 +117,10 @@ def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
         if drift:
             v[0, : n_each // 2] += drift
             v[0, n_each // 2:] -= drift
-        s.set(rng.random(n_each) * cells * dh, rng.random(n_each) * cells * dh, v[0], v[1], v[2])
+        if a.workload == "seed":
+            s.set(rng.random(n_each) * 0.5 * (nx - 1) * dh, (0.25 + 0.5 * rng.random(n_each)) * (ny - 1) * dh, v[0], v[1], v[2])
+        else:
+            s.set(rng.random(n_each) * cells * dh, rng.random(n_each) * cells * dh, v[0], v[1], v[2])
         sp.append(s)
     nn = nx * ny
     E = (rng.standard_normal(3 * nn) * 10.0)
@@ -135,8 +149,8 @@ def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
         t0 = time.perf_counter()
         fn(probe.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), (C.c_int32 * 2)(1, 1))
         tt.append(time.perf_counter() - t0)
-    use_mt = cores > 1 and tt[1] < 0.8 * tt[0] and a.workload != "walls"
-    adv = Lc.orc_advance_mt if use_mt else Lc.orc_advance
+    use_mt = cores > 1 and tt[1] < 0.8 * tt[0] and a.workload not in ("walls", "seed")
+    adv = Lc.orc_advance_mt if use_mt else (Lc.orc_advance_rz if a.workload == "seed" else Lc.orc_advance)
     dep = Lc.orc_deposit_mt if use_mt else Lc.orc_deposit
     if not use_mt:
         cores = 1
@@ -267,6 +281,7 @@ def run_b200(a):
     t_build = time.perf_counter()
     wl = (workloads.build_c5(ppg, cells, n_gpus_total=8, device=local) if a.workload == "c5"
           else workloads.build_walls(ppg, cells, device=local) if a.workload == "walls"
+          else workloads.build_seed(ppg, device=local) if a.workload == "seed"
           else workloads.build_c4(ppg, cells, device=local))
     rt = wl.rt
     rt.use_torch_stream()

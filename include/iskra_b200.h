@@ -263,6 +263,22 @@ int32_t iskb_surface_charge(iskb_tracker *st, int32_t surface_id, double *dq_out
  * routes dq/area into it (the evident intent); default 0 = the reference's behaviour. */
 int32_t iskb_tracker_route_hits_to_sigma(iskb_tracker *st, int32_t on);
 
+/* ---- axisymmetric r-z variant ------------------------------------------------- */
+/* create_axial_grid(rr, zz)  RegularGrids.jl:84-97 is iskb_grid_set with (dr, dz); gather and deposit of an
+ * AxialGrid{2} (cloud_in_cell.jl:38-73) are the Cartesian ones.  What differs: */
+/* cell_volume(g::AxialGrid{2})  RegularGrids.jl:40-53 (ring volumes) -- or any other node volume array */
+int32_t iskb_cell_volume_set(iskb_ctx *ctx, const double *V /* nx*ny */);
+/* create_poisson_solver(grid::AxialGrid{2}, eps0)  generalized_poisson.jl:70-199: the caller assembles the
+ * operator with the reference's own assembler and hands it over (nn*nn, column-major, nn = nx*ny); Dirichlet /
+ * Neumann rows set through this API are applied on top as in the reference.  Dense path (nn <= 8192). */
+int32_t iskb_poisson_set_dense(iskb_ctx *ctx, const double *A, int64_t nn);
+/* create_boris_pusher() / create_axial_boris_pusher()  pushers.jl:5-6 for iskb_step and iskb_push */
+#define ISKB_PUSHER_XY 0
+#define ISKB_PUSHER_RZ 1   /* push_in_cartesian! then transform_from_cartesian_to_cylindrical!  pushers.jl:13-17 */
+int32_t iskb_set_pusher(iskb_ctx *ctx, int32_t kind);
+/* transform_from_cartesian_to_cylindrical!(part, dt)  pushers.jl:52-66 on its own */
+int32_t iskb_transform_cylindrical(iskb_species *sp, double dt);
+
 /* ---- MCC: Chemistry/src/mcc.jl ----------------------------------------------------------- */
 /* mcc(reactions) -> MonteCarloCollisions(collisions)  mcc.jl:313-320, :27-51.
  * One source species colliding with one fluid target (accept, :291-311).  Process k has

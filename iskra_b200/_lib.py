@@ -12,6 +12,7 @@ OK = 0
 E_INVALID, E_CUDA, E_CAPACITY, E_PMAX, E_PK, E_OOB, E_NCCL, E_UNSUPPORTED, E_SINGULAR = range(-1, -10, -1)
 BND_NONE, BND_WRAP, BND_DISCARD = 0, 1, 2
 BC_OPEN, BC_PERIODIC = 0, 1
+PUSHER_XY, PUSHER_RZ = 0, 1
 EDGE_LEFT, EDGE_RIGHT, EDGE_BOTTOM, EDGE_TOP = 0, 1, 2, 3
 SURF_PERIODIC, SURF_ABSORBING, SURF_REFLECTIVE, SURF_ELECTRODE_FIXED, SURF_ELECTRODE_FLOATING = range(5)
 MCC_ELASTIC_ISOTROPIC, MCC_ELASTIC_BACKWARD, MCC_INELASTIC_BACKWARD, MCC_EXCITATION, MCC_IONIZATION = range(5)
@@ -97,6 +98,10 @@ SIGNATURES = {
     "iskb_surface_charge": [vp, i32, C.POINTER(f64), i32],
     "iskb_tracker_route_hits_to_sigma": [vp, i32],
     "iskb_warning_too_fast": [vp, C.POINTER(i32)],
+    "iskb_cell_volume_set": [vp, vp],
+    "iskb_poisson_set_dense": [vp, vp, i64],
+    "iskb_set_pusher": [vp, i32],
+    "iskb_transform_cylindrical": [vp, f64],
 }
 _RESTYPES = {"iskb_last_error": C.c_char_p}
 

@@ -615,7 +615,8 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   ISKB_TRY(poisson_prepare(c));
   for (int it = 0; it < n_steps; ++it) {
-    const bool tiled = c->sort_interval > 0;
+    const bool tiled = c->sort_interval > 0 && !c->pusher_rz;   // the r-z transform lives in the simple kernels
+    if (c->pusher_rz && c->tracker) return iskb_fail(ISKB_E_UNSUPPORTED, "surface tracker with the axial pusher");
     if (tiled)
       for (iskb_species *s : c->species) ISKB_TRY(maybe_sort(c, s));
     for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));       // :109-111

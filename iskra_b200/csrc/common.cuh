@@ -91,6 +91,9 @@ struct PoissonState {
   double *d_Ainv = nullptr;
   int64_t nn_dense = 0;
   double *d_rowscale = nullptr;   // row equilibration of the dense system (dh^2 / 1 / Neumann row scale)
+  // --- operator assembled by the caller (axial grids, generalized_poisson.jl:70-199) ---
+  bool has_custom = false;
+  std::vector<double> custom_A;   // nn x nn column-major, before Dirichlet / Neumann rows
   // --- sigma dofs and Neumann rows (add_new_dof / apply_neumann, generalized_poisson.jl:217-269) ---
   int n_sigma = 0;
   std::vector<double> sigma;        // host copy of b[sigma dofs], authoritative while sigma_host_newer
@@ -133,6 +136,7 @@ struct iskb_ctx {
   int sort_max_interval = 0;          //           ... or this many steps have passed
   int sort_full_interval = 0;         // > 0: between full sorts re-group by tile only (cheaper)
   int64_t step_count = 0;
+  int pusher_rz = 0;                 // BorisPusher{:rz}: transform_from_cartesian_to_cylindrical! after the push
   bool warn_too_fast = false;        // check!'s "particle is too fast" message condition was seen (sticky until read)
   // optional per-kernel timing of the dominant (advance) kernel, CUDA events on the launch stream
   bool profile = false;

@@ -57,7 +57,7 @@ __global__ void k_gather(const double *__restrict__ x, const double *__restrict_
 // partE == nullptr: gather on the fly (advance!, ParticleInCell.jl:57-59)
 __global__ void k_push(double *x, double *y, double *vx, double *vy, double *vz,
                        const int64_t *__restrict__ cnt, GridDev g, const double2 *__restrict__ E2,
-                       const double *__restrict__ pE, int64_t ld, double qm, double dt, int *status) {
+                       const double *__restrict__ pE, int64_t ld, double qm, double dt, int *status, int rz) {
   const int64_t n = cnt[CNT_NSLOTS];
   const double c1 = __dmul_rn(__dmul_rn(0.5, dt), qm);   // (0.5dt)*qm  pushers.jl:41
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
@@ -72,14 +72,27 @@ __global__ void k_push(double *x, double *y, double *vx, double *vy, double *vz,
     } else if (!gather_E(E2, g, px, py, ex, ey)) {
       atomicOr(status, ISKB_ST_OOB);
     }
-    const double nvx = push_v(vx[p], ex, c1, qm, dt);
+    double nvx = push_v(vx[p], ex, c1, qm, dt);
     const double nvy = push_v(vy[p], ey, c1, qm, dt);
-    const double nvz = push_v(vz[p], ez, c1, qm, dt);
+    double nvz = push_v(vz[p], ez, c1, qm, dt);
+    double nx_ = push_x(px, nvx, dt);
+    if (rz) to_cylindrical(nx_, nvx, nvz, dt);   // push_particles!(::BorisPusher{:rz}, ...)  pushers.jl:13-17
     vx[p] = nvx;
     vy[p] = nvy;
     vz[p] = nvz;
-    x[p] = push_x(px, nvx, dt);
+    x[p] = nx_;
     y[p] = push_x(py, nvy, dt);
+  }
+}
+
+__global__ void k_to_cylindrical(double *x, double *vx, double *vz, const int64_t *__restrict__ cnt, double dt) {
+  const int64_t n = cnt[CNT_NSLOTS];
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    double px = x[p], pvx = vx[p], pvz = vz[p];
+    if (is_dead(px)) continue;
+    to_cylindrical(px, pvx, pvz, dt);
+    x[p] = px; vx[p] = pvx; vz[p] = pvz;
   }
 }
 
@@ -179,7 +192,7 @@ __global__ void k_rho_finalize(RhoFin f, const double *__restrict__ V, double *r
 __global__ void k_advance_simple(double *x, double *y, double *vx, double *vy, double *vz,
                                  const double *__restrict__ wg, int64_t *cnt, int first_from_begin,
                                  GridDev g, const double2 *__restrict__ E2, double qm, double dt,
-                                 int mode_x, int mode_y, double *u, int *status, unsigned long long *vmax2) {
+                                 int mode_x, int mode_y, double *u, int *status, unsigned long long *vmax2, int rz) {
   const int64_t n = cnt[CNT_NSLOTS];
   const int64_t first = first_from_begin ? cnt[CNT_BEGIN] : 0;
   double vm2 = 0.0;
@@ -193,11 +206,12 @@ __global__ void k_advance_simple(double *x, double *y, double *vx, double *vy, d
       if (!is_dead(px)) {
         double ex, ey;
         if (!gather_E(E2, g, px, py, ex, ey)) atomicOr(status, ISKB_ST_OOB);
-        const double nvx = push_v(vx[p], ex, c1, qm, dt);
+        double nvx = push_v(vx[p], ex, c1, qm, dt);
         const double nvy = push_v(vy[p], ey, c1, qm, dt);
-        const double nvz = push_v(vz[p], 0.0, c1, qm, dt);
+        double nvz = push_v(vz[p], 0.0, c1, qm, dt);
         px = push_x(px, nvx, dt);
         py = push_x(py, nvy, dt);
+        if (rz) to_cylindrical(px, nvx, nvz, dt);
         vm2 = fmax(vm2, (nvx * nvx + nvy * nvy) + nvz * nvz);
         bool dead = (mode_x == ISKB_BND_DISCARD) && boundary_axis(px, g.ox, g.Lx, mode_x);
         if (!dead) dead = (mode_y == ISKB_BND_DISCARD) && boundary_axis(py, g.oy, g.Ly, mode_y);
@@ -352,7 +366,7 @@ extern "C" int32_t iskb_push(iskb_species *sp, const double *partE, double dt) {
   const double qm = sp->q / sp->m;   // pushers.jl:39
   ISKB_TRY(sp_vmax_unknown(sp));
   k_push<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4],
-                                              sp->d_cnt, c->g, c->d_E2, d, n, qm, dt, c->d_status);
+                                              sp->d_cnt, c->g, c->d_E2, d, n, qm, dt, c->d_status, c->pusher_rz);
   LAUNCH_CHECK(c);
   if (d) {
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -459,10 +473,13 @@ int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_
   const double qm = sp->q / sp->m;
   int blocks = from_begin ? c->n_sm : grid_for(sp);
   if (!from_begin) ISKB_TRY(sp_vmax_reset(sp));
+  if (!from_begin) ISKB_TRY(prof_begin(c));
   k_advance_simple<<<blocks, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4],
                                                   sp->col[5], sp->d_cnt, from_begin ? 1 : 0, c->g, c->d_E2, qm,
-                                                  dt, mode_x, mode_y, deposit ? sp->d_u : nullptr, c->d_status, sp->d_vmax2);
+                                                  dt, mode_x, mode_y, deposit ? sp->d_u : nullptr, c->d_status, sp->d_vmax2,
+                                                  c->pusher_rz);
   LAUNCH_CHECK(c);
+  if (!from_begin) ISKB_TRY(prof_end(c));
   if (mode_x == ISKB_BND_DISCARD || mode_y == ISKB_BND_DISCARD) sp->counts_stale = true;
   return ISKB_OK;
 }
@@ -516,5 +533,28 @@ extern "C" int32_t iskb_species_remove_in_cells(iskb_species *sp, const uint8_t 
   ISKB_TRY(sp_sync_counts(sp));
   cudaFree(d);
   if (n_removed) *n_removed = before - (sp->h_nslots - sp->h_ndead);
+  return ISKB_OK;
+}
+
+// ---- axisymmetric variant -----------------------------------------------------
+extern "C" int32_t iskb_set_pusher(iskb_ctx *c, int32_t kind) {
+  if (!c || (kind != ISKB_PUSHER_XY && kind != ISKB_PUSHER_RZ)) return iskb_fail(ISKB_E_INVALID, "bad pusher kind");
+  c->pusher_rz = kind == ISKB_PUSHER_RZ;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_transform_cylindrical(iskb_species *sp, double dt) {
+  if (!sp) return iskb_fail(ISKB_E_INVALID, "null species");
+  iskb_ctx *c = sp->ctx;
+  ISKB_TRY(sp_vmax_unknown(sp));
+  k_to_cylindrical<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[2], sp->col[4], sp->d_cnt, dt);
+  LAUNCH_CHECK(c);
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_cell_volume_set(iskb_ctx *c, const double *V) {
+  if (!c || !c->has_grid || !V) return iskb_fail(ISKB_E_INVALID, "no grid / V");
+  CU_TRY(cudaMemcpyAsync(c->d_V, V, (int64_t)c->g.nx * c->g.ny * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(cudaStreamSynchronize(c->stream));
   return ISKB_OK;
 }

@@ -80,6 +80,22 @@ __device__ __forceinline__ double push_x(double x, double v, double dt) {
   return __dadd_rn(__dmul_rn(dt, v), x);
 }
 
+// transform_from_cartesian_to_cylindrical!(part, dt)  pushers.jl:52-66 for one particle (BorisPusher{:rz}):
+//   y = dt*vz ; r = sqrt(x^2 + y^2) ; sin = y/r (0 where r == 0: `r .~ 0.0` with the default tolerances is an
+//   exact zero test) ; cos = sqrt(1 - sin^2) ; vr = cos*vx + sin*vz ; vy = -sin*vx + cos*vz ; x = r
+__device__ __forceinline__ void to_cylindrical(double &x, double &vx, double &vz, double dt) {
+  const double y = __dmul_rn(dt, vz);
+  const double r = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+  double sn = __ddiv_rn(y, r);
+  if (r == 0.0) sn = 0.0;
+  const double cs = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(sn, sn)));
+  const double vr = __dadd_rn(__dmul_rn(cs, vx), __dmul_rn(sn, vz));
+  const double vy = __dadd_rn(__dmul_rn(-sn, vx), __dmul_rn(cs, vz));
+  x = r;
+  vx = vr;
+  vz = vy;
+}
+
 // Julia Base mod(x, y) for Float64 (float.jl) and fld = round((x - mod(x,y))/y) (div.jl).
 __device__ __forceinline__ double jl_fld(double x, double y) {
   const double r = fmod(x, y);

@@ -41,7 +41,10 @@ void assemble_dense(const iskb_ctx *c, std::vector<double> &A, std::vector<doubl
   A.assign((size_t)(nn * nn), 0.0);
   b.assign((size_t)nn, 0.0);
   auto at = [&](int64_t r, int64_t col) -> double & { return A[(size_t)(r + col * nn)]; };
-  for (int j = 0; j < ny; ++j)
+  if (ps.has_custom)                                     // operator assembled by the caller (axial grid :70-199)
+    for (int64_t col = 0; col < nnodes; ++col)
+      for (int64_t r = 0; r < nnodes; ++r) at(r, col) = ps.custom_A[(size_t)(r + col * nnodes)];
+  for (int j = 0; j < ny && !ps.has_custom; ++j)
     for (int i = 0; i < nx; ++i) {                       // :42-61
       const int64_t r = i + (int64_t)j * nx;
       if (i < nx - 1) { at(r, r) -= 1.0; at(r, r + 1) += 1.0; }
@@ -50,12 +53,13 @@ void assemble_dense(const iskb_ctx *c, std::vector<double> &A, std::vector<doubl
       if (j > 0) { at(r, r) -= 1.0; at(r, r - nx) += 1.0; }
     }
   const double d2 = c->g.dx * c->g.dx;                   // :65
-  for (auto &v : A) v /= d2;
+  if (!ps.has_custom)
+    for (auto &v : A) v /= d2;
   for (int k = 0; k < ps.n_sigma; ++k) {                 // :227-228
     at(nnodes + k, nnodes + k) = 1.0;
     b[(size_t)(nnodes + k)] = ps.sigma[(size_t)k];
   }
-  if (ps.periodic_j) {                                   // apply_periodic(ps, 1) :291-306
+  if (ps.periodic_j && !ps.has_custom) {                 // apply_periodic(ps, 1) :291-306
     const double cc = (0.5 + 0.5) / (c->g.dx * c->g.dx);
     for (int jj = 0; jj < 2; ++jj) {
       const int j = jj == 0 ? 0 : ny - 1;
@@ -66,7 +70,7 @@ void assemble_dense(const iskb_ctx *c, std::vector<double> &A, std::vector<doubl
       }
     }
   }
-  if (ps.periodic_i) {                                   // apply_periodic(ps, 2) :308-323
+  if (ps.periodic_i && !ps.has_custom) {                 // apply_periodic(ps, 2) :308-323
     const double cc = (0.5 + 0.5) / (c->g.dy * c->g.dy);
     for (int j = 0; j < ny; ++j)
       for (int ii = 0; ii < 2; ++ii) {
@@ -622,7 +626,7 @@ static int32_t prepare_dense(iskb_ctx *c) {
   assemble_dense(c, A, b);
   const double d2 = c->g.dx * c->g.dx;
   std::vector<double> rowscale((size_t)nn, 1.0);
-  if (ps.n_sigma > 0 || !ps.neu_kind.empty()) {
+  if (ps.n_sigma > 0 || !ps.neu_kind.empty() || ps.has_custom) {
     // keep the phi block; the sigma columns go to the right-hand side (k_dense_rhs_sigma)
     const int64_t nt = nn + ps.n_sigma;
     std::vector<double> P((size_t)(nn * nn)), coef((size_t)nn, 0.0);
@@ -647,7 +651,7 @@ static int32_t prepare_dense(iskb_ctx *c) {
   for (int64_t r = 0; r < nn; ++r) {
     if (ps.isdir[(size_t)r]) continue;
     double sc = d2;
-    if (!ps.neu_kind.empty() && ps.neu_kind[(size_t)r]) {
+    if (ps.has_custom || (!ps.neu_kind.empty() && ps.neu_kind[(size_t)r])) {
       double mx = 0.0;
       for (int64_t col = 0; col < nn; ++col) mx = std::fmax(mx, std::fabs(A[(size_t)(r + col * nn)]));
       sc = mx > 0.0 ? 1.0 / mx : 1.0;
@@ -691,7 +695,7 @@ int32_t poisson_prepare(iskb_ctx *c) {
     AxisInfo axi{}, axj{};
     bool has_neumann = ps.n_sigma > 0;
     for (uint8_t k : ps.neu_kind) has_neumann |= k != 0;
-    bool sep = whole && c->g.dx == c->g.dy && !has_neumann;
+    bool sep = whole && c->g.dx == c->g.dy && !has_neumann && !ps.has_custom;
     sep = sep && classify_axis(ps.periodic_i, eL, eR, nx, axi) && classify_axis(ps.periodic_j, eB, eT, ny, axj);
     // choose the transform axis: the solve axis needs >= 3 unknowns when cyclic, >= 1 otherwise
     auto ok_solve = [](const AxisInfo &b) { return b.kind == AX_RING ? b.m >= 3 : b.m >= 1; };
@@ -835,7 +839,7 @@ int32_t poisson_solve(iskb_ctx *c) {
   const int nx = c->g.nx, ny = c->g.ny;
   const int64_t nn = (int64_t)nx * ny;
   if (ps.mode == 2) {
-    if (ps.d_neu_coef && ps.n_sigma > 0)
+    if (ps.d_neu_coef && (ps.n_sigma > 0 || ps.has_custom))
       k_dense_rhs_sigma<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(c->d_rho, ps.d_isdir, ps.d_dval, ps.eps0, ps.d_rowscale,
                                                                   ps.d_neu_coef, ps.d_neu_dof, ps.d_sigma, nn, ps.d_w1);
     else
@@ -904,6 +908,8 @@ extern "C" int32_t iskb_poisson_create(iskb_ctx *c, double eps0) {
   ps.n_sigma = 0;
   ps.sigma.clear();
   ps.neu_kind.clear(); ps.neu_i2.clear(); ps.neu_j2.clear(); ps.neu_dof.clear();
+  ps.has_custom = false;
+  ps.custom_A.clear();
   ps.structure_dirty = ps.values_dirty = true;
   return ISKB_OK;
 }
@@ -1077,6 +1083,16 @@ extern "C" int32_t iskb_phi_at(iskb_ctx *c, int32_t i, int32_t j, double *out) {
   CU_TRY(cudaMemcpyAsync(c->h_scratch, c->d_phi + (i - 1) + (int64_t)(j - 1) * c->g.nx, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   memcpy(out, c->h_scratch, sizeof(double));
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_poisson_set_dense(iskb_ctx *c, const double *A, int64_t nn) {
+  if (!c || !c->ps.created || !A) return iskb_fail(ISKB_E_INVALID, "no Poisson solver / operator");
+  if (nn != (int64_t)c->g.nx * c->g.ny) return iskb_fail(ISKB_E_INVALID, "operator must be (nx*ny)^2");
+  if (nn > 8192) return iskb_fail(ISKB_E_UNSUPPORTED, "caller-assembled operators use the dense path (at most 8192 nodes)");
+  c->ps.custom_A.assign(A, A + nn * nn);
+  c->ps.has_custom = true;
+  c->ps.structure_dirty = true;
   return ISKB_OK;
 }
 

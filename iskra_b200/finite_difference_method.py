@@ -34,8 +34,58 @@ class PoissonSolver:
 
 
 def create_poisson_solver(grid, eps0):
-    """create_poisson_solver(grid::CartesianGrid{2}, eps0)  :27-30"""
-    return PoissonSolver(grid, eps0)
+    """create_poisson_solver(grid::CartesianGrid{2}, eps0)  :27-30 / (grid::AxialGrid{2}, eps0)  :70-199"""
+    ps = PoissonSolver(grid, eps0)
+    from .regular_grids import AxialGrid
+    if isinstance(grid, AxialGrid):
+        A = np.asfortranarray(assemble_axial_operator(grid))
+        L.check(ps._rt.lib.iskb_poisson_set_dense(ps._rt.h, L.ptr(A), A.shape[0]))
+    return ps
+
+
+def assemble_axial_operator(grid):
+    """The matrix of create_poisson_solver(grid::AxialGrid{2}, eps0)  :70-199, row by row in the reference's
+    accumulation order (every entry is a short sum of +-1/dr^2, +-1/dz^2, +-0.5/dr/r terms; the order in which the
+    diagonal collects them differs between the row families and is kept).  In a Julia deployment the reference's
+    own assembler produces this array; it is handed to the device as is (iskb_poisson_set_dense)."""
+    nr, nz = grid.n
+    dr, dz = grid.dh
+    nn = nr * nz
+    A = np.zeros((nn, nn), order="F")
+    ar, az = 1.0 / dr ** 2, 1.0 / dz ** 2
+    idx = lambda i, j: (i - 1) + (j - 1) * nr            # 1-based (i, j) -> 0-based dof
+    for j in range(1, nz + 1):
+        for i in range(1, nr + 1):
+            r_ = idx(i, j)
+            d = 0.0
+            # radial part
+            if i == nr:
+                d = (d + ar) - 2.0 * ar                   # :151-152, :181-182, :191-192
+                A[r_, idx(i - 1, j)] += ar
+            else:
+                A[r_, idx(i + 1, j)] += ar
+                d = d - 2.0 * ar
+                if i == 1:
+                    d = d + ar                            # :137-139, :161-163, :171-173
+                else:
+                    A[r_, idx(i - 1, j)] += ar
+            # axial part
+            if j == nz:
+                d = (d + az) - 2.0 * az                   # :123-124, :175-176, :195-196
+                A[r_, idx(i, j - 1)] += az
+            else:
+                A[r_, idx(i, j + 1)] += az
+                d = d - 2.0 * az
+                if j == 1:
+                    d = d + az                            # :106-108, :165-167, :185-187
+                else:
+                    A[r_, idx(i, j - 1)] += az
+            A[r_, r_] = d
+            if 1 < i < nr:                                # 1/r dphi/dr :94-95, :110-111, :127-128
+                r = (i - 1) * dr
+                A[r_, idx(i + 1, j)] += 0.5 / dr / r
+                A[r_, idx(i - 1, j)] -= 0.5 / dr / r
+    return A
 
 
 def apply_periodic(ps, axis):

@@ -258,11 +258,31 @@ def density(species, grid):
 
 
 class BorisPusher:
-    """BorisPusher{:xy}  pushers.jl:4-5"""
+    """BorisPusher{T}  pushers.jl:4-6 ; kind "xy" or "rz" """
+
+    def __init__(self, kind="xy"):
+        self.kind = kind
 
 
 def create_boris_pusher():
-    return BorisPusher()
+    return BorisPusher("xy")
+
+
+def create_axial_boris_pusher():
+    """create_axial_boris_pusher()  pushers.jl:6"""
+    return BorisPusher("rz")
+
+
+def _set_pusher(rt, pusher):
+    kind = L.PUSHER_RZ if (pusher is not None and getattr(pusher, "kind", "xy") == "rz") else L.PUSHER_XY
+    L.check(rt.lib.iskb_set_pusher(rt.h, kind))
+
+
+def transform_from_cartesian_to_cylindrical_(part, dt):
+    """transform_from_cartesian_to_cylindrical!(part, dt)  pushers.jl:52-66"""
+    part._push()
+    L.check(part._rt.lib.iskb_transform_cylindrical(part._h, float(dt)))
+    part._touched_on_device()
 
 
 def push_particles_(pusher, part, E, B, dt, grid=None):
@@ -271,6 +291,7 @@ def push_particles_(pusher, part, E, B, dt, grid=None):
     if B is not None and np.any(np.asarray(B) != 0):
         raise NotImplementedError("B != 0 is outside the hot path (calculate_magnetic_field == 0)")
     part._push(grid)
+    _set_pusher(part._rt, pusher)
     pe = None if E is None else np.asfortranarray(E, dtype=np.float64)
     L.check(part._rt.lib.iskb_push(part._h, L.ptr(pe), float(dt)))
     part._touched_on_device()
@@ -511,6 +532,7 @@ def solve(config, dt=1e-5, timesteps=200, after_push=None, sort_interval=0, fuse
         s._push(grid)
     for inter in config.interactions:
         inter._bind(config)
+    _set_pusher(rt, config.pusher)
     if fused:
         mx, my = after_push if after_push is not None else (L.BND_WRAP, L.BND_WRAP)
         rt.set_after_push(mx, my)

@@ -6,7 +6,7 @@ import numpy as np
 from . import _lib as L
 from .runtime import Runtime
 
-_BC = {"open": L.BC_OPEN, "periodic": L.BC_PERIODIC}
+_BC = {"open": L.BC_OPEN, "periodic": L.BC_PERIODIC, "other": L.BC_OPEN}
 
 
 class UniformGrid:
@@ -36,6 +36,37 @@ class UniformGrid:
 
 
 CartesianGrid = UniformGrid
+
+
+class AxialGrid(UniformGrid):
+    """AxialGrid{2} = UniformGrid{:rz,2}  RegularGrids.jl:18; create_axial_grid :84-97.  Coordinates (r, z); the node
+    volumes are rings (cell_volume :40-53), uploaded once."""
+
+    def __init__(self, rr, zz, bottom="open", top="open", device=None):
+        super().__init__(rr, zz, "other", "other", bottom, top, device)
+        L.check(self._rt.lib.iskb_cell_volume_set(self._rt.h, L.ptr(np.asfortranarray(axial_cell_volume(self)))))
+
+
+def create_axial_grid(rr, zz, bottom="open", top="open", device=None):
+    """create_axial_grid(rr, zz; bottom, top)  RegularGrids.jl:84-97"""
+    return AxialGrid(rr, zz, bottom, top, device)
+
+
+def axial_cell_volume(g):
+    """cell_volume(g::AxialGrid{2})  RegularGrids.jl:40-53"""
+    dr, dz = g.dh
+    nr, nz = g.n
+    i = np.arange(1, nr + 1, dtype=np.float64)
+    ring = np.pi * dz * ((i * dr - 0.5 * dr) ** 2 - (i * dr - 1.5 * dr) ** 2)
+    ring[0] = np.pi * dz * (0.5 * dr) ** 2
+    ring[nr - 1] = np.pi * dz * ((nr * dr - 1.0 * dr) ** 2 - (nr * dr - 1.5 * dr) ** 2)
+    V = np.repeat(ring[:, None], nz, axis=1)
+    (_, _), (bottom, top) = g.bcs
+    if bottom != "periodic":
+        V[:, 0] *= 0.5
+    if top != "periodic":
+        V[:, nz - 1] *= 0.5
+    return V
 
 
 def create_uniform_grid(xx, yy, left="open", right="open", bottom="open", top="open", device=None):

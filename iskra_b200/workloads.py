@@ -9,6 +9,9 @@
        (i = 1) and the grounded one (i = nx) registered as FixedPotentialElectrode surfaces, default
        AbsorbingSurface on the other two faces, a ReflectiveSurface block inside, e- + He+ loaded
        uniformly outside the block, no MCC.  advance! runs with config.tracker (track! / check!).
+  seed  : SURVEY.md 8f row N3 at scale -- problem/13_seed.jl geometry (axial r-z grid, plates at z = 0 / Lz, axial
+       Boris pusher, discard! dim 2) with a plasma column instead of a single seed electron: 65 x 125 nodes (the
+       operator of an AxialGrid is dense: <= 8192 nodes), e- + Ar+ loaded in r < R/2, no MCC.
   c4 : 2-D XY two-stream (configs[3]) -- 1025x1025 nodes, dh and CFL of problem/10_two_streams.jl,
        fully "periodic", two +-1e7 m/s electron beams at 300 K + co-located ions, wrap! both axes.
 """
@@ -193,3 +196,37 @@ def build_walls(particles_per_gpu=100_000_000, cells=1024, seed=3, device=None):
     meta = {"grid_nodes": [nx, ny], "dh": dh, "dt": dt, "particles_per_gpu": 2 * n_each, "mcc_processes": [],
             "surfaces": "2 fixed electrodes (whole edges), default absorbing, reflective block %d..%d" % (b0, b1)}
     return Workload("walls", cfg, dt, (L.BND_DISCARD, L.BND_DISCARD), rf=(L.EDGE_LEFT, 450.0, f), meta=meta)
+
+
+def build_seed(particles_per_gpu=40_000_000, seed=5, device=None):
+    """N3 at scale (see the module docstring).  The grid is fixed at 65 x 125 nodes."""
+    nr, nz = 65, 125
+    dh = 0.08 / 32                                    # 13_seed.jl:9-13
+    dt = 0.075e-9                                     # :18
+    n_each = particles_per_gpu // 2
+    grid = RG.create_axial_grid(np.arange(nr) * dh, np.arange(nz) * dh, device=device)
+    grid._rt.comm_init_torch()
+    cap = n_each + 1024
+    wgt = 5e5 * 200_000 / n_each
+    e = PIC.create_kinetic_species("e-", cap, -qe, me, wgt)
+    iAr = PIC.create_kinetic_species("Ar+", cap, +qe, 3.99 * mp, wgt)
+    solver = FDM.create_poisson_solver(grid, eps0)
+    bot = np.zeros((nr, nz), dtype=bool)
+    bot[:, 0] = True
+    top = np.zeros((nr, nz), dtype=bool)
+    top[:, nz - 1] = True
+    FDM.apply_dirichlet(solver, bot, 0.0)             # :49-52
+    FDM.apply_dirichlet(solver, top, 20.0)
+    R, Lz = (nr - 1) * dh, (nz - 1) * dh
+    for sp, T, sd in ((e, 11600.0, 1), (iAr, 300.0, 2)):
+        src = PIC.create_thermalized_beam(sp, [0.5 * R, 0.5 * Lz], [0.0, 0.0, 0.0], dx=[0.0, 0.25 * Lz], T=T, rate=1.0)
+        sp._push(grid)
+        L.check(sp._rt.lib.iskb_species_sample_maxwellian(sp._h, int(n_each), L.ptr(src.wx), L.ptr(src.dx), L.ptr(src.wv),
+                                                          L.ptr(src.dv), int(seed * 1000 + sd)))
+        sp._touched_on_device()
+    cfg = Config()
+    cfg.grid, cfg.solver, cfg.pusher = grid, solver, PIC.create_axial_boris_pusher()
+    cfg.species, cfg.interactions = [e, iAr], []
+    PIC._set_pusher(grid._rt, cfg.pusher)
+    meta = {"grid_nodes": [nr, nz], "dh": dh, "dt": dt, "particles_per_gpu": 2 * n_each, "mcc_processes": []}
+    return Workload("seed", cfg, dt, (L.BND_NONE, L.BND_DISCARD), meta=meta)

@@ -711,3 +711,32 @@ int64_t orc_advance_tracked(orc_species *s, const orc_grid *g, orc_tracker *t, c
   for (int d = 0; d < 2; ++d) if (bmode[d] == 1) orc_wrap(s, g, d + 1);
   return nabs;
 }
+
+/* ==== SURVEY.md 8f row N3: axisymmetric r-z pusher (ParticleInCell/src/pic/pushers.jl:13-17, 52-66) ========= */
+static inline void to_cylindrical1(double *x, double *vx, double *vz, double dt) {
+  double y = dt * *vz;                               /* :54 */
+  double r = sqrt(*x * *x + y * y);                  /* :55 */
+  double sn = y / r;                                 /* :57 */
+  if (r == 0.0) sn = 0.0;                            /* :58  r .~ 0.0 is an exact zero test */
+  double cs = sqrt(1.0 - sn * sn);                   /* :59 */
+  double vr = cs * *vx + sn * *vz;                   /* :61 */
+  double vy = -sn * *vx + cs * *vz;                  /* :62 */
+  *x = r; *vx = vr; *vz = vy;                        /* :63-65 */
+}
+
+void orc_to_cylindrical(orc_species *s, double dt) {
+  for (int64_t p = 0; p < s->np; ++p) to_cylindrical1(&s->x[p], &s->vx[p], &s->vz[p], dt);
+}
+
+/* advance! with BorisPusher{:rz}: gather, push_in_cartesian!, transform, after_push */
+void orc_advance_rz(orc_species *s, const orc_grid *g, const double *E, double dt, const int32_t *bmode) {
+  const double qm = s->q / s->m;
+  for (int64_t p = 0; p < s->np; ++p) {
+    double e3[3];
+    gather1(g, E, s->x[p], s->y[p], e3);
+    push1(&s->x[p], &s->y[p], &s->vx[p], &s->vy[p], &s->vz[p], e3, qm, dt);
+    to_cylindrical1(&s->x[p], &s->vx[p], &s->vz[p], dt);
+  }
+  for (int d = 1; d <= 2; ++d) if (bmode[d - 1] == 2) orc_discard(s, g, d);
+  for (int d = 1; d <= 2; ++d) if (bmode[d - 1] == 1) orc_wrap(s, g, d);
+}
