@@ -48,7 +48,7 @@ def workload_defaults(a):
     if a.workload == "c5":
         return a.particles_per_gpu or 125_000_000, a.cells or 2048
     if a.workload == "seed":
-        return a.particles_per_gpu or 40_000_000, 64
+        return a.particles_per_gpu or 40_000_000, a.cells or 32
     return a.particles_per_gpu or 100_000_000, a.cells or 1024
 
 
@@ -99,7 +99,7 @@ def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
         dh, dt = 0.08 / 32, 0.075e-9
         spec = [("e-", -O.qe, O.me, 11600.0, 0.0), ("Ar+", O.qe, 3.99 * O.mp, 300.0, 0.0)]
         bmode = (0, 2)
-        cells = 64
+        cells = a.cells or 32
     else:
         w = 2 * math.pi * 9e3 * math.sqrt(2e-6 * 1e24)
         dh = 5e-3 * O.c0 / w
@@ -108,7 +108,7 @@ def cpu_port_run(a, cells, n_particles, steps, warmup, ppc=None):
         bmode = (1, 1)
     nx = ny = cells + 1
     if a.workload == "seed":
-        nx, ny = 65, 125
+        nx, ny = cells + 1, min(2 * cells + 1, 8192 // (cells + 1) - 1)
     cg = CO.make_grid(nx, ny, dh, dh)
     sp = []
     for name, q, m, T, drift in spec:
@@ -281,7 +281,7 @@ def run_b200(a):
     t_build = time.perf_counter()
     wl = (workloads.build_c5(ppg, cells, n_gpus_total=8, device=local) if a.workload == "c5"
           else workloads.build_walls(ppg, cells, device=local) if a.workload == "walls"
-          else workloads.build_seed(ppg, device=local) if a.workload == "seed"
+          else workloads.build_seed(ppg, cells, device=local) if a.workload == "seed"
           else workloads.build_c4(ppg, cells, device=local))
     rt = wl.rt
     rt.use_torch_stream()

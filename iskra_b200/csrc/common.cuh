@@ -136,6 +136,9 @@ struct iskb_ctx {
   int sort_max_interval = 0;          //           ... or this many steps have passed
   int sort_full_interval = 0;         // > 0: between full sorts re-group by tile only (cheaper)
   int64_t step_count = 0;
+  // small grids (<= PRIV_MAX_NODES): the simple advance deposits into PRIV_COPIES private copies of u (block b uses
+  // copy b % PRIV_COPIES) that are summed afterwards -- divides the same-address atomic pressure by PRIV_COPIES
+  double *d_upriv = nullptr;
   int pusher_rz = 0;                 // BorisPusher{:rz}: transform_from_cartesian_to_cylindrical! after the push
   bool warn_too_fast = false;        // check!'s "particle is too fast" message condition was seen (sticky until read)
   // optional per-kernel timing of the dominant (advance) kernel, CUDA events on the launch stream
@@ -254,6 +257,8 @@ struct iskb_tracker {
   unsigned long long *d_counts = nullptr;   // [0] tracked, [1] absorbed
 };
 constexpr int ISKB_MAX_SURFACES = 250;
+constexpr int PRIV_COPIES = 64;
+constexpr int64_t PRIV_MAX_NODES = 16384;
 
 // ---- internal entry points across translation units ------------------------------------------
 int32_t sp_sync_counts(iskb_species *sp);

@@ -151,6 +151,18 @@ __global__ void k_deposit_atomic(const double *__restrict__ x, const double *__r
   }
 }
 
+// u += sum of the private copies (and clear them for the next launch)
+__global__ void k_reduce_copies(double *upriv, int64_t nn, double *u) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nn; k += (int64_t)gridDim.x * blockDim.x) {
+    double s = u[k];
+    for (int c = 0; c < PRIV_COPIES; ++c) {
+      s += upriv[(int64_t)c * nn + k];
+      upriv[(int64_t)c * nn + k] = 0.0;
+    }
+    u[k] = s;
+  }
+}
+
 // n = u ./ cell_volume(grid)   kinetic.jl:53
 __global__ void k_density(const double *__restrict__ u, const double *__restrict__ V, double *n,
                           int64_t nn) {
@@ -192,7 +204,9 @@ __global__ void k_rho_finalize(RhoFin f, const double *__restrict__ V, double *r
 __global__ void k_advance_simple(double *x, double *y, double *vx, double *vy, double *vz,
                                  const double *__restrict__ wg, int64_t *cnt, int first_from_begin,
                                  GridDev g, const double2 *__restrict__ E2, double qm, double dt,
-                                 int mode_x, int mode_y, double *u, int *status, unsigned long long *vmax2, int rz) {
+                                 int mode_x, int mode_y, double *u, int *status, unsigned long long *vmax2, int rz,
+                                 double *upriv) {
+  if (upriv) u = upriv + (int64_t)(blockIdx.x % PRIV_COPIES) * ((int64_t)g.nx * g.ny);   // private copy of this block
   const int64_t n = cnt[CNT_NSLOTS];
   const int64_t first = first_from_begin ? cnt[CNT_BEGIN] : 0;
   double vm2 = 0.0;
@@ -473,12 +487,22 @@ int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_
   const double qm = sp->q / sp->m;
   int blocks = from_begin ? c->n_sm : grid_for(sp);
   if (!from_begin) ISKB_TRY(sp_vmax_reset(sp));
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  const bool priv = deposit && nn <= PRIV_MAX_NODES && blocks >= 2 * PRIV_COPIES;
+  if (priv && !c->d_upriv) {
+    CU_TRY(cudaMalloc(&c->d_upriv, PRIV_COPIES * nn * sizeof(double)));
+    CU_TRY(cudaMemsetAsync(c->d_upriv, 0, PRIV_COPIES * nn * sizeof(double), c->stream));
+  }
   if (!from_begin) ISKB_TRY(prof_begin(c));
   k_advance_simple<<<blocks, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4],
                                                   sp->col[5], sp->d_cnt, from_begin ? 1 : 0, c->g, c->d_E2, qm,
                                                   dt, mode_x, mode_y, deposit ? sp->d_u : nullptr, c->d_status, sp->d_vmax2,
-                                                  c->pusher_rz);
+                                                  c->pusher_rz, priv ? c->d_upriv : nullptr);
   LAUNCH_CHECK(c);
+  if (priv) {
+    k_reduce_copies<<<(int)((nn + TPB - 1) / TPB), TPB, 0, c->stream>>>(c->d_upriv, nn, sp->d_u);
+    LAUNCH_CHECK(c);
+  }
   if (!from_begin) ISKB_TRY(prof_end(c));
   if (mode_x == ISKB_BND_DISCARD || mode_y == ISKB_BND_DISCARD) sp->counts_stale = true;
   return ISKB_OK;

@@ -10,7 +10,7 @@
        AbsorbingSurface on the other two faces, a ReflectiveSurface block inside, e- + He+ loaded
        uniformly outside the block, no MCC.  advance! runs with config.tracker (track! / check!).
   seed  : SURVEY.md 8f row N3 at scale -- problem/13_seed.jl geometry (axial r-z grid, plates at z = 0 / Lz, axial
-       Boris pusher, discard! dim 2) with a plasma column instead of a single seed electron: 65 x 125 nodes (the
+       Boris pusher, discard! dim 2) with a plasma column instead of a single seed electron: 33 x 65 nodes (or 65 x 125; the
        operator of an AxialGrid is dense: <= 8192 nodes), e- + Ar+ loaded in r < R/2, no MCC.
   c4 : 2-D XY two-stream (configs[3]) -- 1025x1025 nodes, dh and CFL of problem/10_two_streams.jl,
        fully "periodic", two +-1e7 m/s electron beams at 300 K + co-located ions, wrap! both axes.
@@ -198,9 +198,11 @@ def build_walls(particles_per_gpu=100_000_000, cells=1024, seed=3, device=None):
     return Workload("walls", cfg, dt, (L.BND_DISCARD, L.BND_DISCARD), rf=(L.EDGE_LEFT, 450.0, f), meta=meta)
 
 
-def build_seed(particles_per_gpu=40_000_000, seed=5, device=None):
-    """N3 at scale (see the module docstring).  The grid is fixed at 65 x 125 nodes."""
-    nr, nz = 65, 125
+def build_seed(particles_per_gpu=40_000_000, cells=32, seed=5, device=None):
+    """N3 at scale (see the module docstring).  cells = radial cells: 32 -> 33 x 65 nodes (13_seed.jl's own grid),
+    64 -> 65 x 125 nodes (the largest the dense path takes; its one-off host inversion needs minutes)."""
+    nr = cells + 1
+    nz = min(2 * cells + 1, 8192 // (cells + 1) - 1)
     dh = 0.08 / 32                                    # 13_seed.jl:9-13
     dt = 0.075e-9                                     # :18
     n_each = particles_per_gpu // 2

@@ -294,6 +294,25 @@ function advance_circuit!(circuit, ps :: B200Poisson, Δt)
   dσ
 end
 
+# ---- axisymmetric r-z variant (SURVEY.md 8f row N3) -----------------------------------------------------
+# AxialGrid{2}: ring volumes and the operator come from the reference's own code (RegularGrids.cell_volume,
+# FiniteDifferenceMethod.create_poisson_solver(::AxialGrid{2}, eps0)) and are handed to the device as arrays.
+function upload_cell_volume!(ctx :: Context, V :: Matrix{Float64})
+  GC.@preserve V check(ccall((:iskb_cell_volume_set, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.h, V))
+end
+function B200Poisson(ctx :: Context, reference_solver :: FiniteDifferenceMethod.PoissonSolver{:rz, 2})
+  ps = B200Poisson(ctx, reference_solver.ε0)
+  A = Matrix{Float64}(reference_solver.A)
+  GC.@preserve A check(ccall((:iskb_poisson_set_dense, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx.h, A, size(A, 1)))
+  ps
+end
+function ParticleInCell.push_particles!(:: ParticleInCell.BorisPusher{:rz}, sp :: B200Species, E, B, Δt)
+  check(ccall((:iskb_set_pusher, LIB), Int32, (Ptr{Cvoid}, Int32), sp.ctx.h, Int32(1)))
+  upload!(sp)
+  check(ccall((:iskb_push, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64), sp.h, C_NULL, Δt))
+  sp.device_newer = true
+end
+
 # ---- fused loop: drop-in for ParticleInCell.solve that still fires the hooks (ParticleInCell.jl:84-139)
 function solve(ctx :: Context, species :: Vector{B200Species}, Δt, timesteps; after_push = (1, 1), sort_interval = 8)
   check(ccall((:iskb_set_after_push, LIB), Int32, (Ptr{Cvoid}, Int32, Int32), ctx.h, after_push...))
