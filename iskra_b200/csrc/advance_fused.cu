@@ -187,7 +187,7 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
                 double *__restrict__ VZ, const double *__restrict__ WG, int64_t *cnt, GridDev g,
                 const double2 *__restrict__ E2, double qm, double dt, double c1, double *u, int *status,
                 unsigned long long *vmax2, int64_t n_sorted, const uint8_t *__restrict__ trk_cells, uint32_t *trk_list,
-                unsigned *trk_n, double v_too_fast, int dbg) {
+                unsigned *trk_n, double v_too_fast) {
   typedef typename SmemOf<WE, WR, TRACK>::type Smem;
   constexpr int mode_x = MX, mode_y = MY;   // after_push modes are compile-time: no mode branches per row
   constexpr int OFF = (WE - WR) / 2;        // the rho window is the central part of the E window
@@ -283,7 +283,7 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
         if constexpr (TRACK) {
           // track!: rows in cells next to a surface go to the tracked list (warp-aggregated append) and are
           // advanced by k_advance_tracked after this kernel
-          trkrow = fit && !(dbg & 2) && sm.trk[(j - 1 - ej0) * WE + (i - 1 - ei0)] != 0;
+          trkrow = fit && sm.trk[(j - 1 - ej0) * WE + (i - 1 - ei0)] != 0;
           const unsigned tm = __ballot_sync(0xffffffffu, trkrow);
           if (tm) {
             unsigned nt = sm.tcnt;
@@ -335,7 +335,7 @@ k_advance_tiled(double *__restrict__ X, double *__restrict__ Y, double *__restri
         py = push_x(py, vy, dt);
         vm2 = fmaxf(vm2, __double2float_ru(fma(vz, vz, fma(vy, vy, vx * vx))));
         if constexpr (TRACK) {   // check!'s message condition, check.jl:41-46 (queued rows: in drain_rows)
-          if (!(dbg & 1)) too_fast |= fmax(fmax(fabs(vx), fabs(vy)), fabs(vz)) > v_too_fast;
+          too_fast |= fmax(fmax(fabs(vx), fabs(vy)), fabs(vz)) > v_too_fast;
         }
         // ---- after_push: discards first, then wraps ----
         bool dead = (mode_x == ISKB_BND_DISCARD) && boundary_axis(px, g.ox, g.Lx, mode_x);
@@ -476,7 +476,6 @@ static int32_t launch_modes(iskb_species *sp, double dt) {
   }
   const uint8_t *trk_cells = nullptr;
   double v_too_fast = 0.0;
-  static const int dbg = getenv("ISKB_DEBUG_TRK") ? atoi(getenv("ISKB_DEBUG_TRK")) : 0;   // timing experiments only
   if (TRACK) {
     TrackerDev t;
     memset(&t, 0, sizeof(t));
@@ -499,9 +498,9 @@ static int32_t launch_modes(iskb_species *sp, double dt) {
   ISKB_TRY(prof_begin(c));
   k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM, TRACK><<<(int)blocks, WARPS * 32, SMEM, c->stream>>>(
       sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->d_cnt, c->g, c->d_E2, qm, dt,
-      0.5 * dt * qm, sp->d_u, c->d_status, sp->d_vmax2, sp->h_nsorted, trk_cells, sp->d_trk_list, sp->d_trk_n, v_too_fast, dbg);
+      0.5 * dt * qm, sp->d_u, c->d_status, sp->d_vmax2, sp->h_nsorted, trk_cells, sp->d_trk_list, sp->d_trk_n, v_too_fast);
   LAUNCH_CHECK(c);
-  if (TRACK && !(dbg & 4)) ISKB_TRY(launch_advance_tracked_list(sp, dt, MX, MY));   // the rows this kernel left to track! / check!
+  if (TRACK) ISKB_TRY(launch_advance_tracked_list(sp, dt, MX, MY));   // the rows this kernel left to track! / check!
   ISKB_TRY(prof_end(c));
   if (MX == ISKB_BND_DISCARD || MY == ISKB_BND_DISCARD || TRACK) sp->counts_stale = true;
   return ISKB_OK;

@@ -627,8 +627,7 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
         // config.tracker != nothing: track! -> gather -> push -> check! -> after_push  (:56-61), one pass
         ISKB_TRY(launch_advance_tracked(s, dt, c->after_push[0], c->after_push[1], true));
       } else if (tiled) {
-        static const bool ignore_tracker = getenv("ISKB_DEBUG_IGNORE_TRACKER") != nullptr;   // timing experiments only
-        if (c->tracker && !ignore_tracker) ISKB_TRY(launch_advance_tiled_tracked(s, dt, c->after_push[0], c->after_push[1]));
+        if (c->tracker) ISKB_TRY(launch_advance_tiled_tracked(s, dt, c->after_push[0], c->after_push[1]));
         else ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
         ISKB_TRY(post_advance_stats(c, s));
         s->steps_since_sort++;
