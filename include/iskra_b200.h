@@ -256,7 +256,7 @@ int32_t iskb_tracker_check(iskb_tracker *st, iskb_species *sp, double dt, int64_
  * "ERROR: ... particle is too fast", check.jl:41-46, and carries on); reading clears it. */
 int32_t iskb_warning_too_fast(iskb_ctx *ctx, int32_t *out);
 /* electrode.dq: charge collected by the surface so far (circuit_coupling.jl:49-50); reset != 0 zeroes it
- * (foo!, :30) */
+ * (foo!, :30).  With particles sharded over several ranks this is the rank's own share. */
 int32_t iskb_surface_charge(iskb_tracker *st, int32_t surface_id, double *dq_out, int32_t reset);
 /* The reference builds its floating electrodes with sigma and phi swapped (problem/configuration.jl:69-70
  * vs circuit_coupling.jl:11-16), so collected charge never reaches the sigma right-hand side.  on != 0

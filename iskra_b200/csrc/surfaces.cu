@@ -313,6 +313,8 @@ int32_t tracker_prepare(iskb_tracker *st, TrackerDev *out) {
     st->dirty = false;
   }
   double *d_sigma = nullptr;
+  if (st->route_hits && c->n_ranks > 1)   // every rank would add only its own hits to its replica of sigma
+    return iskb_fail(ISKB_E_UNSUPPORTED, "route_hits_to_sigma with more than one rank: sum iskb_surface_charge over the ranks instead");
   if (st->route_hits && c->ps.created && c->ps.n_sigma > 0) ISKB_TRY(poisson_sigma_device(c, &d_sigma));
   out->nx = nx; out->ny = ny;
   out->dh = c->g.dx;                      // create_surface_tracker(grid): dx, ~ = grid.dh  build.jl:96-97
