@@ -34,6 +34,7 @@ typedef struct iskb_ctx iskb_ctx;
 typedef struct iskb_species iskb_species;
 typedef struct iskb_mcc iskb_mcc;
 typedef struct iskb_tracker iskb_tracker;
+typedef struct iskb_dsmc iskb_dsmc;
 
 /* status codes */
 #define ISKB_OK 0
@@ -206,7 +207,7 @@ int32_t iskb_set_sort_policy(iskb_ctx *ctx, double miss_threshold, int32_t max_i
  * have passed since the last full one; otherwise rows are re-grouped by tile only (stable, about
  * half the cost).  0 = every re-sort is full. */
 int32_t iskb_set_sort_full_interval(iskb_ctx *ctx, int32_t full_interval);
-/* n_steps iterations of: MCC (registered interactions, in order) -> advance! every species
+/* n_steps iterations of: MCC, then DSMC (registered interactions, each kind in creation order) -> advance! every species
  * (gather, push, after_push) -> density / rho -> all-reduce -> phi -> E.  With a surface tracker on
  * the context advance! is track! -> gather -> push -> check! -> after_push (ParticleInCell.jl:56-61);
  * the circuit (advance!(circuit, ...), :116) stays on the host between steps: call iskb_step(ctx, dt, 1)
@@ -298,6 +299,16 @@ int32_t iskb_mcc_perform(iskb_mcc *mcc, double dt, double *nu_out, int64_t *n_ca
                          int64_t *n_collisions);
 /* totals accumulated by iskb_step since creation: [candidates, collisions, per-process...] */
 int32_t iskb_mcc_totals(iskb_mcc *mcc, int64_t *out /* 2 + N */);
+
+/* ---- DSMC: Chemistry/src/dsmc.jl ---------------------------------------------- */
+/* dsmc(reactions) -> DirectSimulationMonteCarlo  dsmc.jl:143-166 with ONE DSMC.ElasticCollision (source, target kinetic
+ * species, possibly the same one; rate = CrossSection over the relative speed g, cross_section.jl:3-14).  More than one
+ * collision per object is ill defined in the reference (its cell lists accumulate across collisions, :94-99). */
+int32_t iskb_dsmc_create(iskb_ctx *ctx, iskb_species *source, iskb_species *target, const double *g_nodes,
+                         const double *sigma, int32_t n_nodes, uint64_t seed, iskb_dsmc **out);
+/* PIC.perform!(dsmc, E, dt, config)  dsmc.jl:87-142.  nu_out: collisions per cell of this call (nx*ny, nullable);
+ * n_candidates: sum over cells of floor(Nc) (:109-122), independent of the random stream. */
+int32_t iskb_dsmc_perform(iskb_dsmc *dsmc, double dt, double *nu_out, int64_t *n_candidates, int64_t *n_collisions);
 
 #ifdef __cplusplus
 }

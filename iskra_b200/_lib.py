@@ -98,6 +98,8 @@ SIGNATURES = {
     "iskb_surface_charge": [vp, i32, C.POINTER(f64), i32],
     "iskb_tracker_route_hits_to_sigma": [vp, i32],
     "iskb_warning_too_fast": [vp, C.POINTER(i32)],
+    "iskb_dsmc_create": [vp, vp, vp, vp, vp, i32, u64, C.POINTER(vp)],
+    "iskb_dsmc_perform": [vp, f64, vp, C.POINTER(i64), C.POINTER(i64)],
     "iskb_cell_volume_set": [vp, vp],
     "iskb_poisson_set_dense": [vp, vp, i64],
     "iskb_set_pusher": [vp, i32],

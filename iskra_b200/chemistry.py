@@ -197,3 +197,62 @@ class MonteCarloCollisions:
 def mcc(reaction_list, seed=0):
     """mcc(reactions)  mcc.jl:313-320"""
     return MonteCarloCollisions([accept(r) for r in reaction_list], seed=seed)
+
+
+# ---- DSMC (Chemistry/src/dsmc.jl; SURVEY.md 8f N4) ------------------------------------------------------
+class DSMC:
+    """module DSMC  dsmc.jl:1-14"""
+
+    class ElasticCollision:
+        def __init__(self, rate, source, target):
+            self.rate, self.source, self.target = rate, source, target
+
+
+class DirectSimulationMonteCarlo:
+    """DirectSimulationMonteCarlo  dsmc.jl:16-23; perform! runs on the device, one thread per cell."""
+
+    def __init__(self, collisions, seed=0):
+        if len(collisions) != 1:
+            raise NotImplementedError("one collision per DSMC object: the reference's cell lists accumulate across "
+                                      "collisions (dsmc.jl:94-99), more than one is ill defined there")
+        self.collisions, self.seed = collisions, int(seed)
+        self._h = self._rt = None
+
+    def _bind(self, config):
+        if self._h is not None:
+            return
+        grid, c = config.grid, self.collisions[0]
+        c.source._push(grid)
+        c.target._push(grid)
+        nodes = np.ascontiguousarray(c.rate.nodes)
+        gn, sg = np.ascontiguousarray(nodes[:, 0]), np.ascontiguousarray(nodes[:, 1])
+        h = L.vp()
+        L.check(grid._rt.lib.iskb_dsmc_create(grid._rt.h, c.source._h, c.target._h, L.ptr(gn), L.ptr(sg), len(gn), self.seed,
+                                              C.byref(h)))
+        self._h, self._rt = h, grid._rt
+
+    def perform_(self, E, dt, config, want_nu=True):
+        """PIC.perform!(dsmc, E, dt, config)  dsmc.jl:87-142 -> (nu, n_candidate_pairs, n_collisions)"""
+        self._bind(config)
+        c = self.collisions[0]
+        c.source._push(config.grid)
+        c.target._push(config.grid)
+        nu = np.zeros(config.grid.n, order="F") if want_nu else None
+        nc, ncoll = L.i64(), L.i64()
+        L.check(self._rt.lib.iskb_dsmc_perform(self._h, float(dt), L.ptr(nu), C.byref(nc), C.byref(ncoll)))
+        c.source._touched_on_device()
+        c.target._touched_on_device()
+        return nu, nc.value, ncoll.value
+
+
+def dsmc(reaction_list, seed=0):
+    """dsmc(reactions)  dsmc.jl:143-166: two kinetic reactants, no products -> DSMC.ElasticCollision"""
+    collisions = []
+    for r in reaction_list:
+        if len(r.reactants) != 2:
+            raise AssertionError("Direct Simulation Monte Carlo support only two reacting, kinetic species")
+        (source, _), (target, _) = r.reactants
+        if any(cf > 0 for _, cf in r.stoichiometry):
+            raise NotImplementedError("DSMC.IonizationCollision has no perform! method in the reference (dsmc.jl:8-13)")
+        collisions.append(DSMC.ElasticCollision(r.rate, source, target))
+    return DirectSimulationMonteCarlo(collisions, seed=seed)

@@ -172,6 +172,7 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
     delete m;
   }
   for (iskb_species *s : c->species) free_species(s);
+  for (iskb_dsmc *d : c->dsmcs) dsmc_free(d);
   tracker_free(c->tracker);
   poisson_free(c);
   cudaFree(c->d_upriv); cudaFree(c->d_V); cudaFree(c->d_rho); cudaFree(c->d_phi); cudaFree(c->d_E2); cudaFree(c->d_status);
@@ -620,6 +621,7 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
     if (tiled)
       for (iskb_species *s : c->species) ISKB_TRY(maybe_sort(c, s));
     for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));       // :109-111
+    for (iskb_dsmc *d : c->dsmcs) ISKB_TRY(dsmc_launch(d, dt, false));
     ISKB_TRY(fields_join(c));   // E of the previous step (the re-sort and MCC above did not need it)
     for (iskb_species *s : c->species) {                                   // :113-115
       CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));

@@ -129,6 +129,7 @@ struct iskb_ctx {
   PoissonState ps;
   std::vector<iskb_species *> species;
   std::vector<iskb_mcc *> mccs;
+  std::vector<iskb_dsmc *> dsmcs;
   iskb_tracker *tracker = nullptr;   // config.tracker (create_surface_tracker); nullptr == `nothing`
   int after_push[2] = {ISKB_BND_WRAP, ISKB_BND_WRAP};   // default hook wrap!, ParticleInCell.jl:41
   int sort_interval = 0;
@@ -279,6 +280,8 @@ int32_t launch_advance(iskb_species *sp, double dt, int mode_x, int mode_y, bool
 int32_t launch_rho_finalize(iskb_ctx *ctx);
 int32_t sp_vmax_unknown(iskb_species *sp);
 int32_t sp_vmax_reset(iskb_species *sp);
+int32_t dsmc_launch(iskb_dsmc *d, double dt, bool want_nu);
+int32_t dsmc_free(iskb_dsmc *d);
 int32_t tracker_prepare(iskb_tracker *st, TrackerDev *out);
 int32_t tracker_free(iskb_tracker *st);
 int32_t launch_advance_tracked(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit);
