@@ -313,6 +313,34 @@ function ParticleInCell.push_particles!(:: ParticleInCell.BorisPusher{:rz}, sp :
   sp.device_newer = true
 end
 
+# ---- DSMC (SURVEY.md 8f row N4): Chemistry/src/dsmc.jl ----------------------------------------------------
+mutable struct B200DSMC
+  h :: Ptr{Cvoid}
+  source :: B200Species
+  target :: B200Species
+end
+
+# dsmc(@reactions ...) with ONE DSMC.ElasticCollision; `lookup` maps the reference species to their device twins
+function B200DSMC(ctx :: Context, d :: Chemistry.DirectSimulationMonteCarlo, lookup; seed = UInt64(0))
+  length(d.collisions) == 1 || error("one collision per DSMC object (the reference's cell lists accumulate, dsmc.jl:94-99)")
+  c = d.collisions[1]
+  s, t = lookup(c.source), lookup(c.target)
+  upload!(s); upload!(t)
+  gn, sg = Vector{Float64}(c.rate.nodes[:, 1]), Vector{Float64}(c.rate.nodes[:, 2])
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  GC.@preserve gn sg check(ccall((:iskb_dsmc_create, LIB), Int32,
+                                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, UInt64, Ref{Ptr{Cvoid}}),
+                                 ctx.h, s.h, t.h, gn, sg, Int32(length(gn)), seed, h))
+  B200DSMC(h[], s, t)
+end
+
+function ParticleInCell.perform!(d :: B200DSMC, E, Δt, config)
+  nc, ncoll = Ref{Int64}(0), Ref{Int64}(0)
+  check(ccall((:iskb_dsmc_perform, LIB), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ref{Int64}, Ref{Int64}), d.h, Δt, C_NULL, nc, ncoll))
+  d.source.device_newer = true
+  d.target.device_newer = true
+end
+
 # ---- fused loop: drop-in for ParticleInCell.solve that still fires the hooks (ParticleInCell.jl:84-139)
 function solve(ctx :: Context, species :: Vector{B200Species}, Δt, timesteps; after_push = (1, 1), sort_interval = 8)
   check(ccall((:iskb_set_after_push, LIB), Int32, (Ptr{Cvoid}, Int32, Int32), ctx.h, after_push...))
