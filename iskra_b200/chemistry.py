@@ -129,6 +129,7 @@ class MonteCarloCollisions:
         self._rt = None
         self.max_sigma_g = None
         self.m = None
+        self.last_nu = None          # nu of the last perform_ (the reference's "nuMCC-<source>-<k>" fields, mcc.jl:287)
 
     def _bind(self, config):
         if self._h is not None:
@@ -186,6 +187,7 @@ class MonteCarloCollisions:
             for p in c.products:
                 if not is_fluid(p):
                     p._touched_on_device()
+        self.last_nu = nu
         return nu, nc.value, ncoll.value
 
     def totals(self):

@@ -532,6 +532,8 @@ def solve(config, dt=1e-5, timesteps=200, after_push=None, sort_interval=0, fuse
         s._push(grid)
     for inter in config.interactions:
         inter._bind(config)
+    from . import diagnostics
+    diagnostics.register_solve_records(config)      # @field / @particle of :63-71,:122-133 -- fetched on demand only
     _set_pusher(rt, config.pusher)
     if fused:
         mx, my = after_push if after_push is not None else (L.BND_WRAP, L.BND_WRAP)
