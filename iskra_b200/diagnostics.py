@@ -78,6 +78,8 @@ class ParticleRecord:
 
 
 records = {}          # const records = Dict{String, Record}()  Diagnostics.jl:22
+_solve_keys = set()   # keys registered by register_solve_records: dropped when another solve() registers (their closures
+                      # hold the previous run's species and device context alive otherwise)
 
 
 def register_field(key, units, fetch, grid, **kw):
@@ -98,6 +100,10 @@ def register_solve_records(config):
     grid = config.grid
     rt = grid._rt
     nx, ny = grid.n
+    for k in _solve_keys:
+        records.pop(k, None)
+    _solve_keys.clear()
+    before = set(records)
     register_field("rho", "C/m^2", lambda: rt.fields(phi=False, E=False)[0], grid)
     register_field("phi", "V", lambda: rt.fields(rho=False, E=False)[1], grid)
     register_field("E", "V/m", lambda: rt.fields(rho=False, phi=False)[2], grid, withcomponents=True)
@@ -128,6 +134,7 @@ def register_solve_records(config):
             for k in range(len(inter.collisions)):
                 register_field("nuMCC-%s-%d" % (src.name, k + 1), "1/m^2",
                                (lambda m=inter, kk=k: m.last_nu[:, :, kk] if m.last_nu is not None else np.zeros((nx, ny))), grid)
+    _solve_keys.update(set(records) - before)
 
 
 # ---- sinks: hdf5.jl ------------------------------------------------------------------------------------
