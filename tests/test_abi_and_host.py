@@ -124,3 +124,41 @@ def test_sharding_slices():
             assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
             sizes = [b - a for a, b in sl]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_circuit_mirror_matches_oracle_recurrence():
+    """iskra_b200.circuit (host mirror of Circuit.jl) against the oracle restatement, 200 steps, bit for bit."""
+    import math
+    from iskra_b200 import circuit as CIR
+    from oracle import surfaces_oracle as S
+    V = lambda t: math.sin(2 * math.pi * 5e6 * t)
+    cir = CIR.rlc(CIR.netlist([("V1", 3, "GND", V), ("L1", "NOD", "VCC", 1000e-9), ("C1", "NOD", "VCC", 1000e-9),
+                               ("R1", "GND", "NOD", 1.0)]))                     # problem/06_circuit.jl:40-45
+    ref = S.CircuitRLC(R=1.0, L=1000e-9, C=1000e-9, V=V)
+    assert (cir.R, cir.L, cir.C) == (1.0, 1000e-9, 1000e-9) and isinstance(cir.ext, CIR.ShortedConnection)
+    for _ in range(200):
+        CIR.advance_circuit_(cir, 0, 10e-9)
+        S.advance_circuit_(ref, 10e-9)
+        assert cir.i == ref.i and cir.q == ref.q and cir.t == ref.t
+    assert cir.probes["I1"] == cir.i and cir.probes["Vext"] == 0.0
+    assert CIR.resonant_frequency(1e-6, 1e-6) == pytest.approx(1 / (2 * math.pi * 1e-6))
+    with pytest.raises(ValueError):
+        CIR.netlist([("X1", 1, 2, 3.0)])                                         # Circuit.jl:114 throw("unknown element")
+
+
+def test_dsmc_constructor_semantics():
+    """dsmc(reactions)  Chemistry/src/dsmc.jl:143-166 on the host mirror: two kinetic reactants, no products."""
+    from iskra_b200 import chemistry as CH
+    from iskra_b200 import particle_in_cell as PIC
+    e = PIC.create_kinetic_species("e-", 10, -1.0, 1.0, 1.0)
+    o = PIC.create_kinetic_species("O", 10, 0.0, 16.0, 1.0)
+    io = PIC.create_kinetic_species("O+", 10, 1.0, 16.0, 1.0)
+    sig = CH.CrossSection([3e6, 4e6, 5e6, 6e6], [0.01, 0.1, 2.0, 0.01])
+    d = CH.dsmc(CH.reactions([(sig, "e + O --> O + e")], {"e": e, "O": o}))
+    assert len(d.collisions) == 1 and d.collisions[0].source is e and d.collisions[0].target is o
+    with pytest.raises(NotImplementedError):                                      # IonizationCollision has no perform! (:8-13)
+        CH.dsmc(CH.reactions([(sig, "e + O --> e + e + iO")], {"e": e, "O": o, "iO": io}))
+    with pytest.raises(NotImplementedError):                                      # quirk D1: one collision per object
+        CH.dsmc(CH.reactions([(sig, "e + O --> O + e"), (sig, "e + O --> O + e")], {"e": e, "O": o}))
+    with pytest.raises(AssertionError):                                           # :147 two reacting species
+        CH.dsmc(CH.reactions([(sig, "O + O --> O + O")], {"O": o}))
