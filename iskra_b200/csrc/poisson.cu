@@ -895,6 +895,14 @@ int32_t poisson_solve(iskb_ctx *c) {
 }
 
 // ---- C ABI ------------------------------------------------------------------------------------
+// test hook: the host-side dense inversion on its own (no GPU needed); A is n*n column-major, overwritten by its inverse
+extern "C" int32_t iskb_debug_invert_dense(double *A, int64_t n) {
+  std::vector<double> M(A, A + n * n);
+  if (!invert_dense(M, n)) return ISKB_E_SINGULAR;
+  memcpy(A, M.data(), (size_t)(n * n) * sizeof(double));
+  return ISKB_OK;
+}
+
 static int32_t sigma_pull(iskb_ctx *c);
 extern "C" int32_t iskb_poisson_create(iskb_ctx *c, double eps0) {
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "iskb_grid_set must be called first");

@@ -162,3 +162,30 @@ def test_dsmc_constructor_semantics():
         CH.dsmc(CH.reactions([(sig, "e + O --> O + e"), (sig, "e + O --> O + e")], {"e": e, "O": o}))
     with pytest.raises(AssertionError):                                           # :147 two reacting species
         CH.dsmc(CH.reactions([(sig, "O + O --> O + O")], {"O": o}))
+
+
+def test_host_dense_inversion_hook():
+    """The host-side Gauss-Jordan behind the dense Poisson path (csrc/poisson.cu invert_dense), without a GPU: a random
+    well-conditioned matrix, the row-equilibrated 13_seed-like axial operator with Dirichlet plates, and a singular one."""
+    import ctypes as C
+    from iskra_b200 import _lib as L
+    from oracle import axial_oracle as AX
+    from oracle import pic_oracle as O
+    fn = L.lib().iskb_debug_invert_dense
+    fn.argtypes, fn.restype = [C.POINTER(C.c_double), C.c_int64], C.c_int32
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rng = np.random.default_rng(0)
+    M = np.asfortranarray(rng.standard_normal((200, 200)) + 200 * np.eye(200))
+    A = M.copy(order="F")
+    assert fn(dp(A), 200) == 0 and np.abs(A @ M - np.eye(200)).max() < 1e-13
+    og = AX.AxialGrid2(np.arange(17) * 0.0025, np.arange(33) * 0.0025)
+    ps = AX.PoissonSolver(og, 1.0)
+    bot, top = np.zeros((17, 33), bool), np.zeros((17, 33), bool)
+    bot[:, 0], top[:, 32] = True, True
+    O.apply_dirichlet(ps, bot, 0.0)
+    O.apply_dirichlet(ps, top, 1.0)
+    As = np.asfortranarray(ps.A / np.abs(ps.A).max(axis=1)[:, None])
+    B = As.copy(order="F")
+    assert fn(dp(B), As.shape[0]) == 0 and np.abs(B @ As - np.eye(As.shape[0])).max() < 1e-12
+    S = np.zeros((5, 5), order="F")
+    assert fn(dp(S), 5) == L.E_SINGULAR
