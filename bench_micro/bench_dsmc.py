@@ -24,7 +24,6 @@ def main():
     import torch
     import iskra_b200 as ib
     from iskra_b200 import _lib as L
-    from oracle import dsmc_oracle as D
     from oracle import pic_oracle as O
     PIC, CH = ib.particle_in_cell, ib.chemistry
     dh = 0.05
@@ -58,28 +57,35 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / a.calls
-    # oracle on a small sample with the same particles per cell
-    cs = 16
+    # the C oracle (one thread, like the reference) on a bounded sample with the same particles per cell
+    import ctypes as C
+    from oracle import c_oracle as CO
+    cs = 256
     no = int(ppc * cs * cs)
-    og = O.CartesianGrid2(np.arange(cs + 1) * dh, np.arange(cs + 1) * dh)
+    cg = CO.make_grid(cs + 1, cs + 1, dh, dh)
     rng = np.random.default_rng(0)
-    osp = []
+    csp = []
     for m, vth in ((O.me, 3e6), (8 * O.mp, 560.0)):
-        s = O.KineticSpecies("s", no, 0.0, m, 1.0)
-        s.x[:] = rng.random((no, 2)) * cs * dh
-        s.v[:] = rng.standard_normal((no, 3)) * vth
-        s.np = no
-        osp.append(s)
-    od = D.DirectSimulationMonteCarlo(D.ElasticCollision(O.CrossSection(sig), osp[0], osp[1]))
+        s = CO.CSpecies(no, 0.0, m, 1.0)
+        vv = rng.standard_normal((3, no)) * vth
+        s.set(rng.random(no) * cs * dh, rng.random(no) * cs * dh, vv[0], vv[1], vv[2])
+        csp.append(s)
+    gn, sgv = np.ascontiguousarray(sig[:, 0]), np.ascontiguousarray(sig[:, 1])
+    rem = np.zeros((cs + 1) * (cs + 1))
+    crng = CO.make_rng(1)
+    fn = CO.lib().orc_dsmc_perform
+    fn.restype = C.c_int64
     t0 = time.perf_counter()
-    D.perform_(od, dt, og, rng)
-    cpu_s = time.perf_counter() - t0
+    for _ in range(3):
+        fn(csp[0].ref(), csp[1].ref(), C.byref(cg), CO.dp(gn), CO.dp(sgv), C.c_int32(len(gn)), C.c_double(dt), CO.dp(rem), None, None,
+           C.byref(crng))
+    cpu_s = (time.perf_counter() - t0) / 3
     print(json.dumps({"what": "PIC.perform!(dsmc) on the device (cell lists + one thread per cell)", "grid_cells": [a.cells, a.cells],
                       "particles": 2 * n, "particles_per_cell_per_species": ppc, "ms_per_call": ms,
                       "particle_visits_per_s": 2 * n / (ms * 1e-3), "candidate_pairs_per_call": cand / a.calls,
                       "collisions_per_call": coll / a.calls,
                       "list_build_bytes_per_particle": 16 + 4 + 4 + 4, "list_build_GBps_if_alone": 2 * n * 28 / (ms * 1e-3) / 1e9,
-                      "cpu_oracle_python": {"particles": 2 * no, "seconds_per_call": cpu_s, "particle_visits_per_s": 2 * no / cpu_s}}))
+                      "cpu_oracle_c_1_thread": {"particles": 2 * no, "seconds_per_call": cpu_s, "particle_visits_per_s": 2 * no / cpu_s}}))
 
 
 if __name__ == "__main__":

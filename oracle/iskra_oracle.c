@@ -740,3 +740,93 @@ void orc_advance_rz(orc_species *s, const orc_grid *g, const double *E, double d
   for (int d = 1; d <= 2; ++d) if (bmode[d - 1] == 2) orc_discard(s, g, d);
   for (int d = 1; d <= 2; ++d) if (bmode[d - 1] == 1) orc_wrap(s, g, d);
 }
+
+/* ==== SURVEY.md 8f row N4: DSMC (Chemistry/src/dsmc.jl:25-142), one DSMC.ElasticCollision ====================
+ * Same restatement as oracle/dsmc_oracle.py (quirks D1-D5 there); RNG = this file's xoshiro256++, so only the
+ * stream-independent parts (candidate pairs per cell, carry) agree exactly with the Python oracle.
+ * work: int64[2*(nn+1) + np_s + np_t] scratch for the cell lists (cache!, :25-30). */
+static void dsmc_lists(const orc_grid *g, const orc_species *s, int64_t *start /* nn+1 */, int64_t *list) {
+  const int64_t nn = (int64_t)g->nx * g->ny;
+  memset(start, 0, sizeof(int64_t) * (size_t)(nn + 1));
+  for (int64_t p = 0; p < s->np; ++p) {
+    int64_t i, j; double hx, hy;
+    cell1(s->x[p], g->dx, &i, &hx);
+    cell1(s->y[p], g->dy, &j, &hy);
+    start[(i - 1) + (j - 1) * g->nx + 1]++;
+  }
+  for (int64_t c = 0; c < nn; ++c) start[c + 1] += start[c];
+  int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * (size_t)nn);
+  memcpy(cur, start, sizeof(int64_t) * (size_t)nn);
+  for (int64_t p = 0; p < s->np; ++p) {
+    int64_t i, j; double hx, hy;
+    cell1(s->x[p], g->dx, &i, &hx);
+    cell1(s->y[p], g->dy, &j, &hy);
+    list[cur[(i - 1) + (j - 1) * g->nx]++] = p;      /* push!(candidates[i, j], p): rows in increasing order */
+  }
+  free(cur);
+}
+
+int64_t orc_dsmc_perform(orc_species *src, orc_species *tgt, const orc_grid *g, const double *gn, const double *sg,
+                         int32_t n_nodes, double dt, double *remaining /* nx*ny */, double *nu /* nx*ny or NULL */,
+                         int64_t *n_candidates, orc_rng *rng) {
+  const int64_t nn = (int64_t)g->nx * g->ny;
+  const int same = src == tgt;
+  int64_t *ss = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nn + 1)), *ls = (int64_t *)malloc(sizeof(int64_t) * (size_t)(src->np + 1));
+  int64_t *st = ss, *lt = ls;
+  dsmc_lists(g, src, ss, ls);
+  if (!same) {
+    st = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nn + 1));
+    lt = (int64_t *)malloc(sizeof(int64_t) * (size_t)(tgt->np + 1));
+    dsmc_lists(g, tgt, st, lt);
+  }
+  int kmax = 0;
+  for (int k = 1; k < n_nodes; ++k) if (sg[k] > sg[kmax]) kmax = k;
+  const double sgmax = sg[kmax] * gn[kmax];                                   /* :107 */
+  const double Wa = src->w0, Wb = tgt->w0;
+  double Pab, Pba;
+  if (Wa > Wb) { Pab = Wb / Wa; Pba = 1.0; } else { Pab = 1.0; Pba = Wa / Wb; }   /* :101-105 */
+  const double mr1 = src->m / (src->m + tgt->m), mr2 = tgt->m / (src->m + tgt->m);
+  int64_t ncoll = 0, ncand = 0;
+  for (int64_t i = 0; i < g->nx; ++i)                                         /* :108-109 for i, for j */
+    for (int64_t j = 0; j < g->ny; ++j) {
+      const int64_t c = i + j * g->nx;
+      const int64_t Na = ss[c + 1] - ss[c], Nb = st[c + 1] - st[c];
+      if (nu) nu[c] = 0.0;
+      if (Na < 2 || Nb < 2) continue;
+      const double na = (double)Na * Wa / (g->dx * g->dy);
+      double Nc = na * (double)Nb * dt * sgmax;
+      Nc /= Pab + (Wb / Wa) * Pba;
+      if (!same) Nc *= 2;
+      Nc += remaining[c];
+      const double fl = floor(Nc);
+      remaining[c] = Nc - fl;
+      ncand += (int64_t)fl;
+      for (int64_t it = 0; it < (int64_t)fl; ++it) {
+        const int64_t s = ls[ss[c] + (int64_t)(rng_u01(rng) * (double)Na)];
+        int64_t t = lt[st[c] + (int64_t)(rng_u01(rng) * (double)Nb)];
+        while (!same && s == t) t = lt[st[c] + (int64_t)(rng_u01(rng) * (double)Nb)];      /* D3 */
+        const double gx = src->vx[s] - tgt->vx[t], gy = src->vy[s] - tgt->vy[t], gz = src->vz[s] - tgt->vz[t];
+        const double gg = sqrt(gx * gx + gy * gy + gz * gz);
+        const double sgg = orc_xsec_eval(gn, sg, n_nodes, gg) * gg;
+        if (sgg / sgmax < rng_u01(rng)) continue;
+        const double cmx = mr1 * src->vx[s] + mr2 * tgt->vx[t], cmy = mr1 * src->vy[s] + mr2 * tgt->vy[t],
+                     cmz = mr1 * src->vz[s] + mr2 * tgt->vz[t];
+        const double B = 2 * rng_u01(rng) - 1.0, A = sqrt(1 - B * B), C = 2 * M_PI * rng_u01(rng);
+        const double rx = gg * B, ry = gg * (A * cos(C)), rz = gg * (A * sin(C));
+        if (src->wg[s] == tgt->wg[t]) {
+          src->vx[s] = cmx + mr2 * rx; src->vy[s] = cmy + mr2 * ry; src->vz[s] = cmz + mr2 * rz;
+          tgt->vx[t] = cmx - mr1 * rx; tgt->vy[t] = cmy - mr1 * ry; tgt->vz[t] = cmz - mr1 * rz;
+        } else {
+          const double Pab2 = tgt->wg[t] / src->wg[s], Pba2 = src->wg[s] / tgt->wg[t], R2 = rng_u01(rng);
+          if (Pab2 > R2) { src->vx[s] = cmx + mr2 * rx; src->vy[s] = cmy + mr2 * ry; src->vz[s] = cmz + mr2 * rz; }
+          if (Pba2 > R2 && s < tgt->np) { tgt->vx[s] = cmx - mr2 * rx; tgt->vy[s] = cmy - mr2 * ry; tgt->vz[s] = cmz - mr2 * rz; }   /* D2 */
+        }
+        if (nu) nu[c] += 1.0;
+        ++ncoll;
+      }
+    }
+  if (n_candidates) *n_candidates = ncand;
+  free(ss); free(ls);
+  if (!same) { free(st); free(lt); }
+  return ncoll;
+}

@@ -63,6 +63,47 @@ def test_oracle_conserves_momentum_and_energy():
     assert np.abs(p1 - p0).max() <= 1e-12 * np.abs(e.m * e.v).sum() and abs(k1 - k0) <= 1e-12 * k0
 
 
+def test_c_and_numpy_oracles_agree_on_the_stream_independent_parts():
+    """Two independent restatements (Python FIFO-free loops, C) with different RNGs: candidate pairs and the per-cell carry are
+    equal exactly on every call, the accepted fraction agrees statistically, both conserve momentum and energy."""
+    from oracle import c_oracle as CO
+    nxn = 6
+    g = O.CartesianGrid2(np.arange(nxn) * 0.2, np.arange(nxn) * 0.2)
+    cg = CO.make_grid(nxn, nxn, 0.2, 0.2)
+    n = 800
+    x, v = _load(n, 7)
+    osp, csp = [], []
+    for k, m in enumerate((O.me, 8 * O.mp)):
+        o = O.KineticSpecies("s%d" % k, n, 0.0, m, 1.0)
+        o.x[:], o.v[:], o.np = x[k], v[k], n
+        c = CO.CSpecies(n, 0.0, m, 1.0)
+        c.set(x[k][:, 0], x[k][:, 1], v[k][:, 0], v[k][:, 1], v[k][:, 2])
+        osp.append(o)
+        csp.append(c)
+    d = D.DirectSimulationMonteCarlo(D.ElasticCollision(O.CrossSection(SIG), osp[0], osp[1]))
+    gn, sg = np.ascontiguousarray(SIG[:, 0]), np.ascontiguousarray(SIG[:, 1])
+    rem = np.zeros(nxn * nxn)
+    fn = CO.lib().orc_dsmc_perform
+    fn.restype = C.c_int64
+    rng, crng = np.random.default_rng(3), CO.make_rng(4)
+    co = cc = cand = 0
+    k0 = 0.5 * O.me * (v[0] ** 2).sum() + 0.5 * 8 * O.mp * (v[1] ** 2).sum()
+    for _ in range(6):
+        nu_o, nc_o = D.perform_(d, 1e-10, g, rng)
+        ncand = C.c_int64(0)
+        ncoll = fn(csp[0].ref(), csp[1].ref(), C.byref(cg), CO.dp(gn), CO.dp(sg), C.c_int32(len(gn)), C.c_double(1e-10), CO.dp(rem),
+                   None, C.byref(ncand), C.byref(crng))
+        assert ncand.value == nc_o
+        assert np.array_equal(rem.reshape((nxn, nxn), order="F"), d.collisions_remaining)
+        co += nu_o.sum()
+        cc += ncoll
+        cand += nc_o
+    pa = co / cand
+    assert abs(cc / cand - pa) <= 5 * math.sqrt(2 * pa * (1 - pa) / cand), (cc / cand, pa)
+    k1 = 0.5 * O.me * (csp[0].v ** 2).sum() + 0.5 * 8 * O.mp * (csp[1].v ** 2).sum()
+    assert abs(k1 - k0) <= 1e-12 * k0
+
+
 def _hook():
     from iskra_b200 import _lib
     fn = _lib.lib().iskb_debug_dsmc_cell
