@@ -15,6 +15,7 @@ import ParticleInCell: KineticSpecies, FluidSpecies
 import FiniteDifferenceMethod
 import RegularGrids: CartesianGrid
 import Chemistry
+import Circuit
 
 const LIB = get(ENV, "ISKRA_B200_LIB", "libiskra_b200.so")
 
@@ -288,7 +289,7 @@ phi_at(ps :: B200Poisson, i, j) = (v = Ref{Float64}(0.0);
 # stays Julia; only `σ .+= dσ` crosses the boundary (8 bytes).
 function advance_circuit!(circuit, ps :: B200Poisson, Δt)
   circuit === nothing && return 0.0
-  ParticleInCell.Circuit.advance_circuit!(circuit, 0, Δt)
+  Circuit.advance_circuit!(circuit, 0, Δt)
   dσ = ParticleInCell.foo!(circuit.ext, circuit.i, Δt)
   sigma_rhs_add!(ps, 1, dσ)
   dσ
