@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--sort-miss", type=float, default=0.03, help="adaptive re-sort: window-miss fraction threshold (0 = fixed interval)")
     ap.add_argument("--sort-max", type=int, default=64)
     ap.add_argument("--sort-full", type=int, default=64, help="steps between FULL sorts; re-sorts in between only re-group by tile")
+    ap.add_argument("--advance-path", type=int, default=0, help="0: tile directory + incremental re-group, 1: per-warp windows + radix re-group")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=4_000_000)
@@ -285,6 +286,7 @@ def run_b200(a):
           else workloads.build_c4(ppg, cells, device=local))
     rt = wl.rt
     rt.use_torch_stream()
+    rt.set_advance_path(a.advance_path)
     wl.prepare(a.sort_interval, a.sort_miss, a.sort_max, a.sort_full)
     rt.synchronize()
     build_s = time.perf_counter() - t_build

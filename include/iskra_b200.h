@@ -196,23 +196,38 @@ int32_t iskb_rho_allreduce(iskb_ctx *ctx);
 /* ---- fused fast path: the loop body of ParticleInCell.solve  ParticleInCell.jl:102-135 ---- */
 /* after_push hook (ParticleInCell.jl:41; problem scripts override it), applied to every species */
 int32_t iskb_set_after_push(iskb_ctx *ctx, int32_t mode_x, int32_t mode_y);
-/* re-sort every `interval` steps (0 = never) */
+/* interval > 0 keeps the rows of every species grouped by 8x8-cell tile (new relative to the reference: the row
+ * order of a KineticSpecies carries no meaning there) and runs advance! + density as one fused kernel;
+ * 0 = one simple kernel per operator.  Fixed mode: the rows are re-grouped every `interval` steps. */
 int32_t iskb_set_sort_interval(iskb_ctx *ctx, int32_t interval);
-/* Adaptive variant: a species is re-sorted when at least `interval` steps have passed since its
- * last sort AND (the fraction of its rows that missed the shared window in the last measured step
- * exceeds miss_threshold OR max_interval steps have passed).  miss_threshold = 0 restores the
- * fixed interval.  Slow species (ions) are then sorted rarely, fast ones (electrons) often. */
+/* Adaptive mode (miss_threshold > 0): a species is re-grouped when the fraction of its rows that lay outside
+ * their tile's shared-memory window in the last measured step exceeds miss_threshold, when discarded rows make up
+ * more than 2 % of its slots, or after max_interval steps (0 = no limit).  Slow species (ions) are then
+ * re-grouped rarely, fast ones (electrons) every few steps. */
 int32_t iskb_set_sort_policy(iskb_ctx *ctx, double miss_threshold, int32_t max_interval);
-/* full_interval > 0: a due re-sort is a FULL sort (cells + interleave) only when that many steps
- * have passed since the last full one; otherwise rows are re-grouped by tile only (stable, about
- * half the cost).  0 = every re-sort is full. */
+/* A re-group is folded into the advance kernel (rows are written to their new place instead of in place); a FULL
+ * sort (radix sort by cell) happens when a species has no tile directory yet, when its unsorted tail (appended
+ * rows) exceeds 1 % of its rows, and every full_interval steps if full_interval > 0. */
 int32_t iskb_set_sort_full_interval(iskb_ctx *ctx, int32_t full_interval);
+/* 0 (default): tile directory + incremental re-group (advance_tile.cu); 1: per-warp windows that follow the
+ * rows (advance_fused.cu, re-grouped by radix sort) -- the path a context with a surface tracker always takes. */
+int32_t iskb_set_advance_path(iskb_ctx *ctx, int32_t path);
+/* out[0] full sorts, out[1] re-grouping launches so far, out[2] steps since the last full sort, out[3] since the last re-group */
+int32_t iskb_species_sort_stats(iskb_species *sp, int64_t out[4]);
 /* n_steps iterations of: MCC, then DSMC (registered interactions, each kind in creation order) -> advance! every species
  * (gather, push, after_push) -> density / rho -> all-reduce -> phi -> E.  With a surface tracker on
  * the context advance! is track! -> gather -> push -> check! -> after_push (ParticleInCell.jl:56-61);
  * the circuit (advance!(circuit, ...), :116) stays on the host between steps: call iskb_step(ctx, dt, 1)
  * and iskb_poisson_sigma_add from the after_loop hook's side. */
 int32_t iskb_step(iskb_ctx *ctx, double dt, int32_t n_steps);
+/* What iskb_step runs: config.species (kinetic ones) and config.interactions in the reference's order
+ * (ParticleInCell.jl:109-115).  interactions[] holds iskb_mcc* / iskb_dsmc* handles.  Species or interaction
+ * objects that merely exist on the context (a source buffer for add!, a scratch species for density) are then
+ * neither advanced nor deposited.  n_species < 0 restores the default: everything created on the context, MCC
+ * objects before DSMC objects, each in creation order. */
+int32_t iskb_step_set_active(iskb_ctx *ctx, iskb_species *const *species, int32_t n_species,
+                             void *const *interactions, int32_t n_interactions);
+int32_t iskb_ctx_counts(iskb_ctx *ctx, int64_t *n_species, int64_t *n_mcc, int64_t *n_dsmc);
 /* The field solve of a step runs on a private stream so that the next step's re-sort and MCC overlap
  * it.  Every entry point that touches rho / phi / E joins it automatically; call this to make the
  * ctx stream wait for it explicitly (stream-ordered, no host sync), e.g. before recording a timing

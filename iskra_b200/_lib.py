@@ -77,6 +77,10 @@ SIGNATURES = {
     "iskb_set_sort_interval": [vp, i32],
     "iskb_set_sort_policy": [vp, f64, i32],
     "iskb_set_sort_full_interval": [vp, i32],
+    "iskb_set_advance_path": [vp, i32],
+    "iskb_step_set_active": [vp, vp, i32, vp, i32],
+    "iskb_ctx_counts": [vp, vp, vp, vp],
+    "iskb_species_sort_stats": [vp, vp],
     "iskb_step": [vp, f64, i32],
     "iskb_stream_join": [vp],
     "iskb_mcc_create": [vp, vp, f64, f64, f64, vp, i32, vp, vp, vp, vp, vp, vp, u64, C.POINTER(vp)],

@@ -469,11 +469,8 @@ template <int WE, int WR, int WARPS, int MINB, int MX, int MY, bool CLAIM, bool 
 static int32_t launch_modes(iskb_species *sp, double dt) {
   iskb_ctx *c = sp->ctx;
   constexpr int SMEM = WARPS * (int)sizeof(typename SmemOf<WE, WR, TRACK>::type);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CU_TRY(cudaFuncSetAttribute(k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM, TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  // per device, not per process: set on every launch (a second context may live on another GPU)
+  CU_TRY(cudaFuncSetAttribute(k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM, TRACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   const uint8_t *trk_cells = nullptr;
   double v_too_fast = 0.0;
   if (TRACK) {
@@ -495,6 +492,7 @@ static int32_t launch_modes(iskb_species *sp, double dt) {
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
   ISKB_TRY(sp_vmax_reset(sp));
+  sp_touch(sp);
   ISKB_TRY(prof_begin(c));
   k_advance_tiled<WE, WR, WARPS, MINB, MX, MY, CLAIM, TRACK><<<(int)blocks, WARPS * 32, SMEM, c->stream>>>(
       sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->d_cnt, c->g, c->d_E2, qm, dt,
@@ -544,9 +542,6 @@ int32_t launch_advance_tiled(iskb_species *sp, double dt, int mode_x, int mode_y
   ISKB_TRY(fields_join(c));
   if (c->g.nx < 20 || c->g.ny < 20)   // windows do not fit small / quasi-1D grids: use the simple kernel
     return launch_advance_simple(sp, dt, mode_x, mode_y, true, false);
-  static const int variant = getenv("ISKB_ADV_VARIANT") ? atoi(getenv("ISKB_ADV_VARIANT")) : 1;
-  if (variant == 0) return launch_variant<16, 16, 8, 3, false>(sp, dt, mode_x, mode_y);
-  if (variant == 2) return launch_variant<16, 16, 7, 3, true>(sp, dt, mode_x, mode_y);
-  if (variant == 3) return launch_variant<16, 16, 6, 4, true>(sp, dt, mode_x, mode_y);
+  // 8 warps x 3 CTAs per SM with claim rounds; the variants measured against it are listed in profiles/r1_ncu_advance_tiled.md
   return launch_variant<16, 16, 8, 3, true>(sp, dt, mode_x, mode_y);
 }

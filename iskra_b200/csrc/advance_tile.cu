@@ -1,0 +1,725 @@
+// Tile-aware fused advance! + density with an INCREMENTAL re-group folded into the same pass.
+//   gather E (cloud_in_cell.jl:20-36) -> push (pushers.jl:8-17,37-50) -> after_push (wrap.jl:1-33)
+//   -> CIC deposit of wg (cloud_in_cell.jl:1-18), 88 B per particle-step.
+//
+// Row layout (DESIGN.md "tile directory"): rows [0, ns) are grouped by 8x8-cell tile in tile-ordinal order,
+// ts[t] is the first row of tile t (ts[ntiles] = ns); rows [ns, n) are the unsorted TAIL (rows appended by
+// ionisation, rows that left their tile's neighbourhood).  A row may lag behind: it is STORED in tile S but its
+// position is in a neighbour of S -- the windows below have a 3.5-cell margin for exactly that.
+//
+// Every warp owns whole tiles (wr[w] .. wr[w+1]).  Per tile it anchors its two private shared-memory windows
+// (16x16 nodes: E as double2, rho accumulator) on the tile and walks the tile's rows in 32-row batches:
+// exact cell index -> gather from the shared E window -> push -> boundary -> store -> cell of the new position
+// -> deposit into the shared rho window in claim rounds (advance_fused.cu describes why not atomics).
+// Rows whose cell lies outside the window go to a list that k_advance_list advances from global memory.
+//
+// MARK (every launch): for each row the kernel records where its NEW position lies relative to its storage
+// tile (1 byte, tiles.cuh) and counts rows per (storage tile, code).  MOVE (a launch that re-groups): the counts
+// of the previous launch give, after one small scan (k_regroup_*), the destination of every row in a layout that is
+// grouped by the tile of its CURRENT position; the kernel then writes its results (and wg, id) there instead of in
+// place.  The rows of a destination tile are ordered by (source tile in a fixed neighbour order, previous row
+// order): a pure function of the previous layout, no atomics involved in the placement.  This replaces the
+// radix sort + 104 B/row permutation pass of a re-group by +16 B/row on the launch that moves.
+#include <cstdlib>
+#include <cstring>
+
+#include "tiles.cuh"
+
+namespace {
+
+constexpr int WE = 16;    // window nodes per side (tile 9 nodes + 3.5 cells of margin each side)
+constexpr int WRS = 18;   // row stride of the rho window in doubles: rows 2 bank-pairs apart, so the 32 cells of a
+                          // checkerboard batch (sort.cu) hit 16 different bank pairs twice = the 2-wavefront minimum
+
+struct TileArgs {
+  double *col[6];           // x y vx vy vz wg  (read; written in place unless MOVE)
+  uint32_t *id;
+  uint8_t *code;
+  double *ocol[6];          // MOVE: destination buffers
+  uint32_t *oid;
+  uint8_t *ocode;
+  int64_t *cnt;
+  GridDev g;
+  const double2 *E2;
+  double qm, dt, c1, w0;
+  double *u;
+  int *status;
+  unsigned long long *vmax2;
+  const uint32_t *ts;       // [ntiles + 1]
+  const uint32_t *wr;       // [n_warps + 1] first tile of every warp
+  uint32_t ntiles, mtx, tiles_x, tiles_y;
+  uint32_t *tcnt;           // [ntiles * NCODE] rows per (storage tile, code) after this launch
+  const uint32_t *tbase;    // MOVE: [ntiles * NCODE] first destination row per (storage tile, code)
+  const uint32_t *seg;      // MOVE: scan results (see k_regroup_seg): [2*ntiles] = tail destination
+  uint2 *mlist;             // rows left to k_advance_list: (source row, destination row)
+  unsigned *mlist_n;
+  unsigned mlist_cap;
+};
+
+struct WarpSm {
+  double2 E[WE * WE];
+  double rho[WE * WRS];
+  unsigned char claim[WE * WE];
+  unsigned tc[NCODE];     // rows of the current tile per code of their new position
+  unsigned mv[NCODE];     // MOVE: next destination row per code of the current tile
+  unsigned stats[4];      // window misses, deposits outside the window, tiles, discards
+  unsigned misc[4];       // first tile of the next warp, last readable row, tile coordinates of the current tile
+};
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ int clamp_origin(int o, int n, int wn) {
+  if (o > n - wn) o = n - wn;
+  return o < 0 ? 0 : o;
+}
+
+__device__ __forceinline__ void flush_rho(double *rho, int i0, int j0, int nx, double *u, int lane) {
+#pragma unroll
+  for (int k = 0; k < WE * WE / 32; ++k) {
+    const int e = k * 32 + lane;
+    const int o = (e >> 4) * WRS + (e & 15);
+    const double v = rho[o];
+    if (v != 0.0) {
+      atomicAdd(&u[(int64_t)(i0 + (e & 15)) + (int64_t)(j0 + (e >> 4)) * nx], v);
+      rho[o] = 0.0;
+    }
+  }
+}
+__device__ __forceinline__ void load_E(double2 *sE, int i0, int j0, int nx, const double2 *__restrict__ E2, int lane) {
+#pragma unroll
+  for (int k = 0; k < WE * WE / 32; ++k) {
+    const int e = k * 32 + lane;
+    sE[e] = __ldg(&E2[(int64_t)(i0 + (e & 15)) + (int64_t)(j0 + (e >> 4)) * nx]);
+  }
+}
+
+// code of tile (ntx, nty) seen from tile (stx, sty)
+__device__ __forceinline__ unsigned rel_code(int ntx, int nty, int stx, int sty) {
+  const unsigned ddx = (unsigned)(ntx - stx + 1), ddy = (unsigned)(nty - sty + 1);
+  return (ddx < 3u && ddy < 3u) ? ddy * 3u + ddx : (unsigned)CODE_FAR;
+}
+
+// One particle, from registers to registers: gather is the caller's business (shared window or global memory).
+// Returns true when the row was discarded.
+template <int MX, int MY, bool RZ>
+__device__ __forceinline__ bool push_and_bound(double &px, double &py, double &vx, double &vy, double &vz, double ex,
+                                               double ey, const TileArgs &a) {
+  vx = push_v(vx, ex, a.c1, a.qm, a.dt);
+  vy = push_v(vy, ey, a.c1, a.qm, a.dt);
+  vz = push_v(vz, 0.0, a.c1, a.qm, a.dt);
+  px = push_x(px, vx, a.dt);
+  if (RZ) to_cylindrical(px, vx, vz, a.dt);   // push_particles!(::BorisPusher{:rz}, ...)  pushers.jl:13-17
+  py = push_x(py, vy, a.dt);
+  bool dead = (MX == ISKB_BND_DISCARD) && boundary_axis(px, a.g.ox, a.g.Lx, MX);
+  if (!dead) dead = (MY == ISKB_BND_DISCARD) && boundary_axis(py, a.g.oy, a.g.Ly, MY);
+  if (!dead) {
+    if (MX == ISKB_BND_WRAP) boundary_axis(px, a.g.ox, a.g.Lx, MX);
+    if (MY == ISKB_BND_WRAP) boundary_axis(py, a.g.oy, a.g.Ly, MY);
+  }
+  return dead;
+}
+
+#define OUTC(q) (MOVE ? a.ocol[q] : a.col[q])   // column the launch writes to
+
+template <int MX, int MY, bool MOVE, bool RZ>
+__global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
+  extern __shared__ double2 s_dyn[];
+  const int lane = threadIdx.x & 31;
+  WarpSm &sm = ((WarpSm *)s_dyn)[threadIdx.x >> 5];
+  for (int e = lane; e < WE * WRS; e += 32) sm.rho[e] = 0.0;
+  if (lane < NCODE) { sm.tc[lane] = 0; sm.mv[lane] = 0; }
+  if (lane < 4) sm.stats[lane] = 0;
+  // The loop-carried state is kept small (tile, its row range, the batch, the window origin, a float velocity
+  // bound); everything else that is constant per warp or per tile sits in shared memory: the body must fit
+  // 80 registers without spills (a spill reload shares its scoreboard with the row prefetch).
+  if (lane == 0) {
+    sm.misc[0] = a.wr[blockIdx.x * 8 + (threadIdx.x >> 5) + 1];   // first tile of the next warp
+    sm.misc[1] = (unsigned)a.cnt[CNT_NSLOTS] - 1u;                 // last row that may be read
+  }
+  __syncwarp();
+  unsigned t = a.wr[blockIdx.x * 8 + (threadIdx.x >> 5)];
+  float vm2 = 0.0f;
+  constexpr int NOT_ANCHORED = -(1 << 20);
+  int ei0 = NOT_ANCHORED, ej0 = 0;
+  unsigned r0 = 0, r1 = 0;
+  for (; t < sm.misc[0]; ++t) {   // first non-empty tile
+    r0 = a.ts[t];
+    r1 = a.ts[t + 1];
+    if (r1 > r0) break;
+  }
+  if (t < sm.misc[0]) {
+    unsigned rb = r0 & ~31u;
+    double px, py, vx, vy, vz, wq;
+    uint32_t pid = 0;
+    unsigned pcode = 0;
+    {
+      const unsigned r = min(rb + lane, sm.misc[1]);
+      px = a.col[0][r]; py = a.col[1][r]; vx = a.col[2][r]; vy = a.col[3][r]; vz = a.col[4][r]; wq = a.col[5][r];
+      if (MOVE) { pid = a.id[r]; pcode = a.code[r]; }
+    }
+    for (;;) {
+      // ---- register prefetch of the next batch (next tile: the batch that holds its first row) ----
+      unsigned rn = rb + 32;
+      if (rn >= r1) {
+        for (unsigned nt = t + 1; nt < sm.misc[0]; ++nt) {
+          const unsigned q0 = a.ts[nt];
+          if (a.ts[nt + 1] > q0) { rn = q0 & ~31u; break; }
+        }
+      }
+      rn = min(rn + lane, sm.misc[1]);   // index clamped instead of branching
+      const double nx_ = a.col[0][rn], ny_ = a.col[1][rn], nvx_ = a.col[2][rn], nvy_ = a.col[3][rn], nvz_ = a.col[4][rn],
+                   nwq_ = a.col[5][rn];
+      uint32_t nid_ = 0;
+      unsigned ncode_ = 0;
+      if (MOVE) { nid_ = a.id[rn]; ncode_ = a.code[rn]; }
+
+      if (ei0 == NOT_ANCHORED) {   // first batch of a tile: anchor the windows on it
+        int stx, sty;
+        tile_coords(t, a.mtx, stx, sty);
+        ei0 = clamp_origin(stx * 8 - (WE - 9) / 2, a.g.nx, WE);
+        ej0 = clamp_origin(sty * 8 - (WE - 9) / 2, a.g.ny, WE);
+        load_E(sm.E, ei0, ej0, a.g.nx, a.E2, lane);
+        if (MOVE && lane < NCODE) sm.mv[lane] = a.tbase[t * NCODE + lane];
+        if (lane == 0) {
+          sm.stats[2] += 1;
+          sm.misc[2] = (unsigned)stx;
+          sm.misc[3] = (unsigned)sty;
+        }
+        __syncwarp();
+      }
+
+      const unsigned row = rb + lane;
+      const bool valid = row >= r0 && row < r1;
+      const bool live = valid && !is_dead(px);
+      int i = 0, j = 0;
+      double hx = 0, hy = 0;
+      bool ing = false;
+      if (live) {
+        cell1(px, a.g.dx, a.g.rdx, a.g.fast_div, i, hx);
+        cell1(py, a.g.dy, a.g.rdy, a.g.fast_div, j, hy);
+        ing = cell_in_grid(i, j, a.g.nx, a.g.ny);
+        if (!ing) atomicOr(a.status, ISKB_ST_OOB);
+      }
+      const bool fit = ing && (unsigned)(i - 1 - ei0) < (unsigned)(WE - 1) && (unsigned)(j - 1 - ej0) < (unsigned)(WE - 1);
+      const bool miss = ing && !fit;
+
+      // ---- MOVE: destination row = base(storage tile, code) + rank among the tile's rows with that code ----
+      unsigned dest = row;
+      unsigned scode = CODE_STAY;   // code of the row in the layout it is written to
+      if (MOVE) {
+        // the stored code decides (the counts were taken with it): a row that was discarded by k_advance_list
+        // still carries CODE_FAR and goes to the tail as a dead row
+        scode = valid ? pcode : 31u;
+        unsigned rem = __ballot_sync(0xffffffffu, valid);
+        while (rem) {
+          const int ld = __ffs(rem) - 1;
+          const unsigned cl = __shfl_sync(0xffffffffu, scode, ld);
+          const unsigned m = __ballot_sync(0xffffffffu, scode == cl);
+          const unsigned b = sm.mv[cl];
+          if (scode == cl) dest = b + __popc(m & lanemask_lt());
+          __syncwarp();
+          if (lane == ld) sm.mv[cl] = b + __popc(m);
+          rem &= ~m;
+          __syncwarp();
+        }
+      }
+
+      bool dead_now = false, dep_win = false;
+      double d00 = 0, d10 = 0, d01 = 0, d11 = 0;
+      int ci = 0;
+      unsigned ncode = CODE_FAR;
+      if (live && !miss) {
+        double ex = 0.0, ey = 0.0;
+        if (ing) {
+          const CicW gw = cic_weights(hx, hy);
+          const int o = (j - 1 - ej0) * WE + (i - 1 - ei0);
+          const double2 e00 = sm.E[o], e10 = sm.E[o + 1], e01 = sm.E[o + WE], e11 = sm.E[o + WE + 1];
+          ex = cic_gather(gw, e00.x, e10.x, e01.x, e11.x);
+          ey = cic_gather(gw, e00.y, e10.y, e01.y, e11.y);
+        }
+        const bool dead = push_and_bound<MX, MY, RZ>(px, py, vx, vy, vz, ex, ey, a);
+        vm2 = fmaxf(vm2, __double2float_ru(fma(vz, vz, fma(vy, vy, vx * vx))));
+        OUTC(2)[dest] = vx; OUTC(3)[dest] = vy; OUTC(4)[dest] = vz; OUTC(1)[dest] = py;
+        if (MOVE) { a.ocol[5][dest] = wq; a.oid[dest] = pid; }
+        if (dead) {
+          OUTC(0)[dest] = __longlong_as_double(0x7ff8000000000000LL);
+          dead_now = true;
+          ncode = CODE_DEAD;
+        } else {
+          OUTC(0)[dest] = px;
+          cell1(px, a.g.dx, a.g.rdx, a.g.fast_div, i, hx);
+          cell1(py, a.g.dy, a.g.rdy, a.g.fast_div, j, hy);
+          if (cell_in_grid(i, j, a.g.nx, a.g.ny)) {
+            const CicW cw = cic_weights(hx, hy);
+            d00 = __dmul_rn(cw.w00, wq); d10 = __dmul_rn(cw.w10, wq);
+            d01 = __dmul_rn(cw.w01, wq); d11 = __dmul_rn(cw.w11, wq);
+            // code of the new position seen from the tile the row is stored in after this launch
+            int dtx = (int)sm.misc[2], dty = (int)sm.misc[3];
+            if (MOVE && scode < 9u) { dtx += (int)(scode % 3u) - 1; dty += (int)(scode / 3u) - 1; }
+            ncode = rel_code((i - 1) >> 3, (j - 1) >> 3, dtx, dty);
+            const int ri = i - 1 - ei0, rj = j - 1 - ej0;
+            if ((unsigned)ri < (unsigned)(WE - 1) && (unsigned)rj < (unsigned)(WE - 1)) {
+              ci = rj * WE + ri;
+              dep_win = true;
+            } else {
+              const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * a.g.nx;
+              atomicAdd(&a.u[n00], d00);
+              atomicAdd(&a.u[n00 + 1], d10);
+              atomicAdd(&a.u[n00 + a.g.nx], d01);
+              atomicAdd(&a.u[n00 + a.g.nx + 1], d11);
+              atomicAdd(&sm.stats[1], 1u);
+            }
+          } else {
+            atomicOr(a.status, ISKB_ST_OOB);
+          }
+        }
+      } else if (valid && !live) {
+        ncode = CODE_DEAD;
+        if (MOVE) {   // parked behind the live rows with its id; the slot's weight is reset like remove! does (kinetic.jl:24)
+          a.ocol[0][dest] = __longlong_as_double(0x7ff8000000000000LL);
+          a.ocol[5][dest] = a.w0;
+          a.oid[dest] = pid;
+        }
+      }
+      // rows outside the window: k_advance_list advances them; they join the tail at the next re-group
+      {
+        const unsigned mm = __ballot_sync(0xffffffffu, miss);
+        if (mm) {
+          const int ld = __ffs(mm) - 1;
+          unsigned b = 0;
+          if (lane == ld) { b = atomicAdd(a.mlist_n, (unsigned)__popc(mm)); sm.stats[0] += __popc(mm); }
+          b = __shfl_sync(0xffffffffu, b, ld);
+          if (miss) {
+            const unsigned slot = b + __popc(mm & lanemask_lt());
+            if (slot < a.mlist_cap) a.mlist[slot] = make_uint2(row, dest);
+            else atomicOr(a.status, ISKB_ST_CAPACITY);
+          }
+        }
+      }
+      // ---- MARK: code of the new position + counts per (storage tile, code) ----
+      if (valid) (MOVE ? a.ocode : a.code)[dest] = (uint8_t)ncode;
+      {
+        const bool here = valid && (!MOVE || scode == (unsigned)CODE_STAY);   // stored in THIS tile after the launch
+        const unsigned ms = __ballot_sync(0xffffffffu, here && ncode == (unsigned)CODE_STAY);
+        if (lane == 0 && ms) sm.tc[CODE_STAY] += __popc(ms);
+        if (here && ncode != (unsigned)CODE_STAY) atomicAdd(&sm.tc[ncode], 1u);
+        if (MOVE && valid && scode < 9u && scode != (unsigned)CODE_STAY) {   // moved into a neighbour tile: its counters
+          const int dtx = (int)sm.misc[2] + (int)(scode % 3u) - 1, dty = (int)sm.misc[3] + (int)(scode / 3u) - 1;
+          atomicAdd(&a.tcnt[tile_ordinal((uint32_t)dtx, (uint32_t)dty, a.mtx) * NCODE + ncode], 1u);
+        }
+      }
+      // ---- deposit rounds without atomics (advance_fused.cu) ----
+      {
+        unsigned pend = __ballot_sync(0xffffffffu, dep_win);
+        double *r0p = sm.rho + ci + 2 * (ci >> 4);
+        while (pend) {
+          if (dep_win) sm.claim[ci] = (unsigned char)lane;
+          __syncwarp();
+          const bool win = dep_win && sm.claim[ci] == (unsigned char)lane;
+          if (win) r0p[0] = __dadd_rn(r0p[0], d00);
+          __syncwarp();
+          if (win) r0p[1] = __dadd_rn(r0p[1], d10);
+          __syncwarp();
+          if (win) r0p[WRS] = __dadd_rn(r0p[WRS], d01);
+          __syncwarp();
+          if (win) r0p[WRS + 1] = __dadd_rn(r0p[WRS + 1], d11);
+          __syncwarp();
+          if (win) dep_win = false;
+          pend = __ballot_sync(0xffffffffu, dep_win);
+        }
+      }
+      if (MX == ISKB_BND_DISCARD || MY == ISKB_BND_DISCARD) {
+        const unsigned dmask = __ballot_sync(0xffffffffu, dead_now);
+        if (dmask && lane == 0) sm.stats[3] += __popc(dmask);
+      }
+      __syncwarp();
+      if (rb + 32 >= r1) {   // tile finished: flush its window, publish its counts, go to the next non-empty tile
+        flush_rho(sm.rho, ei0, ej0, a.g.nx, a.u, lane);
+        ei0 = NOT_ANCHORED;
+        if (lane < NCODE) {
+          const unsigned c = sm.tc[lane];
+          if (c) atomicAdd(&a.tcnt[t * NCODE + lane], c);
+          sm.tc[lane] = 0;
+        }
+        __syncwarp();
+        const unsigned t_end = sm.misc[0];
+        for (++t; t < t_end; ++t) {
+          r0 = a.ts[t];
+          r1 = a.ts[t + 1];
+          if (r1 > r0) break;
+        }
+        if (t >= t_end) break;
+        rb = r0 & ~31u;
+      } else {
+        rb += 32;
+      }
+      px = nx_; py = ny_; vx = nvx_; vy = nvy_; vz = nvz_; wq = nwq_;
+      if (MOVE) { pid = nid_; pcode = ncode_; }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) vm2 = fmaxf(vm2, __shfl_xor_sync(0xffffffffu, vm2, d));
+  if (lane == 0) {
+    if (vm2 > 0.0f) atomicMax(a.vmax2, (unsigned long long)__double_as_longlong((double)vm2));
+    if (sm.stats[3]) atomicAdd((unsigned long long *)&a.cnt[CNT_NDEAD], (unsigned long long)sm.stats[3]);
+    atomicAdd((unsigned long long *)&a.cnt[3], (unsigned long long)sm.stats[0]);
+    atomicAdd((unsigned long long *)&a.cnt[4], (unsigned long long)sm.stats[1]);
+    atomicAdd((unsigned long long *)&a.cnt[5], (unsigned long long)sm.stats[2]);
+  }
+}
+
+// Rows the tiled kernel left out -- its miss list and the unsorted tail [ns, n) -- advanced one per thread straight
+// from / to global memory: same arithmetic, E gathered from the global field, deposit with global REDs.
+// MOVE: miss rows go where the tiled kernel said; tail row ns + k goes to seg[2*ntiles] + k.
+template <int MX, int MY, bool MOVE, bool RZ>
+__global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned nm = min(*a.mlist_n, a.mlist_cap);
+  const unsigned n = (unsigned)a.cnt[CNT_NSLOTS], ns = a.ts[a.ntiles];
+  const unsigned ntail = n > ns ? n - ns : 0u;
+  const unsigned tail_dst = MOVE ? a.seg[2 * a.ntiles] : ns;
+  const unsigned total = nm + ntail;
+  const unsigned total_pad = (total + 31u) & ~31u;
+  double vm2 = 0.0;
+  unsigned ndead = 0;
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total_pad; k += gridDim.x * blockDim.x) {
+    bool dead_now = false;
+    if (k < total) {
+      unsigned src, dst;
+      if (k < nm) { const uint2 e = a.mlist[k]; src = e.x; dst = e.y; }
+      else { src = ns + (k - nm); dst = tail_dst + (k - nm); }
+      double px = a.col[0][src];
+      if (is_dead(px)) {
+        if (MOVE) { a.ocol[0][dst] = px; a.ocol[5][dst] = a.col[5][src]; a.oid[dst] = a.id[src]; }
+      } else {
+        double py = a.col[1][src], vx = a.col[2][src], vy = a.col[3][src], vz = a.col[4][src];
+        const double wq = a.col[5][src];
+        double ex, ey;
+        if (!gather_E(a.E2, a.g, px, py, ex, ey)) atomicOr(a.status, ISKB_ST_OOB);
+        const bool dead = push_and_bound<MX, MY, RZ>(px, py, vx, vy, vz, ex, ey, a);
+        vm2 = fmax(vm2, fma(vz, vz, fma(vy, vy, vx * vx)));
+        OUTC(2)[dst] = vx; OUTC(3)[dst] = vy; OUTC(4)[dst] = vz; OUTC(1)[dst] = py;
+        if (MOVE) { a.ocol[5][dst] = wq; a.oid[dst] = a.id[src]; }
+        if (dead) {
+          OUTC(0)[dst] = __longlong_as_double(0x7ff8000000000000LL);
+          dead_now = true;
+        } else {
+          OUTC(0)[dst] = px;
+          int i, j;
+          double hx, hy;
+          cell1(px, a.g.dx, a.g.rdx, a.g.fast_div, i, hx);
+          cell1(py, a.g.dy, a.g.rdy, a.g.fast_div, j, hy);
+          if (cell_in_grid(i, j, a.g.nx, a.g.ny)) {
+            const CicW cw = cic_weights(hx, hy);
+            const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * a.g.nx;
+            atomicAdd(&a.u[n00], __dmul_rn(cw.w00, wq));
+            atomicAdd(&a.u[n00 + 1], __dmul_rn(cw.w10, wq));
+            atomicAdd(&a.u[n00 + a.g.nx], __dmul_rn(cw.w01, wq));
+            atomicAdd(&a.u[n00 + a.g.nx + 1], __dmul_rn(cw.w11, wq));
+          } else {
+            atomicOr(a.status, ISKB_ST_OOB);
+          }
+        }
+      }
+    }
+    ndead += __popc(__ballot_sync(0xffffffffu, dead_now));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) vm2 = fmax(vm2, __shfl_xor_sync(0xffffffffu, vm2, d));
+  if (lane == 0) {
+    if (vm2 > 0.0) {
+      // the bound is kept as a float rounded up (the tiled kernel does the same)
+      const double up = (double)__double2float_ru(vm2);
+      atomicMax(a.vmax2, (unsigned long long)__double_as_longlong(up));
+    }
+    if (ndead) atomicAdd((unsigned long long *)&a.cnt[CNT_NDEAD], (unsigned long long)ndead);
+  }
+}
+
+// ---- tile directory -----------------------------------------------------------------------------
+// ts[t] = first row whose sorted cell key is >= t << 6 (keys of a FULL sort, sort.cu); ts[ntiles] = ns.
+__global__ void k_tile_starts(const uint32_t *__restrict__ keys, int64_t n, uint32_t ntiles, uint32_t *ts) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += gridDim.x * blockDim.x) {
+    const uint32_t v = t << 6;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (keys[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    ts[t] = (uint32_t)lo;
+  }
+}
+
+// wr[w] = first tile that starts at or after row w * per (per = rows per warp): every tile belongs to one warp
+__global__ void k_warp_ranges(const uint32_t *__restrict__ ts, uint32_t ntiles, uint32_t nwarps, uint32_t *wr) {
+  const uint32_t ns = ts[ntiles];
+  const uint32_t per = (ns + nwarps - 1) / nwarps;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w <= nwarps; w += gridDim.x * blockDim.x) {
+    uint32_t r = ntiles;
+    if (w < nwarps) {
+      const uint64_t v = (uint64_t)w * per;
+      uint32_t lo = 0, hi = ntiles;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ts[mid] < v) lo = mid + 1; else hi = mid;
+      }
+      r = lo;
+    }
+    wr[w] = r;
+  }
+}
+
+// ---- incremental re-group: destinations from the counts of the previous launch --------------------
+// seg = [ rows per destination tile (ntiles) | FAR rows per source tile (ntiles) | tail length (1) |
+//         DEAD rows per source tile (ntiles) | 0 ] ; its exclusive scan gives every base of the new layout.
+__global__ void k_regroup_seg(const uint32_t *__restrict__ tcnt, const uint32_t *__restrict__ ts, const int64_t *__restrict__ cnt,
+                              uint32_t ntiles, uint32_t mtx, uint32_t tiles_x, uint32_t tiles_y, uint32_t *seg) {
+  for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < ntiles; d += gridDim.x * blockDim.x) {
+    int tx, ty;
+    tile_coords(d, mtx, tx, ty);
+    uint32_t tot = 0;
+    if ((uint32_t)tx < tiles_x && (uint32_t)ty < tiles_y) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        // source tile = d - (dx, dy) of code c
+        const int sx = tx - (c % 3 - 1), sy = ty - (c / 3 - 1);
+        if ((uint32_t)sx < tiles_x && (uint32_t)sy < tiles_y) tot += tcnt[tile_ordinal((uint32_t)sx, (uint32_t)sy, mtx) * NCODE + c];
+      }
+    }
+    seg[d] = tot;
+    seg[ntiles + d] = tcnt[d * NCODE + CODE_FAR];
+    seg[2 * ntiles + 1 + d] = tcnt[d * NCODE + CODE_DEAD];
+    if (d == 0) {
+      const uint32_t n = (uint32_t)cnt[CNT_NSLOTS], ns = ts[ntiles];
+      seg[2 * ntiles] = n > ns ? n - ns : 0u;
+      seg[3 * ntiles + 1] = 0;
+    }
+  }
+}
+
+// after the scan: tbase[s][c] for every (source tile, code) and the new tile starts
+__global__ void k_regroup_bases(const uint32_t *__restrict__ tcnt, const uint32_t *__restrict__ seg, uint32_t ntiles, uint32_t mtx,
+                                uint32_t tiles_x, uint32_t tiles_y, uint32_t *tbase, uint32_t *ts_new) {
+  for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d <= ntiles; d += gridDim.x * blockDim.x) {
+    ts_new[d] = seg[d];
+    if (d == ntiles) break;
+    int tx, ty;
+    tile_coords(d, mtx, tx, ty);
+    uint32_t run = seg[d];
+    if ((uint32_t)tx < tiles_x && (uint32_t)ty < tiles_y) {
+      // rows that stay come first, then the arrivals in the fixed order of the codes
+      tbase[d * NCODE + CODE_STAY] = run;
+      run += tcnt[d * NCODE + CODE_STAY];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        if (c == CODE_STAY) continue;
+        const int sx = tx - (c % 3 - 1), sy = ty - (c / 3 - 1);
+        if ((uint32_t)sx < tiles_x && (uint32_t)sy < tiles_y) {
+          const uint32_t s = tile_ordinal((uint32_t)sx, (uint32_t)sy, mtx);
+          tbase[s * NCODE + c] = run;
+          run += tcnt[s * NCODE + c];
+        }
+      }
+    }
+    tbase[d * NCODE + CODE_FAR] = seg[ntiles + d];
+    tbase[d * NCODE + CODE_DEAD] = seg[2 * ntiles + 1 + d];
+  }
+}
+
+// counters after a MOVE: live slots end where the parked (discarded) rows begin; those rows leave the dead count
+__global__ void k_after_move(int64_t *cnt, const uint32_t *__restrict__ seg, uint32_t ntiles) {
+  const int64_t n_new = seg[2 * ntiles + 1], parked = (int64_t)seg[3 * ntiles + 1] - n_new;
+  cnt[CNT_NSLOTS] = n_new;
+  cnt[CNT_NDEAD] -= parked;
+}
+
+// rows beyond the slot count (parked ids of removed rows, default weights) must survive the buffer swap of a MOVE
+__global__ void k_copy_parked(const uint32_t *__restrict__ id, uint32_t *oid, const double *__restrict__ wg, double *owg,
+                              const int64_t *__restrict__ cnt, int64_t cap) {
+  for (int64_t p = cnt[CNT_NSLOTS] + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < cap; p += (int64_t)gridDim.x * blockDim.x) {
+    oid[p] = id[p];
+    owg[p] = wg[p];
+  }
+}
+
+// MARK state right after a full sort: every sorted row sits in its own tile
+__global__ void k_marks_after_sort(const uint32_t *__restrict__ ts, uint32_t ntiles, uint32_t *tcnt, uint8_t *code, int64_t n) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = gid; t < (int64_t)ntiles * NCODE; t += gsz) {
+    const uint32_t tile = (uint32_t)(t / NCODE), c = (uint32_t)(t % NCODE);
+    tcnt[t] = c == (uint32_t)CODE_STAY ? ts[tile + 1] - ts[tile] : 0u;
+  }
+  for (int64_t p = gid; p < n; p += gsz) code[p] = (uint8_t)CODE_STAY;
+}
+
+}  // namespace
+
+int32_t exclusive_scan_u32(iskb_ctx *c, uint32_t *d, int64_t n, uint32_t *partial);
+int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit, bool from_begin);
+
+static int advance_grid(const iskb_ctx *c) { return c->n_sm * 3 * 4; }   // 4 CTAs per resident slot: tail balance
+
+int32_t tdir_ensure(iskb_species *sp) {
+  iskb_ctx *c = sp->ctx;
+  if (sp->d_ts[0]) return ISKB_OK;
+  const TileGeom tg = tile_geom(c->g);
+  const size_t nt = tg.ntiles;
+  for (int k = 0; k < 2; ++k) CU_TRY(cudaMalloc(&sp->d_ts[k], (nt + 1) * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&sp->d_tcnt, nt * NCODE * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&sp->d_tbase, nt * NCODE * sizeof(uint32_t)));
+  const size_t nseg = 3 * nt + 2;
+  CU_TRY(cudaMalloc(&sp->d_seg, (nseg + (nseg + 2047) / 2048 + 16) * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&sp->d_wr, ((size_t)advance_grid(c) * 8 + 1) * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&sp->d_code, sp->cap));
+  CU_TRY(cudaMalloc(&sp->alt_code, sp->cap));
+  CU_TRY(cudaMalloc(&sp->d_mlist, sp->cap * sizeof(uint2)));
+  CU_TRY(cudaMalloc(&sp->d_mlist_n, sizeof(unsigned)));
+  return sp_ensure_alt(sp);
+}
+
+void sp_touch(iskb_species *sp) {
+  sp->tdir_valid = false;
+  sp->marks_valid = false;
+}
+
+void tdir_free(iskb_species *sp) {
+  if (sp->h_tstats) cudaFreeHost(sp->h_tstats);
+  for (int k = 0; k < 2; ++k) if (sp->ev_tstats[k]) cudaEventDestroy(sp->ev_tstats[k]);
+  for (int k = 0; k < 2; ++k) cudaFree(sp->d_ts[k]);
+  cudaFree(sp->d_tcnt); cudaFree(sp->d_tbase); cudaFree(sp->d_seg); cudaFree(sp->d_wr);
+  cudaFree(sp->d_code); cudaFree(sp->alt_code); cudaFree(sp->d_mlist); cudaFree(sp->d_mlist_n);
+}
+
+static int32_t warp_ranges(iskb_species *sp) {
+  iskb_ctx *c = sp->ctx;
+  const TileGeom tg = tile_geom(c->g);
+  const uint32_t nw = (uint32_t)advance_grid(c) * 8;
+  k_warp_ranges<<<(nw + 256) / 256, 256, 0, c->stream>>>(sp->d_ts[0], tg.ntiles, nw, sp->d_wr);
+  LAUNCH_CHECK(c);
+  return ISKB_OK;
+}
+
+// called by the full sort (sort.cu) with the sorted cell keys still in place
+int32_t tdir_build(iskb_species *sp, const uint32_t *sorted_keys, int64_t n) {
+  iskb_ctx *c = sp->ctx;
+  ISKB_TRY(tdir_ensure(sp));
+  const TileGeom tg = tile_geom(c->g);
+  k_tile_starts<<<(tg.ntiles + 256) / 256, 256, 0, c->stream>>>(sorted_keys, n, tg.ntiles, sp->d_ts[0]);
+  LAUNCH_CHECK(c);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
+  if (blocks < 1) blocks = 1;
+  k_marks_after_sort<<<blocks, 256, 0, c->stream>>>(sp->d_ts[0], tg.ntiles, sp->d_tcnt, sp->d_code, n);
+  LAUNCH_CHECK(c);
+  ISKB_TRY(warp_ranges(sp));
+  sp->tdir_valid = true;
+  sp->marks_valid = true;
+  sp->steps_since_move = 0;
+  return ISKB_OK;
+}
+
+template <int MX, int MY, bool RZ>
+static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
+  iskb_ctx *c = sp->ctx;
+  const TileGeom tg = tile_geom(c->g);
+  TileArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int q = 0; q < 6; ++q) { a.col[q] = sp->col[q]; a.ocol[q] = sp->alt[q]; }
+  a.id = sp->id; a.oid = sp->alt_id;
+  a.code = sp->d_code; a.ocode = sp->alt_code;
+  a.cnt = sp->d_cnt;
+  a.g = c->g;
+  a.E2 = c->d_E2;
+  a.qm = sp->q / sp->m;
+  a.dt = dt;
+  a.c1 = 0.5 * dt * a.qm;
+  a.w0 = sp->w0;
+  a.u = sp->d_u;
+  a.status = c->d_status;
+  a.vmax2 = sp->d_vmax2;
+  a.ts = sp->d_ts[0];
+  a.wr = sp->d_wr;
+  a.ntiles = tg.ntiles; a.mtx = tg.mtx; a.tiles_x = tg.tiles_x; a.tiles_y = tg.tiles_y;
+  a.tcnt = sp->d_tcnt;
+  a.tbase = sp->d_tbase;
+  a.seg = sp->d_seg;
+  a.mlist = sp->d_mlist;
+  a.mlist_n = sp->d_mlist_n;
+  a.mlist_cap = (unsigned)sp->cap;
+  const int grid = advance_grid(c);
+  constexpr int SMEM = 8 * (int)sizeof(WarpSm);
+  if (move) {
+    // destinations of this launch from the counts of the previous one
+    const int nb = (int)((tg.ntiles + 255) / 256);
+    const int64_t nseg = 3 * (int64_t)tg.ntiles + 2;
+    k_regroup_seg<<<nb, 256, 0, c->stream>>>(sp->d_tcnt, sp->d_ts[0], sp->d_cnt, tg.ntiles, tg.mtx, tg.tiles_x, tg.tiles_y, sp->d_seg);
+    LAUNCH_CHECK(c);
+    ISKB_TRY(exclusive_scan_u32(c, sp->d_seg, nseg, sp->d_seg + nseg));
+    k_regroup_bases<<<nb + 1, 256, 0, c->stream>>>(sp->d_tcnt, sp->d_seg, tg.ntiles, tg.mtx, tg.tiles_x, tg.tiles_y, sp->d_tbase,
+                                                  sp->d_ts[1]);
+    LAUNCH_CHECK(c);
+  }
+  CU_TRY(cudaMemsetAsync(sp->d_tcnt, 0, (size_t)tg.ntiles * NCODE * sizeof(uint32_t), c->stream));
+  CU_TRY(cudaMemsetAsync(sp->d_mlist_n, 0, sizeof(unsigned), c->stream));
+  ISKB_TRY(sp_vmax_reset(sp));
+  ISKB_TRY(prof_begin(c));
+  if (move) {
+    CU_TRY(cudaFuncSetAttribute(k_advance_tile<MX, MY, true, RZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    k_advance_tile<MX, MY, true, RZ><<<grid, 256, SMEM, c->stream>>>(a);
+    LAUNCH_CHECK(c);
+    k_advance_list<MX, MY, true, RZ><<<c->n_sm * 4, 256, 0, c->stream>>>(a);
+    LAUNCH_CHECK(c);
+  } else {
+    CU_TRY(cudaFuncSetAttribute(k_advance_tile<MX, MY, false, RZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    k_advance_tile<MX, MY, false, RZ><<<grid, 256, SMEM, c->stream>>>(a);
+    LAUNCH_CHECK(c);
+    k_advance_list<MX, MY, false, RZ><<<c->n_sm * 4, 256, 0, c->stream>>>(a);
+    LAUNCH_CHECK(c);
+  }
+  ISKB_TRY(prof_end(c));
+  if (move) {
+    // rows beyond the old slot count (parked ids, default weights) must survive the buffer swap
+    k_copy_parked<<<c->n_sm * 2, 256, 0, c->stream>>>(sp->id, sp->alt_id, sp->col[5], sp->alt[5], sp->d_cnt, sp->cap);
+    LAUNCH_CHECK(c);
+    k_after_move<<<1, 1, 0, c->stream>>>(sp->d_cnt, sp->d_seg, tg.ntiles);
+    LAUNCH_CHECK(c);
+    for (int q = 0; q < 6; ++q) std::swap(sp->col[q], sp->alt[q]);
+    std::swap(sp->id, sp->alt_id);
+    std::swap(sp->d_code, sp->alt_code);
+    std::swap(sp->d_ts[0], sp->d_ts[1]);
+    ISKB_TRY(warp_ranges(sp));
+    sp->steps_since_move = 0;
+  }
+  sp->counts_stale = true;
+  sp->marks_valid = true;
+  return ISKB_OK;
+}
+
+template <bool RZ>
+static int32_t launch_tile_rz(iskb_species *sp, double dt, int mx, int my, bool move) {
+  switch (mx * 3 + my) {
+    case 0: return launch_tile_modes<0, 0, RZ>(sp, dt, move);
+    case 1: return launch_tile_modes<0, 1, RZ>(sp, dt, move);
+    case 2: return launch_tile_modes<0, 2, RZ>(sp, dt, move);
+    case 3: return launch_tile_modes<1, 0, RZ>(sp, dt, move);
+    case 4: return launch_tile_modes<1, 1, RZ>(sp, dt, move);
+    case 5: return launch_tile_modes<1, 2, RZ>(sp, dt, move);
+    case 6: return launch_tile_modes<2, 0, RZ>(sp, dt, move);
+    case 7: return launch_tile_modes<2, 1, RZ>(sp, dt, move);
+    default: return launch_tile_modes<2, 2, RZ>(sp, dt, move);
+  }
+}
+
+// advance! + density of one species on the tile directory; `move` re-groups the rows on the way out
+int32_t launch_advance_tile(iskb_species *sp, double dt, int mode_x, int mode_y, bool move) {
+  iskb_ctx *c = sp->ctx;
+  ISKB_TRY(fields_join(c));
+  if (!sp->tdir_valid) return iskb_fail(ISKB_E_INVALID, "tile directory not built (internal)");
+  if (move && !sp->marks_valid) return iskb_fail(ISKB_E_INVALID, "re-group without valid marks (internal)");
+  if (c->pusher_rz) return launch_tile_rz<true>(sp, dt, mode_x, mode_y, move);
+  return launch_tile_rz<false>(sp, dt, mode_x, mode_y, move);
+}

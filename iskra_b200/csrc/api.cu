@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "pic_device.cuh"
+#include "tiles.cuh"
 
 int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit, bool from_begin);
 int32_t launch_advance_tiled(iskb_species *sp, double dt, int mode_x, int mode_y);
@@ -158,6 +158,7 @@ static void free_species(iskb_species *s) {
   if (s->h_wstats) cudaFreeHost(s->h_wstats);
   for (int k = 0; k < 2; ++k) if (s->ev_wstats[k]) cudaEventDestroy(s->ev_wstats[k]);
   cudaFree(s->d_hist); cudaFree(s->d_trk_list); cudaFree(s->d_trk_n);
+  tdir_free(s);
   delete s;
 }
 
@@ -423,6 +424,7 @@ static int32_t set_counts(iskb_species *s, int64_t nslots, int64_t ndead) {
   LAUNCH_CHECK(c);
   s->h_nslots = nslots; s->h_ndead = ndead; s->counts_stale = false;
   s->h_nsorted = 0;   // set_counts is only used by upload / sample / copy: the layout is unknown
+  sp_touch(s);
   return ISKB_OK;
 }
 
@@ -610,25 +612,173 @@ extern "C" int32_t iskb_rho_allreduce(iskb_ctx *c) {
   return comm_allreduce_sum(c, c->d_rho, (int64_t)c->g.nx * c->g.ny);
 }
 
+// ---- re-group policy of the tile-aware path (advance_tile.cu) -----------------------------------------
+// Per species and step: a FULL sort (radix sort by cell + interleave, builds the tile directory) when there is no
+// valid directory, when the unsorted tail has grown past 1 % of the rows, or every sort_full_interval steps if
+// that is set; otherwise the advance itself re-groups the rows on its way out (`move`) when the window-miss
+// rate of the launch two steps back exceeds the threshold, when discarded rows make up more than 2 % of the
+// slots, or after sort_max_interval steps (fixed mode: every sort_interval steps).  The statistics travel
+// through an async copy + event, two steps late, so the host never waits for the step it has just queued.
+static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move) {
+  *move = false;
+  if (s->h_tstats) {
+    const int slot = (int)(s->tstats_step & 1);   // the older of the two snapshots
+    if (s->tstats_pending[slot]) {
+      CU_TRY(cudaEventSynchronize(s->ev_tstats[slot]));
+      const int64_t *h = s->h_tstats + 10 * slot;
+      const int64_t n = h[CNT_NSLOTS] > 0 ? h[CNT_NSLOTS] : 1;
+      const int64_t g = h[3];
+      const int64_t d = g >= s->last_gmiss ? g - s->last_gmiss : g;   // the counters may have been reset by the caller
+      s->last_gmiss = g;
+      if (s->tstats_step - 2 >= s->tstats_sort_mark) {   // ignore snapshots that predate the last re-ordering
+        s->miss_rate = (double)d / (double)n;
+        s->tail_frac = (double)(h[CNT_NSLOTS] - h[9]) / (double)n;
+        s->dead_frac = (double)h[CNT_NDEAD] / (double)n;
+      }
+      s->tstats_pending[slot] = false;
+    }
+  }
+  const bool full = !s->tdir_valid || s->tail_frac > 0.01 ||
+                    (c->sort_full_interval > 0 && s->steps_since_full >= c->sort_full_interval);
+  if (full) {
+    ISKB_TRY(sp_sort(s, nullptr, true));
+    s->steps_since_full = 0;
+    s->full_sorts++;
+    s->miss_rate = s->tail_frac = s->dead_frac = 0.0;
+    s->tstats_sort_mark = s->tstats_step;
+    return ISKB_OK;
+  }
+  if (!s->marks_valid) return ISKB_OK;
+  const int64_t since = s->steps_since_move + 1;
+  if (c->sort_miss_threshold > 0.0) {
+    *move = s->miss_rate > c->sort_miss_threshold || s->dead_frac > 0.02 ||
+            (c->sort_max_interval > 0 && since >= c->sort_max_interval);
+  } else {
+    *move = since >= c->sort_interval;
+  }
+  if (*move) {
+    s->miss_rate = s->dead_frac = 0.0;
+    s->tstats_sort_mark = s->tstats_step;
+    s->moves++;
+  }
+  return ISKB_OK;
+}
+
+static int32_t tile_stats_snapshot(iskb_ctx *c, iskb_species *s) {
+  if (!s->h_tstats) {
+    CU_TRY(cudaMallocHost(&s->h_tstats, 20 * sizeof(int64_t)));
+    memset(s->h_tstats, 0, 20 * sizeof(int64_t));
+    CU_TRY(cudaEventCreateWithFlags(&s->ev_tstats[0], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&s->ev_tstats[1], cudaEventDisableTiming));
+  }
+  const int slot = (int)(s->tstats_step & 1);
+  const TileGeom tg = tile_geom(c->g);
+  s->h_tstats[10 * slot + 9] = 0;
+  CU_TRY(cudaMemcpyAsync(s->h_tstats + 10 * slot, s->d_cnt, CNT_N * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaMemcpyAsync(s->h_tstats + 10 * slot + 9, s->d_ts[0] + tg.ntiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(cudaEventRecord(s->ev_tstats[slot], c->stream));
+  s->tstats_pending[slot] = true;
+  s->tstats_step++;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_set_advance_path(iskb_ctx *c, int32_t path) {
+  if (!c || path < 0 || path > 1) return iskb_fail(ISKB_E_INVALID, "advance path is 0 (tile directory) or 1 (per-warp windows)");
+  c->adv_path = path;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_species_sort_stats(iskb_species *s, int64_t out[4]) {
+  if (!s || !out) return iskb_fail(ISKB_E_INVALID, "null");
+  out[0] = s->full_sorts;
+  out[1] = s->moves;
+  out[2] = s->steps_since_full;
+  out[3] = s->steps_since_move;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_ctx_counts(iskb_ctx *c, int64_t *n_species, int64_t *n_mcc, int64_t *n_dsmc) {
+  if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  if (n_species) *n_species = (int64_t)c->species.size();
+  if (n_mcc) *n_mcc = (int64_t)c->mccs.size();
+  if (n_dsmc) *n_dsmc = (int64_t)c->dsmcs.size();
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_step_set_active(iskb_ctx *c, iskb_species *const *species, int32_t n_species,
+                                        void *const *interactions, int32_t n_interactions) {
+  if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  if (n_species < 0) {   // back to "everything on the context"
+    c->active_set = false;
+    c->active_species.clear();
+    c->active_inter.clear();
+    return ISKB_OK;
+  }
+  if ((n_species > 0 && !species) || (n_interactions > 0 && !interactions) || n_interactions < 0)
+    return iskb_fail(ISKB_E_INVALID, "iskb_step_set_active: null list");
+  std::vector<iskb_species *> sp;
+  std::vector<std::pair<int, void *>> in;
+  for (int k = 0; k < n_species; ++k) {
+    bool ok = false;
+    for (iskb_species *s : c->species) ok = ok || s == species[k];
+    if (!ok) return iskb_fail(ISKB_E_INVALID, "iskb_step_set_active: species %d does not belong to this context", k);
+    sp.push_back(species[k]);
+  }
+  for (int k = 0; k < n_interactions; ++k) {
+    int kind = -1;
+    for (iskb_mcc *m : c->mccs) if ((void *)m == interactions[k]) kind = 0;
+    for (iskb_dsmc *d : c->dsmcs) if ((void *)d == interactions[k]) kind = 1;
+    if (kind < 0) return iskb_fail(ISKB_E_INVALID, "iskb_step_set_active: interaction %d does not belong to this context", k);
+    in.push_back(std::make_pair(kind, interactions[k]));
+  }
+  c->active_species.swap(sp);
+  c->active_inter.swap(in);
+  c->active_set = true;
+  return ISKB_OK;
+}
+
 extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
   if (!c || !c->has_grid || !c->ps.created) return iskb_fail(ISKB_E_INVALID, "grid and Poisson solver must be set");
   CU_TRY(cudaSetDevice(c->device));
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   ISKB_TRY(poisson_prepare(c));
+  const std::vector<iskb_species *> &species = c->active_set ? c->active_species : c->species;
   for (int it = 0; it < n_steps; ++it) {
-    const bool tiled = c->sort_interval > 0 && !c->pusher_rz;   // the r-z transform lives in the simple kernels
+    const bool windows_fit = c->g.nx >= 20 && c->g.ny >= 20;   // small / quasi-1D grids use the simple kernels
+    const bool tiled = c->sort_interval > 0 && windows_fit;
+    // tile directory path: everything but the surface tracker (which still runs on the per-warp windows of advance_fused.cu)
+    const bool tile_dir = tiled && !c->tracker && c->adv_path == 0;
+    const bool legacy = tiled && !tile_dir && !c->pusher_rz;
     if (c->pusher_rz && c->tracker) return iskb_fail(ISKB_E_UNSUPPORTED, "surface tracker with the axial pusher");
-    if (tiled)
-      for (iskb_species *s : c->species) ISKB_TRY(maybe_sort(c, s));
-    for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));       // :109-111
-    for (iskb_dsmc *d : c->dsmcs) ISKB_TRY(dsmc_launch(d, dt, false));
+    bool move[64];
+    if (species.size() > 64) return iskb_fail(ISKB_E_UNSUPPORTED, "more than 64 species");
+    if (tile_dir) {
+      for (size_t k = 0; k < species.size(); ++k) ISKB_TRY(tile_policy(c, species[k], &move[k]));
+    } else if (legacy) {
+      for (iskb_species *s : species) ISKB_TRY(maybe_sort(c, s));
+    }
+    if (c->active_set) {                                                   // :109-111, config.interactions in order
+      for (const std::pair<int, void *> &in : c->active_inter) {
+        if (in.first == 0) ISKB_TRY(mcc_launch((iskb_mcc *)in.second, dt, false));
+        else ISKB_TRY(dsmc_launch((iskb_dsmc *)in.second, dt, false));
+      }
+    } else {
+      for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));
+      for (iskb_dsmc *d : c->dsmcs) ISKB_TRY(dsmc_launch(d, dt, false));
+    }
     ISKB_TRY(fields_join(c));   // E of the previous step (the re-sort and MCC above did not need it)
-    for (iskb_species *s : c->species) {                                   // :113-115
+    for (size_t k = 0; k < species.size(); ++k) {                          // :113-115
+      iskb_species *s = species[k];
       CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
-      if (c->tracker && !tiled) {
+      if (tile_dir) {
+        ISKB_TRY(launch_advance_tile(s, dt, c->after_push[0], c->after_push[1], move[k]));
+        ISKB_TRY(tile_stats_snapshot(c, s));
+        s->steps_since_move++;
+        s->steps_since_full++;
+      } else if (c->tracker && !legacy) {
         // config.tracker != nothing: track! -> gather -> push -> check! -> after_push  (:56-61), one pass
         ISKB_TRY(launch_advance_tracked(s, dt, c->after_push[0], c->after_push[1], true));
-      } else if (tiled) {
+      } else if (legacy) {
         if (c->tracker) ISKB_TRY(launch_advance_tiled_tracked(s, dt, c->after_push[0], c->after_push[1]));
         else ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
         ISKB_TRY(post_advance_stats(c, s));
@@ -638,10 +788,9 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
         ISKB_TRY(launch_advance_simple(s, dt, c->after_push[0], c->after_push[1], true, false));
       }
     }
-    ISKB_TRY(launch_rho_finalize(c));                                      // :118-124
+    ISKB_TRY(launch_rho_finalize(c, &species));                            // :118-124
     if (c->n_ranks > 1) ISKB_TRY(comm_allreduce_sum(c, c->d_rho, nn));
-    static const bool skip_solve = getenv("ISKB_DEBUG_SKIP_SOLVE") != nullptr;   // timing experiments only
-    if (!skip_solve) ISKB_TRY(poisson_solve(c));                           // :126-128
+    ISKB_TRY(poisson_solve(c));                                            // :126-128
     c->step_count++;
   }
   return ISKB_OK;

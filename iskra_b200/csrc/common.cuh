@@ -130,6 +130,11 @@ struct iskb_ctx {
   std::vector<iskb_species *> species;
   std::vector<iskb_mcc *> mccs;
   std::vector<iskb_dsmc *> dsmcs;
+  // what iskb_step runs, in this order (config.species / config.interactions, ParticleInCell.jl:109-115);
+  // unset: everything created on the context, MCC objects before DSMC objects
+  bool active_set = false;
+  std::vector<iskb_species *> active_species;
+  std::vector<std::pair<int, void *>> active_inter;   // (0 = MCC, 1 = DSMC, handle)
   iskb_tracker *tracker = nullptr;   // config.tracker (create_surface_tracker); nullptr == `nothing`
   int after_push[2] = {ISKB_BND_WRAP, ISKB_BND_WRAP};   // default hook wrap!, ParticleInCell.jl:41
   int sort_interval = 0;
@@ -140,6 +145,7 @@ struct iskb_ctx {
   // small grids (<= PRIV_MAX_NODES): the simple advance deposits into PRIV_COPIES private copies of u (block b uses
   // copy b % PRIV_COPIES) that are summed afterwards -- divides the same-address atomic pressure by PRIV_COPIES
   double *d_upriv = nullptr;
+  int adv_path = 0;                  // 0: tile directory (advance_tile.cu), 1: per-warp windows (advance_fused.cu)
   int pusher_rz = 0;                 // BorisPusher{:rz}: transform_from_cartesian_to_cylindrical! after the push
   bool warn_too_fast = false;        // check!'s "particle is too fast" message condition was seen (sticky until read)
   // optional per-kernel timing of the dominant (advance) kernel, CUDA events on the launch stream
@@ -189,6 +195,24 @@ struct iskb_species {
   // rows the tiled advance leaves to the surface tracker (cells next to a surface), filled per launch
   uint32_t *d_trk_list = nullptr;
   unsigned *d_trk_n = nullptr;
+  // ---- tile directory and incremental re-group (advance_tile.cu) ----
+  uint32_t *d_ts[2] = {nullptr, nullptr};   // [ntiles+1] first row of every tile ([0] current, [1] next layout)
+  uint32_t *d_wr = nullptr;                 // [warps+1] first tile of every warp of the advance grid
+  uint32_t *d_tcnt = nullptr;               // [ntiles*NCODE] rows per (storage tile, code), rebuilt by every advance
+  uint32_t *d_tbase = nullptr;              // [ntiles*NCODE] destination bases of a re-grouping launch
+  uint32_t *d_seg = nullptr;                // scan scratch of the re-group (3*ntiles+2 words + partials)
+  uint8_t *d_code = nullptr, *alt_code = nullptr;   // per row: where its position lies relative to its storage tile
+  uint2 *d_mlist = nullptr;                 // rows outside their tile's window: (source row, destination row)
+  unsigned *d_mlist_n = nullptr;
+  bool tdir_valid = false;                  // d_ts describes the current row layout
+  bool marks_valid = false;                 // d_code / d_tcnt describe the current positions
+  int64_t steps_since_move = 0;
+  int64_t moves = 0, full_sorts = 0;        // statistics (iskb_species_sort_stats)
+  double tail_frac = 0.0, dead_frac = 0.0;  // from the last snapshot
+  int64_t *h_tstats = nullptr;              // pinned ring (2 x 10): cnt[0..8), -, rows in the tile directory
+  cudaEvent_t ev_tstats[2] = {nullptr, nullptr};
+  bool tstats_pending[2] = {false, false};
+  int64_t tstats_step = 0, tstats_sort_mark = 0;
 };
 
 struct MccProc {
@@ -277,7 +301,7 @@ int32_t comm_allreduce_sum(iskb_ctx *ctx, double *d_buf, int64_t n);
 int32_t comm_destroy(iskb_ctx *ctx);
 int32_t launch_advance(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit,
                        int64_t first_slot_from_cnt_begin);
-int32_t launch_rho_finalize(iskb_ctx *ctx);
+int32_t launch_rho_finalize(iskb_ctx *ctx, const std::vector<iskb_species *> *list = nullptr);
 int32_t sp_vmax_unknown(iskb_species *sp);
 int32_t sp_vmax_reset(iskb_species *sp);
 int32_t dsmc_launch(iskb_dsmc *d, double dt, bool want_nu);
@@ -288,5 +312,10 @@ int32_t launch_advance_tracked(iskb_species *sp, double dt, int mode_x, int mode
 int32_t launch_advance_tiled_tracked(iskb_species *sp, double dt, int mode_x, int mode_y);
 int32_t launch_advance_tracked_list(iskb_species *sp, double dt, int mode_x, int mode_y);
 int32_t poisson_sigma_device(iskb_ctx *ctx, double **d_sigma_out);
+int32_t launch_advance_tile(iskb_species *sp, double dt, int mode_x, int mode_y, bool move);
+int32_t tdir_build(iskb_species *sp, const uint32_t *sorted_keys, int64_t n);
+void tdir_free(iskb_species *sp);
+void sp_touch(iskb_species *sp);   // rows were changed outside the tile-aware advance: its marks no longer hold
+int32_t exclusive_scan_u32(iskb_ctx *c, uint32_t *d, int64_t n, uint32_t *partial);
 int32_t prof_begin(iskb_ctx *ctx);
 int32_t prof_end(iskb_ctx *ctx);

@@ -324,6 +324,10 @@ int32_t dsmc_free(iskb_dsmc *d) {
 
 int32_t dsmc_launch(iskb_dsmc *d, double dt, bool want_nu) {
   iskb_ctx *c = d->ctx;
+  // Candidate pairs per cell go with N_a * N_b of that cell (dsmc.jl:109-122).  Ranks own index slices of every
+  // species, so each would see only N/R of both lists and the collision frequency would drop by ~R.
+  if (c->n_ranks > 1)
+    return iskb_fail(ISKB_E_UNSUPPORTED, "DSMC with particles sharded over %d ranks: per-cell pair counts need all rows of a cell on one rank", c->n_ranks);
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   const bool same = d->source == d->target;
   for (int k = 0; k < (same ? 1 : 2); ++k) {          // cache!  :98-99

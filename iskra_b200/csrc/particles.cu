@@ -379,6 +379,7 @@ extern "C" int32_t iskb_push(iskb_species *sp, const double *partE, double dt) {
   }
   const double qm = sp->q / sp->m;   // pushers.jl:39
   ISKB_TRY(sp_vmax_unknown(sp));
+  sp_touch(sp);
   k_push<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4],
                                               sp->d_cnt, c->g, c->d_E2, d, n, qm, dt, c->d_status, c->pusher_rz);
   LAUNCH_CHECK(c);
@@ -397,6 +398,7 @@ extern "C" int32_t iskb_boundary(iskb_species *sp, int32_t mode_x, int32_t mode_
     ISKB_TRY(sp_sync_counts(sp));
     before = sp->h_nslots - sp->h_ndead;
   }
+  sp_touch(sp);
   k_boundary<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->d_cnt, c->g, mode_x, mode_y);
   LAUNCH_CHECK(c);
   if (mode_x == ISKB_BND_DISCARD || mode_y == ISKB_BND_DISCARD) sp->counts_stale = true;
@@ -461,16 +463,17 @@ extern "C" int32_t iskb_rho_accumulate(iskb_ctx *c, iskb_species *sp) {
   return ISKB_OK;
 }
 
-int32_t launch_rho_finalize(iskb_ctx *c) {
+int32_t launch_rho_finalize(iskb_ctx *c, const std::vector<iskb_species *> *list) {
   if (c) ISKB_TRY(fields_join(c));
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
-  if (c->species.size() > 8) return iskb_fail(ISKB_E_UNSUPPORTED, "more than 8 kinetic species");
+  const std::vector<iskb_species *> &sp = list ? *list : c->species;
+  if (sp.size() > 8) return iskb_fail(ISKB_E_UNSUPPORTED, "more than 8 kinetic species");
   RhoFin f;
-  f.ns = (int)c->species.size();
+  f.ns = (int)sp.size();
   for (int s = 0; s < f.ns; ++s) {
-    f.u[s] = c->species[s]->d_u;
-    f.n[s] = c->species[s]->d_n;
-    f.q[s] = c->species[s]->q;
+    f.u[s] = sp[s]->d_u;
+    f.n[s] = sp[s]->d_n;
+    f.q[s] = sp[s]->q;
   }
   int blocks = (int)((nn + TPB - 1) / TPB);
   if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
@@ -494,6 +497,7 @@ int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_
     CU_TRY(cudaMemsetAsync(c->d_upriv, 0, PRIV_COPIES * nn * sizeof(double), c->stream));
   }
   if (!from_begin) ISKB_TRY(prof_begin(c));
+  sp_touch(sp);
   k_advance_simple<<<blocks, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4],
                                                   sp->col[5], sp->d_cnt, from_begin ? 1 : 0, c->g, c->d_E2, qm,
                                                   dt, mode_x, mode_y, deposit ? sp->d_u : nullptr, c->d_status, sp->d_vmax2,
@@ -514,6 +518,7 @@ extern "C" int32_t iskb_species_remove(iskb_species *sp, int64_t i) {
   iskb_ctx *c = sp->ctx;
   ISKB_TRY(sp_compact(sp));
   if (i < 1 || i > sp->h_nslots) return iskb_fail(ISKB_E_INVALID, "remove!: row %lld outside 1..np = %lld", (long long)i, (long long)sp->h_nslots);
+  sp_touch(sp);
   k_remove_one<<<1, 1, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->id, sp->d_cnt,
                                        i - 1, sp->w0);
   LAUNCH_CHECK(c);
@@ -551,6 +556,7 @@ extern "C" int32_t iskb_species_remove_in_cells(iskb_species *sp, const uint8_t 
   uint8_t *d = nullptr;
   CU_TRY(cudaMalloc(&d, nn));
   CU_TRY(cudaMemcpyAsync(d, cell_mask, nn, cudaMemcpyHostToDevice, c->stream));
+  sp_touch(sp);
   k_remove_in_cells<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->d_cnt, c->g, d);
   LAUNCH_CHECK(c);
   sp->counts_stale = true;
@@ -571,6 +577,7 @@ extern "C" int32_t iskb_transform_cylindrical(iskb_species *sp, double dt) {
   if (!sp) return iskb_fail(ISKB_E_INVALID, "null species");
   iskb_ctx *c = sp->ctx;
   ISKB_TRY(sp_vmax_unknown(sp));
+  sp_touch(sp);
   k_to_cylindrical<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[2], sp->col[4], sp->d_cnt, dt);
   LAUNCH_CHECK(c);
   return ISKB_OK;

@@ -12,7 +12,9 @@
 // memory, so the gather of a re-sort finds the rows that crossed a tile edge in L2.  Out-of-grid rows get key_max and
 // dead rows key_max+1, so they land at the end.  The sort is stable in the previous row order, so the resulting
 // permutation is a pure function of the cell indices (bit-exact contract of north_star).
-#include "pic_device.cuh"
+#include "tiles.cuh"
+
+int32_t tdir_build(iskb_species *sp, const uint32_t *sorted_keys, int64_t n);
 
 namespace {
 
@@ -20,20 +22,6 @@ constexpr int TPB = 256;
 constexpr int RS_ITEMS = 16;
 constexpr int RS_WARPS = TPB / 32;
 constexpr int RS_TILE = TPB * RS_ITEMS;   // 4096 keys per block
-
-__device__ __forceinline__ uint32_t tile_ordinal(uint32_t tx, uint32_t ty, uint32_t mtx) {
-  return (((ty >> 4) * mtx + (tx >> 4)) << 8) | ((ty & 15u) << 4) | (tx & 15u);
-}
-struct TileGeom {
-  uint32_t mtx, ntiles;   // meta-tiles per row, padded tile count (multiple of 256)
-};
-static TileGeom tile_geom(const GridDev &g) {
-  const uint32_t tiles_x = (uint32_t)(g.nx - 1 + 7) / 8, tiles_y = (uint32_t)(g.ny - 1 + 7) / 8;
-  TileGeom t;
-  t.mtx = (tiles_x + 15) / 16;
-  t.ntiles = t.mtx * ((tiles_y + 15) / 16) * 256u;
-  return t;
-}
 
 __global__ void k_cell_keys(const double *__restrict__ x, const double *__restrict__ y, int64_t n,
                             GridDev g, uint32_t mtx, uint32_t key_max, uint32_t *keys) {
@@ -343,6 +331,8 @@ __global__ void k_counts_after_sort(int64_t *cnt) {
   cnt[CNT_NDEAD] = 0;
 }
 
+}  // namespace
+
 int32_t exclusive_scan_u32(iskb_ctx *c, uint32_t *d, int64_t n, uint32_t *partial) {
   const int nb = (int)((n + SC_PER_BLOCK - 1) / SC_PER_BLOCK);
   k_scan_reduce<<<nb, TPB, 0, c->stream>>>(d, n, partial);
@@ -353,6 +343,8 @@ int32_t exclusive_scan_u32(iskb_ctx *c, uint32_t *d, int64_t n, uint32_t *partia
   LAUNCH_CHECK(c);
   return ISKB_OK;
 }
+
+namespace {
 
 int32_t ensure_sort_scratch(iskb_species *sp) {
   if (!sp->d_key[0]) {
@@ -406,21 +398,7 @@ int32_t sort_by_keys(iskb_species *sp, int64_t n, int bits, uint32_t *perm_out_h
   }
   cols.id_in = sp->id;
   cols.id_out = sp->alt_id;
-  if (getenv("ISKB_DEBUG_SORT")) {
-    std::vector<uint32_t> h(n);
-    cudaMemcpy(h.data(), sp->d_idx[cur], n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-    int64_t seq = 0, near1k = 0, near300k = 0, sect = 0;
-    for (int64_t k = 0; k + 1 < n; ++k) {
-      seq += h[k + 1] == h[k] + 1;
-      sect += (h[k + 1] >> 3) == (h[k] >> 3);
-      const int64_t d = (int64_t)h[k] - k;
-      near1k += d > -4096 && d < 4096;
-      near300k += d > -300000 && d < 300000;
-    }
-    fprintf(stderr, "[sort] n=%lld bits=%d il=%u seq=%.3f same64B=%.3f |d|<4096=%.3f |d|<3e5=%.3f\n", (long long)n, bits,
-            interleave_tiles, (double)seq / n, (double)sect / n, (double)near1k / n, (double)near300k / n);
-  }
-  static const int PERM_CHUNK = getenv("ISKB_PERM_CHUNK") ? atoi(getenv("ISKB_PERM_CHUNK")) : 512;
+  constexpr int PERM_CHUNK = 512;
   int blocks = (int)((n + PERM_CHUNK - 1) / PERM_CHUNK);
   if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
   uint32_t *ticket = sp->d_hist + sp->hist_cap - 1;   // last scratch word (hist_cap has 16 words of slack)
@@ -438,6 +416,10 @@ int32_t sort_by_keys(iskb_species *sp, int64_t n, int bits, uint32_t *perm_out_h
   std::swap(sp->id, sp->alt_id);
   k_counts_after_sort<<<1, 1, 0, c->stream>>>(sp->d_cnt);
   LAUNCH_CHECK(c);
+  // the tile directory of the tile-aware advance (advance_tile.cu) describes the layout of a FULL sort only
+  sp->tdir_valid = false;
+  sp->marks_valid = false;
+  if (interleave_tiles) ISKB_TRY(tdir_build(sp, sp->d_key[cur], n));
   const int64_t nlive = n - sp->h_ndead;
   if (perm_out_host && nlive > 0)
     CU_TRY(cudaMemcpyAsync(perm_out_host, sp->d_idx[cur], nlive * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -488,7 +470,7 @@ int32_t sp_sort(iskb_species *sp, uint32_t *perm_out_host, bool interleave) {
   if (!c->has_grid) return iskb_fail(ISKB_E_INVALID, "iskb_grid_set must be called first");
   ISKB_TRY(sp_sync_counts(sp));
   const int64_t n = sp->h_nslots;
-  if (n == 0) return ISKB_OK;
+  if (n == 0) return interleave ? tdir_build(sp, nullptr, 0) : ISKB_OK;   // an empty species still gets its (empty) tile directory
   ISKB_TRY(ensure_sort_scratch(sp));
   const TileGeom tg = tile_geom(c->g);
   const uint64_t kmax64 = (uint64_t)tg.ntiles * 64u;

@@ -363,6 +363,7 @@ extern "C" int32_t iskb_tracker_check(iskb_tracker *st, iskb_species *sp, double
   TrackerDev t;
   memset(&t, 0, sizeof(t));
   ISKB_TRY(tracker_prepare(st, &t));
+  sp_touch(sp);
   k_check<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5], sp->d_cnt,
                                                t, dt, sp->q, st->d_ti, st->d_tj, st->d_thx, st->d_thy, st->d_counts, c->d_status);
   LAUNCH_CHECK(c);
@@ -398,6 +399,7 @@ int32_t launch_advance_tracked(iskb_species *sp, double dt, int mode_x, int mode
   const double qm = sp->q / sp->m;
   ISKB_TRY(sp_vmax_reset(sp));
   ISKB_TRY(prof_begin(c));
+  sp_touch(sp);
   k_advance_tracked<<<grid_for(sp), TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5],
                                                          sp->d_cnt, c->g, t, c->d_E2, sp->q, qm, dt, mode_x, mode_y,
                                                          deposit ? sp->d_u : nullptr, c->d_status, sp->d_vmax2,
@@ -416,6 +418,7 @@ int32_t launch_advance_tracked_list(iskb_species *sp, double dt, int mode_x, int
   ISKB_TRY(tracker_prepare(c->tracker, &t));
   const double qm = sp->q / sp->m;
   // the list length is only known on the device; a few blocks per SM cover the usual <1 % of the rows
+  sp_touch(sp);
   k_advance_tracked<<<c->n_sm * 2, TPB, 0, c->stream>>>(sp->col[0], sp->col[1], sp->col[2], sp->col[3], sp->col[4], sp->col[5],
                                                       sp->d_cnt, c->g, t, c->d_E2, sp->q, qm, dt, mode_x, mode_y, sp->d_u,
                                                       c->d_status, sp->d_vmax2, c->tracker->d_counts, sp->d_trk_list,

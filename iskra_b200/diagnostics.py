@@ -120,12 +120,12 @@ def register_solve_records(config):
             return out
         register_field("n" + sp.name, "1/m^2", dens, grid)
         n = sp.name
-        register_particle(n + "/id", "1", (lambda s=sp: s.id[: s.np].copy()), sp)
+        register_particle(n + "/id", "1", (lambda s=sp: s.id_ro[: s.np].copy()), sp)
         register_particle(n + "/mass", "kg", (lambda s=sp: np.array([s.m])), sp)
         register_particle(n + "/charge", "C", (lambda s=sp: np.array([s.q])), sp)
-        register_particle(n + "/weighting", "1", (lambda s=sp: s.wg[: s.np].copy()), sp, weighted=True)
-        register_particle(n + "/momentum", "kg*m/s", (lambda s=sp: s.m * s.v[: s.np]), sp, withcomponents=True)
-        register_particle(n + "/position", "m", (lambda s=sp: s.x[: s.np].copy()), sp, withcomponents=True)
+        register_particle(n + "/weighting", "1", (lambda s=sp: s.wg_ro[: s.np].copy()), sp, weighted=True)
+        register_particle(n + "/momentum", "kg*m/s", (lambda s=sp: s.m * s.v_ro[: s.np]), sp, withcomponents=True)
+        register_particle(n + "/position", "m", (lambda s=sp: s.x_ro[: s.np].copy()), sp, withcomponents=True)
         for ax in "xyz":
             register_particle(n + "/positionOffset/" + ax, "m", (lambda: np.array([0.0])), sp)
     for inter in config.interactions:

@@ -4,7 +4,10 @@
 Julia's `f!` functions are spelled `f_` here.  KineticSpecies keeps lazily-synced host mirrors so
 that script idioms like `e.np = 0`, `iHe.x .= e.x` (problem/10_two_streams.jl:62-68) keep working:
 reading `.x/.v/.wg/.id` pulls from the device if it is newer and marks the host copy as the
-authority until the next device operation pushes it back.
+authority (the caller may write through the returned array) until the next device operation
+pushes it back; `.x_ro/.v_ro/.wg_ro/.id_ro` are read-only views that leave the device copy the
+authority (diagnostics use those).  Every device operation -- the fused loop included -- pushes
+first, so a host copy that was only read is never stale when it goes back.
 """
 import ctypes as C
 import math
@@ -85,7 +88,9 @@ class KineticSpecies:
         return out
 
     def _touched_on_device(self):
+        """a device operation changed the rows: the host copy (pushed just before) is no longer current"""
         self._dev_newer = True
+        self._host_newer = False
 
     @property
     def np(self):
@@ -111,10 +116,22 @@ class KineticSpecies:
             self._host_newer = True
         return property(get, set_)
 
+    def _host_ro(name):
+        def get(self):
+            self._pull()
+            a = getattr(self, name).view()
+            a.flags.writeable = False
+            return a
+        return property(get)
+
     x = _host("_x")
     v = _host("_v")
     wg = _host("_wg")
     id = _host("_id")
+    x_ro = _host_ro("_x")
+    v_ro = _host_ro("_v")
+    wg_ro = _host_ro("_wg")
+    id_ro = _host_ro("_id")
 
 
 class FluidSpecies:
@@ -182,6 +199,8 @@ class MaxwellianSource:
         self.dx = np.zeros_like(self.wx) if dx is None else np.asarray(dx, dtype=np.float64).reshape(-1)
         self.dv = np.zeros_like(self.wv) if dv is None else np.asarray(dv, dtype=np.float64).reshape(-1)
         self.seed = 0
+        # solve() samples `src.species` for every src in config.sources (ParticleInCell.jl:104-106); the reference's
+        # struct has no such field (sources.jl:8-22), so a script that fills config.sources must attach it
 
 
 def thermal_speed(T, m):
@@ -518,6 +537,14 @@ def perform_(interaction, E, dt, config):
     return interaction.perform_(E, dt, config)
 
 
+def _check_active_lists(rt, config, kinetic):
+    """iskb_step advances everything registered on the context; that must be exactly config's lists, in order."""
+    handles = (L.vp * max(1, len(kinetic)))(*[s._h for s in kinetic])
+    inter = [i._h for i in config.interactions]
+    ih = (L.vp * max(1, len(inter)))(*inter)
+    L.check(rt.lib.iskb_step_set_active(rt.h, handles, len(kinetic), ih, len(inter)))
+
+
 def solve(config, dt=1e-5, timesteps=200, after_push=None, sort_interval=0, fused=True):
     """solve(config, dt, timesteps)  ParticleInCell.jl:84-139.
 
@@ -539,10 +566,25 @@ def solve(config, dt=1e-5, timesteps=200, after_push=None, sort_interval=0, fuse
         mx, my = after_push if after_push is not None else (L.BND_WRAP, L.BND_WRAP)
         rt.set_after_push(mx, my)
         rt.set_sort_interval(sort_interval)
+    for s in config.species:
+        # advance!(::FluidSpecies) (:74-82) and the fluid term of rho (:119-124) are not on the path (DESIGN.md
+        # "out of scope"): a fluid that would need either must not be dropped silently
+        if is_fluid(s) and (s.q != 0.0 or s.mu != 0.0 and getattr(s, "mobile", False)):
+            raise NotImplementedError("FluidSpecies %s carries charge: fluid advection / fluid charge density are out of scope" % s)
+    if not fused and after_push is not None:
+        raise ValueError("after_push=(mode_x, mode_y) belongs to the fused loop; with fused=False set hooks.after_push")
+    if fused:
+        # the device step runs every species / interaction bound to the context, in creation order
+        # (iskb_step); the reference runs config.species / config.interactions (:109-115).  Refuse to diverge.
+        _check_active_lists(rt, config, kinetic)
     for it in range(1, timesteps + 1):
         if fused and config.circuit is not None:
             raise NotImplementedError("the circuit advances between advance! and density (:116); use fused=False")
+        for src in config.sources:                                            # :104-106  sample!(src, src.species, dt)
+            sample_(src, src.species, dt, grid)      # AttributeError without .species, like the reference's field access
         if fused:
+            for s in kinetic:
+                s._push(grid)      # host edits made in after_loop (e.np = 0, e.x[...] = ...) reach the device
             rt.step(dt, 1)
             for s in kinetic:
                 s._touched_on_device()

@@ -102,6 +102,10 @@ class Runtime:
     def set_sort_interval(self, k):
         L.check(self.lib.iskb_set_sort_interval(self.h, int(k)))
 
+    def set_advance_path(self, path):
+        """0: tile directory + incremental re-group (default); 1: per-warp windows re-grouped by radix sort."""
+        L.check(self.lib.iskb_set_advance_path(self.h, int(path)))
+
     def join(self):
         """Make the context stream wait for a field solve still in flight on the field stream."""
         L.check(self.lib.iskb_stream_join(self.h))

@@ -1,0 +1,152 @@
+"""GPU tests of the tile-directory advance (csrc/advance_tile.cu): rows grouped by 8x8-cell tile, windows anchored per
+tile, re-group folded into the advance kernel (rows written to their new place, destinations from per-tile counts).
+
+Everything is compared with the C oracle (orc_advance / orc_density: ParticleInCell.jl:51-72, cloud_in_cell.jl,
+pushers.jl:37-50, wrap.jl) keyed by particle id -- the row order differs by construction.
+Positions and velocities are bit-exact (same operation order, no FMA), rho within 1e-12 (summation order).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import pic_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import iskra_b200
+    return iskra_b200
+
+
+def _setup(ib, nx, ny, dx, n, cap, seed, vscale, q=-O.qe, m=O.me):
+    PIC, FDM = ib.particle_in_cell, ib.finite_difference_method
+    g = ib.regular_grids.create_uniform_grid(np.arange(nx) * dx, np.arange(ny) * dx)
+    cg = CO.make_grid(nx, ny, dx, dx)
+    ps = FDM.create_poisson_solver(g, O.eps0)
+    FDM.apply_periodic(ps, 1)
+    FDM.apply_periodic(ps, 2)
+    rng = np.random.default_rng(seed)
+    x = rng.random(n) * (nx - 1) * dx
+    y = rng.random(n) * (ny - 1) * dx
+    v = rng.standard_normal((n, 3)) * vscale
+    wg = 0.5 + rng.random(n)
+    pc = CO.CSpecies(cap, q, m, 1.0)
+    pc.set(x, y, v[:, 0], v[:, 1], v[:, 2], wg)
+    pg = PIC.create_kinetic_species("s", cap, q, m, 1.0)
+    pg.x[:n, 0], pg.x[:n, 1] = x, y
+    pg.v[:n] = v
+    pg.wg[:n] = wg
+    pg.np = n
+    cfg = ib.configuration.Config()
+    cfg.grid, cfg.solver, cfg.pusher, cfg.species = g, ps, PIC.create_boris_pusher(), [pg]
+    return g, cg, pc, pg, cfg
+
+
+def _by_id(ids, *cols):
+    o = np.argsort(ids, kind="stable")
+    return [np.asarray(c)[o] for c in cols]
+
+
+def _check_state(pc, pg, cap):
+    m = pc.np
+    assert pg.np == m
+    ids = pg.id
+    assert np.array_equal(np.sort(ids), np.arange(1, cap + 1, dtype=ids.dtype))       # id stays a permutation (kinetic.jl:20-27)
+    assert np.array_equal(np.sort(ids[:m]), np.sort(pc.id[:m]))
+    xg, yg, v0, v1, v2, wg = _by_id(ids[:m], pg.x[:m, 0], pg.x[:m, 1], pg.v[:m, 0], pg.v[:m, 1], pg.v[:m, 2], pg.wg[:m])
+    xc, yc, c0, c1, c2, wc = _by_id(pc.id[:m], pc.xy[0, :m], pc.xy[1, :m], pc.v[0, :m], pc.v[1, :m], pc.v[2, :m], pc.wg[:m])
+    for a, r in ((xg, xc), (yg, yc), (v0, c0), (v1, c1), (v2, c2), (wg, wc)):
+        assert np.array_equal(a, r)                                                    # bit-exact
+
+
+@pytest.mark.parametrize("interval,bmode,vcells", [(1, (1, 1), 0.3), (2, (2, 1), 0.3), (3, (2, 2), 1.2), (4, (1, 2), 0.05)])
+def test_tile_advance_with_regroup_bitexact(ib, interval, bmode, vcells):
+    """E frozen (uploaded each step), so that the particle state is a pure function of the kernels under test:
+    12 steps, re-group every `interval` steps, wrap / discard mixes, slow and fast rows (vcells cells per step)."""
+    PIC = ib.particle_in_cell
+    nx, ny, dx, dt = 97, 129, 1e-3, 1e-9
+    n, cap = 150_000, 150_100
+    g, cg, pc, pg, cfg = _setup(ib, nx, ny, dx, n, cap, seed=3 + interval, vscale=vcells * dx / dt)
+    nn = nx * ny
+    rng = np.random.default_rng(99)
+    E = np.zeros(3 * nn)
+    E[: 2 * nn] = rng.standard_normal(2 * nn) * 50.0
+    E3 = E.reshape(3, ny, nx).transpose(2, 1, 0)          # (nx, ny, 3) view of the column-major planes
+    rt = g._rt
+    pg._push(g)
+    rt.set_after_push(*bmode)
+    rt.set_sort_interval(interval)
+    V = np.zeros(nn)
+    CO.lib().orc_cell_volume(C.byref(cg), CO.dp(V))
+    for step in range(12):
+        rt.set_fields(E=E3)
+        rt.step(dt, 1)
+        CO.lib().orc_advance(pc.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), (C.c_int32 * 2)(*bmode))
+    rt.synchronize()
+    pg._touched_on_device()
+    dens = np.zeros(nn)
+    CO.lib().orc_density(C.byref(cg), pc.ref(), CO.dp(V), CO.dp(dens))
+    n_g = PIC.density(pg, g)
+    assert np.abs(n_g.ravel(order="F") - dens).max() <= 1e-12 * np.abs(dens).max()
+    if 2 in bmode:
+        assert pc.np < n
+    _check_state(pc, pg, cap)
+    st = (C.c_int64 * 4)()
+    ib._lib.check(rt.lib.iskb_species_sort_stats(pg._h, st))
+    assert st[0] >= 1 and st[1] >= 12 // interval - 1      # one full sort, then re-grouping launches only
+
+
+def test_tile_rho_of_the_fused_step_matches_oracle(ib):
+    """rho left by iskb_step (deposit inside the tiled kernel + list kernel) against orc_density after the same steps."""
+    nx, ny, dx, dt = 129, 129, 1e-3, 1e-9
+    n, cap = 200_000, 200_000
+    g, cg, pc, pg, cfg = _setup(ib, nx, ny, dx, n, cap, seed=5, vscale=0.4 * dx / dt)
+    nn = nx * ny
+    rt = g._rt
+    pg._push(g)
+    rt.set_after_push(1, 1)
+    rt.set_sort_interval(2)
+    E = np.zeros(3 * nn)
+    V = np.zeros(nn)
+    CO.lib().orc_cell_volume(C.byref(cg), CO.dp(V))
+    for step in range(5):
+        rt.set_fields(E=np.zeros((nx, ny, 3)))
+        rt.step(dt, 1)
+        CO.lib().orc_advance(pc.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), (C.c_int32 * 2)(1, 1))
+    dens = np.zeros(nn)
+    CO.lib().orc_density(C.byref(cg), pc.ref(), CO.dp(V), CO.dp(dens))
+    rho_g = rt.fields()[0]
+    assert np.abs(rho_g.ravel(order="F") - pc.c.q * dens).max() <= 1e-12 * np.abs(pc.c.q * dens).max()
+
+
+def test_tile_advance_with_appended_rows_and_mcc(ib):
+    """Ionisation appends rows behind the sorted rows (the unsorted tail) while the advance re-groups: counts must add
+    up (np = initial + created - discarded), ids stay a permutation, no row is lost or duplicated."""
+    PIC, CH = ib.particle_in_cell, ib.chemistry
+    nx, ny, dx, dt = 65, 65, 5.234375e-4, 1.8436578171091445e-10
+    n, cap = 60_000, 100_000
+    g, cg, pc, e, cfg = _setup(ib, nx, ny, dx, n, cap, seed=8, vscale=3.0e6)
+    ion = PIC.create_kinetic_species("i", cap, O.qe, 3.99 * O.mp, 1.0)
+    He = PIC.FluidSpecies("He", 1.0, 0.0, 3.99 * O.mp, 3e20 * np.ones((nx, ny)), 300.0)
+    sig = CH.CrossSection(np.array([[0.0, 0.0], [24.587, 0.0], [30.0, 3e-20], [1000.0, 3e-20]]))
+    mc = CH.mcc(CH.reactions([(sig, "e + He --> e + e + i", CH.MCC.Ionization(24.587))], {"e": e, "He": He, "i": ion}), seed=4)
+    cfg.species, cfg.interactions = [e, ion, He], [mc]
+    PIC.solve(cfg, dt, 9, after_push=(2, 1), sort_interval=2)
+    tot = (C.c_int64 * 18)()
+    ib._lib.check(g._rt.lib.iskb_mcc_totals(mc._h, tot))
+    created = tot[1]
+    assert created > 200
+    assert ion.np == created                       # every ionisation appended one ion (w0 ratio 1), ions barely move
+    assert e.np <= n + created and e.np > n // 2
+    for s in (e, ion):
+        ids = s.id
+        assert np.array_equal(np.sort(ids), np.arange(1, cap + 1, dtype=ids.dtype))
+        m = s.np
+        assert np.all(np.isfinite(s.x[:m])) and np.all(s.x[:m, 0] >= 0) and np.all(s.x[:m, 0] < (nx - 1) * dx)
+        assert np.all(s.x[:m, 1] >= 0) and np.all(s.x[:m, 1] < (ny - 1) * dx)
+    # new electrons sit on their parents' positions when born; after <= 9 steps every ion still marks one
+    assert np.all(ion.wg[:ion.np] == 1.0)
