@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--sort-max", type=int, default=64)
     ap.add_argument("--sort-full", type=int, default=64, help="steps between FULL sorts; re-sorts in between only re-group by tile")
     ap.add_argument("--advance-path", type=int, default=0, help="0: tile directory + incremental re-group, 1: per-warp windows + radix re-group")
+    ap.add_argument("--no-lean", action="store_true", help="read and write every column (88 B per particle-step) even where v_z / wg cannot change")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=4_000_000)
@@ -287,6 +288,7 @@ def run_b200(a):
     rt = wl.rt
     rt.use_torch_stream()
     rt.set_advance_path(a.advance_path)
+    rt.set_lean(not a.no_lean)
     wl.prepare(a.sort_interval, a.sort_miss, a.sort_max, a.sort_full)
     rt.synchronize()
     build_s = time.perf_counter() - t_build

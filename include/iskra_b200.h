@@ -212,6 +212,10 @@ int32_t iskb_set_sort_full_interval(iskb_ctx *ctx, int32_t full_interval);
 /* 0 (default): tile directory + incremental re-group (advance_tile.cu); 1: per-warp windows that follow the
  * rows (advance_fused.cu, re-grouped by radix sort) -- the path a context with a surface tracker always takes. */
 int32_t iskb_set_advance_path(iskb_ctx *ctx, int32_t path);
+/* 1 (default): the fused advance does not touch what cannot change -- v_z under B == 0, E_z == 0 (pushers.jl:41-48 add
+ * zero to it) and the wg column of a species whose weights all equal w0 -- 64 instead of 88 B per particle-step,
+ * bit-identical results.  0: every launch reads and writes all columns (A/B measurements). */
+int32_t iskb_set_lean(iskb_ctx *ctx, int32_t on);
 /* out[0] full sorts, out[1] re-grouping launches so far, out[2] steps since the last full sort, out[3] since the last re-group */
 int32_t iskb_species_sort_stats(iskb_species *sp, int64_t out[4]);
 /* n_steps iterations of: MCC, then DSMC (registered interactions, each kind in creation order) -> advance! every species

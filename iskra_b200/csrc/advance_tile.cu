@@ -51,6 +51,9 @@ struct TileArgs {
   uint32_t *tcnt;           // [ntiles * NCODE] rows per (storage tile, code) after this launch
   const uint32_t *tbase;    // MOVE: [ntiles * NCODE] first destination row per (storage tile, code)
   const uint32_t *seg;      // MOVE: scan results (see k_regroup_seg): [2*ntiles] = tail destination
+  const unsigned long long *vz2max;   // LEAN: bits of the kept bound of v_z^2
+  unsigned *ticket;         // chunk dispenser
+  unsigned nchunks;
   uint2 *mlist;             // rows left to k_advance_list: (source row, destination row)
   unsigned *mlist_n;
   unsigned mlist_cap;
@@ -60,10 +63,11 @@ struct WarpSm {
   double2 E[WE * WE];
   double rho[WE * WRS];
   unsigned char claim[WE * WE];
-  unsigned tc[NCODE];     // rows of the current tile per code of their new position
+  unsigned tc[9 * NCODE]; // [code of the tile the row is stored in after the launch][code of its new position]
   unsigned mv[NCODE];     // MOVE: next destination row per code of the current tile
   unsigned stats[4];      // window misses, deposits outside the window, tiles, discards
-  unsigned misc[4];       // first tile of the next warp, last readable row, tile coordinates of the current tile
+  unsigned misc[8];       // first tile of the next warp, last readable row, tile coordinates of the current tile, staged misses
+  uint2 mq[64];           // staged miss-list entries (at most 31 left over + 32 new ones)
 };
 
 __device__ __forceinline__ unsigned lanemask_lt() {
@@ -104,12 +108,12 @@ __device__ __forceinline__ unsigned rel_code(int ntx, int nty, int stx, int sty)
 
 // One particle, from registers to registers: gather is the caller's business (shared window or global memory).
 // Returns true when the row was discarded.
-template <int MX, int MY, bool RZ>
+template <int MX, int MY, bool RZ, bool LEAN>
 __device__ __forceinline__ bool push_and_bound(double &px, double &py, double &vx, double &vy, double &vz, double ex,
                                                double ey, const TileArgs &a) {
   vx = push_v(vx, ex, a.c1, a.qm, a.dt);
   vy = push_v(vy, ey, a.c1, a.qm, a.dt);
-  vz = push_v(vz, 0.0, a.c1, a.qm, a.dt);
+  if (!LEAN) vz = push_v(vz, 0.0, a.c1, a.qm, a.dt);   // v_z + 0: LEAN leaves the column alone
   px = push_x(px, vx, a.dt);
   if (RZ) to_cylindrical(px, vx, vz, a.dt);   // push_particles!(::BorisPusher{:rz}, ...)  pushers.jl:13-17
   py = push_x(py, vy, a.dt);
@@ -124,44 +128,64 @@ __device__ __forceinline__ bool push_and_bound(double &px, double &py, double &v
 
 #define OUTC(q) (MOVE ? a.ocol[q] : a.col[q])   // column the launch writes to
 
-template <int MX, int MY, bool MOVE, bool RZ>
+// LEAN: the launch neither reads nor writes what cannot change.  With B == 0 (generalized_poisson.jl:412-419) and
+// E_z == 0 (:398-410) push_in_cartesian! leaves v_z as it is (v_z + 0, pushers.jl:41-48), so the column is not
+// touched (a re-grouping launch still has to carry it along); and a species whose weights are all w0 (every
+// BASELINE config: configuration.jl:99 `ones(N) * weight`) needs no wg column traffic either.  72 -> 64 B per row
+// instead of 88; positions, velocities and rho are bit-identical to the full path (tests/test_gpu_tile.py).
+template <int MX, int MY, bool MOVE, bool RZ, bool LEAN>
 __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
   extern __shared__ double2 s_dyn[];
   const int lane = threadIdx.x & 31;
   WarpSm &sm = ((WarpSm *)s_dyn)[threadIdx.x >> 5];
   for (int e = lane; e < WE * WRS; e += 32) sm.rho[e] = 0.0;
-  if (lane < NCODE) { sm.tc[lane] = 0; sm.mv[lane] = 0; }
+  for (int e = lane; e < 9 * NCODE; e += 32) sm.tc[e] = 0;
+  if (lane < NCODE) sm.mv[lane] = 0;
   if (lane < 4) sm.stats[lane] = 0;
   // The loop-carried state is kept small (tile, its row range, the batch, the window origin, a float velocity
   // bound); everything else that is constant per warp or per tile sits in shared memory: the body must fit
   // 80 registers without spills (a spill reload shares its scoreboard with the row prefetch).
   if (lane == 0) {
-    sm.misc[0] = a.wr[blockIdx.x * 8 + (threadIdx.x >> 5) + 1];   // first tile of the next warp
-    sm.misc[1] = (unsigned)a.cnt[CNT_NSLOTS] - 1u;                 // last row that may be read
+    sm.misc[1] = (unsigned)a.cnt[CNT_NSLOTS] - 1u;   // last row that may be read
+    sm.misc[4] = 0;
   }
   __syncwarp();
-  unsigned t = a.wr[blockIdx.x * 8 + (threadIdx.x >> 5)];
   float vm2 = 0.0f;
   constexpr int NOT_ANCHORED = -(1 << 20);
   int ei0 = NOT_ANCHORED, ej0 = 0;
-  unsigned r0 = 0, r1 = 0;
-  for (; t < sm.misc[0]; ++t) {   // first non-empty tile
-    r0 = a.ts[t];
-    r1 = a.ts[t + 1];
-    if (r1 > r0) break;
-  }
-  if (t < sm.misc[0]) {
-    unsigned rb = r0 & ~31u;
-    double px, py, vx, vy, vz, wq;
-    uint32_t pid = 0;
-    unsigned pcode = 0;
-    {
-      const unsigned r = min(rb + lane, sm.misc[1]);
-      px = a.col[0][r]; py = a.col[1][r]; vx = a.col[2][r]; vy = a.col[3][r]; vz = a.col[4][r]; wq = a.col[5][r];
-      if (MOVE) { pid = a.id[r]; pcode = a.code[r]; }
+  // Chunks of whole tiles (~2000 rows, wr[]) are handed out through a ticket: the grid is persistent (3 CTAs per
+  // SM) and no warp waits for the slowest sibling of its CTA.
+  for (;;) {
+    unsigned chunk = 0;
+    if (lane == 0) chunk = atomicAdd(a.ticket, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= a.nchunks) break;
+    unsigned t = a.wr[chunk];
+    if (lane == 0) sm.misc[0] = a.wr[chunk + 1];   // first tile of the next chunk
+    __syncwarp();
+    unsigned r0 = 0, r1 = 0;
+    for (; t < sm.misc[0]; ++t) {   // first non-empty tile
+      r0 = a.ts[t];
+      r1 = a.ts[t + 1];
+      if (r1 > r0) break;
     }
+    if (t >= sm.misc[0]) continue;
+    // Register prefetch, one batch ahead, issued ONLY inside the loop: the loop starts one (empty) batch before the
+    // first real one, with dead rows in the registers.  If the first batch were loaded ahead of the loop, the
+    // body's first use of px would have to wait on those loads' scoreboard -- and ptxas attaches the in-loop
+    // prefetch to the same scoreboard, so every iteration would wait for the loads it has just issued
+    // (measured: stall_long_sb 5.2 per issue, 1.49 instead of 1.09 ms per launch).
+    unsigned rb = (r0 & ~31u) - 32u;   // may wrap: the rows of this batch are never valid
+    const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
+    double nx_ = nan_, ny_ = 0.0, nvx_ = 0.0, nvy_ = 0.0, nvz_ = 0.0, nwq_ = 0.0;
+    uint32_t nid_ = 0;
+    unsigned ncode_ = 0;
     for (;;) {
-      // ---- register prefetch of the next batch (next tile: the batch that holds its first row) ----
+      double px = nx_, py = ny_, vx = nvx_, vy = nvy_, vz = nvz_;
+      const double wq = LEAN ? a.w0 : nwq_;
+      const uint32_t pid = nid_;
+      const unsigned pcode = ncode_;
+      // ---- prefetch of the next batch (next tile: the batch that holds its first row) ----
       unsigned rn = rb + 32;
       if (rn >= r1) {
         for (unsigned nt = t + 1; nt < sm.misc[0]; ++nt) {
@@ -170,10 +194,9 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
         }
       }
       rn = min(rn + lane, sm.misc[1]);   // index clamped instead of branching
-      const double nx_ = a.col[0][rn], ny_ = a.col[1][rn], nvx_ = a.col[2][rn], nvy_ = a.col[3][rn], nvz_ = a.col[4][rn],
-                   nwq_ = a.col[5][rn];
-      uint32_t nid_ = 0;
-      unsigned ncode_ = 0;
+      nx_ = a.col[0][rn]; ny_ = a.col[1][rn]; nvx_ = a.col[2][rn]; nvy_ = a.col[3][rn];
+      if (!LEAN || MOVE) nvz_ = a.col[4][rn];
+      if (!LEAN) nwq_ = a.col[5][rn];
       if (MOVE) { nid_ = a.id[rn]; ncode_ = a.code[rn]; }
 
       if (ei0 == NOT_ANCHORED) {   // first batch of a tile: anchor the windows on it
@@ -213,7 +236,14 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
         // the stored code decides (the counts were taken with it): a row that was discarded by k_advance_list
         // still carries CODE_FAR and goes to the tail as a dead row
         scode = valid ? pcode : 31u;
-        unsigned rem = __ballot_sync(0xffffffffu, valid);
+        {   // most rows stay: one ballot
+          const unsigned m = __ballot_sync(0xffffffffu, scode == (unsigned)CODE_STAY);
+          const unsigned b = sm.mv[CODE_STAY];
+          if (scode == (unsigned)CODE_STAY) dest = b + __popc(m & lanemask_lt());
+          __syncwarp();
+          if (lane == 0) sm.mv[CODE_STAY] = b + __popc(m);
+        }
+        unsigned rem = __ballot_sync(0xffffffffu, valid && scode != (unsigned)CODE_STAY);
         while (rem) {
           const int ld = __ffs(rem) - 1;
           const unsigned cl = __shfl_sync(0xffffffffu, scode, ld);
@@ -223,8 +253,8 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
           __syncwarp();
           if (lane == ld) sm.mv[cl] = b + __popc(m);
           rem &= ~m;
-          __syncwarp();
         }
+        __syncwarp();
       }
 
       bool dead_now = false, dep_win = false;
@@ -240,10 +270,15 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
           ex = cic_gather(gw, e00.x, e10.x, e01.x, e11.x);
           ey = cic_gather(gw, e00.y, e10.y, e01.y, e11.y);
         }
-        const bool dead = push_and_bound<MX, MY, RZ>(px, py, vx, vy, vz, ex, ey, a);
-        vm2 = fmaxf(vm2, __double2float_ru(fma(vz, vz, fma(vy, vy, vx * vx))));
-        OUTC(2)[dest] = vx; OUTC(3)[dest] = vy; OUTC(4)[dest] = vz; OUTC(1)[dest] = py;
-        if (MOVE) { a.ocol[5][dest] = wq; a.oid[dest] = pid; }
+        const bool dead = push_and_bound<MX, MY, RZ, LEAN>(px, py, vx, vy, vz, ex, ey, a);
+        if (LEAN) vm2 = fmaxf(vm2, __double2float_ru(fma(vy, vy, vx * vx)));
+        else vm2 = fmaxf(vm2, __double2float_ru(fma(vz, vz, fma(vy, vy, vx * vx))));
+        OUTC(2)[dest] = vx; OUTC(3)[dest] = vy; OUTC(1)[dest] = py;
+        if (!LEAN || MOVE) OUTC(4)[dest] = vz;
+        if (MOVE) {
+          if (!LEAN) a.ocol[5][dest] = wq;
+          a.oid[dest] = pid;
+        }
         if (dead) {
           OUTC(0)[dest] = __longlong_as_double(0x7ff8000000000000LL);
           dead_now = true;
@@ -280,36 +315,44 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
         ncode = CODE_DEAD;
         if (MOVE) {   // parked behind the live rows with its id; the slot's weight is reset like remove! does (kinetic.jl:24)
           a.ocol[0][dest] = __longlong_as_double(0x7ff8000000000000LL);
-          a.ocol[5][dest] = a.w0;
+          if (!LEAN) a.ocol[5][dest] = a.w0;
           a.oid[dest] = pid;
         }
       }
-      // rows outside the window: k_advance_list advances them; they join the tail at the next re-group
+      // rows outside the window: k_advance_list advances them; they join the tail at the next re-group.  The entries
+      // are staged per warp and appended 32 at a time: one same-address atomic per batch cost 2-4 ms per launch
+      // once most batches held a miss (same-address atomics serialise at ~2 ns each on B200).
       {
         const unsigned mm = __ballot_sync(0xffffffffu, miss);
         if (mm) {
-          const int ld = __ffs(mm) - 1;
-          unsigned b = 0;
-          if (lane == ld) { b = atomicAdd(a.mlist_n, (unsigned)__popc(mm)); sm.stats[0] += __popc(mm); }
-          b = __shfl_sync(0xffffffffu, b, ld);
-          if (miss) {
-            const unsigned slot = b + __popc(mm & lanemask_lt());
-            if (slot < a.mlist_cap) a.mlist[slot] = make_uint2(row, dest);
+          unsigned q = sm.misc[4];
+          if (miss) sm.mq[q + __popc(mm & lanemask_lt())] = make_uint2(row, dest);
+          q += __popc(mm);
+          __syncwarp();
+          if (q >= 32) {
+            unsigned b = 0;
+            if (lane == 0) b = atomicAdd(a.mlist_n, 32u);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b + 32u <= a.mlist_cap) a.mlist[b + lane] = sm.mq[lane];
             else atomicOr(a.status, ISKB_ST_CAPACITY);
+            q -= 32;
+            __syncwarp();
+            if (lane < (int)q) sm.mq[lane] = sm.mq[lane + 32];
           }
+          if (lane == 0) { sm.misc[4] = q; sm.stats[0] += __popc(mm); }
+          __syncwarp();
         }
       }
-      // ---- MARK: code of the new position + counts per (storage tile, code) ----
+      // ---- MARK: code of the new position + counts per (tile the row is stored in, code) ----
       if (valid) (MOVE ? a.ocode : a.code)[dest] = (uint8_t)ncode;
       {
-        const bool here = valid && (!MOVE || scode == (unsigned)CODE_STAY);   // stored in THIS tile after the launch
-        const unsigned ms = __ballot_sync(0xffffffffu, here && ncode == (unsigned)CODE_STAY);
-        if (lane == 0 && ms) sm.tc[CODE_STAY] += __popc(ms);
-        if (here && ncode != (unsigned)CODE_STAY) atomicAdd(&sm.tc[ncode], 1u);
-        if (MOVE && valid && scode < 9u && scode != (unsigned)CODE_STAY) {   // moved into a neighbour tile: its counters
-          const int dtx = (int)sm.misc[2] + (int)(scode % 3u) - 1, dty = (int)sm.misc[3] + (int)(scode / 3u) - 1;
-          atomicAdd(&a.tcnt[tile_ordinal((uint32_t)dtx, (uint32_t)dty, a.mtx) * NCODE + ncode], 1u);
-        }
+        // counters of this tile and, on a MOVE, of its eight neighbours (rows that move there); rows that go to
+        // the tail (FAR) or are parked (DEAD) belong to no tile any more
+        const bool counted = valid && scode < 9u;
+        const bool common = counted && scode == (unsigned)CODE_STAY && ncode == (unsigned)CODE_STAY;
+        const unsigned ms = __ballot_sync(0xffffffffu, common);
+        if (lane == 0 && ms) sm.tc[CODE_STAY * NCODE + CODE_STAY] += __popc(ms);
+        if (counted && !common) atomicAdd(&sm.tc[scode * NCODE + ncode], 1u);
       }
       // ---- deposit rounds without atomics (advance_fused.cu) ----
       {
@@ -339,10 +382,14 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
       if (rb + 32 >= r1) {   // tile finished: flush its window, publish its counts, go to the next non-empty tile
         flush_rho(sm.rho, ei0, ej0, a.g.nx, a.u, lane);
         ei0 = NOT_ANCHORED;
-        if (lane < NCODE) {
-          const unsigned c = sm.tc[lane];
-          if (c) atomicAdd(&a.tcnt[t * NCODE + lane], c);
-          sm.tc[lane] = 0;
+        for (int e = lane; e < (MOVE ? 9 : 1) * NCODE; e += 32) {
+          const int sc = MOVE ? e / NCODE : CODE_STAY, nc = e % NCODE;
+          const unsigned c = sm.tc[sc * NCODE + nc];
+          if (c) {
+            const int dtx = (int)sm.misc[2] + sc % 3 - 1, dty = (int)sm.misc[3] + sc / 3 - 1;
+            atomicAdd(&a.tcnt[(sc == CODE_STAY ? t : tile_ordinal((uint32_t)dtx, (uint32_t)dty, a.mtx)) * NCODE + nc], c);
+            sm.tc[sc * NCODE + nc] = 0;
+          }
         }
         __syncwarp();
         const unsigned t_end = sm.misc[0];
@@ -356,15 +403,30 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
       } else {
         rb += 32;
       }
-      px = nx_; py = ny_; vx = nvx_; vy = nvy_; vz = nvz_; wq = nwq_;
-      if (MOVE) { pid = nid_; pcode = ncode_; }
     }
   }
   __syncwarp();
+  {   // staged misses left over
+    const unsigned q = sm.misc[4];
+    if (q) {
+      unsigned b = 0;
+      if (lane == 0) b = atomicAdd(a.mlist_n, q);
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (lane < (int)q) {
+        if (b + lane < a.mlist_cap) a.mlist[b + lane] = sm.mq[lane];
+        else atomicOr(a.status, ISKB_ST_CAPACITY);
+      }
+    }
+  }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) vm2 = fmaxf(vm2, __shfl_xor_sync(0xffffffffu, vm2, d));
   if (lane == 0) {
-    if (vm2 > 0.0f) atomicMax(a.vmax2, (unsigned long long)__double_as_longlong((double)vm2));
+    if (vm2 > 0.0f) {
+      // float -> double is exact and the float was rounded up: still an upper bound; LEAN adds the kept bound of v_z^2
+      double b = (double)vm2;
+      if (LEAN) b = __dadd_ru(b, __longlong_as_double((long long)*a.vz2max));
+      atomicMax(a.vmax2, (unsigned long long)__double_as_longlong(b));
+    }
     if (sm.stats[3]) atomicAdd((unsigned long long *)&a.cnt[CNT_NDEAD], (unsigned long long)sm.stats[3]);
     atomicAdd((unsigned long long *)&a.cnt[3], (unsigned long long)sm.stats[0]);
     atomicAdd((unsigned long long *)&a.cnt[4], (unsigned long long)sm.stats[1]);
@@ -375,7 +437,7 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
 // Rows the tiled kernel left out -- its miss list and the unsorted tail [ns, n) -- advanced one per thread straight
 // from / to global memory: same arithmetic, E gathered from the global field, deposit with global REDs.
 // MOVE: miss rows go where the tiled kernel said; tail row ns + k goes to seg[2*ntiles] + k.
-template <int MX, int MY, bool MOVE, bool RZ>
+template <int MX, int MY, bool MOVE, bool RZ, bool LEAN>
 __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned nm = min(*a.mlist_n, a.mlist_cap);
@@ -394,16 +456,24 @@ __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
       else { src = ns + (k - nm); dst = tail_dst + (k - nm); }
       double px = a.col[0][src];
       if (is_dead(px)) {
-        if (MOVE) { a.ocol[0][dst] = px; a.ocol[5][dst] = a.col[5][src]; a.oid[dst] = a.id[src]; }
+        if (MOVE) {
+          a.ocol[0][dst] = px;
+          if (!LEAN) a.ocol[5][dst] = a.col[5][src];
+          a.oid[dst] = a.id[src];
+        }
       } else {
-        double py = a.col[1][src], vx = a.col[2][src], vy = a.col[3][src], vz = a.col[4][src];
-        const double wq = a.col[5][src];
+        double py = a.col[1][src], vx = a.col[2][src], vy = a.col[3][src], vz = (!LEAN || MOVE) ? a.col[4][src] : 0.0;
+        const double wq = LEAN ? a.w0 : a.col[5][src];
         double ex, ey;
         if (!gather_E(a.E2, a.g, px, py, ex, ey)) atomicOr(a.status, ISKB_ST_OOB);
-        const bool dead = push_and_bound<MX, MY, RZ>(px, py, vx, vy, vz, ex, ey, a);
-        vm2 = fmax(vm2, fma(vz, vz, fma(vy, vy, vx * vx)));
-        OUTC(2)[dst] = vx; OUTC(3)[dst] = vy; OUTC(4)[dst] = vz; OUTC(1)[dst] = py;
-        if (MOVE) { a.ocol[5][dst] = wq; a.oid[dst] = a.id[src]; }
+        const bool dead = push_and_bound<MX, MY, RZ, LEAN>(px, py, vx, vy, vz, ex, ey, a);
+        vm2 = fmax(vm2, LEAN ? fma(vy, vy, vx * vx) : fma(vz, vz, fma(vy, vy, vx * vx)));
+        OUTC(2)[dst] = vx; OUTC(3)[dst] = vy; OUTC(1)[dst] = py;
+        if (!LEAN || MOVE) OUTC(4)[dst] = vz;
+        if (MOVE) {
+          if (!LEAN) a.ocol[5][dst] = wq;
+          a.oid[dst] = a.id[src];
+        }
         if (dead) {
           OUTC(0)[dst] = __longlong_as_double(0x7ff8000000000000LL);
           dead_now = true;
@@ -433,7 +503,8 @@ __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
   if (lane == 0) {
     if (vm2 > 0.0) {
       // the bound is kept as a float rounded up (the tiled kernel does the same)
-      const double up = (double)__double2float_ru(vm2);
+      double up = (double)__double2float_ru(vm2);
+      if (LEAN) up = __dadd_ru(up, __longlong_as_double((long long)*a.vz2max));
       atomicMax(a.vmax2, (unsigned long long)__double_as_longlong(up));
     }
     if (ndead) atomicAdd((unsigned long long *)&a.cnt[CNT_NDEAD], (unsigned long long)ndead);
@@ -454,7 +525,20 @@ __global__ void k_tile_starts(const uint32_t *__restrict__ keys, int64_t n, uint
   }
 }
 
-// wr[w] = first tile that starts at or after row w * per (per = rows per warp): every tile belongs to one warp
+// bits of max v_z^2 over the rows (dead rows carry finite velocities; they only loosen the bound)
+__global__ void k_vz2max(const double *__restrict__ vz, const int64_t *__restrict__ cnt, unsigned long long *out) {
+  const int64_t n = cnt[CNT_NSLOTS];
+  double m = 0.0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const double v = vz[p];
+    m = fmax(m, v * v);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// wr[w] = first tile that starts at or after row w * per (per = rows per chunk): every tile belongs to one chunk
 __global__ void k_warp_ranges(const uint32_t *__restrict__ ts, uint32_t ntiles, uint32_t nwarps, uint32_t *wr) {
   const uint32_t ns = ts[ntiles];
   const uint32_t per = (ns + nwarps - 1) / nwarps;
@@ -561,7 +645,8 @@ __global__ void k_marks_after_sort(const uint32_t *__restrict__ ts, uint32_t nti
 int32_t exclusive_scan_u32(iskb_ctx *c, uint32_t *d, int64_t n, uint32_t *partial);
 int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit, bool from_begin);
 
-static int advance_grid(const iskb_ctx *c) { return c->n_sm * 3 * 4; }   // 4 CTAs per resident slot: tail balance
+static int advance_grid(const iskb_ctx *c) { return c->n_sm * 3; }          // persistent: 3 CTAs of 8 warps per SM
+static int advance_chunks(const iskb_ctx *c) { return c->n_sm * 3 * 8 * 8; }   // 8 chunks per resident warp
 
 int32_t tdir_ensure(iskb_species *sp) {
   iskb_ctx *c = sp->ctx;
@@ -573,7 +658,8 @@ int32_t tdir_ensure(iskb_species *sp) {
   CU_TRY(cudaMalloc(&sp->d_tbase, nt * NCODE * sizeof(uint32_t)));
   const size_t nseg = 3 * nt + 2;
   CU_TRY(cudaMalloc(&sp->d_seg, (nseg + (nseg + 2047) / 2048 + 16) * sizeof(uint32_t)));
-  CU_TRY(cudaMalloc(&sp->d_wr, ((size_t)advance_grid(c) * 8 + 1) * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&sp->d_wr, ((size_t)advance_chunks(c) + 1) * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&sp->d_ticket, sizeof(unsigned)));
   CU_TRY(cudaMalloc(&sp->d_code, sp->cap));
   CU_TRY(cudaMalloc(&sp->alt_code, sp->cap));
   CU_TRY(cudaMalloc(&sp->d_mlist, sp->cap * sizeof(uint2)));
@@ -584,6 +670,7 @@ int32_t tdir_ensure(iskb_species *sp) {
 void sp_touch(iskb_species *sp) {
   sp->tdir_valid = false;
   sp->marks_valid = false;
+  sp->vz2_known = false;
 }
 
 void tdir_free(iskb_species *sp) {
@@ -591,13 +678,13 @@ void tdir_free(iskb_species *sp) {
   for (int k = 0; k < 2; ++k) if (sp->ev_tstats[k]) cudaEventDestroy(sp->ev_tstats[k]);
   for (int k = 0; k < 2; ++k) cudaFree(sp->d_ts[k]);
   cudaFree(sp->d_tcnt); cudaFree(sp->d_tbase); cudaFree(sp->d_seg); cudaFree(sp->d_wr);
-  cudaFree(sp->d_code); cudaFree(sp->alt_code); cudaFree(sp->d_mlist); cudaFree(sp->d_mlist_n);
+  cudaFree(sp->d_code); cudaFree(sp->alt_code); cudaFree(sp->d_mlist); cudaFree(sp->d_mlist_n); cudaFree(sp->d_ticket);
 }
 
 static int32_t warp_ranges(iskb_species *sp) {
   iskb_ctx *c = sp->ctx;
   const TileGeom tg = tile_geom(c->g);
-  const uint32_t nw = (uint32_t)advance_grid(c) * 8;
+  const uint32_t nw = (uint32_t)advance_chunks(c);
   k_warp_ranges<<<(nw + 256) / 256, 256, 0, c->stream>>>(sp->d_ts[0], tg.ntiles, nw, sp->d_wr);
   LAUNCH_CHECK(c);
   return ISKB_OK;
@@ -622,7 +709,7 @@ int32_t tdir_build(iskb_species *sp, const uint32_t *sorted_keys, int64_t n) {
   return ISKB_OK;
 }
 
-template <int MX, int MY, bool RZ>
+template <int MX, int MY, bool RZ, bool LEAN>
 static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
   iskb_ctx *c = sp->ctx;
   const TileGeom tg = tile_geom(c->g);
@@ -650,6 +737,15 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
   a.mlist = sp->d_mlist;
   a.mlist_n = sp->d_mlist_n;
   a.mlist_cap = (unsigned)sp->cap;
+  a.vz2max = sp->d_vz2max;
+  a.ticket = sp->d_ticket;
+  a.nchunks = (unsigned)advance_chunks(c);
+  if (LEAN && !sp->vz2_known) {   // bound of v_z^2 (MCC pruning): the lean kernels do not see the column
+    CU_TRY(cudaMemsetAsync(sp->d_vz2max, 0, sizeof(unsigned long long), c->stream));
+    k_vz2max<<<c->n_sm * 4, 256, 0, c->stream>>>(sp->col[4], sp->d_cnt, sp->d_vz2max);
+    LAUNCH_CHECK(c);
+    sp->vz2_known = true;
+  }
   const int grid = advance_grid(c);
   constexpr int SMEM = 8 * (int)sizeof(WarpSm);
   if (move) {
@@ -665,19 +761,20 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
   }
   CU_TRY(cudaMemsetAsync(sp->d_tcnt, 0, (size_t)tg.ntiles * NCODE * sizeof(uint32_t), c->stream));
   CU_TRY(cudaMemsetAsync(sp->d_mlist_n, 0, sizeof(unsigned), c->stream));
+  CU_TRY(cudaMemsetAsync(sp->d_ticket, 0, sizeof(unsigned), c->stream));
   ISKB_TRY(sp_vmax_reset(sp));
   ISKB_TRY(prof_begin(c));
   if (move) {
-    CU_TRY(cudaFuncSetAttribute(k_advance_tile<MX, MY, true, RZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    k_advance_tile<MX, MY, true, RZ><<<grid, 256, SMEM, c->stream>>>(a);
+    CU_TRY(cudaFuncSetAttribute(k_advance_tile<MX, MY, true, RZ, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    k_advance_tile<MX, MY, true, RZ, LEAN><<<grid, 256, SMEM, c->stream>>>(a);
     LAUNCH_CHECK(c);
-    k_advance_list<MX, MY, true, RZ><<<c->n_sm * 4, 256, 0, c->stream>>>(a);
+    k_advance_list<MX, MY, true, RZ, LEAN><<<c->n_sm * 4, 256, 0, c->stream>>>(a);
     LAUNCH_CHECK(c);
   } else {
-    CU_TRY(cudaFuncSetAttribute(k_advance_tile<MX, MY, false, RZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    k_advance_tile<MX, MY, false, RZ><<<grid, 256, SMEM, c->stream>>>(a);
+    CU_TRY(cudaFuncSetAttribute(k_advance_tile<MX, MY, false, RZ, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    k_advance_tile<MX, MY, false, RZ, LEAN><<<grid, 256, SMEM, c->stream>>>(a);
     LAUNCH_CHECK(c);
-    k_advance_list<MX, MY, false, RZ><<<c->n_sm * 4, 256, 0, c->stream>>>(a);
+    k_advance_list<MX, MY, false, RZ, LEAN><<<c->n_sm * 4, 256, 0, c->stream>>>(a);
     LAUNCH_CHECK(c);
   }
   ISKB_TRY(prof_end(c));
@@ -699,18 +796,18 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
   return ISKB_OK;
 }
 
-template <bool RZ>
+template <bool RZ, bool LEAN>
 static int32_t launch_tile_rz(iskb_species *sp, double dt, int mx, int my, bool move) {
   switch (mx * 3 + my) {
-    case 0: return launch_tile_modes<0, 0, RZ>(sp, dt, move);
-    case 1: return launch_tile_modes<0, 1, RZ>(sp, dt, move);
-    case 2: return launch_tile_modes<0, 2, RZ>(sp, dt, move);
-    case 3: return launch_tile_modes<1, 0, RZ>(sp, dt, move);
-    case 4: return launch_tile_modes<1, 1, RZ>(sp, dt, move);
-    case 5: return launch_tile_modes<1, 2, RZ>(sp, dt, move);
-    case 6: return launch_tile_modes<2, 0, RZ>(sp, dt, move);
-    case 7: return launch_tile_modes<2, 1, RZ>(sp, dt, move);
-    default: return launch_tile_modes<2, 2, RZ>(sp, dt, move);
+    case 0: return launch_tile_modes<0, 0, RZ, LEAN>(sp, dt, move);
+    case 1: return launch_tile_modes<0, 1, RZ, LEAN>(sp, dt, move);
+    case 2: return launch_tile_modes<0, 2, RZ, LEAN>(sp, dt, move);
+    case 3: return launch_tile_modes<1, 0, RZ, LEAN>(sp, dt, move);
+    case 4: return launch_tile_modes<1, 1, RZ, LEAN>(sp, dt, move);
+    case 5: return launch_tile_modes<1, 2, RZ, LEAN>(sp, dt, move);
+    case 6: return launch_tile_modes<2, 0, RZ, LEAN>(sp, dt, move);
+    case 7: return launch_tile_modes<2, 1, RZ, LEAN>(sp, dt, move);
+    default: return launch_tile_modes<2, 2, RZ, LEAN>(sp, dt, move);
   }
 }
 
@@ -720,6 +817,7 @@ int32_t launch_advance_tile(iskb_species *sp, double dt, int mode_x, int mode_y,
   ISKB_TRY(fields_join(c));
   if (!sp->tdir_valid) return iskb_fail(ISKB_E_INVALID, "tile directory not built (internal)");
   if (move && !sp->marks_valid) return iskb_fail(ISKB_E_INVALID, "re-group without valid marks (internal)");
-  if (c->pusher_rz) return launch_tile_rz<true>(sp, dt, mode_x, mode_y, move);
-  return launch_tile_rz<false>(sp, dt, mode_x, mode_y, move);
+  if (c->pusher_rz) return launch_tile_rz<true, false>(sp, dt, mode_x, mode_y, move);   // the r-z transform rotates (v_x, v_z)
+  if (sp->wg_uniform && c->lean_ok) return launch_tile_rz<false, true>(sp, dt, mode_x, mode_y, move);
+  return launch_tile_rz<false, false>(sp, dt, mode_x, mode_y, move);
 }

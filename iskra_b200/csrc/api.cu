@@ -153,7 +153,7 @@ extern "C" int32_t iskb_create(int32_t device, iskb_ctx **out) {
 
 static void free_species(iskb_species *s) {
   for (int q = 0; q < 6; ++q) { cudaFree(s->col[q]); cudaFree(s->alt[q]); }
-  cudaFree(s->id); cudaFree(s->alt_id); cudaFree(s->d_cnt); cudaFree(s->d_vmax2); cudaFree(s->d_u); cudaFree(s->d_n);
+  cudaFree(s->id); cudaFree(s->alt_id); cudaFree(s->d_cnt); cudaFree(s->d_vmax2); cudaFree(s->d_vz2max); cudaFree(s->d_u); cudaFree(s->d_n);
   for (int k = 0; k < 2; ++k) { cudaFree(s->d_key[k]); cudaFree(s->d_idx[k]); }
   if (s->h_wstats) cudaFreeHost(s->h_wstats);
   for (int k = 0; k < 2; ++k) if (s->ev_wstats[k]) cudaEventDestroy(s->ev_wstats[k]);
@@ -374,6 +374,7 @@ extern "C" int32_t iskb_species_create(iskb_ctx *c, int64_t capacity, double q, 
   }
   CU_TRY(cudaMalloc(&s->id, capacity * sizeof(uint32_t)));
   CU_TRY(cudaMalloc(&s->d_vmax2, sizeof(unsigned long long)));
+  CU_TRY(cudaMalloc(&s->d_vz2max, sizeof(unsigned long long)));
   CU_TRY(cudaMalloc(&s->d_cnt, CNT_N * sizeof(int64_t)));
   CU_TRY(cudaMemsetAsync(s->d_cnt, 0, CNT_N * sizeof(int64_t), c->stream));
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
@@ -393,6 +394,8 @@ extern "C" int32_t iskb_species_create(iskb_ctx *c, int64_t capacity, double q, 
 int32_t sp_vmax_unknown(iskb_species *s) {
   static const unsigned long long inf_bits = 0x7ff0000000000000ull;
   CU_TRY(cudaMemcpyAsync(s->d_vmax2, &inf_bits, sizeof(inf_bits), cudaMemcpyHostToDevice, s->ctx->stream));
+  CU_TRY(cudaMemcpyAsync(s->d_vz2max, &inf_bits, sizeof(inf_bits), cudaMemcpyHostToDevice, s->ctx->stream));
+  s->vz2_known = false;
   return ISKB_OK;
 }
 int32_t sp_vmax_reset(iskb_species *s) {
@@ -404,6 +407,8 @@ int32_t sp_ensure_alt(iskb_species *s) {
   if (s->alt[0]) return ISKB_OK;
   for (int k = 0; k < 6; ++k) CU_TRY(cudaMalloc(&s->alt[k], s->cap * sizeof(double)));
   CU_TRY(cudaMalloc(&s->alt_id, s->cap * sizeof(uint32_t)));
+  // the lean re-grouping launches never write wg (all weights are w0 then): the twin column must hold them already
+  CU_TRY(cudaMemcpyAsync(s->alt[5], s->col[5], s->cap * sizeof(double), cudaMemcpyDeviceToDevice, s->ctx->stream));
   return ISKB_OK;
 }
 
@@ -442,7 +447,13 @@ extern "C" int32_t iskb_species_upload(iskb_species *s, const double *x, const d
     CU_TRY(cudaMemcpyAsync(s->col[3], v + ld, b, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaMemcpyAsync(s->col[4], v + 2 * ld, b, cudaMemcpyHostToDevice, c->stream));
   }
-  if (wg) CU_TRY(cudaMemcpyAsync(s->col[5], wg, s->cap * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (wg) {
+    CU_TRY(cudaMemcpyAsync(s->col[5], wg, s->cap * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    bool uni = true;   // every weight equal to w0 (the reference's `ones(N) * weight`): the lean kernels skip the column
+    for (int64_t k = 0; k < s->cap && uni; ++k) uni = wg[k] == s->w0;
+    s->wg_uniform = uni;
+    if (s->alt[5]) CU_TRY(cudaMemcpyAsync(s->alt[5], wg, s->cap * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
   if (id) CU_TRY(cudaMemcpyAsync(s->id, id, s->cap * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   ISKB_TRY(set_counts(s, np, 0));
   ISKB_TRY(sp_vmax_unknown(s));
@@ -632,6 +643,7 @@ static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move) {
       s->last_gmiss = g;
       if (s->tstats_step - 2 >= s->tstats_sort_mark) {   // ignore snapshots that predate the last re-ordering
         s->miss_rate = (double)d / (double)n;
+        if (s->miss_rate > 1e-5) s->drifting = true;
         s->tail_frac = (double)(h[CNT_NSLOTS] - h[9]) / (double)n;
         s->dead_frac = (double)h[CNT_NDEAD] / (double)n;
       }
@@ -651,8 +663,9 @@ static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move) {
   if (!s->marks_valid) return ISKB_OK;
   const int64_t since = s->steps_since_move + 1;
   if (c->sort_miss_threshold > 0.0) {
+    // a species whose rows hardly ever leave their windows (ions) is not re-grouped just because time has passed
     *move = s->miss_rate > c->sort_miss_threshold || s->dead_frac > 0.02 ||
-            (c->sort_max_interval > 0 && since >= c->sort_max_interval);
+            (c->sort_max_interval > 0 && since >= c->sort_max_interval && s->drifting);
   } else {
     *move = since >= c->sort_interval;
   }
@@ -679,6 +692,12 @@ static int32_t tile_stats_snapshot(iskb_ctx *c, iskb_species *s) {
   CU_TRY(cudaEventRecord(s->ev_tstats[slot], c->stream));
   s->tstats_pending[slot] = true;
   s->tstats_step++;
+  return ISKB_OK;
+}
+
+extern "C" int32_t iskb_set_lean(iskb_ctx *c, int32_t on) {
+  if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
+  c->lean_ok = on != 0;
   return ISKB_OK;
 }
 

@@ -145,6 +145,7 @@ struct iskb_ctx {
   // small grids (<= PRIV_MAX_NODES): the simple advance deposits into PRIV_COPIES private copies of u (block b uses
   // copy b % PRIV_COPIES) that are summed afterwards -- divides the same-address atomic pressure by PRIV_COPIES
   double *d_upriv = nullptr;
+  bool lean_ok = true;               // iskb_set_lean(ctx, 0) forces the full 88 B/row kernels (A/B measurements)
   int adv_path = 0;                  // 0: tile directory (advance_tile.cu), 1: per-warp windows (advance_fused.cu)
   int pusher_rz = 0;                 // BorisPusher{:rz}: transform_from_cartesian_to_cylindrical! after the push
   bool warn_too_fast = false;        // check!'s "particle is too fast" message condition was seen (sticky until read)
@@ -209,6 +210,11 @@ struct iskb_species {
   int64_t steps_since_move = 0;
   int64_t moves = 0, full_sorts = 0;        // statistics (iskb_species_sort_stats)
   double tail_frac = 0.0, dead_frac = 0.0;  // from the last snapshot
+  unsigned *d_ticket = nullptr;             // chunk dispenser of the advance grid
+  unsigned long long *d_vz2max = nullptr;   // bits of a bound of v_z^2 (the lean advance does not touch the column)
+  bool vz2_known = false;
+  bool wg_uniform = true;                   // every wg[p] == w0 (configuration.jl:99) until an upload says otherwise
+  bool drifting = false;                    // some launch saw more than 1e-5 of the rows outside their window
   int64_t *h_tstats = nullptr;              // pinned ring (2 x 10): cnt[0..8), -, rows in the tile directory
   cudaEvent_t ev_tstats[2] = {nullptr, nullptr};
   bool tstats_pending[2] = {false, false};

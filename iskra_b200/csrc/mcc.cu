@@ -32,7 +32,7 @@ struct SpDev {
   double *col[6];
   int64_t *cnt;
   int64_t cap;
-  unsigned long long *vmax2;
+  unsigned long long *vmax2, *vz2max;
 };
 
 struct ProcDev {
@@ -65,7 +65,6 @@ struct MccDev {
   double sig_last[8];
   double n0max;
   const unsigned long long *vmax2;   // bits of the species-wide bound of |v|^2 (+inf = unknown)
-  int debug;
   double *pk_dev;       // [8] pruning bounds valid for EVERY live row, computed on the device per call
   uint32_t k0, k1;   // Philox key
   uint32_t call;
@@ -141,9 +140,11 @@ __device__ void diffuse_reflection(const double *v, Rng &g, double *out) {     /
   scatter3(v, sc, cc, se, ce, out);
 }
 
-__device__ __forceinline__ void raise_vmax(unsigned long long *vmax2, const double *v) {
+__device__ __forceinline__ void raise_vmax(const SpDev &s, const double *v) {
   const unsigned long long b = (unsigned long long)__double_as_longlong((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
-  if (b > *(volatile unsigned long long *)vmax2) atomicMax(vmax2, b);   // almost never taken: same-address atomics are slow
+  if (b > *(volatile unsigned long long *)s.vmax2) atomicMax(s.vmax2, b);   // almost never taken: same-address atomics are slow
+  const unsigned long long bz = (unsigned long long)__double_as_longlong(v[2] * v[2]);   // kept for the lean advance (advance_tile.cu)
+  if (bz > *(volatile unsigned long long *)s.vz2max) atomicMax(s.vz2max, bz);
 }
 
 __device__ bool append_row(const SpDev &s, double x, double y, const double *v, int *status) {
@@ -155,7 +156,7 @@ __device__ bool append_row(const SpDev &s, double x, double y, const double *v, 
   }
   s.col[0][slot] = x; s.col[1][slot] = y;
   s.col[2][slot] = v[0]; s.col[3][slot] = v[1]; s.col[4][slot] = v[2];
-  raise_vmax(s.vmax2, v);
+  raise_vmax(s, v);
   // wg and id of the slot stay as parked there (kinetic.jl:29-37 "dst has already correct ID")
   return true;
 }
@@ -179,7 +180,7 @@ __device__ void collide(const MccDev &m, const ProcDev &pc, int64_t p, Rng &g) {
     else { mag = g.u01() * mag; diffuse_reflection(vr, g, dir); }
     double nv[3];
     for (int k = 0; k < 3; ++k) { nv[k] = w[k] + m.mr2 * (mag * dir[k]); m.src.col[2 + k][p] = nv[k]; }
-    raise_vmax(m.src.vmax2, nv);
+    raise_vmax(m.src, nv);
     return;
   }
   const double sE = 0.5 * m.m_eV * ((sv[0] * sv[0] + sv[1] * sv[1]) + sv[2] * sv[2]) - pc.threshold;
@@ -190,7 +191,7 @@ __device__ void collide(const MccDev &m, const ProcDev &pc, int64_t p, Rng &g) {
     isotropic_scattering(sv, g, dir);
     double nv[3];
     for (int k = 0; k < 3; ++k) { nv[k] = ev * dir[k]; m.src.col[2 + k][p] = nv[k]; }
-    raise_vmax(m.src.vmax2, nv);
+    raise_vmax(m.src, nv);
     return;
   }
   // ionization :184-212
@@ -199,7 +200,7 @@ __device__ void collide(const MccDev &m, const ProcDev &pc, int64_t p, Rng &g) {
   double d1[3], d2[3];
   diffuse_reflection(sv, g, d1);
   for (int k = 0; k < 3; ++k) { sv[k] = e1v * d1[k]; m.src.col[2 + k][p] = sv[k]; }
-  raise_vmax(m.src.vmax2, sv);
+  raise_vmax(m.src, sv);
   diffuse_reflection(sv, g, d2);
   const double x = m.src.col[0][p], y = m.src.col[1][p];
   double nv[3] = {e2v * d2[0], e2v * d2[1], e2v * d2[2]};
@@ -228,8 +229,6 @@ __global__ void k_snapshot_begin(int64_t *cnt, unsigned int *lists_cnt, MccDev m
       pk = (1.0 - exp(-m.n0max * sg * m.dt)) / m.p_cand * (1.0 + 1e-9) + 1e-300;
     }
     m.pk_dev[k] = pk;
-    if (m.debug) printf("mcc bound k=%d v2=%g sup_sg=%g sig_last=%g n0=%g dt=%g p_cand=%g pk=%g (1/N=%g)\n", k, v2, m.sup_sg[k],
-                        m.sig_last[k], m.n0max, m.dt, m.p_cand, pk, 1.0 / m.N);
   }
 }
 
@@ -313,7 +312,7 @@ __global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *list
 // draws gaps until it leaves them: the work is proportional to the candidates (6 % / 1 % of the rows at
 // C5) instead of the rows (one Philox call per 4 rows before: 2 x 120 us per step under ncu).  Measured on
 // the C5 step: 3.82 -> 3.77 ms -- most of the selection was already hidden behind the field solve on the
-// side stream.  ISKB_MCC_SELECT_PER_ROW=1 restores the per-row kernel.  One Philox call yields four gaps;
+// side stream.  k_mcc_select (one draw per row) remains for p = 0 / p = 1.  One Philox call yields four gaps;
 // counter = (first row of the chunk, call, 0x40000000 + k), disjoint from the per-row streams (draws 0, 1, ...).
 constexpr int SKIP_ROWS = 64;
 __global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int *lists_cnt, uint32_t *cand,
@@ -383,15 +382,26 @@ __global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int 
 
 constexpr int TEST_TPB = 128;
 constexpr int TEST_BUF = 512;
+constexpr int TEST_SMEM_TABLE_MAX = 6144;   // table entries (eps + sigma = 16 B each) staged in shared memory
 
+// One thread per candidate.  The phase is latency bound (a candidate costs one DRAM round trip for its row and a
+// binary search in sigma(eps)), so: the grid covers every candidate at once (a capped grid walked the list in 26
+// dependent rounds: 110 us per launch at C5), the row's five columns are requested together, and the tables are
+// searched in shared memory.
 __global__ void __launch_bounds__(TEST_TPB) k_mcc_test(MccDev m, unsigned int *lists_cnt, const uint32_t *__restrict__ cand,
-                                                       unsigned int cand_cap, uint2 *coll) {
+                                                       unsigned int cand_cap, uint2 *coll, int ntab) {
+  extern __shared__ double s_tab[];   // eps[ntab] | sigma[ntab]  (ntab == 0: search the global tables)
   __shared__ uint2 s_hit[TEST_BUF];
   __shared__ unsigned int s_nhit, s_base;
   __shared__ unsigned int s_proc[8];
   if (threadIdx.x == 0) s_nhit = 0;
   if (threadIdx.x < 8) s_proc[threadIdx.x] = 0;
+  for (int e = threadIdx.x; e < ntab; e += TEST_TPB) {
+    s_tab[e] = m.eps[e];
+    s_tab[ntab + e] = m.sig[e];
+  }
   __syncthreads();
+  const double *teps = ntab ? s_tab : m.eps, *tsig = ntab ? s_tab + ntab : m.sig;
   unsigned int nc = lists_cnt[0];
   if (nc > cand_cap) nc = cand_cap;
   const unsigned int nc_pad = (nc + TEST_TPB - 1) / TEST_TPB * TEST_TPB;   // block-uniform trip count
@@ -406,17 +416,17 @@ __global__ void __launch_bounds__(TEST_TPB) k_mcc_test(MccDev m, unsigned int *l
       // exact early-out before touching the row: P_k <= pk_dev[k] for every live row of the species
       if (delta < m.pk_dev[k - 1]) {
         const double vx = m.src.col[2][p], vy = m.src.col[3][p], vz = m.src.col[4][p];
+        const double px = m.src.col[0][p], py = m.src.col[1][p];
         bool maybe = true;
         if (m.tqm == 0.0) {   // second exact early-out with the row's own energy (target at rest: g = |v|)
           const double g2 = (vx * vx + vy * vy) + vz * vz;
           if (0.5 * m.m_eV * g2 <= m.eps_hi && delta >= m.pk_bound[k - 1]) maybe = false;
         }
-        const double px = maybe ? m.src.col[0][p] : 0.0;
         if (maybe && !is_dead(px)) {
           int i, j;
           double hx, hy;
           cell1(px, m.g.dx, m.g.rdx, m.g.fast_div, i, hx);
-          cell1(m.src.col[1][p], m.g.dy, m.g.rdy, m.g.fast_div, j, hy);
+          cell1(py, m.g.dy, m.g.rdy, m.g.fast_div, j, hy);
           if (!cell_in_grid(i, j, m.g.nx, m.g.ny)) {
             atomicOr(m.status, ISKB_ST_OOB);
           } else {
@@ -433,7 +443,7 @@ __global__ void __launch_bounds__(TEST_TPB) k_mcc_test(MccDev m, unsigned int *l
               d[2] = (m.tqm * 0.0) * m.dt - vz;
               const double gg = norm3(d);
               const double eps = 0.5 * m.m_eV * (gg * gg);                        // :268
-              const double skg = xsec_eval(m.eps + pc.offset, m.sig + pc.offset, pc.len, eps) * gg;
+              const double skg = xsec_eval(teps + pc.offset, tsig + pc.offset, pc.len, eps) * gg;
               double Pk = 1.0 - exp(-dens * skg * m.dt);                          // :271
               Pk /= m.p_cand;                                                     // :272  N*max_Pt
               if (Pk > 1.0) atomicOr(m.status, ISKB_ST_PK);                       // :273-279
@@ -483,6 +493,7 @@ SpDev spdev(const iskb_species *s) {
   d.cnt = s->d_cnt;
   d.cap = s->cap;
   d.vmax2 = s->d_vmax2;
+  d.vz2max = s->d_vz2max;
   return d;
 }
 
@@ -549,7 +560,6 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
   m.vmax2 = src->d_vmax2;
   if (!mc->d_pk) CU_TRY(cudaMalloc(&mc->d_pk, 8 * sizeof(double)));
   m.pk_dev = mc->d_pk;
-  m.debug = getenv("ISKB_DEBUG") ? 1 : 0;
   m.k0 = (uint32_t)mc->seed;
   m.k1 = (uint32_t)(mc->seed >> 32) ^ (0x9E3779B9u * (uint32_t)(c->rank + 1));
   m.call = (uint32_t)(mc->calls++);
@@ -575,8 +585,7 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
   int64_t blocks = (bound / 4 + TPB) / TPB;
   if (blocks > (int64_t)c->n_sm * 8) blocks = (int64_t)c->n_sm * 8;
   if (blocks < 1) blocks = 1;
-  static const bool per_row = getenv("ISKB_MCC_SELECT_PER_ROW") != nullptr;   // the earlier one-draw-per-row kernel (A/B)
-  if (per_row || !(m.p_cand > 0.0)) {
+  if (!(m.p_cand > 0.0) || m.p_cand >= 1.0) {   // degenerate probabilities: one draw per row
     k_mcc_select<<<(int)blocks, TPB, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
   } else {
     int64_t bs = (bound / SKIP_ROWS + TPB) / TPB;
@@ -586,10 +595,16 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
   }
   LAUNCH_CHECK(c);
   // the list lengths live on the device: size the dense phases from the expected candidate count
-  int64_t exp_cand = (int64_t)(m.p_cand * (double)bound) + 1024;
+  int64_t exp_cand = (int64_t)(m.p_cand * (double)bound * 1.05) + 1024;
   int64_t b2 = (exp_cand + TEST_TPB - 1) / TEST_TPB;
-  if (b2 > (int64_t)c->n_sm * 8) b2 = (int64_t)c->n_sm * 8;
-  k_mcc_test<<<(int)b2, TEST_TPB, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap, mc->d_coll);
+  if (b2 > (int64_t)c->n_sm * 256) b2 = (int64_t)c->n_sm * 256;
+  int ntab = 0;
+  for (const MccProc &p : mc->procs) ntab += p.len;
+  if (ntab > TEST_SMEM_TABLE_MAX) ntab = 0;
+  const size_t tab_bytes = (size_t)ntab * 2 * sizeof(double);
+  if (tab_bytes > 40 * 1024)
+    CU_TRY(cudaFuncSetAttribute(k_mcc_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+  k_mcc_test<<<(int)b2, TEST_TPB, tab_bytes, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap, mc->d_coll, ntab);
   LAUNCH_CHECK(c);
   int64_t b3 = (exp_cand / 8 + 127) / 128;
   if (b3 > (int64_t)c->n_sm * 4) b3 = (int64_t)c->n_sm * 4;

@@ -106,6 +106,9 @@ class Runtime:
         """0: tile directory + incremental re-group (default); 1: per-warp windows re-grouped by radix sort."""
         L.check(self.lib.iskb_set_advance_path(self.h, int(path)))
 
+    def set_lean(self, on):
+        L.check(self.lib.iskb_set_lean(self.h, 1 if on else 0))
+
     def join(self):
         """Make the context stream wait for a field solve still in flight on the field stream."""
         L.check(self.lib.iskb_stream_join(self.h))

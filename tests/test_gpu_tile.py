@@ -22,7 +22,7 @@ def ib():
     return iskra_b200
 
 
-def _setup(ib, nx, ny, dx, n, cap, seed, vscale, q=-O.qe, m=O.me):
+def _setup(ib, nx, ny, dx, n, cap, seed, vscale, q=-O.qe, m=O.me, uniform=False):
     PIC, FDM = ib.particle_in_cell, ib.finite_difference_method
     g = ib.regular_grids.create_uniform_grid(np.arange(nx) * dx, np.arange(ny) * dx)
     cg = CO.make_grid(nx, ny, dx, dx)
@@ -33,7 +33,7 @@ def _setup(ib, nx, ny, dx, n, cap, seed, vscale, q=-O.qe, m=O.me):
     x = rng.random(n) * (nx - 1) * dx
     y = rng.random(n) * (ny - 1) * dx
     v = rng.standard_normal((n, 3)) * vscale
-    wg = 0.5 + rng.random(n)
+    wg = np.ones(n) if uniform else 0.5 + rng.random(n)   # uniform weights: the lean kernels (no v_z / wg traffic)
     pc = CO.CSpecies(cap, q, m, 1.0)
     pc.set(x, y, v[:, 0], v[:, 1], v[:, 2], wg)
     pg = PIC.create_kinetic_species("s", cap, q, m, 1.0)
@@ -63,14 +63,15 @@ def _check_state(pc, pg, cap):
         assert np.array_equal(a, r)                                                    # bit-exact
 
 
-@pytest.mark.parametrize("interval,bmode,vcells", [(1, (1, 1), 0.3), (2, (2, 1), 0.3), (3, (2, 2), 1.2), (4, (1, 2), 0.05)])
-def test_tile_advance_with_regroup_bitexact(ib, interval, bmode, vcells):
+@pytest.mark.parametrize("interval,bmode,vcells,uniform", [(1, (1, 1), 0.3, False), (2, (2, 1), 0.3, False), (3, (2, 2), 1.2, False),
+                                                          (4, (1, 2), 0.05, False), (1, (2, 1), 0.3, True), (3, (1, 2), 1.2, True)])
+def test_tile_advance_with_regroup_bitexact(ib, interval, bmode, vcells, uniform):
     """E frozen (uploaded each step), so that the particle state is a pure function of the kernels under test:
     12 steps, re-group every `interval` steps, wrap / discard mixes, slow and fast rows (vcells cells per step)."""
     PIC = ib.particle_in_cell
     nx, ny, dx, dt = 97, 129, 1e-3, 1e-9
     n, cap = 150_000, 150_100
-    g, cg, pc, pg, cfg = _setup(ib, nx, ny, dx, n, cap, seed=3 + interval, vscale=vcells * dx / dt)
+    g, cg, pc, pg, cfg = _setup(ib, nx, ny, dx, n, cap, seed=3 + interval, vscale=vcells * dx / dt, uniform=uniform)
     nn = nx * ny
     rng = np.random.default_rng(99)
     E = np.zeros(3 * nn)
