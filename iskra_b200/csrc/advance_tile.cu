@@ -28,8 +28,11 @@
 namespace {
 
 constexpr int WE = 16;    // window nodes per side (tile 9 nodes + 3.5 cells of margin each side)
-constexpr int WRS = 18;   // row stride of the rho window in doubles: rows 2 bank-pairs apart, so the 32 cells of a
-                          // checkerboard batch (sort.cu) hit 16 different bank pairs twice = the 2-wavefront minimum
+constexpr int WRS = 20;   // row stride of the rho window in doubles.  64-bit shared accesses are served per half warp (16 lanes,
+                          // 16 bank pairs); in the interleaved row order of a full sort (sort.cu: cells of one parity, row by row)
+                          // 16 consecutive rows sit in 4 cell rows x 4 cells of alternating column parity, and with a row
+                          // stride of 4 bank pairs (20 mod 16) those 16 nodes fall into 16 different bank pairs.  (Stride 16:
+                          // 4-way conflicts; 18: 2-way.  The E window, double2 with stride 16, is conflict free per quarter warp.)
 
 struct TileArgs {
   double *col[6];           // x y vx vy vz wg  (read; written in place unless MOVE)
@@ -41,7 +44,7 @@ struct TileArgs {
   int64_t *cnt;
   GridDev g;
   const double2 *E2;
-  double qm, dt, c1, w0;
+  double qm, hqm, dt, c1, w0;   // q/m, 0.5*(q/m), dt, (0.5dt)*(q/m), default weight
   double *u;
   int *status;
   unsigned long long *vmax2;
@@ -59,16 +62,19 @@ struct TileArgs {
   unsigned mlist_cap;
 };
 
+constexpr int MQ_FLUSH = 16, MQ_CAP = MQ_FLUSH + 31 + 1;   // staged miss-list entries: flushed 16 or more at a time
+template <bool MOVE>
 struct WarpSm {
   double2 E[WE * WE];
   double rho[WE * WRS];
   unsigned char claim[WE * WE];
-  unsigned tc[9 * NCODE]; // [code of the tile the row is stored in after the launch][code of its new position]
-  unsigned mv[NCODE];     // MOVE: next destination row per code of the current tile
+  // [code of the tile the row is stored in after the launch][code of its new position]; in-place launches: row CODE_STAY only
+  unsigned tc[(MOVE ? 9 : 1) * NCODE];
+  unsigned mv[MOVE ? NCODE : 1];   // MOVE: next destination row per code of the current tile
   unsigned stats[4];      // window misses, deposits outside the window, tiles, discards
-  unsigned misc[8];       // first tile of the next warp, last readable row, tile coordinates of the current tile, staged misses
-  uint2 mq[64];           // staged miss-list entries (at most 31 left over + 32 new ones)
-};
+  unsigned misc[8];       // first tile of the next chunk, last readable row, tile coordinates of the current tile, staged misses
+  uint2 mq[MQ_CAP];
+};   // 6.7 KB (in place: 4 CTAs of 8 warps per SM) / 7.3 KB (MOVE: 3 CTAs)
 
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
@@ -111,9 +117,9 @@ __device__ __forceinline__ unsigned rel_code(int ntx, int nty, int stx, int sty)
 template <int MX, int MY, bool RZ, bool LEAN>
 __device__ __forceinline__ bool push_and_bound(double &px, double &py, double &vx, double &vy, double &vz, double ex,
                                                double ey, const TileArgs &a) {
-  vx = push_v(vx, ex, a.c1, a.qm, a.dt);
-  vy = push_v(vy, ey, a.c1, a.qm, a.dt);
-  if (!LEAN) vz = push_v(vz, 0.0, a.c1, a.qm, a.dt);   // v_z + 0: LEAN leaves the column alone
+  vx = push_v_h(vx, ex, a.c1, a.hqm, a.dt);
+  vy = push_v_h(vy, ey, a.c1, a.hqm, a.dt);
+  if (!LEAN) vz = push_v_h(vz, 0.0, a.c1, a.hqm, a.dt);   // v_z + 0: LEAN leaves the column alone
   px = push_x(px, vx, a.dt);
   if (RZ) to_cylindrical(px, vx, vz, a.dt);   // push_particles!(::BorisPusher{:rz}, ...)  pushers.jl:13-17
   py = push_x(py, vy, a.dt);
@@ -134,13 +140,14 @@ __device__ __forceinline__ bool push_and_bound(double &px, double &py, double &v
 // BASELINE config: configuration.jl:99 `ones(N) * weight`) needs no wg column traffic either.  72 -> 64 B per row
 // instead of 88; positions, velocities and rho are bit-identical to the full path (tests/test_gpu_tile.py).
 template <int MX, int MY, bool MOVE, bool RZ, bool LEAN>
-__global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
+__global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(const TileArgs a) {
   extern __shared__ double2 s_dyn[];
   const int lane = threadIdx.x & 31;
-  WarpSm &sm = ((WarpSm *)s_dyn)[threadIdx.x >> 5];
+  WarpSm<MOVE> &sm = ((WarpSm<MOVE> *)s_dyn)[threadIdx.x >> 5];
+  constexpr int TCS = MOVE ? CODE_STAY * NCODE : 0;   // counters of the rows that are stored in this tile after the launch
   for (int e = lane; e < WE * WRS; e += 32) sm.rho[e] = 0.0;
-  for (int e = lane; e < 9 * NCODE; e += 32) sm.tc[e] = 0;
-  if (lane < NCODE) sm.mv[lane] = 0;
+  for (int e = lane; e < (MOVE ? 9 : 1) * NCODE; e += 32) sm.tc[e] = 0;
+  if (MOVE && lane < NCODE) sm.mv[lane] = 0;
   if (lane < 4) sm.stats[lane] = 0;
   // The loop-carried state is kept small (tile, its row range, the batch, the window origin, a float velocity
   // bound); everything else that is constant per warp or per tile sits in shared memory: the body must fit
@@ -217,17 +224,14 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
       const unsigned row = rb + lane;
       const bool valid = row >= r0 && row < r1;
       const bool live = valid && !is_dead(px);
-      int i = 0, j = 0;
-      double hx = 0, hy = 0;
-      bool ing = false;
-      if (live) {
-        cell1(px, a.g.dx, a.g.rdx, a.g.fast_div, i, hx);
-        cell1(py, a.g.dy, a.g.rdy, a.g.fast_div, j, hy);
-        ing = cell_in_grid(i, j, a.g.nx, a.g.ny);
-        if (!ing) atomicOr(a.status, ISKB_ST_OOB);
-      }
-      const bool fit = ing && (unsigned)(i - 1 - ei0) < (unsigned)(WE - 1) && (unsigned)(j - 1 - ej0) < (unsigned)(WE - 1);
-      const bool miss = ing && !fit;
+      // cell of the old position (dead rows: NaN -> cell 0, fits nowhere); live rows outside the window -- outside
+      // the grid included -- are left to k_advance_list
+      int i, j;
+      double hx, hy;
+      cell1_fast(px, a.g.dx, a.g.rdx, i, hx);
+      cell1_fast(py, a.g.dy, a.g.rdy, j, hy);
+      const bool fit = live && (unsigned)(i - 1 - ei0) < (unsigned)(WE - 1) && (unsigned)(j - 1 - ej0) < (unsigned)(WE - 1);
+      const bool miss = live && !fit;
 
       // ---- MOVE: destination row = base(storage tile, code) + rank among the tile's rows with that code ----
       unsigned dest = row;
@@ -261,9 +265,9 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
       double d00 = 0, d10 = 0, d01 = 0, d11 = 0;
       int ci = 0;
       unsigned ncode = CODE_FAR;
-      if (live && !miss) {
-        double ex = 0.0, ey = 0.0;
-        if (ing) {
+      if (fit) {
+        double ex, ey;
+        {
           const CicW gw = cic_weights(hx, hy);
           const int o = (j - 1 - ej0) * WE + (i - 1 - ei0);
           const double2 e00 = sm.E[o], e10 = sm.E[o + 1], e01 = sm.E[o + WE], e11 = sm.E[o + WE + 1];
@@ -285,8 +289,8 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
           ncode = CODE_DEAD;
         } else {
           OUTC(0)[dest] = px;
-          cell1(px, a.g.dx, a.g.rdx, a.g.fast_div, i, hx);
-          cell1(py, a.g.dy, a.g.rdy, a.g.fast_div, j, hy);
+          cell1_fast(px, a.g.dx, a.g.rdx, i, hx);
+          cell1_fast(py, a.g.dy, a.g.rdy, j, hy);
           if (cell_in_grid(i, j, a.g.nx, a.g.ny)) {
             const CicW cw = cic_weights(hx, hy);
             d00 = __dmul_rn(cw.w00, wq); d10 = __dmul_rn(cw.w10, wq);
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
         }
       }
       // rows outside the window: k_advance_list advances them; they join the tail at the next re-group.  The entries
-      // are staged per warp and appended 32 at a time: one same-address atomic per batch cost 2-4 ms per launch
+      // are staged per warp and appended 16 or more at a time: one same-address atomic per batch cost 2-4 ms per launch
       // once most batches held a miss (same-address atomics serialise at ~2 ns each on B200).
       {
         const unsigned mm = __ballot_sync(0xffffffffu, miss);
@@ -329,15 +333,16 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
           if (miss) sm.mq[q + __popc(mm & lanemask_lt())] = make_uint2(row, dest);
           q += __popc(mm);
           __syncwarp();
-          if (q >= 32) {
+          if (q >= MQ_FLUSH) {
             unsigned b = 0;
-            if (lane == 0) b = atomicAdd(a.mlist_n, 32u);
+            if (lane == 0) b = atomicAdd(a.mlist_n, q);
             b = __shfl_sync(0xffffffffu, b, 0);
-            if (b + 32u <= a.mlist_cap) a.mlist[b + lane] = sm.mq[lane];
-            else atomicOr(a.status, ISKB_ST_CAPACITY);
-            q -= 32;
+            for (unsigned e = lane; e < q; e += 32) {
+              if (b + e < a.mlist_cap) a.mlist[b + e] = sm.mq[e];
+              else atomicOr(a.status, ISKB_ST_CAPACITY);
+            }
+            q = 0;
             __syncwarp();
-            if (lane < (int)q) sm.mq[lane] = sm.mq[lane + 32];
           }
           if (lane == 0) { sm.misc[4] = q; sm.stats[0] += __popc(mm); }
           __syncwarp();
@@ -351,13 +356,13 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
         const bool counted = valid && scode < 9u;
         const bool common = counted && scode == (unsigned)CODE_STAY && ncode == (unsigned)CODE_STAY;
         const unsigned ms = __ballot_sync(0xffffffffu, common);
-        if (lane == 0 && ms) sm.tc[CODE_STAY * NCODE + CODE_STAY] += __popc(ms);
-        if (counted && !common) atomicAdd(&sm.tc[scode * NCODE + ncode], 1u);
+        if (lane == 0 && ms) sm.tc[TCS + CODE_STAY] += __popc(ms);
+        if (counted && !common) atomicAdd(&sm.tc[(MOVE ? scode * NCODE : 0u) + ncode], 1u);
       }
       // ---- deposit rounds without atomics (advance_fused.cu) ----
       {
         unsigned pend = __ballot_sync(0xffffffffu, dep_win);
-        double *r0p = sm.rho + ci + 2 * (ci >> 4);
+        double *r0p = sm.rho + ci + (WRS - WE) * (ci >> 4);
         while (pend) {
           if (dep_win) sm.claim[ci] = (unsigned char)lane;
           __syncwarp();
@@ -384,11 +389,11 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
         ei0 = NOT_ANCHORED;
         for (int e = lane; e < (MOVE ? 9 : 1) * NCODE; e += 32) {
           const int sc = MOVE ? e / NCODE : CODE_STAY, nc = e % NCODE;
-          const unsigned c = sm.tc[sc * NCODE + nc];
+          const unsigned c = sm.tc[e];
           if (c) {
             const int dtx = (int)sm.misc[2] + sc % 3 - 1, dty = (int)sm.misc[3] + sc / 3 - 1;
             atomicAdd(&a.tcnt[(sc == CODE_STAY ? t : tile_ordinal((uint32_t)dtx, (uint32_t)dty, a.mtx)) * NCODE + nc], c);
-            sm.tc[sc * NCODE + nc] = 0;
+            sm.tc[e] = 0;
           }
         }
         __syncwarp();
@@ -645,8 +650,8 @@ __global__ void k_marks_after_sort(const uint32_t *__restrict__ ts, uint32_t nti
 int32_t exclusive_scan_u32(iskb_ctx *c, uint32_t *d, int64_t n, uint32_t *partial);
 int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit, bool from_begin);
 
-static int advance_grid(const iskb_ctx *c) { return c->n_sm * 3; }          // persistent: 3 CTAs of 8 warps per SM
-static int advance_chunks(const iskb_ctx *c) { return c->n_sm * 3 * 8 * 8; }   // 8 chunks per resident warp
+static int advance_grid(const iskb_ctx *c, bool lean_inplace) { return c->n_sm * (lean_inplace ? 4 : 3); }   // persistent CTAs of 8 warps
+static int advance_chunks(const iskb_ctx *c) { return c->n_sm * 3 * 8 * 8; }   // ~8 chunks per resident warp
 
 int32_t tdir_ensure(iskb_species *sp) {
   iskb_ctx *c = sp->ctx;
@@ -722,6 +727,7 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
   a.g = c->g;
   a.E2 = c->d_E2;
   a.qm = sp->q / sp->m;
+  a.hqm = 0.5 * a.qm;
   a.dt = dt;
   a.c1 = 0.5 * dt * a.qm;
   a.w0 = sp->w0;
@@ -746,8 +752,8 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
     LAUNCH_CHECK(c);
     sp->vz2_known = true;
   }
-  const int grid = advance_grid(c);
-  constexpr int SMEM = 8 * (int)sizeof(WarpSm);
+  const int grid = advance_grid(c, LEAN && !move);
+  const int SMEM = 8 * (int)(move ? sizeof(WarpSm<true>) : sizeof(WarpSm<false>));
   if (move) {
     // destinations of this launch from the counts of the previous one
     const int nb = (int)((tg.ntiles + 255) / 256);

@@ -766,8 +766,8 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
     const bool windows_fit = c->g.nx >= 20 && c->g.ny >= 20;   // small / quasi-1D grids use the simple kernels
     const bool tiled = c->sort_interval > 0 && windows_fit;
     // tile directory path: everything but the surface tracker (which still runs on the per-warp windows of advance_fused.cu)
-    const bool tile_dir = tiled && !c->tracker && c->adv_path == 0;
-    const bool legacy = tiled && !tile_dir && !c->pusher_rz;
+    const bool tile_dir = tiled && !c->tracker && c->adv_path == 0 && c->g.fast_div;   // (a dh with an all-ones significand: simple kernels)
+    const bool legacy = tiled && !tile_dir && !c->pusher_rz && (c->tracker || c->adv_path == 1);
     if (c->pusher_rz && c->tracker) return iskb_fail(ISKB_E_UNSUPPORTED, "surface tracker with the axial pusher");
     bool move[64];
     if (species.size() > 64) return iskb_fail(ISKB_E_UNSUPPORTED, "more than 64 species");

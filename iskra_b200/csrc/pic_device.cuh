@@ -40,6 +40,14 @@ __device__ __forceinline__ void cell1(double x, double d, double rd, int fast, i
   i = (int)fl;
   h = __dsub_rn(f, fl);
 }
+// the same with the three-operation division unconditionally (callers checked GridDev::fast_div on the host)
+__device__ __forceinline__ void cell1_fast(double x, double d, double rd, int &i, double &h) {
+  const double q0 = __dmul_rn(x, rd);
+  const double f = __dadd_rn(1.0, __fma_rn(__fma_rn(-q0, d, x), rd, q0));
+  const double fl = floor(f);
+  i = (int)fl;
+  h = __dsub_rn(f, fl);
+}
 __device__ __forceinline__ void cell1(double x, double d, int &i, double &h) {
   const double f = __dadd_rn(1.0, __ddiv_rn(x, d));
   const double fl = floor(f);
@@ -75,6 +83,14 @@ __device__ __forceinline__ double push_v(double v, double e, double c1, double q
   double vm = __dadd_rn(__dmul_rn(c1, e), v);
   vm = __dadd_rn(vm, 0.0);   // :44 v' = v- + v- x B ; :46 v+ = v- + v' x s   (B = s = 0)
   return __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(dt, e), qm), 0.5), vm);
+}
+// Same value with one multiplication less: ((dt*e)*qm)*0.5 == (dt*e)*(0.5*qm) bit for bit, because scaling by a power
+// of two commutes with rounding (hqm = 0.5*qm is exact) -- except where the product is subnormal (|.| < 2^-1022),
+// which no velocity increment of a plasma reaches.
+__device__ __forceinline__ double push_v_h(double v, double e, double c1, double hqm, double dt) {
+  double vm = __dadd_rn(__dmul_rn(c1, e), v);
+  vm = __dadd_rn(vm, 0.0);
+  return __dadd_rn(__dmul_rn(__dmul_rn(dt, e), hqm), vm);
 }
 __device__ __forceinline__ double push_x(double x, double v, double dt) {
   return __dadd_rn(__dmul_rn(dt, v), x);
