@@ -141,6 +141,9 @@ extern "C" int32_t iskb_create(int32_t device, iskb_ctx **out) {
     CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CU_TRY(cudaStreamCreateWithPriority(&c->fstream, cudaStreamNonBlocking, hi));
   }
+  CU_TRY(cudaStreamCreateWithFlags(&c->mstream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_m0, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_m1, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&c->ev_rho, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&c->ev_E, cudaEventDisableTiming));
   CU_TRY(cudaMalloc(&c->d_status, sizeof(int)));
@@ -179,6 +182,7 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
   cudaFree(c->d_upriv); cudaFree(c->d_V); cudaFree(c->d_rho); cudaFree(c->d_phi); cudaFree(c->d_E2); cudaFree(c->d_status);
   cudaFreeHost(c->h_status); cudaFreeHost(c->h_scratch);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+  cudaEventDestroy(c->ev_m0); cudaEventDestroy(c->ev_m1); cudaStreamDestroy(c->mstream);
   cudaEventDestroy(c->ev_rho);
   cudaEventDestroy(c->ev_E);
   cudaStreamDestroy(c->fstream);
@@ -776,18 +780,39 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
     } else if (legacy) {
       for (iskb_species *s : species) ISKB_TRY(maybe_sort(c, s));
     }
-    if (c->active_set) {                                                   // :109-111, config.interactions in order
-      for (const std::pair<int, void *> &in : c->active_inter) {
-        if (in.first == 0) ISKB_TRY(mcc_launch((iskb_mcc *)in.second, dt, false));
-        else ISKB_TRY(dsmc_launch((iskb_dsmc *)in.second, dt, false));
+    // :109-111, config.interactions in order.  The last one, if it is an MCC with a neutral target, runs on its own
+    // stream: it only touches its source and product species, so the species advanced before those overlap it.
+    std::vector<std::pair<int, void *>> inter;
+    if (c->active_set) inter = c->active_inter;
+    else {
+      for (iskb_mcc *m : c->mccs) inter.push_back(std::make_pair(0, (void *)m));
+      for (iskb_dsmc *d : c->dsmcs) inter.push_back(std::make_pair(1, (void *)d));
+    }
+    iskb_mcc *deferred = nullptr;
+    for (size_t k = 0; k < inter.size(); ++k) {
+      if (inter[k].first == 1) { ISKB_TRY(dsmc_launch((iskb_dsmc *)inter[k].second, dt, false)); continue; }
+      iskb_mcc *m = (iskb_mcc *)inter[k].second;
+      if (k + 1 == inter.size() && inter.size() > 1 && m->tq == 0.0 && tile_dir) {
+        CU_TRY(cudaEventRecord(c->ev_m0, c->stream));
+        CU_TRY(cudaStreamWaitEvent(c->mstream, c->ev_m0, 0));
+        ISKB_TRY(mcc_launch(m, dt, false, c->mstream));
+        CU_TRY(cudaEventRecord(c->ev_m1, c->mstream));
+        deferred = m;
+      } else {
+        ISKB_TRY(mcc_launch(m, dt, false));
       }
-    } else {
-      for (iskb_mcc *m : c->mccs) ISKB_TRY(mcc_launch(m, dt, false));
-      for (iskb_dsmc *d : c->dsmcs) ISKB_TRY(dsmc_launch(d, dt, false));
     }
     ISKB_TRY(fields_join(c));   // E of the previous step (the re-sort and MCC above did not need it)
     for (size_t k = 0; k < species.size(); ++k) {                          // :113-115
       iskb_species *s = species[k];
+      if (deferred) {   // the species the deferred MCC reads or appends to wait for it
+        bool touches = deferred->source == s;
+        for (const MccProc &p : deferred->procs) touches = touches || p.product == s;
+        if (touches) {
+          CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_m1, 0));
+          deferred = nullptr;
+        }
+      }
       CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
       if (tile_dir) {
         ISKB_TRY(launch_advance_tile(s, dt, c->after_push[0], c->after_push[1], move[k]));
@@ -807,6 +832,7 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
         ISKB_TRY(launch_advance_simple(s, dt, c->after_push[0], c->after_push[1], true, false));
       }
     }
+    if (deferred) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_m1, 0));
     ISKB_TRY(launch_rho_finalize(c, &species));                            // :118-124
     if (c->n_ranks > 1) ISKB_TRY(comm_allreduce_sum(c, c->d_rho, nn));
     ISKB_TRY(poisson_solve(c));                                            // :126-128

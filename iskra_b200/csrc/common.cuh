@@ -83,6 +83,8 @@ struct PoissonState {
   double *d_msing = nullptr;    // Thomas factors of the pinned singular mode
   int singular_mode = -1;
   double *d_cp = nullptr;       // Thomas c' table  (ma x mb)
+  double *d_cpT = nullptr, *d_qT = nullptr;   // the same tables as [k + q*ma] (FFT path, k_thomas_seg)
+  double *d_fvec = nullptr;     // Sherman-Morrison factor per mode of the current solve
   double *d_q = nullptr;        // Sherman-Morrison q table (ma x mb), cyclic only
   double *d_qden = nullptr;     // 1/(1 + v.q) per mode
   double *d_w1 = nullptr, *d_w2 = nullptr, *d_w3 = nullptr;   // work arrays (nx*ny)
@@ -112,6 +114,9 @@ struct iskb_ctx {
   // The field solve (rho -> phi -> E) runs on its own stream so that the next step's re-sort and MCC,
   // which do not read E, overlap it.  ev_rho: rho is final (main stream); ev_E: E is final (field stream).
   cudaStream_t fstream = nullptr;
+  // the LAST interaction of a step runs on its own stream next to the advance of the species it does not touch
+  cudaStream_t mstream = nullptr;
+  cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;
   cudaEvent_t ev_rho = nullptr, ev_E = nullptr;
   bool fields_pending = false;   // a solve is in flight on fstream; main-stream users of rho/phi/E must join first
   int64_t launches = 0;
@@ -236,6 +241,7 @@ struct iskb_mcc {
   std::vector<MccProc> procs;
   double max_sigma_g = 0, m_eV = 0;
   double max_n0 = 0;
+  bool uniform_n = false;            // the target density is the same on every node
   double eps_hi = 0;                 // largest tabulated energy
   std::vector<double> sup_sigma_g;   // per process: sup of sigma_k*g on [0, eps_hi]
   std::vector<double> sig_last;      // per process: sigma_k at its last knot
@@ -302,7 +308,7 @@ int32_t ctx_check_status(iskb_ctx *ctx);
 int32_t poisson_prepare(iskb_ctx *ctx);
 int32_t poisson_solve(iskb_ctx *ctx);
 int32_t poisson_free(iskb_ctx *ctx);
-int32_t mcc_launch(iskb_mcc *mcc, double dt, bool count_nu);
+int32_t mcc_launch(iskb_mcc *mcc, double dt, bool count_nu, cudaStream_t st = nullptr);
 int32_t comm_allreduce_sum(iskb_ctx *ctx, double *d_buf, int64_t n);
 int32_t comm_destroy(iskb_ctx *ctx);
 int32_t launch_advance(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit,

@@ -64,6 +64,7 @@ struct MccDev {
   double sup_sg[8];     // sup of sigma_k*g on the tables; sig_last: sigma_k at its last knot (Flat() beyond)
   double sig_last[8];
   double n0max;
+  int need_cell;     // 0: the target density is the same on every node and no nu map is asked for
   const unsigned long long *vmax2;   // bits of the species-wide bound of |v|^2 (+inf = unknown)
   double *pk_dev;       // [8] pruning bounds valid for EVERY live row, computed on the device per call
   uint32_t k0, k1;   // Philox key
@@ -416,7 +417,8 @@ __global__ void __launch_bounds__(TEST_TPB) k_mcc_test(MccDev m, unsigned int *l
       // exact early-out before touching the row: P_k <= pk_dev[k] for every live row of the species
       if (delta < m.pk_dev[k - 1]) {
         const double vx = m.src.col[2][p], vy = m.src.col[3][p], vz = m.src.col[4][p];
-        const double px = m.src.col[0][p], py = m.src.col[1][p];
+        const double px = m.src.col[0][p];                          // (dead rows carry x = NaN)
+        const double py = m.need_cell ? m.src.col[1][p] : px;       // uniform target density, no nu map: the cell is not needed
         bool maybe = true;
         if (m.tqm == 0.0) {   // second exact early-out with the row's own energy (target at rest: g = |v|)
           const double g2 = (vx * vx + vy * vy) + vz * vz;
@@ -427,11 +429,11 @@ __global__ void __launch_bounds__(TEST_TPB) k_mcc_test(MccDev m, unsigned int *l
           double hx, hy;
           cell1(px, m.g.dx, m.g.rdx, m.g.fast_div, i, hx);
           cell1(py, m.g.dy, m.g.rdy, m.g.fast_div, j, hy);
-          if (!cell_in_grid(i, j, m.g.nx, m.g.ny)) {
+          if (m.need_cell && !cell_in_grid(i, j, m.g.nx, m.g.ny)) {
             atomicOr(m.status, ISKB_ST_OOB);
           } else {
-            const int64_t node = (int64_t)(i - 1) + (int64_t)(j - 1) * m.g.nx;   // lower-left node :252-253
-            const double dens = m.tn[node];
+            const int64_t node = m.need_cell ? (int64_t)(i - 1) + (int64_t)(j - 1) * m.g.nx : 0;   // lower-left node :252-253
+            const double dens = m.need_cell ? m.tn[node] : m.n0max;
             if (dens >= 0) {                                                      // :254-257
               const ProcDev pc = m.proc[k - 1];
               // neutral target (tqm == 0): (0*E)*dt contributes exactly +0 for any finite E, so E is not
@@ -508,8 +510,9 @@ double xsec_eval_host(const double *xs, const double *ys, int n, double x) {
 
 }  // namespace
 
-int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
+int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st) {
   iskb_ctx *c = mc->ctx;
+  if (!st) st = st;
   iskb_species *src = mc->source;
   const int N = mc->N;
   const double max_Pt = 1.0 - exp(-mc->max_n0 * mc->max_sigma_g * dt);     // mcc.jl:243
@@ -557,6 +560,7 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
     m.sig_last[k] = mc->sig_last[(size_t)k];
   }
   m.n0max = mc->max_n0;
+  m.need_cell = (mc->uniform_n && !count_nu && mc->tq == 0.0) ? 0 : 1;
   m.vmax2 = src->d_vmax2;
   if (!mc->d_pk) CU_TRY(cudaMalloc(&mc->d_pk, 8 * sizeof(double)));
   m.pk_dev = mc->d_pk;
@@ -569,7 +573,7 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
   m.nu = nullptr;
   if (count_nu) {
     if (!mc->d_nu) CU_TRY(cudaMalloc(&mc->d_nu, nn * N * sizeof(float)));
-    CU_TRY(cudaMemsetAsync(mc->d_nu, 0, nn * N * sizeof(float), c->stream));
+    CU_TRY(cudaMemsetAsync(mc->d_nu, 0, nn * N * sizeof(float), st));
     m.nu = mc->d_nu;
   }
   // candidate / collider lists (lazy; sized for the worst case of every row being a candidate)
@@ -579,19 +583,19 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
     CU_TRY(cudaMalloc(&mc->d_lists_cnt, 2 * sizeof(unsigned int)));
   }
   const unsigned int cand_cap = (unsigned int)src->cap;
-  k_snapshot_begin<<<1, 1, 0, c->stream>>>(src->d_cnt, mc->d_lists_cnt, m);
+  k_snapshot_begin<<<1, 1, 0, st>>>(src->d_cnt, mc->d_lists_cnt, m);
   LAUNCH_CHECK(c);
   const int64_t bound = src->counts_stale ? src->cap : src->h_nslots;
   int64_t blocks = (bound / 4 + TPB) / TPB;
   if (blocks > (int64_t)c->n_sm * 8) blocks = (int64_t)c->n_sm * 8;
   if (blocks < 1) blocks = 1;
   if (!(m.p_cand > 0.0) || m.p_cand >= 1.0) {   // degenerate probabilities: one draw per row
-    k_mcc_select<<<(int)blocks, TPB, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
+    k_mcc_select<<<(int)blocks, TPB, 0, st>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
   } else {
     int64_t bs = (bound / SKIP_ROWS + TPB) / TPB;
     if (bs > (int64_t)c->n_sm * 8) bs = (int64_t)c->n_sm * 8;
     if (bs < 1) bs = 1;
-    k_mcc_select_skip<<<(int)bs, TPB, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
+    k_mcc_select_skip<<<(int)bs, TPB, 0, st>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
   }
   LAUNCH_CHECK(c);
   // the list lengths live on the device: size the dense phases from the expected candidate count
@@ -604,12 +608,14 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu) {
   const size_t tab_bytes = (size_t)ntab * 2 * sizeof(double);
   if (tab_bytes > 40 * 1024)
     CU_TRY(cudaFuncSetAttribute(k_mcc_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
-  k_mcc_test<<<(int)b2, TEST_TPB, tab_bytes, c->stream>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap, mc->d_coll, ntab);
+  k_mcc_test<<<(int)b2, TEST_TPB, tab_bytes, st>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap, mc->d_coll, ntab);
   LAUNCH_CHECK(c);
-  int64_t b3 = (exp_cand / 8 + 127) / 128;
-  if (b3 > (int64_t)c->n_sm * 4) b3 = (int64_t)c->n_sm * 4;
+  // one thread per collider would do; the count lives on the device, so cover a quarter of the expected candidates
+  // (the kinematics are a long dependent chain: a small grid walking the list in rounds is latency bound)
+  int64_t b3 = (exp_cand / 4 + 127) / 128;
+  if (b3 > (int64_t)c->n_sm * 64) b3 = (int64_t)c->n_sm * 64;
   if (b3 < 1) b3 = 1;
-  k_mcc_collide<<<(int)b3, 128, 0, c->stream>>>(m, mc->d_lists_cnt, mc->d_coll);
+  k_mcc_collide<<<(int)b3, 128, 0, st>>>(m, mc->d_lists_cnt, mc->d_coll);
   LAUNCH_CHECK(c);
   return ISKB_OK;
 }
@@ -680,6 +686,8 @@ extern "C" int32_t iskb_mcc_create(iskb_ctx *c, iskb_species *source, double tar
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   mc->max_n0 = -INFINITY;
   for (int64_t k = 0; k < nn; ++k) mc->max_n0 = std::fmax(mc->max_n0, target_n[k]);   // :242
+  mc->uniform_n = true;
+  for (int64_t k = 0; k < nn && mc->uniform_n; ++k) mc->uniform_n = target_n[k] == mc->max_n0;
   CU_TRY(cudaMalloc(&mc->d_tn, nn * sizeof(double)));
   CU_TRY(cudaMalloc(&mc->d_eps, off * sizeof(double)));
   CU_TRY(cudaMalloc(&mc->d_sig, off * sizeof(double)));

@@ -426,20 +426,54 @@ __global__ void k_transpose(int rows, int cols, const double *__restrict__ in, d
 // Two real columns are packed into one complex sequence (odd extension): with
 // Z = FFT(z_a + i z_b), the sine sums are S_a[k] = -Im Z[k]/2 and S_b[k] = Re Z[k]/2.
 // out[k-1, col] = scale * S[k], scale = sqrt(2/(m+1)) (orthonormal, so forward == inverse).
+// IN = 1: the right-hand side is formed on the fly from rho (what k_build_rhs writes: dx^2*(-rho)/eps0 minus the
+//         Dirichlet neighbours, generalized_poisson.jl:375 with f = -rho) -- one pass over rho less per solve;
+// IN = 2: mode-space input with the Sherman-Morrison correction of the cyclic Thomas solve applied on the way in
+//         (x -= q*f, see k_thomas_seg);
+// OUT = 1: the result goes straight into phi (k_store_phi's job for the unknown nodes).
+struct FftIo {
+  SolveDims s;
+  const double *rho;
+  const uint8_t *isdir;
+  const double *dval;
+  const double *qt;     // [k + q*ma] Sherman-Morrison vector (IN = 2, cyclic)
+  const double *f;      // [ma] per-mode factor (IN = 2, cyclic); nullptr: no correction
+  double *phi;
+};
+
+template <int IN, int OUT>
 __global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, const double2 *__restrict__ tw,
                                                  const double *__restrict__ in, double *__restrict__ out,
-                                                 double scale) {
+                                                 double scale, FftIo io) {
   extern __shared__ double2 zs[];
   const int M = 1 << log2M;
   const int ca = blockIdx.x * 2, cb = ca + 1;
-  const double *xa = in + (int64_t)ca * m;
-  const double *xb = cb < ncols ? in + (int64_t)cb * m : nullptr;
+  const bool has_b = cb < ncols;   // (mb odd: the last block transforms one column)
+  auto fetch = [&](int col, int p) -> double {   // element p (1-based) of column col
+    if (IN == 1) {
+      const SolveDims &s = io.s;
+      const int na = s.transposed ? s.ny : s.nx, nb = s.transposed ? s.nx : s.ny;
+      const int a = s.a0 + p - 1, b = s.b0 + col;
+      double r = -(io.rho[node_of(s, a, b)]) * s.scale;
+      if (p == 1 || p == m || col == 0 || col == ncols - 1) {   // only the rim of the unknown block can touch a Dirichlet node
+        if (a - 1 >= 0 && io.isdir[node_of(s, a - 1, b)]) r -= io.dval[node_of(s, a - 1, b)];
+        if (a + 1 < na && io.isdir[node_of(s, a + 1, b)]) r -= io.dval[node_of(s, a + 1, b)];
+        if (b - 1 >= 0 && io.isdir[node_of(s, a, b - 1)]) r -= io.dval[node_of(s, a, b - 1)];
+        if (b + 1 < nb && io.isdir[node_of(s, a, b + 1)]) r -= io.dval[node_of(s, a, b + 1)];
+      }
+      return r;
+    }
+    const int64_t e = (int64_t)col * m + (p - 1);
+    double v = in[e];
+    if (IN == 2 && io.f) v -= io.qt[e] * io.f[p - 1];
+    return v;
+  };
   // load with bit-reversed addressing; z[0] = z[m+1] = 0, z[M-p] = -z[p]
   for (int p = threadIdx.x; p <= m + 1; p += blockDim.x) {
     double2 v = make_double2(0.0, 0.0);
     if (p >= 1 && p <= m) {
-      v.x = xa[p - 1];
-      v.y = xb ? xb[p - 1] : 0.0;
+      v.x = fetch(ca, p);
+      v.y = has_b ? fetch(cb, p) : 0.0;
     }
     const int r0 = (int)(__brev((unsigned)p) >> (32 - log2M));
     zs[r0] = v;
@@ -494,12 +528,91 @@ __global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, co
     __syncthreads();
   }
   const double h = 0.5 * scale;
-  double *ya = out + (int64_t)ca * m;
-  double *yb = cb < ncols ? out + (int64_t)cb * m : nullptr;
   for (int k = 1 + threadIdx.x; k <= m; k += blockDim.x) {
     const double2 z = zs[k];
-    ya[k - 1] = -h * z.y;
-    if (yb) yb[k - 1] = h * z.x;
+    if (OUT == 1) {
+      io.phi[node_of(io.s, io.s.a0 + k - 1, io.s.b0 + ca)] = -h * z.y;
+      if (has_b) io.phi[node_of(io.s, io.s.a0 + k - 1, io.s.b0 + cb)] = h * z.x;
+    } else {
+      out[(int64_t)ca * m + k - 1] = -h * z.y;
+      if (has_b) out[(int64_t)cb * m + k - 1] = h * z.x;
+    }
+  }
+}
+
+// Thomas solves along b for every mode k on the layout the transform leaves, W[k + q*ma] (k contiguous): one thread
+// per (mode, segment of q), consecutive threads = consecutive modes (coalesced), the SEG warps of a block = the SEG
+// segments of 32 modes.  Both sweeps are first-order recurrences y_q = A_q*y_{q-1} + B_q: every segment first composes
+// its affine map (A, B), the segment carries follow from SEG compositions, then each segment replays its part with
+// the right carry -- 2 x mb/SEG dependent steps per sweep instead of mb, and no transposes around the solve (the
+// warp-per-mode scan this replaces needed q-contiguous data: transpose 12 us + solve 72 us + transpose 12 us at 2049^2).
+//   forward   y_q = (r_q - y_{q-1}) * m_q          A = -m_q, B = r_q*m_q      (m precomputed, [k + q*ma])
+//   backward  x_q = y_q - m_q * x_{q+1}            A = -m_q, B = y_q
+//   cyclic    x -= q*f, f = (x_0 + x_{mb-1}/gamma)*qden  (Sherman-Morrison): f is left in fout, the inverse transform applies it
+constexpr int TSEG = 32;   // 2047 modes x 32 segments = 2047 warps: the sweeps are latency bound, they need the loads in flight
+__global__ void __launch_bounds__(32 * TSEG) k_thomas_seg(int ma, int mb, const double *__restrict__ mt, const double *__restrict__ qden,
+                                                         const double *__restrict__ gam, double *W, double *fout) {
+  __shared__ double sA[TSEG][32], sB[TSEG][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
+  const bool act = k < ma;
+  const int per = (mb + TSEG - 1) / TSEG;
+  const int q0 = seg * per, q1 = min(mb, q0 + per);
+  const double *m = mt + k;
+  double *w = W + k;
+  // ---- forward ----
+  double A = 1.0, B = 0.0;
+  if (act) {
+#pragma unroll 8
+    for (int q = q0; q < q1; ++q) {
+      const double mq = m[(int64_t)q * ma], r = w[(int64_t)q * ma];
+      B = fma(-mq, B, r * mq);
+      A = -mq * A;
+    }
+  }
+  sA[seg][lane] = A; sB[seg][lane] = B;
+  __syncthreads();
+  double carry = 0.0;
+  for (int s2 = 0; s2 < seg; ++s2) carry = fma(sA[s2][lane], carry, sB[s2][lane]);
+  __syncthreads();
+  if (act) {
+    double y = carry;
+#pragma unroll 8
+    for (int q = q0; q < q1; ++q) {
+      const double mq = m[(int64_t)q * ma];
+      y = (w[(int64_t)q * ma] - y) * mq;
+      w[(int64_t)q * ma] = y;
+    }
+  }
+  __syncthreads();   // (each thread re-reads only what it wrote itself; the barrier orders the shared arrays)
+  // ---- backward (q descending; x_{mb} = 0, and the last row has no super-diagonal: A = 0 there) ----
+  A = 1.0; B = 0.0;
+  if (act) {
+#pragma unroll 8
+    for (int q = q1 - 1; q >= q0; --q) {
+      const double mq = q == mb - 1 ? 0.0 : m[(int64_t)q * ma], y = w[(int64_t)q * ma];
+      B = fma(-mq, B, y);
+      A = -mq * A;
+    }
+  }
+  sA[seg][lane] = A; sB[seg][lane] = B;
+  __syncthreads();
+  carry = 0.0;
+  for (int s2 = TSEG - 1; s2 > seg; --s2) carry = fma(sA[s2][lane], carry, sB[s2][lane]);
+  __syncthreads();
+  double x = carry;
+  if (act) {
+#pragma unroll 8
+    for (int q = q1 - 1; q >= q0; --q) {
+      const double mq = q == mb - 1 ? 0.0 : m[(int64_t)q * ma];
+      x = fma(-mq, x, w[(int64_t)q * ma]);
+      w[(int64_t)q * ma] = x;
+    }
+  }
+  if (fout) {   // cyclic: x_0 lives in segment 0, x_{mb-1} in the last one
+    if (seg == TSEG - 1) sA[0][lane] = act ? w[(int64_t)(mb - 1) * ma] : 0.0;
+    __syncthreads();
+    if (seg == 0 && act) fout[k] = (x + sA[0][lane] / gam[k]) * qden[k];
   }
 }
 
@@ -560,6 +673,18 @@ __global__ void k_efield(int nx, int ny, double dx, double dy, const double *__r
   }
 }
 
+// Dirichlet nodes of the separable solver sit on whole edges: phi = prescribed value there (the transform wrote the rest)
+__global__ void k_phi_edges(int nx, int ny, const uint8_t *__restrict__ isdir, const double *__restrict__ dval, double *phi) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n;
+  if (t < ny) n = (int64_t)t * nx;                                   // left
+  else if (t < 2 * ny) n = (nx - 1) + (int64_t)(t - ny) * nx;        // right
+  else if (t < 2 * ny + nx) n = t - 2 * ny;                          // bottom
+  else if (t < 2 * ny + 2 * nx) n = (t - 2 * ny - nx) + (int64_t)(ny - 1) * nx;   // top
+  else return;
+  if (isdir[n]) phi[n] = dval[n];
+}
+
 // per-step update of one Dirichlet edge (the RF drive, 11_rf_discharge.jl:95) without re-uploading
 __global__ void k_set_edge(int nx, int ny, int edge, double v, double *dval) {
   const int len = edge < 2 ? ny : nx;
@@ -594,7 +719,8 @@ int32_t upload(T **dptr, const std::vector<T> &h, cudaStream_t st) {
 int32_t poisson_free(iskb_ctx *c) {
   PoissonState &ps = c->ps;
   double **ptrs[] = {&ps.d_dval, &ps.d_V, &ps.d_lam, &ps.d_cp, &ps.d_q, &ps.d_qden, &ps.d_w1, &ps.d_w2,
-                     &ps.d_Ainv, &ps.d_Vt, &ps.d_gam, &ps.d_msing, &ps.d_rowscale, &ps.d_sigma, &ps.d_neu_coef};
+                     &ps.d_Ainv, &ps.d_Vt, &ps.d_gam, &ps.d_msing, &ps.d_rowscale, &ps.d_sigma, &ps.d_neu_coef, &ps.d_cpT, &ps.d_qT,
+                     &ps.d_fvec};
   if (ps.d_neu_dof) { cudaFree(ps.d_neu_dof); ps.d_neu_dof = nullptr; }
   for (auto p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
   if (ps.d_isdir) { cudaFree(ps.d_isdir); ps.d_isdir = nullptr; }
@@ -800,9 +926,24 @@ int32_t poisson_prepare(iskb_ctx *c) {
         CU_TRY(cudaMalloc(&ps.d_tw, tw.size() * sizeof(double2)));
         CU_TRY(cudaMemcpyAsync(ps.d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
-        CU_TRY(cudaFuncSetAttribute(k_dst_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, M * (int)sizeof(double2)));
+        CU_TRY(cudaFuncSetAttribute(k_dst_fft<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, M * (int)sizeof(double2)));
+        CU_TRY(cudaFuncSetAttribute(k_dst_fft<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M * (int)sizeof(double2)));
         ps.use_fft = true;
         ps.fft_log2M = lg;
+        // Thomas factors in the layout the transform leaves ([k + q*ma], see k_thomas_seg)
+        std::vector<double> mtT((size_t)ma * mb), qtT;
+        for (int k = 0; k < ma; ++k)
+          for (int q = 0; q < mb; ++q) mtT[(size_t)k + (size_t)q * ma] = mt[(size_t)q + (size_t)k * mb];
+        if (ps.b_cyclic) {
+          qtT.assign((size_t)ma * mb, 0.0);
+          for (int k = 0; k < ma; ++k)
+            for (int q = 0; q < mb; ++q) qtT[(size_t)k + (size_t)q * ma] = qt[(size_t)q + (size_t)k * mb];
+        }
+        ISKB_TRY(upload(&ps.d_cpT, mtT, c->stream));
+        ISKB_TRY(upload(&ps.d_qT, qtT, c->stream));
+        if (ps.d_fvec) { cudaFree(ps.d_fvec); ps.d_fvec = nullptr; }
+        CU_TRY(cudaMalloc(&ps.d_fvec, (size_t)ma * sizeof(double)));
+        CU_TRY(cudaStreamSynchronize(c->stream));
       }
       if (ps.d_w1) { cudaFree(ps.d_w1); ps.d_w1 = nullptr; }
       if (ps.d_w2) { cudaFree(ps.d_w2); ps.d_w2 = nullptr; }
@@ -851,41 +992,48 @@ int32_t poisson_solve(iskb_ctx *c) {
   } else {
     SolveDims s{nx, ny, ps.transposed ? 1 : 0, ps.a0, ps.ma, ps.b0, ps.mb, c->g.dx * c->g.dx / ps.eps0};
     const int64_t tot = (int64_t)ps.ma * ps.mb;
-    k_build_rhs<<<blocks_for(c, tot), TPB, 0, c->fstream>>>(s, c->d_rho, ps.d_isdir, ps.d_dval, ps.d_w1);
-    LAUNCH_CHECK(c);
-    dim3 gg((ps.ma + 63) / 64, (ps.mb + 63) / 64);
     const double dst_scale = sqrt(2.0 / (ps.ma + 1));
     const int M = 1 << ps.fft_log2M;
-    // forward transform  w1 -> w2
-    if (ps.use_fft)
-      k_dst_fft<<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, ps.d_w1,
-                                                                         ps.d_w2, dst_scale);
-    else
+    if (ps.use_fft) {
+      // rho --DST (rhs formed on the way in)--> w2[k + q*ma] --Thomas per mode, in place--> w2 --DST--> phi
+      FftIo io{s, c->d_rho, ps.d_isdir, ps.d_dval, ps.d_qT, ps.b_cyclic ? ps.d_fvec : nullptr, c->d_phi};
+      k_dst_fft<1, 0><<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, nullptr,
+                                                                                ps.d_w2, dst_scale, io);
+      LAUNCH_CHECK(c);
+      k_thomas_seg<<<(ps.ma + 31) / 32, 32 * TSEG, 0, c->fstream>>>(ps.ma, ps.mb, ps.d_cpT, ps.d_qden, ps.d_gam, ps.d_w2,
+                                                                   ps.b_cyclic ? ps.d_fvec : nullptr);
+      LAUNCH_CHECK(c);
+      k_dst_fft<2, 1><<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, ps.d_w2,
+                                                                                nullptr, dst_scale, io);
+      LAUNCH_CHECK(c);
+      k_phi_edges<<<(2 * (nx + ny) + 255) / 256, 256, 0, c->fstream>>>(nx, ny, ps.d_isdir, ps.d_dval, c->d_phi);
+      LAUNCH_CHECK(c);
+    } else {
+      k_build_rhs<<<blocks_for(c, tot), TPB, 0, c->fstream>>>(s, c->d_rho, ps.d_isdir, ps.d_dval, ps.d_w1);
+      LAUNCH_CHECK(c);
+      dim3 gg((ps.ma + 63) / 64, (ps.mb + 63) / 64);
+      // forward transform  w1 -> w2
       k_dgemm<<<gg, 256, 0, c->fstream>>>(ps.ma, ps.mb, ps.ma, ps.d_Vt, ps.ma, ps.d_w1, ps.ma, ps.d_w2, ps.ma);
-    LAUNCH_CHECK(c);
-    // tridiagonal solves along b on mode-major data:  w2 --T--> w1, in place, w1 --T--> w2
-    {
-      dim3 tg((ps.ma + 31) / 32, (ps.mb + 31) / 32), tb(32, 8);
-      k_transpose<<<tg, tb, 0, c->fstream>>>(ps.ma, ps.mb, ps.d_w2, ps.d_w1);
       LAUNCH_CHECK(c);
-      k_thomas_warp<<<(ps.ma + 3) / 4, 128, 0, c->fstream>>>(ps.ma, ps.mb, ps.b_cyclic ? 1 : 0, ps.singular_mode, ps.d_cp,
-                                                            ps.d_msing, ps.d_q, ps.d_qden, ps.d_gam, ps.d_w1);
+      // tridiagonal solves along b on mode-major data:  w2 --T--> w1, in place, w1 --T--> w2
+      {
+        dim3 tg((ps.ma + 31) / 32, (ps.mb + 31) / 32), tb(32, 8);
+        k_transpose<<<tg, tb, 0, c->fstream>>>(ps.ma, ps.mb, ps.d_w2, ps.d_w1);
+        LAUNCH_CHECK(c);
+        k_thomas_warp<<<(ps.ma + 3) / 4, 128, 0, c->fstream>>>(ps.ma, ps.mb, ps.b_cyclic ? 1 : 0, ps.singular_mode, ps.d_cp,
+                                                              ps.d_msing, ps.d_q, ps.d_qden, ps.d_gam, ps.d_w1);
+        LAUNCH_CHECK(c);
+        dim3 tg2((ps.mb + 31) / 32, (ps.ma + 31) / 32);
+        k_transpose<<<tg2, tb, 0, c->fstream>>>(ps.mb, ps.ma, ps.d_w1, ps.d_w2);
+        LAUNCH_CHECK(c);
+      }
+      // inverse transform  w2 -> w1
+      k_dgemm<<<gg, 256, 0, c->fstream>>>(ps.ma, ps.mb, ps.ma, ps.d_V, ps.ma, ps.d_w2, ps.ma, ps.d_w1, ps.ma);
       LAUNCH_CHECK(c);
-      dim3 tg2((ps.mb + 31) / 32, (ps.ma + 31) / 32);
-      k_transpose<<<tg2, tb, 0, c->fstream>>>(ps.mb, ps.ma, ps.d_w1, ps.d_w2);
+      ps.d_w3 = ps.d_w1;   // (alias, not owned) result of the inverse transform
+      k_store_phi<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(s, ps.d_w3, ps.d_isdir, ps.d_dval, c->d_phi);
       LAUNCH_CHECK(c);
     }
-    double *cur = ps.d_w2, *other = ps.d_w1;
-    // inverse transform  cur -> other
-    if (ps.use_fft)
-      k_dst_fft<<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, cur, other,
-                                                                         dst_scale);
-    else
-      k_dgemm<<<gg, 256, 0, c->fstream>>>(ps.ma, ps.mb, ps.ma, ps.d_V, ps.ma, cur, ps.ma, other, ps.ma);
-    LAUNCH_CHECK(c);
-    ps.d_w3 = other;   // (alias, not owned) result of the inverse transform
-    k_store_phi<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(s, ps.d_w3, ps.d_isdir, ps.d_dval, c->d_phi);
-    LAUNCH_CHECK(c);
   }
   k_efield<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(nx, ny, c->g.dx, c->g.dy, c->d_phi, c->d_E2);
   LAUNCH_CHECK(c);
