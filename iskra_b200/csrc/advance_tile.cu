@@ -673,6 +673,10 @@ int32_t tdir_ensure(iskb_species *sp) {
 }
 
 void sp_touch(iskb_species *sp) {
+  // an MCC test phase that ran ahead on this species (mcc_launch phase 1) is void now
+  for (iskb_mcc *m : sp->ctx->mccs)
+    if (m->source == sp) mcc_discard_pre(m);
+  sp->epoch++;
   sp->tdir_valid = false;
   sp->marks_valid = false;
   sp->vz2_known = false;

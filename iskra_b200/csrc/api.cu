@@ -142,6 +142,8 @@ extern "C" int32_t iskb_create(int32_t device, iskb_ctx **out) {
     CU_TRY(cudaStreamCreateWithPriority(&c->fstream, cudaStreamNonBlocking, hi));
   }
   CU_TRY(cudaStreamCreateWithFlags(&c->mstream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&c->pstream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_p0, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&c->ev_m0, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&c->ev_m1, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&c->ev_rho, cudaEventDisableTiming));
@@ -169,9 +171,12 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
   if (!c) return ISKB_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->fstream);
+  cudaStreamSynchronize(c->pstream);
+  cudaStreamSynchronize(c->mstream);
   cudaStreamSynchronize(c->stream);
   comm_destroy(c);
   for (iskb_mcc *m : c->mccs) {
+    if (m->ev_pre) cudaEventDestroy(m->ev_pre);
     cudaFree(m->d_tn); cudaFree(m->d_eps); cudaFree(m->d_sig); cudaFree(m->d_stats); cudaFree(m->d_nu); cudaFree(m->d_cand); cudaFree(m->d_coll); cudaFree(m->d_lists_cnt); cudaFree(m->d_pk);
     delete m;
   }
@@ -183,6 +188,7 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
   cudaFreeHost(c->h_status); cudaFreeHost(c->h_scratch);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   cudaEventDestroy(c->ev_m0); cudaEventDestroy(c->ev_m1); cudaStreamDestroy(c->mstream);
+  cudaEventDestroy(c->ev_p0); cudaStreamDestroy(c->pstream);
   cudaEventDestroy(c->ev_rho);
   cudaEventDestroy(c->ev_E);
   cudaStreamDestroy(c->fstream);
@@ -216,6 +222,7 @@ extern "C" int32_t iskb_stream_join(iskb_ctx *c) {
 extern "C" int32_t iskb_synchronize(iskb_ctx *c) {
   if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
   ISKB_TRY(fields_join(c));
+  CU_TRY(cudaStreamSynchronize(c->pstream));   // test phases of the next step's MCC that ran ahead
   CU_TRY(cudaStreamSynchronize(c->stream));
   return ctx_check_status(c);
 }
@@ -443,6 +450,7 @@ extern "C" int32_t iskb_species_upload(iskb_species *s, const double *x, const d
   iskb_ctx *c = s->ctx;
   if (np < 0 || np > s->cap) return iskb_fail(ISKB_E_CAPACITY, "np = %lld exceeds capacity %lld", (long long)np, (long long)s->cap);
   if (np > 0 && (!x || !v || ld < np)) return iskb_fail(ISKB_E_INVALID, "x, v required with ld >= np");
+  sp_touch(s);   // (before the copies: kernels that ran ahead on the old rows are waited for)
   const size_t b = (size_t)np * sizeof(double);
   if (np > 0) {
     CU_TRY(cudaMemcpyAsync(s->col[0], x, b, cudaMemcpyHostToDevice, c->stream));
@@ -789,17 +797,35 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
       for (iskb_dsmc *d : c->dsmcs) inter.push_back(std::make_pair(1, (void *)d));
     }
     iskb_mcc *deferred = nullptr;
+    bool only_neutral_mcc = tile_dir;   // the test phases may run ahead only if nothing else edits velocities in between
+    for (const std::pair<int, void *> &in : inter) only_neutral_mcc = only_neutral_mcc && in.first == 0 && ((iskb_mcc *)in.second)->tq == 0.0;
+    bool waited_pre = false;
     for (size_t k = 0; k < inter.size(); ++k) {
       if (inter[k].first == 1) { ISKB_TRY(dsmc_launch((iskb_dsmc *)inter[k].second, dt, false)); continue; }
       iskb_mcc *m = (iskb_mcc *)inter[k].second;
+      // phase 1 (selection + test) of this step may have run right after the previous advance of the source species
+      int phase = 3;
+      if (m->pre_valid) {
+        if (only_neutral_mcc && m->pre_dt == dt && m->pre_epoch == m->source->epoch) {
+          if (!waited_pre) {   // every test phase that ran ahead has taken its snapshot before anything appends rows
+            CU_TRY(cudaEventRecord(c->ev_p0, c->pstream));
+            CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_p0, 0));
+            waited_pre = true;
+          }
+          phase = 2;
+          m->pre_valid = false;
+        } else {
+          ISKB_TRY(mcc_discard_pre(m));
+        }
+      }
       if (k + 1 == inter.size() && inter.size() > 1 && m->tq == 0.0 && tile_dir) {
         CU_TRY(cudaEventRecord(c->ev_m0, c->stream));
         CU_TRY(cudaStreamWaitEvent(c->mstream, c->ev_m0, 0));
-        ISKB_TRY(mcc_launch(m, dt, false, c->mstream));
+        ISKB_TRY(mcc_launch(m, dt, false, c->mstream, phase));
         CU_TRY(cudaEventRecord(c->ev_m1, c->mstream));
         deferred = m;
       } else {
-        ISKB_TRY(mcc_launch(m, dt, false));
+        ISKB_TRY(mcc_launch(m, dt, false, nullptr, phase));
       }
     }
     ISKB_TRY(fields_join(c));   // E of the previous step (the re-sort and MCC above did not need it)
@@ -819,6 +845,21 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
         ISKB_TRY(tile_stats_snapshot(c, s));
         s->steps_since_move++;
         s->steps_since_full++;
+        if (only_neutral_mcc) {
+          // selection + acceptance test of the NEXT step for the MCC objects that draw from this species: they read
+          // what this launch has just written and nothing else, so they run next to the other species' advance
+          for (const std::pair<int, void *> &in : inter) {
+            iskb_mcc *m = (iskb_mcc *)in.second;
+            if (m->source != s) continue;
+            CU_TRY(cudaEventRecord(c->ev_p0, c->stream));
+            CU_TRY(cudaStreamWaitEvent(c->pstream, c->ev_p0, 0));
+            ISKB_TRY(mcc_launch(m, dt, false, c->pstream, 1));
+            CU_TRY(cudaEventRecord(m->ev_pre, c->pstream));
+            m->pre_valid = true;
+            m->pre_dt = dt;
+            m->pre_epoch = s->epoch;
+          }
+        }
       } else if (c->tracker && !legacy) {
         // config.tracker != nothing: track! -> gather -> push -> check! -> after_push  (:56-61), one pass
         ISKB_TRY(launch_advance_tracked(s, dt, c->after_push[0], c->after_push[1], true));

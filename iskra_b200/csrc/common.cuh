@@ -117,6 +117,8 @@ struct iskb_ctx {
   // the LAST interaction of a step runs on its own stream next to the advance of the species it does not touch
   cudaStream_t mstream = nullptr;
   cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;
+  cudaStream_t pstream = nullptr;   // phase 1 of the next step's MCC objects (see mcc_launch)
+  cudaEvent_t ev_p0 = nullptr;
   cudaEvent_t ev_rho = nullptr, ev_E = nullptr;
   bool fields_pending = false;   // a solve is in flight on fstream; main-stream users of rho/phi/E must join first
   int64_t launches = 0;
@@ -177,6 +179,7 @@ struct iskb_species {
   double *alt[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // sort ping-pong
   uint32_t *alt_id = nullptr;
   int64_t *d_cnt = nullptr;     // CNT_*
+  uint64_t epoch = 0;           // bumped whenever rows change outside the fused step (sp_touch)
   int64_t h_nslots = 0, h_ndead = 0;   // host mirror, valid when !counts_stale
   int64_t h_nsorted = 0;               // rows [0, h_nsorted) are in the sorted layout of the last re-sort
   bool counts_stale = false;
@@ -247,7 +250,12 @@ struct iskb_mcc {
   std::vector<double> sig_last;      // per process: sigma_k at its last knot
   double *d_pk = nullptr;            // device pruning bounds of the current call
   uint64_t seed = 0;
-  uint64_t calls = 0;
+  uint64_t calls = 0, cur_call = 0;
+  // phase 1 of the next step already ran (iskb_step): valid while dt and the source species are what they were
+  bool pre_valid = false;
+  double pre_dt = 0.0;
+  uint64_t pre_epoch = 0;
+  cudaEvent_t ev_pre = nullptr;
   double *d_tn = nullptr;       // target density on nodes
   double *d_eps = nullptr, *d_sig = nullptr;
   void *d_procs = nullptr;      // MccProcDev[N]
@@ -308,7 +316,8 @@ int32_t ctx_check_status(iskb_ctx *ctx);
 int32_t poisson_prepare(iskb_ctx *ctx);
 int32_t poisson_solve(iskb_ctx *ctx);
 int32_t poisson_free(iskb_ctx *ctx);
-int32_t mcc_launch(iskb_mcc *mcc, double dt, bool count_nu, cudaStream_t st = nullptr);
+int32_t mcc_launch(iskb_mcc *mcc, double dt, bool count_nu, cudaStream_t st = nullptr, int phase = 3);
+int32_t mcc_discard_pre(iskb_mcc *mcc);
 int32_t comm_allreduce_sum(iskb_ctx *ctx, double *d_buf, int64_t n);
 int32_t comm_destroy(iskb_ctx *ctx);
 int32_t launch_advance(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit,

@@ -489,6 +489,13 @@ __global__ void k_mcc_collide(MccDev m, const unsigned int *__restrict__ lists_c
   if (blockIdx.x == 0 && threadIdx.x == 0 && nc) atomicAdd(&m.stats[1], (unsigned long long)nc);
 }
 
+__global__ void k_commit_stats(unsigned long long *stats) {
+  if (threadIdx.x < 10) {
+    stats[threadIdx.x] += stats[10 + threadIdx.x];
+    stats[10 + threadIdx.x] = 0;
+  }
+}
+
 SpDev spdev(const iskb_species *s) {
   SpDev d;
   for (int q = 0; q < 6; ++q) d.col[q] = s->col[q];
@@ -510,9 +517,23 @@ double xsec_eval_host(const double *xs, const double *ys, int n, double x) {
 
 }  // namespace
 
-int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st) {
+// phase 1: candidate selection + acceptance test (reads the source species only, leaves the collider list on the
+// device); phase 2: kinematics of the listed colliders (writes velocities, appends ionisation products);
+// 3: both.  iskb_step runs phase 1 of the NEXT step right after the source species has been advanced, on a side
+// stream next to the other species' advance, so only the kinematics remain between two steps.
+// a phase 1 that ran ahead (iskb_step) is dropped: the context stream waits for it, its counts are forgotten
+int32_t mcc_discard_pre(iskb_mcc *mc) {
+  if (!mc->pre_valid) return ISKB_OK;
   iskb_ctx *c = mc->ctx;
-  if (!st) st = st;
+  CU_TRY(cudaStreamWaitEvent(c->stream, mc->ev_pre, 0));
+  CU_TRY(cudaMemsetAsync(mc->d_stats + 10, 0, 10 * sizeof(unsigned long long), c->stream));
+  mc->pre_valid = false;
+  return ISKB_OK;
+}
+
+int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st, int phase) {
+  iskb_ctx *c = mc->ctx;
+  if (!st) st = c->stream;
   iskb_species *src = mc->source;
   const int N = mc->N;
   const double max_Pt = 1.0 - exp(-mc->max_n0 * mc->max_sigma_g * dt);     // mcc.jl:243
@@ -532,9 +553,9 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st) {
       m.prod[nprod] = spdev(p.product);
       d.prod = nprod++;
       d.n_prod = (int)std::rint(src->w0 / p.product->w0);                  // :205-207
-      p.product->counts_stale = true;
+      if (phase & 2) p.product->counts_stale = true;
     }
-    if (p.kind == ISKB_MCC_IONIZATION) src->counts_stale = true;
+    if (p.kind == ISKB_MCC_IONIZATION && (phase & 2)) src->counts_stale = true;
   }
   m.N = N;
   m.eps = mc->d_eps; m.sig = mc->d_sig; m.tn = mc->d_tn; m.E2 = c->d_E2; m.g = c->g;
@@ -566,14 +587,16 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st) {
   m.pk_dev = mc->d_pk;
   m.k0 = (uint32_t)mc->seed;
   m.k1 = (uint32_t)(mc->seed >> 32) ^ (0x9E3779B9u * (uint32_t)(c->rank + 1));
-  m.call = (uint32_t)(mc->calls++);
-  m.stats = mc->d_stats;
+  if (phase & 1) mc->cur_call = mc->calls++;
+  m.call = (uint32_t)mc->cur_call;
+  // phase 1 alone counts into the second half of d_stats; the numbers join the totals when phase 2 runs
+  m.stats = phase == 1 ? mc->d_stats + 10 : mc->d_stats;
   m.status = c->d_status;
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   m.nu = nullptr;
   if (count_nu) {
     if (!mc->d_nu) CU_TRY(cudaMalloc(&mc->d_nu, nn * N * sizeof(float)));
-    CU_TRY(cudaMemsetAsync(mc->d_nu, 0, nn * N * sizeof(float), st));
+    if (phase & 1) CU_TRY(cudaMemsetAsync(mc->d_nu, 0, nn * N * sizeof(float), st));
     m.nu = mc->d_nu;
   }
   // candidate / collider lists (lazy; sized for the worst case of every row being a candidate)
@@ -583,9 +606,11 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st) {
     CU_TRY(cudaMalloc(&mc->d_lists_cnt, 2 * sizeof(unsigned int)));
   }
   const unsigned int cand_cap = (unsigned int)src->cap;
+  const int64_t bound = src->counts_stale ? src->cap : src->h_nslots;
+  int64_t exp_cand = (int64_t)(m.p_cand * (double)bound * 1.05) + 1024;
+  if (phase & 1) {
   k_snapshot_begin<<<1, 1, 0, st>>>(src->d_cnt, mc->d_lists_cnt, m);
   LAUNCH_CHECK(c);
-  const int64_t bound = src->counts_stale ? src->cap : src->h_nslots;
   int64_t blocks = (bound / 4 + TPB) / TPB;
   if (blocks > (int64_t)c->n_sm * 8) blocks = (int64_t)c->n_sm * 8;
   if (blocks < 1) blocks = 1;
@@ -598,8 +623,7 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st) {
     k_mcc_select_skip<<<(int)bs, TPB, 0, st>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap);
   }
   LAUNCH_CHECK(c);
-  // the list lengths live on the device: size the dense phases from the expected candidate count
-  int64_t exp_cand = (int64_t)(m.p_cand * (double)bound * 1.05) + 1024;
+  // the list lengths live on the device: the dense phases are sized from the expected candidate count
   int64_t b2 = (exp_cand + TEST_TPB - 1) / TEST_TPB;
   if (b2 > (int64_t)c->n_sm * 256) b2 = (int64_t)c->n_sm * 256;
   int ntab = 0;
@@ -610,6 +634,12 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st) {
     CU_TRY(cudaFuncSetAttribute(k_mcc_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
   k_mcc_test<<<(int)b2, TEST_TPB, tab_bytes, st>>>(m, mc->d_lists_cnt, mc->d_cand, cand_cap, mc->d_coll, ntab);
   LAUNCH_CHECK(c);
+  }
+  if (!(phase & 2)) return ISKB_OK;
+  if (phase == 2) {
+    k_commit_stats<<<1, 32, 0, st>>>(mc->d_stats);
+    LAUNCH_CHECK(c);
+  }
   // one thread per collider would do; the count lives on the device, so cover a quarter of the expected candidates
   // (the kinematics are a long dependent chain: a small grid walking the list in rounds is latency bound)
   int64_t b3 = (exp_cand / 4 + 127) / 128;
@@ -691,11 +721,12 @@ extern "C" int32_t iskb_mcc_create(iskb_ctx *c, iskb_species *source, double tar
   CU_TRY(cudaMalloc(&mc->d_tn, nn * sizeof(double)));
   CU_TRY(cudaMalloc(&mc->d_eps, off * sizeof(double)));
   CU_TRY(cudaMalloc(&mc->d_sig, off * sizeof(double)));
-  CU_TRY(cudaMalloc(&mc->d_stats, (2 + 8) * sizeof(unsigned long long)));
+  CU_TRY(cudaMalloc(&mc->d_stats, 2 * (2 + 8) * sizeof(unsigned long long)));
+  CU_TRY(cudaEventCreateWithFlags(&mc->ev_pre, cudaEventDisableTiming));
   CU_TRY(cudaMemcpyAsync(mc->d_tn, target_n, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU_TRY(cudaMemcpyAsync(mc->d_eps, eps, off * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU_TRY(cudaMemcpyAsync(mc->d_sig, sigma, off * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CU_TRY(cudaMemsetAsync(mc->d_stats, 0, (2 + 8) * sizeof(unsigned long long), c->stream));
+  CU_TRY(cudaMemsetAsync(mc->d_stats, 0, 2 * (2 + 8) * sizeof(unsigned long long), c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   c->mccs.push_back(mc);
   *out = mc;
@@ -721,6 +752,7 @@ extern "C" int32_t iskb_mcc_perform(iskb_mcc *mc, double dt, double *nu_out, int
   if (!mc) return iskb_fail(ISKB_E_INVALID, "null mcc");
   iskb_ctx *c = mc->ctx;
   unsigned long long before[10], after[10];
+  ISKB_TRY(mcc_discard_pre(mc));
   ISKB_TRY(read_stats(mc, before));
   ISKB_TRY(mcc_launch(mc, dt, nu_out != nullptr));
   ISKB_TRY(read_stats(mc, after));

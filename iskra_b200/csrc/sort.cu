@@ -364,6 +364,7 @@ int32_t ensure_sort_scratch(iskb_species *sp) {
 // columns, fixes counters.  Digits are 8 bits wide, or 9 when that saves a whole pass (17-bit tile keys).
 int32_t sort_by_keys(iskb_species *sp, int64_t n, int bits, uint32_t *perm_out_host, uint32_t interleave_tiles = 0) {
   iskb_ctx *c = sp->ctx;
+  sp_touch(sp);   // rows are about to move: whatever ran ahead on the old layout is void (and is waited for)
   const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
   const int width = (bits + 8) / 9 < (bits + 7) / 8 ? 9 : 8;
   const int passes = (bits + width - 1) / width;
