@@ -431,6 +431,13 @@ __global__ void k_transpose(int rows, int cols, const double *__restrict__ in, d
 // IN = 2: mode-space input with the Sherman-Morrison correction of the cyclic Thomas solve applied on the way in
 //         (x -= q*f, see k_thomas_seg);
 // OUT = 1: the result goes straight into phi (k_store_phi's job for the unknown nodes).
+// Shared-memory index of element i of the transform: one 16-byte slot is skipped after every 8, 64 and 512 elements.
+// 128-bit accesses are served per quarter warp (8 lanes, 8 groups of 4 banks): with this padding the 8 lanes hit 8
+// different groups both in the bit-reversed scatter of the load phase (addresses 128*brev(l) + c) and in the
+// stride-4 accesses of the first butterfly passes -- unpadded, those were 8-way and 4-way conflicts.
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
+static inline int fpad_host(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
+
 struct FftIo {
   SolveDims s;
   const double *rho;
@@ -476,10 +483,10 @@ __global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, co
       v.y = has_b ? fetch(cb, p) : 0.0;
     }
     const int r0 = (int)(__brev((unsigned)p) >> (32 - log2M));
-    zs[r0] = v;
+    zs[fpad(r0)] = v;
     if (p >= 1 && p <= m) {
       const int r1 = (int)(__brev((unsigned)(M - p)) >> (32 - log2M));
-      zs[r1] = make_double2(-v.x, -v.y);
+      zs[fpad(r1)] = make_double2(-v.x, -v.y);
     }
   }
   __syncthreads();
@@ -491,10 +498,13 @@ __global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, co
     for (int t = threadIdx.x; t < M / 4; t += blockDim.x) {
       const int pos = t & (half - 1);
       const int i0 = ((t >> s) << (s + 2)) + pos;
-      const double2 w1 = __ldg(&tw[pos << (log2M - 1 - s)]);
+      // one twiddle load per butterfly: w2a = W^(pos*2^(L-2-s)); the other two follow from it,
+      // w2b = W^((pos+half)*2^(L-2-s)) = w2a * W^(M/4) = -i*w2a  and  w1 = W^(pos*2^(L-1-s)) = w2a^2
       const double2 w2a = __ldg(&tw[pos << (log2M - 2 - s)]);
-      const double2 w2b = __ldg(&tw[(pos + half) << (log2M - 2 - s)]);
-      double2 a0 = zs[i0], a1 = zs[i0 + half], a2 = zs[i0 + 2 * half], a3 = zs[i0 + 3 * half];
+      const double2 w2b = make_double2(w2a.y, -w2a.x);
+      const double2 w1 = make_double2(fma(w2a.x, w2a.x, -(w2a.y * w2a.y)), 2.0 * (w2a.x * w2a.y));
+      const int p0 = fpad(i0), p1 = fpad(i0 + half), p2 = fpad(i0 + 2 * half), p3 = fpad(i0 + 3 * half);
+      double2 a0 = zs[p0], a1 = zs[p1], a2 = zs[p2], a3 = zs[p3];
       {
         const double br = fma(a1.x, w1.x, -(a1.y * w1.y)), bi = fma(a1.x, w1.y, a1.y * w1.x);
         a1 = make_double2(a0.x - br, a0.y - bi);
@@ -505,11 +515,11 @@ __global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, co
       }
       {
         const double br = fma(a2.x, w2a.x, -(a2.y * w2a.y)), bi = fma(a2.x, w2a.y, a2.y * w2a.x);
-        zs[i0] = make_double2(a0.x + br, a0.y + bi);
-        zs[i0 + 2 * half] = make_double2(a0.x - br, a0.y - bi);
+        zs[p0] = make_double2(a0.x + br, a0.y + bi);
+        zs[p2] = make_double2(a0.x - br, a0.y - bi);
         const double cr = fma(a3.x, w2b.x, -(a3.y * w2b.y)), ci = fma(a3.x, w2b.y, a3.y * w2b.x);
-        zs[i0 + half] = make_double2(a1.x + cr, a1.y + ci);
-        zs[i0 + 3 * half] = make_double2(a1.x - cr, a1.y - ci);
+        zs[p1] = make_double2(a1.x + cr, a1.y + ci);
+        zs[p3] = make_double2(a1.x - cr, a1.y - ci);
       }
     }
     __syncthreads();
@@ -520,16 +530,16 @@ __global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, co
       const int pos = t & (half - 1);
       const int i0 = ((t >> s) << (s + 1)) + pos, i1 = i0 + half;
       const double2 w = __ldg(&tw[pos << (log2M - 1 - s)]);
-      const double2 a = zs[i0], b = zs[i1];
+      const double2 a = zs[fpad(i0)], b = zs[fpad(i1)];
       const double br = fma(b.x, w.x, -(b.y * w.y)), bi = fma(b.x, w.y, b.y * w.x);
-      zs[i0] = make_double2(a.x + br, a.y + bi);
-      zs[i1] = make_double2(a.x - br, a.y - bi);
+      zs[fpad(i0)] = make_double2(a.x + br, a.y + bi);
+      zs[fpad(i1)] = make_double2(a.x - br, a.y - bi);
     }
     __syncthreads();
   }
   const double h = 0.5 * scale;
   for (int k = 1 + threadIdx.x; k <= m; k += blockDim.x) {
-    const double2 z = zs[k];
+    const double2 z = zs[fpad(k)];
     if (OUT == 1) {
       io.phi[node_of(io.s, io.s.a0 + k - 1, io.s.b0 + ca)] = -h * z.y;
       if (has_b) io.phi[node_of(io.s, io.s.a0 + k - 1, io.s.b0 + cb)] = h * z.x;
@@ -575,6 +585,10 @@ __global__ void __launch_bounds__(32 * TSEG) k_thomas_seg(int ma, int mb, const 
   double carry = 0.0;
   for (int s2 = 0; s2 < seg; ++s2) carry = fma(sA[s2][lane], carry, sB[s2][lane]);
   __syncthreads();
+  // replay with the right carry; the same pass composes the segment's map of the BACKWARD sweep
+  // (x_q = -m_q x_{q+1} + y_q, applied for descending q: G = F_q0 o ... o F_{q1-1}, built as G <- G o F_q while q ascends;
+  // the last row has no super-diagonal: m = 0 there)
+  A = 1.0; B = 0.0;
   if (act) {
     double y = carry;
 #pragma unroll 8
@@ -582,19 +596,11 @@ __global__ void __launch_bounds__(32 * TSEG) k_thomas_seg(int ma, int mb, const 
       const double mq = m[(int64_t)q * ma];
       y = (w[(int64_t)q * ma] - y) * mq;
       w[(int64_t)q * ma] = y;
+      B = fma(A, y, B);
+      A = q == mb - 1 ? 0.0 : -mq * A;
     }
   }
-  __syncthreads();   // (each thread re-reads only what it wrote itself; the barrier orders the shared arrays)
-  // ---- backward (q descending; x_{mb} = 0, and the last row has no super-diagonal: A = 0 there) ----
-  A = 1.0; B = 0.0;
-  if (act) {
-#pragma unroll 8
-    for (int q = q1 - 1; q >= q0; --q) {
-      const double mq = q == mb - 1 ? 0.0 : m[(int64_t)q * ma], y = w[(int64_t)q * ma];
-      B = fma(-mq, B, y);
-      A = -mq * A;
-    }
-  }
+  __syncthreads();   // (the carries above have been read by every segment)
   sA[seg][lane] = A; sB[seg][lane] = B;
   __syncthreads();
   carry = 0.0;
@@ -609,7 +615,8 @@ __global__ void __launch_bounds__(32 * TSEG) k_thomas_seg(int ma, int mb, const 
       w[(int64_t)q * ma] = x;
     }
   }
-  if (fout) {   // cyclic: x_0 lives in segment 0, x_{mb-1} in the last one
+  if (fout) {   // cyclic: x_0 lives in segment 0, x_{mb-1} in whichever segment holds the last row
+    __syncthreads();
     if (seg == TSEG - 1) sA[0][lane] = act ? w[(int64_t)(mb - 1) * ma] : 0.0;
     __syncthreads();
     if (seg == 0 && act) fout[k] = (x + sA[0][lane] / gam[k]) * qden[k];
@@ -926,8 +933,8 @@ int32_t poisson_prepare(iskb_ctx *c) {
         CU_TRY(cudaMalloc(&ps.d_tw, tw.size() * sizeof(double2)));
         CU_TRY(cudaMemcpyAsync(ps.d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
-        CU_TRY(cudaFuncSetAttribute(k_dst_fft<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, M * (int)sizeof(double2)));
-        CU_TRY(cudaFuncSetAttribute(k_dst_fft<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M * (int)sizeof(double2)));
+        CU_TRY(cudaFuncSetAttribute(k_dst_fft<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpad_host(M) * (int)sizeof(double2)));
+        CU_TRY(cudaFuncSetAttribute(k_dst_fft<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpad_host(M) * (int)sizeof(double2)));
         ps.use_fft = true;
         ps.fft_log2M = lg;
         // Thomas factors in the layout the transform leaves ([k + q*ma], see k_thomas_seg)
@@ -997,13 +1004,13 @@ int32_t poisson_solve(iskb_ctx *c) {
     if (ps.use_fft) {
       // rho --DST (rhs formed on the way in)--> w2[k + q*ma] --Thomas per mode, in place--> w2 --DST--> phi
       FftIo io{s, c->d_rho, ps.d_isdir, ps.d_dval, ps.d_qT, ps.b_cyclic ? ps.d_fvec : nullptr, c->d_phi};
-      k_dst_fft<1, 0><<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, nullptr,
+      k_dst_fft<1, 0><<<(ps.mb + 1) / 2, 512, fpad_host(M) * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, nullptr,
                                                                                 ps.d_w2, dst_scale, io);
       LAUNCH_CHECK(c);
       k_thomas_seg<<<(ps.ma + 31) / 32, 32 * TSEG, 0, c->fstream>>>(ps.ma, ps.mb, ps.d_cpT, ps.d_qden, ps.d_gam, ps.d_w2,
                                                                    ps.b_cyclic ? ps.d_fvec : nullptr);
       LAUNCH_CHECK(c);
-      k_dst_fft<2, 1><<<(ps.mb + 1) / 2, 512, M * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, ps.d_w2,
+      k_dst_fft<2, 1><<<(ps.mb + 1) / 2, 512, fpad_host(M) * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, ps.d_w2,
                                                                                 nullptr, dst_scale, io);
       LAUNCH_CHECK(c);
       k_phi_edges<<<(2 * (nx + ny) + 255) / 256, 256, 0, c->fstream>>>(nx, ny, ps.d_isdir, ps.d_dval, c->d_phi);
