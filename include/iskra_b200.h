@@ -216,8 +216,10 @@ int32_t iskb_set_advance_path(iskb_ctx *ctx, int32_t path);
  * zero to it) and the wg column of a species whose weights all equal w0 -- 64 instead of 88 B per particle-step,
  * bit-identical results.  0: every launch reads and writes all columns (A/B measurements). */
 int32_t iskb_set_lean(iskb_ctx *ctx, int32_t on);
-/* out[0] full sorts, out[1] re-grouping launches so far, out[2] steps since the last full sort, out[3] since the last re-group */
-int32_t iskb_species_sort_stats(iskb_species *sp, int64_t out[4]);
+/* out[0] full sorts, out[1] re-grouping launches so far, out[2] steps since the last full sort, out[3] since the last
+ * re-group; from the newest statistics snapshot the policy has read: out[4] slots, out[5] discarded rows among them,
+ * out[6] rows covered by the tile directory (slots beyond it form the unsorted tail); out[7] reserved */
+int32_t iskb_species_sort_stats(iskb_species *sp, int64_t out[8]);
 /* n_steps iterations of: MCC, then DSMC (registered interactions, each kind in creation order) -> advance! every species
  * (gather, push, after_push) -> density / rho -> all-reduce -> phi -> E.  With a surface tracker on
  * the context advance! is track! -> gather -> push -> check! -> after_push (ParticleInCell.jl:56-61);

@@ -719,12 +719,18 @@ extern "C" int32_t iskb_set_advance_path(iskb_ctx *c, int32_t path) {
   return ISKB_OK;
 }
 
-extern "C" int32_t iskb_species_sort_stats(iskb_species *s, int64_t out[4]) {
+extern "C" int32_t iskb_species_sort_stats(iskb_species *s, int64_t out[8]) {
   if (!s || !out) return iskb_fail(ISKB_E_INVALID, "null");
   out[0] = s->full_sorts;
   out[1] = s->moves;
   out[2] = s->steps_since_full;
   out[3] = s->steps_since_move;
+  // the newest snapshot the policy has looked at (two steps old): slots, discarded rows inside them, rows in the tile directory
+  const int slot = (int)((s->tstats_step + 1) & 1);
+  out[4] = s->h_tstats ? s->h_tstats[10 * slot + CNT_NSLOTS] : 0;
+  out[5] = s->h_tstats ? s->h_tstats[10 * slot + CNT_NDEAD] : 0;
+  out[6] = s->h_tstats ? s->h_tstats[10 * slot + 9] : 0;
+  out[7] = 0;
   return ISKB_OK;
 }
 

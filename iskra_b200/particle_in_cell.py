@@ -571,8 +571,21 @@ def solve(config, dt=1e-5, timesteps=200, after_push=None, sort_interval=0, fuse
         # "out of scope"): a fluid that would need either must not be dropped silently
         if is_fluid(s) and (s.q != 0.0 or s.mu != 0.0 and getattr(s, "mobile", False)):
             raise NotImplementedError("FluidSpecies %s carries charge: fluid advection / fluid charge density are out of scope" % s)
+    saved_hook = None
     if not fused and after_push is not None:
-        raise ValueError("after_push=(mode_x, mode_y) belongs to the fused loop; with fused=False set hooks.after_push")
+        # operator-by-operator loop: the boundary modes become the after_push hook (discards first, then wraps,
+        # like the scripts' overrides: 11_rf_discharge.jl:80-83) for the duration of this call
+        mxy = tuple(after_push)
+        saved_hook = hooks.after_push
+
+        def _modes_hook(part, g_):
+            dd = [d + 1 for d in (0, 1) if mxy[d] == L.BND_DISCARD]
+            ww = [d + 1 for d in (0, 1) if mxy[d] == L.BND_WRAP]
+            if dd:
+                discard_(part, g_, dims=dd)
+            if ww:
+                wrap_(part, g_, dims=ww)
+        hooks.after_push = _modes_hook
     if fused:
         # the device step runs every species / interaction bound to the context, in creation order
         # (iskb_step); the reference runs config.species / config.interactions (:109-115).  Refuse to diverge.
@@ -603,4 +616,6 @@ def solve(config, dt=1e-5, timesteps=200, after_push=None, sort_interval=0, fuse
             L.check(rt.lib.iskb_field_solve(rt.h))                            # :126-128
         hooks.after_loop(it, it * dt - dt, dt)                                # :134
     rt.synchronize()
+    if saved_hook is not None:
+        hooks.after_push = saved_hook
     hooks.exit_loop()                                                         # :137

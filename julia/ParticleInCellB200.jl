@@ -343,17 +343,42 @@ function ParticleInCell.perform!(d :: B200DSMC, E, Δt, config)
 end
 
 # ---- fused loop: drop-in for ParticleInCell.solve that still fires the hooks (ParticleInCell.jl:84-139)
-function solve(ctx :: Context, species :: Vector{B200Species}, Δt, timesteps; after_push = (1, 1), sort_interval = 8)
+# `interactions` :: B200MCC / B200DSMC objects in config.interactions order; species and interactions that exist on the
+# context but are not listed (a source buffer for add!, a scratch species) are neither advanced nor deposited.
+function solve(ctx :: Context, species :: Vector{B200Species}, Δt, timesteps; interactions = [], after_push = (1, 1),
+               sort_interval = 4, miss_threshold = 5e-4, max_interval = 4, full_interval = 0, lean = true)
   check(ccall((:iskb_set_after_push, LIB), Int32, (Ptr{Cvoid}, Int32, Int32), ctx.h, after_push...))
   check(ccall((:iskb_set_sort_interval, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, sort_interval))
+  check(ccall((:iskb_set_sort_policy, LIB), Int32, (Ptr{Cvoid}, Float64, Int32), ctx.h, miss_threshold, max_interval))
+  check(ccall((:iskb_set_sort_full_interval, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, full_interval))
+  check(ccall((:iskb_set_lean, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, lean ? 1 : 0))
+  check(ccall((:iskb_set_advance_path, LIB), Int32, (Ptr{Cvoid}, Int32), ctx.h, 0))
+  foreach(upload!, species)
+  sh = Ptr{Cvoid}[sp.h for sp in species]
+  ih = Ptr{Cvoid}[i.h for i in interactions]
+  GC.@preserve sh ih check(ccall((:iskb_step_set_active, LIB), Int32, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Int32, Ptr{Ptr{Cvoid}}, Int32),
+                                 ctx.h, sh, Int32(length(sh)), ih, Int32(length(ih))))
   ParticleInCell.enter_loop()
   for it in 1:timesteps
+    foreach(upload!, species)                          # host edits made in after_loop reach the device
     check(ccall((:iskb_step, LIB), Int32, (Ptr{Cvoid}, Float64, Int32), ctx.h, float(Δt), 1))
     foreach(sp -> sp.device_newer = true, species)
     ParticleInCell.after_loop(it, it*Δt - Δt, Δt)     # scripts' iteration(): diagnostics, RF apply_dirichlet
   end
   check(ccall((:iskb_synchronize, LIB), Int32, (Ptr{Cvoid},), ctx.h))
   ParticleInCell.exit_loop()
+end
+
+# bookkeeping of the row order (new relative to the reference; diagnostics only)
+function sort_stats(sp :: B200Species)
+  out = zeros(Int64, 8)
+  check(ccall((:iskb_species_sort_stats, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}), sp.h, out))
+  (full_sorts = out[1], regroups = out[2], since_full = out[3], since_regroup = out[4], slots = out[5], dead = out[6], in_directory = out[7])
+end
+function context_counts(ctx :: Context)
+  a, b, c = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+  check(ccall((:iskb_ctx_counts, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), ctx.h, a, b, c))
+  (species = a[], mcc = b[], dsmc = c[])
 end
 
 end # module

@@ -1,4 +1,5 @@
-"""Index-slice sharding of the particles over ranks: rank r owns rows
+"""TEST SCAFFOLDING (the GPU path shards inside workloads.build_c5 and reduces rho in csrc/comm.cu).
+Index-slice sharding of the particles over ranks: rank r owns rows
 [lo, hi) of every species, the grid is replicated, rho is summed with one all-reduce per step.
 No spatial decomposition, hence no particle migration and no halo exchange."""
 

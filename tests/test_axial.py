@@ -167,7 +167,7 @@ def test_axial_operator_on_device_bitexact(ib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, False, "tiled"])
 def test_seed_like_loop_vs_oracle(ib, fused):
     """problem/13_seed.jl without MCC: axial grid 33 x 65, 0 V / E*d plates at z = 0 / Lz, axial pusher,
     discard!(dims = 2); phi against the exact solution of the reference's system."""
@@ -207,7 +207,9 @@ def test_seed_like_loop_vs_oracle(ib, fused):
             ops.b[rd] = (-rho).reshape(-1, order="F")[rd] / ops.eps0
             phi = exact(ops.b).reshape((nr, nz), order="F")
             E = O.calculate_electric_field(ops, phi)
-            PIC.solve(cfg, dt, 1, after_push=(ib._lib.BND_NONE, ib._lib.BND_DISCARD), fused=fused)
+            # "tiled": the axial pusher inside the tile-directory kernels (re-group every 3 steps)
+            PIC.solve(cfg, dt, 1, after_push=(ib._lib.BND_NONE, ib._lib.BND_DISCARD), fused=bool(fused),
+                      sort_interval=3 if fused == "tiled" else 0)
             grho, gphi, gE = g._rt.fields()
             assert np.max(np.abs(gphi - phi)) <= REL * np.max(np.abs(phi)), it
             assert np.max(np.abs(grho - rho)) <= REL * np.max(np.abs(rho)), it

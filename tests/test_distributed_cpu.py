@@ -25,7 +25,7 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from iskra_b200.sharding import max_over_ranks, slice_for_rank, sum_over_ranks
+    from sharding_helpers import max_over_ranks, slice_for_rank, sum_over_ranks
     from oracle import c_oracle as CO
     Lc = CO.lib()
     nx, ny, dx, n = 33, 17, 1e-3, 20001

@@ -96,7 +96,7 @@ def test_tile_advance_with_regroup_bitexact(ib, interval, bmode, vcells, uniform
     if 2 in bmode:
         assert pc.np < n
     _check_state(pc, pg, cap)
-    st = (C.c_int64 * 4)()
+    st = (C.c_int64 * 8)()
     ib._lib.check(rt.lib.iskb_species_sort_stats(pg._h, st))
     assert st[0] >= 1 and st[1] >= 12 // interval - 1      # one full sort, then re-grouping launches only
 
