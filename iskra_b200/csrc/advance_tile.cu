@@ -45,7 +45,8 @@ struct TileArgs {
   GridDev g;
   const double2 *E2;
   double qm, hqm, dt, c1, w0;   // q/m, 0.5*(q/m), dt, (0.5dt)*(q/m), default weight
-  double *u;
+  long long *ufix;          // deposited weights, fixed point (see add_fixed)
+  double fscale;
   int *status;
   unsigned long long *vmax2;
   const uint32_t *ts;       // [ntiles + 1]
@@ -86,14 +87,23 @@ __device__ __forceinline__ int clamp_origin(int o, int n, int wn) {
   return o < 0 ? 0 : o;
 }
 
-__device__ __forceinline__ void flush_rho(double *rho, int i0, int j0, int nx, double *u, int lane) {
+// Everything that leaves a warp goes into a 64-bit FIXED-POINT accumulator (value * fscale, rounded to nearest): integer
+// addition is associative, so the deposited weights do not depend on the order in which warps, tiles, list rows --
+// or ranks, the all-reduce is an integer sum too -- arrive (reproducible rho, run to run and for every
+// number of GPUs).  fscale is a power of two chosen on the host such that the sum over ALL slots of all species fits
+// (api.cu): at the C5 shard one unit is 1.5e-11 of a particle weight, 1e-12 of a typical node value.
+__device__ __forceinline__ void add_fixed(long long *ufix, int64_t node, double v, double fscale) {
+  atomicAdd((unsigned long long *)&ufix[node], (unsigned long long)__double2ll_rn(v * fscale));
+}
+
+__device__ __forceinline__ void flush_rho(double *rho, int i0, int j0, int nx, long long *ufix, double fscale, int lane) {
 #pragma unroll
   for (int k = 0; k < WE * WE / 32; ++k) {
     const int e = k * 32 + lane;
     const int o = (e >> 4) * WRS + (e & 15);
     const double v = rho[o];
     if (v != 0.0) {
-      atomicAdd(&u[(int64_t)(i0 + (e & 15)) + (int64_t)(j0 + (e >> 4)) * nx], v);
+      add_fixed(ufix, (int64_t)(i0 + (e & 15)) + (int64_t)(j0 + (e >> 4)) * nx, v, fscale);
       rho[o] = 0.0;
     }
   }
@@ -305,10 +315,10 @@ __global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(c
               dep_win = true;
             } else {
               const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * a.g.nx;
-              atomicAdd(&a.u[n00], d00);
-              atomicAdd(&a.u[n00 + 1], d10);
-              atomicAdd(&a.u[n00 + a.g.nx], d01);
-              atomicAdd(&a.u[n00 + a.g.nx + 1], d11);
+              add_fixed(a.ufix, n00, d00, a.fscale);
+              add_fixed(a.ufix, n00 + 1, d10, a.fscale);
+              add_fixed(a.ufix, n00 + a.g.nx, d01, a.fscale);
+              add_fixed(a.ufix, n00 + a.g.nx + 1, d11, a.fscale);
               atomicAdd(&sm.stats[1], 1u);
             }
           } else {
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(c
       }
       __syncwarp();
       if (rb + 32 >= r1) {   // tile finished: flush its window, publish its counts, go to the next non-empty tile
-        flush_rho(sm.rho, ei0, ej0, a.g.nx, a.u, lane);
+        flush_rho(sm.rho, ei0, ej0, a.g.nx, a.ufix, a.fscale, lane);
         ei0 = NOT_ANCHORED;
         for (int e = lane; e < (MOVE ? 9 : 1) * NCODE; e += 32) {
           const int sc = MOVE ? e / NCODE : CODE_STAY, nc = e % NCODE;
@@ -491,10 +501,10 @@ __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
           if (cell_in_grid(i, j, a.g.nx, a.g.ny)) {
             const CicW cw = cic_weights(hx, hy);
             const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * a.g.nx;
-            atomicAdd(&a.u[n00], __dmul_rn(cw.w00, wq));
-            atomicAdd(&a.u[n00 + 1], __dmul_rn(cw.w10, wq));
-            atomicAdd(&a.u[n00 + a.g.nx], __dmul_rn(cw.w01, wq));
-            atomicAdd(&a.u[n00 + a.g.nx + 1], __dmul_rn(cw.w11, wq));
+            add_fixed(a.ufix, n00, __dmul_rn(cw.w00, wq), a.fscale);
+            add_fixed(a.ufix, n00 + 1, __dmul_rn(cw.w10, wq), a.fscale);
+            add_fixed(a.ufix, n00 + a.g.nx, __dmul_rn(cw.w01, wq), a.fscale);
+            add_fixed(a.ufix, n00 + a.g.nx + 1, __dmul_rn(cw.w11, wq), a.fscale);
           } else {
             atomicOr(a.status, ISKB_ST_OOB);
           }
@@ -665,6 +675,7 @@ int32_t tdir_ensure(iskb_species *sp) {
   CU_TRY(cudaMalloc(&sp->d_seg, (nseg + (nseg + 2047) / 2048 + 16) * sizeof(uint32_t)));
   CU_TRY(cudaMalloc(&sp->d_wr, ((size_t)advance_chunks(c) + 1) * sizeof(uint32_t)));
   CU_TRY(cudaMalloc(&sp->d_ticket, sizeof(unsigned)));
+  CU_TRY(cudaMalloc(&sp->d_ufix, (size_t)c->g.nx * c->g.ny * sizeof(long long)));
   CU_TRY(cudaMalloc(&sp->d_code, sp->cap));
   CU_TRY(cudaMalloc(&sp->alt_code, sp->cap));
   CU_TRY(cudaMalloc(&sp->d_mlist, sp->cap * sizeof(uint2)));
@@ -687,7 +698,7 @@ void tdir_free(iskb_species *sp) {
   for (int k = 0; k < 2; ++k) if (sp->ev_tstats[k]) cudaEventDestroy(sp->ev_tstats[k]);
   for (int k = 0; k < 2; ++k) cudaFree(sp->d_ts[k]);
   cudaFree(sp->d_tcnt); cudaFree(sp->d_tbase); cudaFree(sp->d_seg); cudaFree(sp->d_wr);
-  cudaFree(sp->d_code); cudaFree(sp->alt_code); cudaFree(sp->d_mlist); cudaFree(sp->d_mlist_n); cudaFree(sp->d_ticket);
+  cudaFree(sp->d_code); cudaFree(sp->alt_code); cudaFree(sp->d_mlist); cudaFree(sp->d_mlist_n); cudaFree(sp->d_ticket); cudaFree(sp->d_ufix);
 }
 
 static int32_t warp_ranges(iskb_species *sp) {
@@ -735,7 +746,8 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
   a.dt = dt;
   a.c1 = 0.5 * dt * a.qm;
   a.w0 = sp->w0;
-  a.u = sp->d_u;
+  a.ufix = sp->d_ufix;
+  a.fscale = c->fscale;
   a.status = c->d_status;
   a.vmax2 = sp->d_vmax2;
   a.ts = sp->d_ts[0];

@@ -184,6 +184,7 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
   for (iskb_dsmc *d : c->dsmcs) dsmc_free(d);
   tracker_free(c->tracker);
   poisson_free(c);
+  cudaFree(c->d_rho_int);
   cudaFree(c->d_upriv); cudaFree(c->d_V); cudaFree(c->d_rho); cudaFree(c->d_phi); cudaFree(c->d_E2); cudaFree(c->d_status);
   cudaFreeHost(c->h_status); cudaFreeHost(c->h_scratch);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
@@ -462,8 +463,13 @@ extern "C" int32_t iskb_species_upload(iskb_species *s, const double *x, const d
   if (wg) {
     CU_TRY(cudaMemcpyAsync(s->col[5], wg, s->cap * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     bool uni = true;   // every weight equal to w0 (the reference's `ones(N) * weight`): the lean kernels skip the column
-    for (int64_t k = 0; k < s->cap && uni; ++k) uni = wg[k] == s->w0;
+    double wmax = s->w0;
+    for (int64_t k = 0; k < s->cap; ++k) {
+      uni = uni && wg[k] == s->w0;
+      if (wg[k] > wmax) wmax = wg[k];
+    }
     s->wg_uniform = uni;
+    s->wmax = wmax;   // bound of the fixed-point deposit (fixed_point_setup)
     if (s->alt[5]) CU_TRY(cudaMemcpyAsync(s->alt[5], wg, s->cap * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
   if (id) CU_TRY(cudaMemcpyAsync(s->id, id, s->cap * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
@@ -734,6 +740,32 @@ extern "C" int32_t iskb_species_sort_stats(iskb_species *s, int64_t out[8]) {
   return ISKB_OK;
 }
 
+// Fixed-point unit of the tile path's deposit (advance_tile.cu, add_fixed).  q0 = the smallest |charge|; every active
+// species must carry an integer multiple Z_s of it (e, -e, 2e ...), so that rho = q0 * sum_s Z_s u_s / V can be formed
+// from integers.  fscale = the largest power of two for which sum_s |Z_s| * capacity_s * wmax_s * fscale < 2^62:
+// even with every slot of every species in one node nothing overflows.
+static int32_t fixed_point_setup(iskb_ctx *c, const std::vector<iskb_species *> &species) {
+  double q0 = 0.0;
+  for (iskb_species *s : species) {
+    const double a = fabs(s->q);
+    if (a > 0.0 && (q0 == 0.0 || a < q0)) q0 = a;
+  }
+  if (q0 == 0.0) q0 = 1.0;   // neutral species only: rho == 0 whatever the unit
+  double total = 0.0;
+  for (iskb_species *s : species) {
+    const double z = s->q / q0, zr = (double)llround(z);
+    if (fabs(z - zr) > 1e-9 * (fabs(z) + 1.0))
+      return iskb_fail(ISKB_E_UNSUPPORTED, "species charges are not integer multiples of the smallest one (%g vs %g)", s->q, q0);
+    if (s->wmax <= 0.0) s->wmax = s->w0 > 0.0 ? s->w0 : 1.0;
+    total += (fabs(zr) > 1.0 ? fabs(zr) : 1.0) * (double)s->cap * s->wmax;
+  }
+  int e = 0;
+  frexp(4.0e18 / total, &e);          // 2^(e-1) <= 4e18 / total < 2^e  (4e18 < 2^62)
+  c->fscale = ldexp(1.0, e - 1);
+  c->q0 = q0;
+  return ISKB_OK;
+}
+
 extern "C" int32_t iskb_ctx_counts(iskb_ctx *c, int64_t *n_species, int64_t *n_mcc, int64_t *n_dsmc) {
   if (!c) return iskb_fail(ISKB_E_INVALID, "null ctx");
   if (n_species) *n_species = (int64_t)c->species.size();
@@ -835,6 +867,7 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
       }
     }
     ISKB_TRY(fields_join(c));   // E of the previous step (the re-sort and MCC above did not need it)
+    if (tile_dir) ISKB_TRY(fixed_point_setup(c, species));
     for (size_t k = 0; k < species.size(); ++k) {                          // :113-115
       iskb_species *s = species[k];
       if (deferred) {   // the species the deferred MCC reads or appends to wait for it
@@ -845,8 +878,8 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
           deferred = nullptr;
         }
       }
-      CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
       if (tile_dir) {
+        CU_TRY(cudaMemsetAsync(s->d_ufix, 0, nn * sizeof(long long), c->stream));
         ISKB_TRY(launch_advance_tile(s, dt, c->after_push[0], c->after_push[1], move[k]));
         ISKB_TRY(tile_stats_snapshot(c, s));
         s->steps_since_move++;
@@ -868,20 +901,27 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
         }
       } else if (c->tracker && !legacy) {
         // config.tracker != nothing: track! -> gather -> push -> check! -> after_push  (:56-61), one pass
+        CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
         ISKB_TRY(launch_advance_tracked(s, dt, c->after_push[0], c->after_push[1], true));
       } else if (legacy) {
+        CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
         if (c->tracker) ISKB_TRY(launch_advance_tiled_tracked(s, dt, c->after_push[0], c->after_push[1]));
         else ISKB_TRY(launch_advance_tiled(s, dt, c->after_push[0], c->after_push[1]));
         ISKB_TRY(post_advance_stats(c, s));
         s->steps_since_sort++;
         s->steps_since_full++;
       } else {
+        CU_TRY(cudaMemsetAsync(s->d_u, 0, nn * sizeof(double), c->stream));
         ISKB_TRY(launch_advance_simple(s, dt, c->after_push[0], c->after_push[1], true, false));
       }
     }
     if (deferred) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_m1, 0));
-    ISKB_TRY(launch_rho_finalize(c, &species));                            // :118-124
-    if (c->n_ranks > 1) ISKB_TRY(comm_allreduce_sum(c, c->d_rho, nn));
+    if (tile_dir) {
+      ISKB_TRY(launch_rho_finalize_fixed(c, species));                     // :118-124, integer all-reduce inside
+    } else {
+      ISKB_TRY(launch_rho_finalize(c, &species));                          // :118-124
+      if (c->n_ranks > 1) ISKB_TRY(comm_allreduce_sum(c, c->d_rho, nn));
+    }
     ISKB_TRY(poisson_solve(c));                                            // :126-128
     c->step_count++;
   }

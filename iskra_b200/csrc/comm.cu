@@ -80,6 +80,13 @@ int32_t comm_allreduce_sum(iskb_ctx *c, double *d_buf, int64_t n) {
   return rc ? nccl_fail(rc, "ncclAllReduce") : ISKB_OK;
 }
 
+int32_t comm_allreduce_sum_i64(iskb_ctx *c, long long *d_buf, int64_t n) {
+  if (c->n_ranks == 1) return ISKB_OK;
+  if (!c->nccl_comm) return iskb_fail(ISKB_E_NCCL, "iskb_comm_init was not called");
+  const int rc = g_nccl.allreduce(d_buf, d_buf, (size_t)n, /*ncclInt64*/ 4, /*ncclSum*/ 0, c->nccl_comm, c->stream);
+  return rc ? nccl_fail(rc, "ncclAllReduce") : ISKB_OK;
+}
+
 int32_t comm_destroy(iskb_ctx *c) {
   if (c->nccl_comm && g_nccl.destroy) g_nccl.destroy(c->nccl_comm);
   c->nccl_comm = nullptr;

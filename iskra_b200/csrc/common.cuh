@@ -152,6 +152,9 @@ struct iskb_ctx {
   // small grids (<= PRIV_MAX_NODES): the simple advance deposits into PRIV_COPIES private copies of u (block b uses
   // copy b % PRIV_COPIES) that are summed afterwards -- divides the same-address atomic pressure by PRIV_COPIES
   double *d_upriv = nullptr;
+  double fscale = 0.0;               // fixed-point unit of the tile path's deposit: value * fscale is accumulated as int64
+  double q0 = 0.0;                   // base charge: every active species carries an integer multiple of it (else 0)
+  long long *d_rho_int = nullptr;    // sum_s Z_s * ufix_s, the quantity that is all-reduced
   bool lean_ok = true;               // iskb_set_lean(ctx, 0) forces the full 88 B/row kernels (A/B measurements)
   int adv_path = 0;                  // 0: tile directory (advance_tile.cu), 1: per-warp windows (advance_fused.cu)
   int pusher_rz = 0;                 // BorisPusher{:rz}: transform_from_cartesian_to_cylindrical! after the push
@@ -218,6 +221,8 @@ struct iskb_species {
   int64_t steps_since_move = 0;
   int64_t moves = 0, full_sorts = 0;        // statistics (iskb_species_sort_stats)
   double tail_frac = 0.0, dead_frac = 0.0;  // from the last snapshot
+  long long *d_ufix = nullptr;              // deposited weights of the tile path in fixed point (nx*ny)
+  double wmax = 0.0;                        // largest weight any slot may carry (w0 unless an upload says otherwise)
   unsigned *d_ticket = nullptr;             // chunk dispenser of the advance grid
   unsigned long long *d_vz2max = nullptr;   // bits of a bound of v_z^2 (the lean advance does not touch the column)
   bool vz2_known = false;
@@ -323,6 +328,8 @@ int32_t comm_destroy(iskb_ctx *ctx);
 int32_t launch_advance(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit,
                        int64_t first_slot_from_cnt_begin);
 int32_t launch_rho_finalize(iskb_ctx *ctx, const std::vector<iskb_species *> *list = nullptr);
+int32_t launch_rho_finalize_fixed(iskb_ctx *ctx, const std::vector<iskb_species *> &list);
+int32_t comm_allreduce_sum_i64(iskb_ctx *ctx, long long *d_buf, int64_t n);
 int32_t sp_vmax_unknown(iskb_species *sp);
 int32_t sp_vmax_reset(iskb_species *sp);
 int32_t dsmc_launch(iskb_dsmc *d, double dt, bool want_nu);

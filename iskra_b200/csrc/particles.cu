@@ -199,6 +199,33 @@ __global__ void k_rho_finalize(RhoFin f, const double *__restrict__ V, double *r
   }
 }
 
+// The same from the fixed-point deposits of the tile path (advance_tile.cu, add_fixed): n_s = (ufix_s / fscale) ./ V and
+// rho from the INTEGER combination sum_s Z_s * ufix_s (Z_s = q_s / q0): that sum is what ranks all-reduce, so rho is
+// bit-identical for every number of GPUs and from run to run.
+struct RhoFix {
+  const long long *u[8];
+  double *n[8];
+  long long z[8];
+  int ns;
+};
+__global__ void k_rho_fixed_local(RhoFix f, const double *__restrict__ V, double inv_scale, long long *rho_int, int64_t nn) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nn; k += (int64_t)gridDim.x * blockDim.x) {
+    const double v = V[k];
+    long long r = 0;
+    for (int s = 0; s < f.ns; ++s) {
+      const long long u = f.u[s][k];
+      f.n[s][k] = __ddiv_rn(__dmul_rn((double)u, inv_scale), v);
+      r += f.z[s] * u;
+    }
+    rho_int[k] = r;
+  }
+}
+__global__ void k_rho_fixed_final(const long long *__restrict__ rho_int, const double *__restrict__ V, double q0_over_scale,
+                                  double *rho, int64_t nn) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nn; k += (int64_t)gridDim.x * blockDim.x)
+    rho[k] = __ddiv_rn(__dmul_rn((double)rho_int[k], q0_over_scale), V[k]);
+}
+
 // simple one-thread-per-particle advance! (gather + push + after_push [+ atomic deposit]);
 // the reference-order building block behind iskb_step when the tiled kernel is not applicable.
 __global__ void k_advance_simple(double *x, double *y, double *vx, double *vy, double *vz,
@@ -478,6 +505,28 @@ int32_t launch_rho_finalize(iskb_ctx *c, const std::vector<iskb_species *> *list
   int blocks = (int)((nn + TPB - 1) / TPB);
   if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
   k_rho_finalize<<<blocks, TPB, 0, c->stream>>>(f, c->d_V, c->d_rho, nn);
+  LAUNCH_CHECK(c);
+  return ISKB_OK;
+}
+
+int32_t launch_rho_finalize_fixed(iskb_ctx *c, const std::vector<iskb_species *> &sp) {
+  ISKB_TRY(fields_join(c));
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  if (sp.size() > 8) return iskb_fail(ISKB_E_UNSUPPORTED, "more than 8 kinetic species");
+  if (!c->d_rho_int) CU_TRY(cudaMalloc(&c->d_rho_int, nn * sizeof(long long)));
+  RhoFix f;
+  f.ns = (int)sp.size();
+  for (int s = 0; s < f.ns; ++s) {
+    f.u[s] = sp[s]->d_ufix;
+    f.n[s] = sp[s]->d_n;
+    f.z[s] = (long long)llround(sp[s]->q / c->q0);
+  }
+  int blocks = (int)((nn + TPB - 1) / TPB);
+  if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
+  k_rho_fixed_local<<<blocks, TPB, 0, c->stream>>>(f, c->d_V, 1.0 / c->fscale, c->d_rho_int, nn);
+  LAUNCH_CHECK(c);
+  if (c->n_ranks > 1) ISKB_TRY(comm_allreduce_sum_i64(c, c->d_rho_int, nn));
+  k_rho_fixed_final<<<blocks, TPB, 0, c->stream>>>(c->d_rho_int, c->d_V, c->q0 / c->fscale, c->d_rho, nn);
   LAUNCH_CHECK(c);
   return ISKB_OK;
 }

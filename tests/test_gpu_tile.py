@@ -101,6 +101,44 @@ def test_tile_advance_with_regroup_bitexact(ib, interval, bmode, vcells, uniform
     assert st[0] >= 1 and st[1] >= 12 // interval - 1      # one full sort, then re-grouping launches only
 
 
+@pytest.mark.parametrize("n_nodes,bmode,uniform", [(2049, (2, 1), True), (1025, (1, 1), False)])
+def test_tile_advance_on_the_benchmark_grids(ib, n_nodes, bmode, uniform):
+    """The benchmarked configuration itself (VERDICT r1 "parity on the benchmarked configuration"): 2049^2 nodes (C5: meta-tile
+    key order beyond one 16x16 block of tiles, discard x / wrap y, lean kernels) and 1025^2 (C4: wrap both), 4e6 rows,
+    20 steps with re-groups every 4, electrons at the C5 thermal speed; state bit-exact, rho of the last step 1e-10."""
+    PIC = ib.particle_in_cell
+    nx = ny = n_nodes
+    dx, dt = 6.7 * 0.01 / 128, 1 / (400 * 13.56e6)
+    n, cap = 4_000_000, 4_000_128
+    vth = O.thermal_speed(30000.0, O.me)
+    g, cg, pc, pg, cfg = _setup(ib, nx, ny, dx, n, cap, seed=n_nodes, vscale=vth, uniform=uniform)
+    nn = nx * ny
+    rng = np.random.default_rng(7)
+    E = np.zeros(3 * nn)
+    E[: 2 * nn] = rng.standard_normal(2 * nn) * 2e3
+    E3 = E.reshape(3, ny, nx).transpose(2, 1, 0)
+    rt = g._rt
+    pg._push(g)
+    rt.set_after_push(*bmode)
+    rt.set_sort_interval(4)
+    V = np.zeros(nn)
+    CO.lib().orc_cell_volume(C.byref(cg), CO.dp(V))
+    for step in range(20):
+        rt.set_fields(E=E3)
+        rt.step(dt, 1)
+        CO.lib().orc_advance(pc.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), (C.c_int32 * 2)(*bmode))
+    dens = np.zeros(nn)
+    CO.lib().orc_density(C.byref(cg), pc.ref(), CO.dp(V), CO.dp(dens))
+    rho_g = rt.fields(phi=False, E=False)[0]
+    assert np.abs(rho_g.ravel(order="F") - pc.c.q * dens).max() <= 1e-10 * np.abs(pc.c.q * dens).max()
+    rt.synchronize()
+    pg._touched_on_device()
+    _check_state(pc, pg, cap)
+    st = (C.c_int64 * 8)()
+    ib._lib.check(rt.lib.iskb_species_sort_stats(pg._h, st))
+    assert st[1] >= 4
+
+
 def test_tile_rho_of_the_fused_step_matches_oracle(ib):
     """rho left by iskb_step (deposit inside the tiled kernel + list kernel) against orc_density after the same steps."""
     nx, ny, dx, dt = 129, 129, 1e-3, 1e-9
