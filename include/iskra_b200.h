@@ -193,6 +193,17 @@ int32_t iskb_rho_accumulate(iskb_ctx *ctx, iskb_species *sp);
 /* sum of rho over ranks (no-op for one rank) */
 int32_t iskb_rho_allreduce(iskb_ctx *ctx);
 
+/* ---- secondary-electron emission at a wall: emit!(primary, secondary, grid, material; boundary, gamma_t, gamma_e, gamma_i)
+ * Chemistry/src/see.jl:114-181.  boundary = ISKB_EDGE_LEFT / RIGHT / BOTTOM / TOP (:all has a zero wall normal in the
+ * reference, see.jl:94, and yields NaN secondaries there: rejected).  The emission coefficients are the reference's own
+ * closures with their parameters by value: coef[12] = { vaughan(w0, w0max, gamma0max, ks) (:17-26), elastic(we, wemax,
+ * gamma_e_max, Delta_e, r_e) (:29-42; gamma_e_max < 0: gamma_e = gamma_0 == 0), inelastic(r_i) (:45-49; r_i < 0: gamma_0),
+ * secondary(r_e, r_i) (:52-56) }.  Rows beyond the wall are reflected (elastic / inelastic), emit true secondaries into
+ * `secondary` (energy ~ LogNormal(1.65, 1.1) eV, cosine law about the inward normal) or are absorbed (removed).
+ * counts_out[4] (nullable) = elastic, inelastic, injected secondaries, absorbed. */
+int32_t iskb_see_emit(iskb_species *primary, iskb_species *secondary, int32_t boundary, const double *coef,
+                      uint64_t seed, int64_t *counts_out);
+
 /* ---- fused fast path: the loop body of ParticleInCell.solve  ParticleInCell.jl:102-135 ---- */
 /* after_push hook (ParticleInCell.jl:41; problem scripts override it), applied to every species */
 int32_t iskb_set_after_push(iskb_ctx *ctx, int32_t mode_x, int32_t mode_y);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "iskb_set_sort_policy": [vp, f64, i32],
     "iskb_set_sort_full_interval": [vp, i32],
     "iskb_set_advance_path": [vp, i32],
+    "iskb_see_emit": [vp, vp, i32, vp, u64, vp],
     "iskb_set_lean": [vp, i32],
     "iskb_step_set_active": [vp, vp, i32, vp, i32],
     "iskb_ctx_counts": [vp, vp, vp, vp],

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libiskra_b200.so")
-SOURCES = ["api.cu", "particles.cu", "advance_fused.cu", "advance_tile.cu", "sort.cu", "poisson.cu", "mcc.cu", "comm.cu", "surfaces.cu", "dsmc.cu"]
+SOURCES = ["api.cu", "particles.cu", "advance_fused.cu", "advance_tile.cu", "sort.cu", "poisson.cu", "mcc.cu", "see.cu", "comm.cu", "surfaces.cu", "dsmc.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

@@ -258,3 +258,72 @@ def dsmc(reaction_list, seed=0):
             raise NotImplementedError("DSMC.IonizationCollision has no perform! method in the reference (dsmc.jl:8-13)")
         collisions.append(DSMC.ElasticCollision(r.rate, source, target))
     return DirectSimulationMonteCarlo(collisions, seed=seed)
+
+
+# ---- secondary-electron emission at a wall (Chemistry/src/see.jl) ------------------------------------
+class Vaughan:
+    """vaughan(; w0, w0max, gamma0max, ks)  see.jl:17-26 -- the coefficient closure, as its parameters"""
+
+    def __init__(self, w0, w0max, g0max, ks=0.0):
+        self.w0, self.w0max, self.g0max, self.ks = float(w0), float(w0max), float(g0max), float(ks)
+
+
+class Elastic:
+    """elastic(gv, we, wemax, gamma_e_max; De = 13, re = 0.03)  see.jl:29-42"""
+
+    def __init__(self, gv, we, wemax, gemax, De=13.0, re=0.03):
+        self.gv, self.we, self.wemax, self.gemax, self.De, self.re = gv, float(we), float(wemax), float(gemax), float(De), float(re)
+
+
+class Inelastic:
+    """inelastic(gv; ri = 0.07)  see.jl:45-49"""
+
+    def __init__(self, gv, ri=0.07):
+        self.gv, self.ri = gv, float(ri)
+
+
+class Secondary:
+    """secondary(gv; re, ri)  see.jl:52-56"""
+
+    def __init__(self, gv, re, ri):
+        self.gv, self.re, self.ri = gv, float(re), float(ri)
+
+
+# the reference's module-level defaults, see.jl:60-63
+gamma_v = Vaughan(13.0, 500.0, 3.0, 1.0)
+gamma_e = Elastic(gamma_v, 2.0, 10.0, 0.55, re=0.03)
+gamma_i = Inelastic(gamma_v, ri=0.07)
+gamma_t = Secondary(gamma_v, re=0.03, ri=0.07)
+gamma_0 = None                                    # see.jl:103  (w, theta) -> 0
+
+_SEE_EDGE = {"left": L.EDGE_LEFT, "right": L.EDGE_RIGHT, "bottom": L.EDGE_BOTTOM, "top": L.EDGE_TOP}
+_see_calls = [0]
+
+
+def emit_(primary, secondary, grid, material=None, boundary="all", gamma_t=None, gamma_e=None, gamma_i=None, seed=None):
+    """emit!(primary, secondary, grid, material; boundary, gamma_t, gamma_e, gamma_i)  see.jl:114-181 on the device.
+    The coefficient arguments are the parameter holders above (arbitrary closures cannot cross the C ABI); all of them must
+    share one Vaughan curve, as the reference's defaults do.  Returns {"elastic", "inelastic", "secondaries", "absorbed"}."""
+    if boundary not in _SEE_EDGE:
+        raise NotImplementedError("emit! with boundary = %r: the reference's wall normal is the zero vector there (see.jl:94) "
+                                  "and its secondaries are NaN" % (boundary,))
+    if not isinstance(gamma_t, Secondary):
+        raise TypeError("gamma_t must be a chemistry.Secondary (the reference's secondary(gv; re, ri) closure)")
+    gv = gamma_t.gv
+    for g in (gamma_e, gamma_i):
+        if g is not None and g.gv is not gv:
+            raise NotImplementedError("all emission coefficients must be built on the same Vaughan curve")
+    coef = np.array([gv.w0, gv.w0max, gv.g0max, gv.ks,
+                     gamma_e.we if gamma_e else 0.0, gamma_e.wemax if gamma_e else 1.0, gamma_e.gemax if gamma_e else -1.0,
+                     gamma_e.De if gamma_e else 1.0, gamma_e.re if gamma_e else 0.0,
+                     gamma_i.ri if gamma_i else -1.0, gamma_t.re, gamma_t.ri], dtype=np.float64)
+    primary._push(grid)
+    secondary._push(grid)
+    if seed is None:
+        _see_calls[0] += 1
+        seed = 0x5EE0000 + _see_calls[0]
+    out = np.zeros(4, dtype=np.int64)
+    L.check(primary._rt.lib.iskb_see_emit(primary._h, secondary._h, _SEE_EDGE[boundary], L.ptr(coef), int(seed), L.ptr(out)))
+    primary._touched_on_device()
+    secondary._touched_on_device()
+    return dict(zip(("elastic", "inelastic", "secondaries", "absorbed"), (int(v) for v in out)))

@@ -184,7 +184,7 @@ extern "C" int32_t iskb_destroy(iskb_ctx *c) {
   for (iskb_dsmc *d : c->dsmcs) dsmc_free(d);
   tracker_free(c->tracker);
   poisson_free(c);
-  cudaFree(c->d_rho_int);
+  cudaFree(c->d_rho_int); cudaFree(c->d_see_counts);
   cudaFree(c->d_upriv); cudaFree(c->d_V); cudaFree(c->d_rho); cudaFree(c->d_phi); cudaFree(c->d_E2); cudaFree(c->d_status);
   cudaFreeHost(c->h_status); cudaFreeHost(c->h_scratch);
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);

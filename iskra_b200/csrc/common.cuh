@@ -154,6 +154,7 @@ struct iskb_ctx {
   double *d_upriv = nullptr;
   double fscale = 0.0;               // fixed-point unit of the tile path's deposit: value * fscale is accumulated as int64
   double q0 = 0.0;                   // base charge: every active species carries an integer multiple of it (else 0)
+  unsigned long long *d_see_counts = nullptr;   // emit! bookkeeping (see.cu)
   long long *d_rho_int = nullptr;    // sum_s Z_s * ufix_s, the quantity that is all-reduced
   bool lean_ok = true;               // iskb_set_lean(ctx, 0) forces the full 88 B/row kernels (A/B measurements)
   int adv_path = 0;                  // 0: tile directory (advance_tile.cu), 1: per-warp windows (advance_fused.cu)
@@ -193,7 +194,7 @@ struct iskb_species {
   uint32_t *d_key[2] = {nullptr, nullptr}, *d_idx[2] = {nullptr, nullptr};
   uint32_t *d_hist = nullptr;
   int64_t hist_cap = 0;
-  uint64_t sample_calls = 0;
+  uint64_t sample_calls = 0, see_calls = 0;
   // adaptive re-sort bookkeeping (iskb_step)
   int64_t steps_since_sort = 1 << 30;   // never sorted yet
   int64_t steps_since_full = 1 << 30;   // steps since the last FULL (cell + interleave) sort

@@ -369,6 +369,23 @@ function solve(ctx :: Context, species :: Vector{B200Species}, Δt, timesteps; i
   ParticleInCell.exit_loop()
 end
 
+# ---- secondary-electron emission at a wall: Chemistry.emit! (see.jl:114-181) for device-backed species.  The coefficient
+# closures of see.jl cannot cross the C ABI; their parameters do (the module defaults of see.jl:60-63 shown here).
+const SEE_EDGE = Dict(:left => 0, :right => 1, :bottom => 2, :top => 3)
+function Chemistry.emit!(primary :: B200Species, secondary :: B200Species, grid, material :: Symbol; boundary = :all,
+                         vaughan = (13., 500., 3., 1.), elastic = (2., 10., 0.55, 13., 0.03), inelastic = 0.07,
+                         secondary_r = (0.03, 0.07), seed = UInt64(1))
+  haskey(SEE_EDGE, boundary) || error("emit! with boundary = :all: the wall normal is the zero vector (see.jl:94)")
+  upload!(primary); upload!(secondary)
+  coef = Float64[vaughan..., elastic..., inelastic, secondary_r...]
+  counts = zeros(Int64, 4)
+  GC.@preserve coef counts check(ccall((:iskb_see_emit, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}, UInt64, Ptr{Int64}),
+                                       primary.h, secondary.h, Int32(SEE_EDGE[boundary]), coef, seed, counts))
+  primary.device_newer = true
+  secondary.device_newer = true
+  (elastic = counts[1], inelastic = counts[2], secondaries = counts[3], absorbed = counts[4])
+end
+
 # bookkeeping of the row order (new relative to the reference; diagnostics only)
 function sort_stats(sp :: B200Species)
   out = zeros(Int64, 8)
