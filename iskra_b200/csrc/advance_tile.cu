@@ -58,25 +58,38 @@ struct TileArgs {
   const unsigned long long *vz2max;   // LEAN: bits of the kept bound of v_z^2
   unsigned *ticket;         // chunk dispenser
   unsigned nchunks;
+  // MOVE with tail merge: destination and key (tile, ntiles = stays in the tail, ntiles + 1 = dead) of tail row ns + k
+  const uint32_t *taildst, *tailkey, *tstart, *tailbase, *tn;
   uint2 *mlist;             // rows left to k_advance_list: (source row, destination row)
   unsigned *mlist_n;
   unsigned mlist_cap;
 };
 
-constexpr int MQ_FLUSH = 16, MQ_CAP = MQ_FLUSH + 31 + 1;   // staged miss-list entries: flushed 16 or more at a time
+// staged miss-list entries: flushed MQ_FLUSH or more at a time.  In place the destination of a row is the row itself: one
+// word per entry.
+template <bool MOVE> struct Mq { static constexpr int FLUSH = 16, CAP = FLUSH + 31 + 1; typedef uint2 T; };
+template <> struct Mq<false> { static constexpr int FLUSH = 8, CAP = FLUSH + 31 + 1; typedef unsigned T; };
+__device__ __forceinline__ void mq_put(uint2 &e, unsigned row, unsigned dest) { e = make_uint2(row, dest); }
+__device__ __forceinline__ void mq_put(unsigned &e, unsigned row, unsigned) { e = row; }
+__device__ __forceinline__ uint2 mq_get(const uint2 &e) { return e; }
+__device__ __forceinline__ uint2 mq_get(const unsigned &e) { return make_uint2(e, e); }
+constexpr int NTC_INPLACE = 12;   // codes 0 .. CODE_DEAD
 template <bool MOVE>
 struct WarpSm {
   double2 E[WE * WE];
   double rho[WE * WRS];
-  unsigned char claim[WE * WE];
+  unsigned char claim[(WE - 1) * WE];   // cells: rows 0 .. WE-2
   // [code of the tile the row is stored in after the launch][code of its new position]; in-place launches: row CODE_STAY only
-  unsigned tc[(MOVE ? 9 : 1) * NCODE];
+  unsigned tc[MOVE ? 9 * NCODE : NTC_INPLACE];
   unsigned mv[MOVE ? NCODE : 1];   // MOVE: next destination row per code of the current tile
   unsigned stats[4];      // window misses, deposits outside the window, tiles, discards
   unsigned misc[8];       // first tile of the next chunk, last readable row, tile coordinates of the current tile, staged misses
-  uint2 mq[MQ_CAP];
-};   // 6.7 KB (in place: 4 CTAs of 8 warps per SM) / 7.3 KB (MOVE: 3 CTAs)
+  typename Mq<MOVE>::T mq[Mq<MOVE>::CAP];
+};   // 7.0 KB in place / 8.0 KB MOVE: three CTAs of 8 warps per SM either way
+static_assert(sizeof(WarpSm<true>) * 8 + 1024 <= 233472 / 3, "three CTAs per SM");
+static_assert(CODE_DEAD < NTC_INPLACE, "in-place counters");
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -150,13 +163,13 @@ __device__ __forceinline__ bool push_and_bound(double &px, double &py, double &v
 // BASELINE config: configuration.jl:99 `ones(N) * weight`) needs no wg column traffic either.  72 -> 64 B per row
 // instead of 88; positions, velocities and rho are bit-identical to the full path (tests/test_gpu_tile.py).
 template <int MX, int MY, bool MOVE, bool RZ, bool LEAN>
-__global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(const TileArgs a) {
+__global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
   extern __shared__ double2 s_dyn[];
   const int lane = threadIdx.x & 31;
   WarpSm<MOVE> &sm = ((WarpSm<MOVE> *)s_dyn)[threadIdx.x >> 5];
   constexpr int TCS = MOVE ? CODE_STAY * NCODE : 0;   // counters of the rows that are stored in this tile after the launch
   for (int e = lane; e < WE * WRS; e += 32) sm.rho[e] = 0.0;
-  for (int e = lane; e < (MOVE ? 9 : 1) * NCODE; e += 32) sm.tc[e] = 0;
+  for (int e = lane; e < (MOVE ? 9 * NCODE : NTC_INPLACE); e += 32) sm.tc[e] = 0;
   if (MOVE && lane < NCODE) sm.mv[lane] = 0;
   if (lane < 4) sm.stats[lane] = 0;
   // The loop-carried state is kept small (tile, its row range, the batch, the window origin, a float velocity
@@ -215,6 +228,17 @@ __global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(c
       if (!LEAN || MOVE) nvz_ = a.col[4][rn];
       if (!LEAN) nwq_ = a.col[5][rn];
       if (MOVE) { nid_ = a.id[rn]; ncode_ = a.code[rn]; }
+      {
+        // pull the rows three batches further into L2: one batch of register prefetch does not always cover DRAM under
+        // the mixed read / write traffic (-0.03 ms per step at the C5 shard).  Tiles are stored back to back, so "the
+        // rows after these" is right except at the end of the warp's chunk.
+        const unsigned rp = min(rn + 96u, sm.misc[1]);
+        prefetch_l2(&a.col[0][rp]); prefetch_l2(&a.col[1][rp]); prefetch_l2(&a.col[2][rp]); prefetch_l2(&a.col[3][rp]);
+        if (!LEAN || MOVE) prefetch_l2(&a.col[4][rp]);
+        if (!LEAN) prefetch_l2(&a.col[5][rp]);
+        if (MOVE && (lane & 1) == 0) prefetch_l2(&a.id[rp]);
+        if (MOVE && (lane & 7) == 0) prefetch_l2(&a.code[rp]);
+      }
 
       if (ei0 == NOT_ANCHORED) {   // first batch of a tile: anchor the windows on it
         int stx, sty;
@@ -340,15 +364,15 @@ __global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(c
         const unsigned mm = __ballot_sync(0xffffffffu, miss);
         if (mm) {
           unsigned q = sm.misc[4];
-          if (miss) sm.mq[q + __popc(mm & lanemask_lt())] = make_uint2(row, dest);
+          if (miss) mq_put(sm.mq[q + __popc(mm & lanemask_lt())], row, dest);
           q += __popc(mm);
           __syncwarp();
-          if (q >= MQ_FLUSH) {
+          if (q >= (unsigned)Mq<MOVE>::FLUSH) {
             unsigned b = 0;
             if (lane == 0) b = atomicAdd(a.mlist_n, q);
             b = __shfl_sync(0xffffffffu, b, 0);
             for (unsigned e = lane; e < q; e += 32) {
-              if (b + e < a.mlist_cap) a.mlist[b + e] = sm.mq[e];
+              if (b + e < a.mlist_cap) a.mlist[b + e] = mq_get(sm.mq[e]);
               else atomicOr(a.status, ISKB_ST_CAPACITY);
             }
             q = 0;
@@ -369,7 +393,10 @@ __global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(c
         if (lane == 0 && ms) sm.tc[TCS + CODE_STAY] += __popc(ms);
         if (counted && !common) atomicAdd(&sm.tc[(MOVE ? scode * NCODE : 0u) + ncode], 1u);
       }
-      // ---- deposit rounds without atomics (advance_fused.cu) ----
+      // ---- deposit rounds without atomics (advance_fused.cu).  The claim is per cell, so the winners' four corner
+      // updates hit distinct nodes in every phase.  Measured alternatives (B200, C5 shard, ms per step): one claim round
+      // followed by atomicAdd(double) on shared memory -- a compare-and-swap loop on sm_100a -- for the losers +0.11;
+      // match.any to merge equal cells in registers first costs ~2 cycles per distinct value (profiles/r1_microbench). ----
       {
         unsigned pend = __ballot_sync(0xffffffffu, dep_win);
         double *r0p = sm.rho + ci + (WRS - WE) * (ci >> 4);
@@ -397,8 +424,8 @@ __global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(c
       if (rb + 32 >= r1) {   // tile finished: flush its window, publish its counts, go to the next non-empty tile
         flush_rho(sm.rho, ei0, ej0, a.g.nx, a.ufix, a.fscale, lane);
         ei0 = NOT_ANCHORED;
-        for (int e = lane; e < (MOVE ? 9 : 1) * NCODE; e += 32) {
-          const int sc = MOVE ? e / NCODE : CODE_STAY, nc = e % NCODE;
+        for (int e = lane; e < (MOVE ? 9 * NCODE : NTC_INPLACE); e += 32) {
+          const int sc = MOVE ? e / NCODE : CODE_STAY, nc = MOVE ? e % NCODE : e;
           const unsigned c = sm.tc[e];
           if (c) {
             const int dtx = (int)sm.misc[2] + sc % 3 - 1, dty = (int)sm.misc[3] + sc / 3 - 1;
@@ -428,7 +455,7 @@ __global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(c
       if (lane == 0) b = atomicAdd(a.mlist_n, q);
       b = __shfl_sync(0xffffffffu, b, 0);
       if (lane < (int)q) {
-        if (b + lane < a.mlist_cap) a.mlist[b + lane] = sm.mq[lane];
+        if (b + lane < a.mlist_cap) a.mlist[b + lane] = mq_get(sm.mq[lane]);
         else atomicOr(a.status, ISKB_ST_CAPACITY);
       }
     }
@@ -451,14 +478,16 @@ __global__ void __launch_bounds__(256, (LEAN && !MOVE) ? 4 : 3) k_advance_tile(c
 
 // Rows the tiled kernel left out -- its miss list and the unsorted tail [ns, n) -- advanced one per thread straight
 // from / to global memory: same arithmetic, E gathered from the global field, deposit with global REDs.
-// MOVE: miss rows go where the tiled kernel said; tail row ns + k goes to seg[2*ntiles] + k.
+// MOVE: miss rows go where the tiled kernel said; tail row ns + k goes where the tail merge put it (k_tail_dest): into
+// the segment of the tile it is in, behind the tile's other arrivals -- the tail never needs a full sort to empty.
 template <int MX, int MY, bool MOVE, bool RZ, bool LEAN>
 __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned nm = min(*a.mlist_n, a.mlist_cap);
   const unsigned n = (unsigned)a.cnt[CNT_NSLOTS], ns = a.ts[a.ntiles];
   const unsigned ntail = n > ns ? n - ns : 0u;
-  const unsigned tail_dst = MOVE ? a.seg[2 * a.ntiles] : ns;
+  const unsigned tmerged = MOVE ? *a.tn : 0u;   // tail rows that took part in the merge (the first tmerged ones)
+  const unsigned tkeep = MOVE ? a.tailbase[a.ntiles] + (a.tstart[a.ntiles + 1] - a.tstart[a.ntiles]) : 0u;
   const unsigned total = nm + ntail;
   const unsigned total_pad = (total + 31u) & ~31u;
   double vm2 = 0.0;
@@ -466,9 +495,16 @@ __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
   for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total_pad; k += gridDim.x * blockDim.x) {
     bool dead_now = false;
     if (k < total) {
-      unsigned src, dst;
+      unsigned src, dst, key = 0xffffffffu;   // key < ntiles: the row joins that tile (MOVE)
       if (k < nm) { const uint2 e = a.mlist[k]; src = e.x; dst = e.y; }
-      else { src = ns + (k - nm); dst = tail_dst + (k - nm); }
+      else {
+        const unsigned kt = k - nm;
+        src = ns + kt;
+        if (!MOVE) dst = src;
+        else if (MOVE && kt < tmerged) { dst = a.taildst[kt]; key = a.tailkey[kt]; }
+        else dst = tkeep + (kt - tmerged);
+      }
+      unsigned ncode = CODE_FAR;
       double px = a.col[0][src];
       if (is_dead(px)) {
         if (MOVE) {
@@ -492,6 +528,7 @@ __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
         if (dead) {
           OUTC(0)[dst] = __longlong_as_double(0x7ff8000000000000LL);
           dead_now = true;
+          ncode = CODE_DEAD;
         } else {
           OUTC(0)[dst] = px;
           int i, j;
@@ -499,6 +536,11 @@ __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
           cell1(px, a.g.dx, a.g.rdx, a.g.fast_div, i, hx);
           cell1(py, a.g.dy, a.g.rdy, a.g.fast_div, j, hy);
           if (cell_in_grid(i, j, a.g.nx, a.g.ny)) {
+            if (MOVE && key < a.ntiles) {
+              int stx, sty;
+              tile_coords(key, a.mtx, stx, sty);
+              ncode = rel_code((i - 1) >> 3, (j - 1) >> 3, stx, sty);
+            }
             const CicW cw = cic_weights(hx, hy);
             const int64_t n00 = (int64_t)(i - 1) + (int64_t)(j - 1) * a.g.nx;
             add_fixed(a.ufix, n00, __dmul_rn(cw.w00, wq), a.fscale);
@@ -508,6 +550,10 @@ __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
           } else {
             atomicOr(a.status, ISKB_ST_OOB);
           }
+        }
+        if (MOVE && key < a.ntiles) {   // MARK of a row that has just joined a tile
+          a.ocode[dst] = (uint8_t)ncode;
+          atomicAdd(&a.tcnt[key * NCODE + ncode], 1u);
         }
       }
     }
@@ -573,10 +619,12 @@ __global__ void k_warp_ranges(const uint32_t *__restrict__ ts, uint32_t ntiles, 
 }
 
 // ---- incremental re-group: destinations from the counts of the previous launch --------------------
-// seg = [ rows per destination tile (ntiles) | FAR rows per source tile (ntiles) | tail length (1) |
-//         DEAD rows per source tile (ntiles) | 0 ] ; its exclusive scan gives every base of the new layout.
+// seg = [ rows per destination tile (ntiles) | FAR rows per source tile (ntiles) | rows that stay in the tail (1) |
+//         DEAD rows per source tile (ntiles) | dead rows of the tail (1) | 0 ] ; its exclusive scan gives every base of the
+// new layout.  tstart[key] = first sorted tail row with that key (k_tail_starts): the tail rows join their tiles.
 __global__ void k_regroup_seg(const uint32_t *__restrict__ tcnt, const uint32_t *__restrict__ ts, const int64_t *__restrict__ cnt,
-                              uint32_t ntiles, uint32_t mtx, uint32_t tiles_x, uint32_t tiles_y, uint32_t *seg) {
+                              uint32_t ntiles, uint32_t mtx, uint32_t tiles_x, uint32_t tiles_y,
+                              const uint32_t *__restrict__ tstart, const uint32_t *__restrict__ tn, uint32_t *seg) {
   for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < ntiles; d += gridDim.x * blockDim.x) {
     int tx, ty;
     tile_coords(d, mtx, tx, ty);
@@ -589,23 +637,29 @@ __global__ void k_regroup_seg(const uint32_t *__restrict__ tcnt, const uint32_t 
         if ((uint32_t)sx < tiles_x && (uint32_t)sy < tiles_y) tot += tcnt[tile_ordinal((uint32_t)sx, (uint32_t)sy, mtx) * NCODE + c];
       }
     }
-    seg[d] = tot;
+    seg[d] = tot + (tstart[d + 1] - tstart[d]);
     seg[ntiles + d] = tcnt[d * NCODE + CODE_FAR];
     seg[2 * ntiles + 1 + d] = tcnt[d * NCODE + CODE_DEAD];
     if (d == 0) {
       const uint32_t n = (uint32_t)cnt[CNT_NSLOTS], ns = ts[ntiles];
-      seg[2 * ntiles] = n > ns ? n - ns : 0u;
-      seg[3 * ntiles + 1] = 0;
+      const uint32_t ntail = n > ns ? n - ns : 0u;
+      seg[2 * ntiles] = (ntail - *tn) + (tstart[ntiles + 1] - tstart[ntiles]);   // not merged (beyond the scratch) + outside the grid
+      seg[3 * ntiles + 1] = tstart[ntiles + 2] - tstart[ntiles + 1];
+      seg[3 * ntiles + 2] = 0;
     }
   }
 }
 
 // after the scan: tbase[s][c] for every (source tile, code) and the new tile starts
 __global__ void k_regroup_bases(const uint32_t *__restrict__ tcnt, const uint32_t *__restrict__ seg, uint32_t ntiles, uint32_t mtx,
-                                uint32_t tiles_x, uint32_t tiles_y, uint32_t *tbase, uint32_t *ts_new) {
+                                uint32_t tiles_x, uint32_t tiles_y, uint32_t *tbase, uint32_t *ts_new, uint32_t *tailbase) {
   for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d <= ntiles; d += gridDim.x * blockDim.x) {
     ts_new[d] = seg[d];
-    if (d == ntiles) break;
+    if (d == ntiles) {
+      tailbase[ntiles] = seg[2 * ntiles];
+      tailbase[ntiles + 1] = seg[3 * ntiles + 1];
+      break;
+    }
     int tx, ty;
     tile_coords(d, mtx, tx, ty);
     uint32_t run = seg[d];
@@ -624,14 +678,63 @@ __global__ void k_regroup_bases(const uint32_t *__restrict__ tcnt, const uint32_
         }
       }
     }
+    tailbase[d] = run;   // the tail rows that are in this tile come last
     tbase[d * NCODE + CODE_FAR] = seg[ntiles + d];
     tbase[d * NCODE + CODE_DEAD] = seg[2 * ntiles + 1 + d];
   }
 }
 
+// ---- tail merge: the unsorted tail [ns, n) -- rows born since the last re-group (sources, ionisation) and rows that jumped
+// further than a neighbouring tile -- joins the tile segments on every MOVE.  Keys are taken from the CURRENT position (the
+// MOVE places every row by where it is before the push, like the codes of the tile rows), sorted stably (sort.cu), so the
+// new order is a pure function of the old one: no full sort is needed in steady state.
+__global__ void k_tail_keys(const double *__restrict__ x, const double *__restrict__ y, const int64_t *__restrict__ cnt,
+                            const uint32_t *__restrict__ ts, GridDev g, uint32_t ntiles, uint32_t mtx, uint32_t tcap, uint32_t *keys,
+                            uint32_t *tn) {
+  const uint32_t n = (uint32_t)cnt[CNT_NSLOTS], ns = ts[ntiles];
+  const uint32_t ntail = n > ns ? n - ns : 0u, T = min(ntail, tcap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *tn = T;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < T; k += gridDim.x * blockDim.x) {
+    const double px = x[ns + k];
+    uint32_t key = ntiles + 1;   // dead: parked
+    if (!is_dead(px)) {
+      int i, j;
+      double hx, hy;
+      cell1(px, g.dx, g.rdx, g.fast_div, i, hx);
+      cell1(y[ns + k], g.dy, g.rdy, g.fast_div, j, hy);
+      key = cell_in_grid(i, j, g.nx, g.ny) ? tile_ordinal((uint32_t)(i - 1) >> 3, (uint32_t)(j - 1) >> 3, mtx) : ntiles;
+    }
+    keys[k] = key;
+  }
+}
+
+// tstart[v] = first sorted tail row whose key is >= v, v = 0 .. ntiles + 2
+__global__ void k_tail_starts(const uint32_t *__restrict__ sk, const uint32_t *__restrict__ tn, uint32_t ntiles, uint32_t *tstart) {
+  const uint32_t T = *tn;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v <= ntiles + 2; v += gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = T;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (sk[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    tstart[v] = lo;
+  }
+}
+
+__global__ void k_tail_dest(const uint32_t *__restrict__ sk, const uint32_t *__restrict__ si, const uint32_t *__restrict__ tn,
+                            const uint32_t *__restrict__ tstart, const uint32_t *__restrict__ tailbase, uint32_t *taildst,
+                            uint32_t *tailkey) {
+  const uint32_t T = *tn;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < T; j += gridDim.x * blockDim.x) {
+    const uint32_t key = sk[j], k = si[j];
+    taildst[k] = tailbase[key] + (j - tstart[key]);
+    tailkey[k] = key;
+  }
+}
+
 // counters after a MOVE: live slots end where the parked (discarded) rows begin; those rows leave the dead count
 __global__ void k_after_move(int64_t *cnt, const uint32_t *__restrict__ seg, uint32_t ntiles) {
-  const int64_t n_new = seg[2 * ntiles + 1], parked = (int64_t)seg[3 * ntiles + 1] - n_new;
+  const int64_t n_new = seg[2 * ntiles + 1], parked = (int64_t)seg[3 * ntiles + 2] - n_new;
   cnt[CNT_NSLOTS] = n_new;
   cnt[CNT_NDEAD] -= parked;
 }
@@ -658,9 +761,14 @@ __global__ void k_marks_after_sort(const uint32_t *__restrict__ ts, uint32_t nti
 }  // namespace
 
 int32_t exclusive_scan_u32(iskb_ctx *c, uint32_t *d, int64_t n, uint32_t *partial);
+int32_t sort_pairs_device_count(iskb_species *sp, int64_t ncap, const uint32_t *n_dev, int bits, uint32_t **keys_out,
+                                uint32_t **idx_out, uint32_t **spare_key, uint32_t **spare_idx);
+int32_t sort_scratch_ensure(iskb_species *sp);
 int32_t launch_advance_simple(iskb_species *sp, double dt, int mode_x, int mode_y, bool deposit, bool from_begin);
 
-static int advance_grid(const iskb_ctx *c, bool lean_inplace) { return c->n_sm * (lean_inplace ? 4 : 3); }   // persistent CTAs of 8 warps
+// persistent CTAs of 8 warps, three per SM.  Four (64 registers, 7 KB per warp) measured +0.16 ms per step at the C5 shard:
+// the kernel is bound by L1/shared wavefronts, not by latency, and the fourth CTA takes the L1 that is left.
+static int advance_grid(const iskb_ctx *c) { return c->n_sm * 3; }
 static int advance_chunks(const iskb_ctx *c) { return c->n_sm * 3 * 8 * 8; }   // ~8 chunks per resident warp
 
 int32_t tdir_ensure(iskb_species *sp) {
@@ -671,8 +779,11 @@ int32_t tdir_ensure(iskb_species *sp) {
   for (int k = 0; k < 2; ++k) CU_TRY(cudaMalloc(&sp->d_ts[k], (nt + 1) * sizeof(uint32_t)));
   CU_TRY(cudaMalloc(&sp->d_tcnt, nt * NCODE * sizeof(uint32_t)));
   CU_TRY(cudaMalloc(&sp->d_tbase, nt * NCODE * sizeof(uint32_t)));
-  const size_t nseg = 3 * nt + 2;
+  const size_t nseg = 3 * nt + 3;
   CU_TRY(cudaMalloc(&sp->d_seg, (nseg + (nseg + 2047) / 2048 + 16) * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&sp->d_tstart, (nt + 3) * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&sp->d_tailbase, (nt + 2) * sizeof(uint32_t)));
+  CU_TRY(cudaMalloc(&sp->d_tn, sizeof(uint32_t)));
   CU_TRY(cudaMalloc(&sp->d_wr, ((size_t)advance_chunks(c) + 1) * sizeof(uint32_t)));
   CU_TRY(cudaMalloc(&sp->d_ticket, sizeof(unsigned)));
   CU_TRY(cudaMalloc(&sp->d_ufix, (size_t)c->g.nx * c->g.ny * sizeof(long long)));
@@ -699,6 +810,7 @@ void tdir_free(iskb_species *sp) {
   for (int k = 0; k < 2; ++k) cudaFree(sp->d_ts[k]);
   cudaFree(sp->d_tcnt); cudaFree(sp->d_tbase); cudaFree(sp->d_seg); cudaFree(sp->d_wr);
   cudaFree(sp->d_code); cudaFree(sp->alt_code); cudaFree(sp->d_mlist); cudaFree(sp->d_mlist_n); cudaFree(sp->d_ticket); cudaFree(sp->d_ufix);
+  cudaFree(sp->d_tstart); cudaFree(sp->d_tailbase); cudaFree(sp->d_tn);
 }
 
 static int32_t warp_ranges(iskb_species *sp) {
@@ -768,18 +880,37 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
     LAUNCH_CHECK(c);
     sp->vz2_known = true;
   }
-  const int grid = advance_grid(c, LEAN && !move);
+  const int grid = advance_grid(c);
   const int SMEM = 8 * (int)(move ? sizeof(WarpSm<true>) : sizeof(WarpSm<false>));
   if (move) {
     // destinations of this launch from the counts of the previous one
     const int nb = (int)((tg.ntiles + 255) / 256);
-    const int64_t nseg = 3 * (int64_t)tg.ntiles + 2;
-    k_regroup_seg<<<nb, 256, 0, c->stream>>>(sp->d_tcnt, sp->d_ts[0], sp->d_cnt, tg.ntiles, tg.mtx, tg.tiles_x, tg.tiles_y, sp->d_seg);
+    const int64_t nseg = 3 * (int64_t)tg.ntiles + 3;
+    // tail merge: keys of the tail rows, stable sort, rows per tile
+    ISKB_TRY(sort_scratch_ensure(sp));
+    // grid of the merge: the tail of the latest snapshot (two steps old) with room to grow; rows beyond it stay in the
+    // tail for the next MOVE (k_tail_keys clamps), a tail beyond 5 % of the rows gets a full sort instead (api.cu)
+    const int64_t tcap = std::min<int64_t>(sp->cap, 4 * std::max<int64_t>(sp->tail_rows, 0) + 262144);
+    int bits = 1;
+    while ((1ull << bits) <= (uint64_t)tg.ntiles + 1u) ++bits;
+    const int tb = (int)std::min<int64_t>((tcap + 255) / 256, (int64_t)c->n_sm * 8);
+    k_tail_keys<<<tb, 256, 0, c->stream>>>(sp->col[0], sp->col[1], sp->d_cnt, sp->d_ts[0], c->g, tg.ntiles, tg.mtx, (uint32_t)tcap,
+                                           sp->d_key[0], sp->d_tn);
+    LAUNCH_CHECK(c);
+    uint32_t *sk, *si, *spare_key, *spare_idx;
+    ISKB_TRY(sort_pairs_device_count(sp, tcap, sp->d_tn, bits, &sk, &si, &spare_key, &spare_idx));
+    k_tail_starts<<<nb + 1, 256, 0, c->stream>>>(sk, sp->d_tn, tg.ntiles, sp->d_tstart);
+    LAUNCH_CHECK(c);
+    k_regroup_seg<<<nb, 256, 0, c->stream>>>(sp->d_tcnt, sp->d_ts[0], sp->d_cnt, tg.ntiles, tg.mtx, tg.tiles_x, tg.tiles_y,
+                                             sp->d_tstart, sp->d_tn, sp->d_seg);
     LAUNCH_CHECK(c);
     ISKB_TRY(exclusive_scan_u32(c, sp->d_seg, nseg, sp->d_seg + nseg));
     k_regroup_bases<<<nb + 1, 256, 0, c->stream>>>(sp->d_tcnt, sp->d_seg, tg.ntiles, tg.mtx, tg.tiles_x, tg.tiles_y, sp->d_tbase,
-                                                  sp->d_ts[1]);
+                                                  sp->d_ts[1], sp->d_tailbase);
     LAUNCH_CHECK(c);
+    k_tail_dest<<<tb, 256, 0, c->stream>>>(sk, si, sp->d_tn, sp->d_tstart, sp->d_tailbase, spare_idx, spare_key);
+    LAUNCH_CHECK(c);
+    a.taildst = spare_idx; a.tailkey = spare_key; a.tstart = sp->d_tstart; a.tailbase = sp->d_tailbase; a.tn = sp->d_tn;
   }
   CU_TRY(cudaMemsetAsync(sp->d_tcnt, 0, (size_t)tg.ntiles * NCODE * sizeof(uint32_t), c->stream));
   CU_TRY(cudaMemsetAsync(sp->d_mlist_n, 0, sizeof(unsigned), c->stream));

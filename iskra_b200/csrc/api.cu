@@ -663,12 +663,15 @@ static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move) {
         s->miss_rate = (double)d / (double)n;
         if (s->miss_rate > 1e-5) s->drifting = true;
         s->tail_frac = (double)(h[CNT_NSLOTS] - h[9]) / (double)n;
+        s->tail_rows = h[CNT_NSLOTS] - h[9];
         s->dead_frac = (double)h[CNT_NDEAD] / (double)n;
       }
       s->tstats_pending[slot] = false;
     }
   }
-  const bool full = !s->tdir_valid || s->tail_frac > 0.01 ||
+  // the unsorted tail (rows born since the last re-group) joins the tiles on a MOVE; a full sort is for a layout that
+  // has no directory yet (upload, host-side edits) or a tail beyond the merge scratch (cap / 16 rows)
+  const bool full = !s->tdir_valid || s->tail_frac > 0.05 ||
                     (c->sort_full_interval > 0 && s->steps_since_full >= c->sort_full_interval);
   if (full) {
     ISKB_TRY(sp_sort(s, nullptr, true));
@@ -682,13 +685,13 @@ static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move) {
   const int64_t since = s->steps_since_move + 1;
   if (c->sort_miss_threshold > 0.0) {
     // a species whose rows hardly ever leave their windows (ions) is not re-grouped just because time has passed
-    *move = s->miss_rate > c->sort_miss_threshold || s->dead_frac > 0.02 ||
+    *move = s->miss_rate > c->sort_miss_threshold || s->dead_frac > 0.02 || s->tail_frac > 0.01 ||
             (c->sort_max_interval > 0 && since >= c->sort_max_interval && s->drifting);
   } else {
-    *move = since >= c->sort_interval;
+    *move = since >= c->sort_interval || s->tail_frac > 0.01;
   }
   if (*move) {
-    s->miss_rate = s->dead_frac = 0.0;
+    s->miss_rate = s->dead_frac = s->tail_frac = 0.0;
     s->tstats_sort_mark = s->tstats_step;
     s->moves++;
   }

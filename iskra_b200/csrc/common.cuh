@@ -213,7 +213,9 @@ struct iskb_species {
   uint32_t *d_wr = nullptr;                 // [warps+1] first tile of every warp of the advance grid
   uint32_t *d_tcnt = nullptr;               // [ntiles*NCODE] rows per (storage tile, code), rebuilt by every advance
   uint32_t *d_tbase = nullptr;              // [ntiles*NCODE] destination bases of a re-grouping launch
-  uint32_t *d_seg = nullptr;                // scan scratch of the re-group (3*ntiles+2 words + partials)
+  uint32_t *d_seg = nullptr;                // scan scratch of the re-group (3*ntiles+3 words + partials)
+  uint32_t *d_tstart = nullptr, *d_tailbase = nullptr, *d_tn = nullptr;   // tail merge of a MOVE (advance_tile.cu)
+  int64_t tail_rows = 0;                    // rows of the unsorted tail at the latest snapshot (sizes the merge grid)
   uint8_t *d_code = nullptr, *alt_code = nullptr;   // per row: where its position lies relative to its storage tile
   uint2 *d_mlist = nullptr;                 // rows outside their tile's window: (source row, destination row)
   unsigned *d_mlist_n = nullptr;

@@ -72,10 +72,11 @@ __global__ void k_dead_keys(const double *__restrict__ x, int64_t n, uint32_t *k
 
 template <int BITS>
 __global__ void k_radix_hist(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t *hist,
-                             int nblocks) {
+                             int nblocks, const uint32_t *__restrict__ n_dev = nullptr) {
   constexpr int BINS = 1 << BITS;
   constexpr uint32_t MASK = BINS - 1;
   __shared__ uint32_t h[BINS];
+  if (n_dev) n = min(n, (int64_t)*n_dev);   // device-side count (tail merge of a MOVE, advance_tile.cu)
   for (int d = threadIdx.x; d < BINS; d += TPB) h[d] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
@@ -159,10 +160,11 @@ __global__ void k_scan_down(uint32_t *data, int64_t n, const uint32_t *__restric
 template <int BITS>
 __global__ void __launch_bounds__(TPB, 4) k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ idx_in,
                                 uint32_t *keys_out, uint32_t *idx_out, int64_t n, int shift,
-                                const uint32_t *__restrict__ offs, int nblocks) {
+                                const uint32_t *__restrict__ offs, int nblocks, const uint32_t *__restrict__ n_dev = nullptr) {
   constexpr int BINS = 1 << BITS;
   constexpr uint32_t MASK = BINS - 1;
   __shared__ uint32_t wcnt[RS_WARPS][BINS];
+  if (n_dev) n = min(n, (int64_t)*n_dev);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
   for (int k = threadIdx.x; k < RS_WARPS * BINS; k += TPB) (&wcnt[0][0])[k] = 0;
@@ -434,6 +436,42 @@ int32_t sort_by_keys(iskb_species *sp, int64_t n, int bits, uint32_t *perm_out_h
 }
 
 }  // namespace
+
+// Stable sort of (key, position) pairs whose count lives on the device: keys in d_key[0][0 .. min(*n_dev, ncap)).  The grid
+// covers ncap keys.  On return *keys_out / *idx_out are the sorted keys and their source positions, *spare_key / *spare_idx
+// the other half of the scratch (free for the caller).  Used by the tail merge of a MOVE (advance_tile.cu).
+int32_t sort_pairs_device_count(iskb_species *sp, int64_t ncap, const uint32_t *n_dev, int bits, uint32_t **keys_out,
+                                uint32_t **idx_out, uint32_t **spare_key, uint32_t **spare_idx) {
+  iskb_ctx *c = sp->ctx;
+  const int nblocks = (int)((ncap + RS_TILE - 1) / RS_TILE);
+  const int width = (bits + 8) / 9 < (bits + 7) / 8 ? 9 : 8;
+  const int passes = (bits + width - 1) / width;
+  const int64_t hn = ((int64_t)1 << width) * nblocks;
+  int cur = 0;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = width * pass;
+    const uint32_t *idx_in = pass == 0 ? nullptr : sp->d_idx[cur];
+    if (width == 9) k_radix_hist<9><<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], ncap, shift, sp->d_hist, nblocks, n_dev);
+    else k_radix_hist<8><<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], ncap, shift, sp->d_hist, nblocks, n_dev);
+    LAUNCH_CHECK(c);
+    ISKB_TRY(exclusive_scan_u32(c, sp->d_hist, hn, sp->d_hist + hn));
+    if (width == 9)
+      k_radix_scatter<9><<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], idx_in, sp->d_key[cur ^ 1], sp->d_idx[cur ^ 1],
+                                                         ncap, shift, sp->d_hist, nblocks, n_dev);
+    else
+      k_radix_scatter<8><<<nblocks, TPB, 0, c->stream>>>(sp->d_key[cur], idx_in, sp->d_key[cur ^ 1], sp->d_idx[cur ^ 1],
+                                                         ncap, shift, sp->d_hist, nblocks, n_dev);
+    LAUNCH_CHECK(c);
+    cur ^= 1;
+  }
+  *keys_out = sp->d_key[cur];
+  *idx_out = sp->d_idx[cur];
+  *spare_key = sp->d_key[cur ^ 1];
+  *spare_idx = sp->d_idx[cur ^ 1];
+  return ISKB_OK;
+}
+
+int32_t sort_scratch_ensure(iskb_species *sp) { return ensure_sort_scratch(sp); }
 
 int32_t sp_compact(iskb_species *sp) {
   ISKB_TRY(sp_sync_counts(sp));

@@ -162,6 +162,62 @@ def test_tile_rho_of_the_fused_step_matches_oracle(ib):
     assert np.abs(rho_g.ravel(order="F") - pc.c.q * dens).max() <= 1e-12 * np.abs(pc.c.q * dens).max()
 
 
+@pytest.mark.parametrize("vcells,uniform", [(0.3, False), (1.5, True)])
+def test_tile_regroup_merges_the_unsorted_tail_bitexact(ib, vcells, uniform):
+    """Rows appended behind the sorted rows (add!, kinetic.jl:29-37 -- what sources and ionisation do every step) form an
+    unsorted tail; every re-group launch sorts the tail by tile and merges it into the tile segments, so no full sort
+    recurs.  Against the C oracle: same rows bit for bit (matched by id), exactly one full sort in the whole run."""
+    PIC = ib.particle_in_cell
+    nx, ny, dx, dt = 97, 129, 1e-3, 1e-9
+    n, m_add, cap = 120_000, 9_000, 160_000
+    g, cg, pc, pg, cfg = _setup(ib, nx, ny, dx, n, cap, seed=17, vscale=vcells * dx / dt, uniform=uniform)
+    nn = nx * ny
+    rng = np.random.default_rng(5)
+    E = np.zeros(3 * nn)
+    E[: 2 * nn] = rng.standard_normal(2 * nn) * 50.0
+    E3 = E.reshape(3, ny, nx).transpose(2, 1, 0)
+    rt = g._rt
+    pg._push(g)
+    rt.set_after_push(1, 1)
+    rt.set_sort_interval(2)
+
+    def steps(k):
+        for _ in range(k):
+            rt.set_fields(E=E3)
+            rt.step(dt, 1)
+            CO.lib().orc_advance(pc.ref(), C.byref(cg), CO.dp(E), C.c_double(dt), (C.c_int32 * 2)(1, 1))
+    steps(3)
+    for batch in range(3):                                   # three batches of new rows, a few steps apart
+        src = PIC.create_kinetic_species("src%d" % batch, m_add, pg.q, pg.m, 1.0)
+        ax = rng.random(m_add) * (nx - 1) * dx
+        ay = rng.random(m_add) * (ny - 1) * dx
+        av = rng.standard_normal((m_add, 3)) * vcells * dx / dt
+        src.x[:m_add, 0], src.x[:m_add, 1], src.v[:m_add] = ax, ay, av
+        src.np = m_add
+        src._push(g)
+        rt.synchronize()
+        pg._touched_on_device()
+        PIC.add_(src, pg)
+        a0 = pc.np
+        pc.xy[0, a0:a0 + m_add], pc.xy[1, a0:a0 + m_add] = ax, ay
+        pc.v[:, a0:a0 + m_add] = av.T
+        pc.np = a0 + m_add
+        steps(3 + batch)
+    rt.synchronize()
+    pg._touched_on_device()
+    assert pc.np == n + 3 * m_add
+    _check_state(pc, pg, cap)
+    st = (C.c_int64 * 8)()
+    ib._lib.check(rt.lib.iskb_species_sort_stats(pg._h, st))
+    assert st[0] == 1 and st[1] >= 5                          # the tail never asked for a second full sort
+    V = np.zeros(nn)
+    CO.lib().orc_cell_volume(C.byref(cg), CO.dp(V))
+    dens = np.zeros(nn)
+    CO.lib().orc_density(C.byref(cg), pc.ref(), CO.dp(V), CO.dp(dens))
+    n_g = PIC.density(pg, g)
+    assert np.abs(n_g.ravel(order="F") - dens).max() <= 1e-12 * np.abs(dens).max()
+
+
 def test_tile_advance_with_appended_rows_and_mcc(ib):
     """Ionisation appends rows behind the sorted rows (the unsorted tail) while the advance re-groups: counts must add
     up (np = initial + created - discarded), ids stay a permutation, no row is lost or duplicated."""
