@@ -254,6 +254,7 @@ struct iskb_mcc {
   double max_n0 = 0;
   bool uniform_n = false;            // the target density is the same on every node
   double eps_hi = 0;                 // largest tabulated energy
+  double sup_total = 0;              // sup of sum_k sigma_k*g on [0, eps_hi]
   std::vector<double> sup_sigma_g;   // per process: sup of sigma_k*g on [0, eps_hi]
   std::vector<double> sig_last;      // per process: sigma_k at its last knot
   double *d_pk = nullptr;            // device pruning bounds of the current call

@@ -2,11 +2,14 @@
 //
 // The reference draws Nc = N*max_Pt*np candidates *with replacement* from one sequential
 // MersenneTwister stream (mcc.jl:248-251).  Here every particle row gets its own counter-based
-// Philox4x32-10 stream keyed (seed, rank) with counter (row, call#, draw#): a row is a candidate
-// with probability N*max_Pt, then process selection, acceptance test and kinematics follow the
-// reference line by line.  Per particle and process the collision probability is
-// 1 - exp(-n sigma_k g dt) in both schemes; they differ at second order in P, so
-// parity for this step is statistical by construction.
+// Philox4x32-10 stream keyed (seed, rank) with counter (row, call#, draw#).  The reference's null-collision rate is
+// N times larger than it has to be: a candidate picks one of the N processes uniformly and accepts it with
+// P_k / max_Pt, where max_Pt already bounds the SUM over the processes (mcc.jl:27-51, 243).  Here a row is a candidate
+// with probability p_sel = n_max * sup(sum_k sigma_k g) * dt >= sum_k P_k, and a candidate collides with process k
+// when U * p_sel falls into [P_1 + .. + P_{k-1}, P_1 + .. + P_k): per particle and process the collision probability
+// is 1 - exp(-n sigma_k g dt) in both schemes (they differ at second order in P, like the reference's sampling with
+// replacement), but only 1/N of the rows are fetched from memory -- the test phase is bound by exactly
+// that random DRAM traffic (profiles/r2_ncu_mcc.md).  Kinematics follow the reference line by line.
 //
 // Three dense phases with warp-aggregated compaction between them (no divergent fat paths):
 //   k_mcc_select  : the candidate decision touches every row but needs no particle data -- one
@@ -49,17 +52,13 @@ struct MccDev {
   double mr1, mr2;   // mass ratios                    mcc.jl:131-132
   double m_eV;       // mass(source)                   mcc.jl:26
   double dt;
-  double p_cand;     // N * max_Pt
-  uint32_t p_cand_u32;
-  double inv_log1mp;   // 1 / log(1 - p_cand): gaps between candidates are geometric (k_mcc_select_skip)
-  double pk_bound[8];   // sup over eps in [0, eps_hi] of P_k (with n = max density): exact pruning bound
-  double eps_hi;        // largest tabulated energy of all processes
-  double sup_sg[8];     // sup of sigma_k*g on the tables; sig_last: sigma_k at its last knot (Flat() beyond)
-  double sig_last[8];
+  double p_cand;     // host estimate of the candidate probability (grid sizes only)
+  double sup_total;      // sup over the tables of sum_k sigma_k(eps)*g(eps), interior maxima included
+  double sig_last_total; // sum_k sigma_k(last knot): Flat() beyond the tables, so sum sigma*g <= sig_last_total*|v|max there
   double n0max;
   int need_cell;     // 0: the target density is the same on every node and no nu map is asked for
   const unsigned long long *vmax2;   // bits of the species-wide bound of |v|^2 (+inf = unknown)
-  double *pk_dev;       // [8] pruning bounds valid for EVERY live row, computed on the device per call
+  double *pk_dev;       // [0] p_sel, [1] 1/log(1 - p_sel) (geometric gaps), [2] p_sel * 2^32: computed on the device per call
   uint32_t k0, k1;   // Philox key
   uint32_t call;
   unsigned long long *stats;
@@ -137,30 +136,20 @@ __global__ void k_snapshot_begin(int64_t *cnt, unsigned int *lists_cnt, MccDev m
   cnt[CNT_BEGIN] = cnt[CNT_NSLOTS];
   lists_cnt[0] = 0;   // candidates
   lists_cnt[1] = 0;   // colliders
-  // Row-independent pruning bounds: P_k <= pk_dev[k] for every live row, from the species-wide
-  // |v|^2 bound kept by the advance kernels.  Neutral target only (g = |v|); beyond the last knot
-  // sigma is flat, so sigma*g <= sig_last*|v|max.  Unknown (+inf) speed bound => no pruning.
+  // candidate probability: p_sel >= sum_k P_k for EVERY live row.  1 - exp(-a) <= a, so n sup(sum sigma g) dt bounds
+  // the sum; beyond the last knot every sigma_k is flat, so there sum sigma g <= sig_last_total*|v|max with the
+  // species-wide bound of |v|^2 kept by the advance kernels (neutral target: g = |v|).  A row that still exceeds the
+  // bound (unknown speed bound, charged target) raises ISKB_ST_PK in the test phase like mcc.jl:273-279.
   const double v2 = __longlong_as_double((long long)*m.vmax2);
-  for (int k = 0; k < m.N; ++k) {
-    double pk = 2.0;   // > any delta: never prunes
-    if (m.tqm == 0.0 && v2 < 1e300) {
-      const double sg = fmax(m.sup_sg[k], m.sig_last[k] * sqrt(v2));
-      pk = (1.0 - exp(-m.n0max * sg * m.dt)) / m.p_cand * (1.0 + 1e-9) + 1e-300;
-    }
-    m.pk_dev[k] = pk;
-  }
-}
-
-// warp-aggregated append: returns the slot of this lane's item (or -1 when pred is false)
-__device__ __forceinline__ int64_t warp_append(bool pred, unsigned int *counter) {
-  const unsigned m = __ballot_sync(0xffffffffu, pred);
-  if (!m) return -1;
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(m) - 1;
-  unsigned base = 0;
-  if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  return pred ? (int64_t)base + __popc(m & ((1u << lane) - 1u)) : -1;
+  double sg = m.sup_total;
+  if (m.tqm == 0.0 && v2 < 1e300) sg = fmax(sg, m.sig_last_total * sqrt(v2));
+  double psel = m.n0max * sg * m.dt * (1.0 + 1e-9);
+  if (!(psel < 1.0)) psel = 1.0;
+  if (!(psel > 0.0)) psel = 0.0;
+  m.pk_dev[0] = psel;
+  m.pk_dev[1] = psel < 1.0 ? 1.0 / log1p(-psel) : 0.0;   // p = 1: every gap is 0
+  const double p32 = psel * 4294967296.0;
+  m.pk_dev[2] = p32 >= 4294967295.0 ? 4294967295.0 : floor(p32);
 }
 
 constexpr int SEL_CALLS = 4;   // Philox calls (groups of 4 rows) per thread and block iteration: 4096 rows per block iteration
@@ -170,6 +159,7 @@ __global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *list
   __shared__ unsigned int s_base;
   const int64_t n = m.src.cnt[CNT_BEGIN];   // rows that existed when the step started
   const int64_t nq = (n + 3) / 4;
+  const uint32_t p_u32 = (uint32_t)m.pk_dev[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long my_cand = 0;
   for (int64_t q0 = (int64_t)blockIdx.x * (256 * SEL_CALLS); q0 < nq; q0 += (int64_t)gridDim.x * (256 * SEL_CALLS)) {
@@ -185,7 +175,7 @@ __global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *list
         const Philox4 o = philox4x32_10((uint32_t)(q * 4), (uint32_t)((q * 4) >> 32), m.call, 0u, m.k0, m.k1);
 #pragma unroll
         for (int s = 0; s < 4; ++s)
-          if (q * 4 + s < n && o.c[s] < m.p_cand_u32) keep |= 1u << (4 * u + s);
+          if (q * 4 + s < n && o.c[s] < p_u32) keep |= 1u << (4 * u + s);
       }
     }
     const unsigned cnt = __popc(keep);
@@ -240,6 +230,7 @@ __global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int 
   __shared__ unsigned int s_base;
   const int64_t n = m.src.cnt[CNT_BEGIN];   // rows that existed when the step started
   const int64_t nchunk = (n + SKIP_ROWS - 1) / SKIP_ROWS;
+  const double inv_log1mp = m.pk_dev[1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned long long my_cand = 0;
   for (int64_t c0 = (int64_t)blockIdx.x * 256; c0 < nchunk; c0 += (int64_t)gridDim.x * 256) {
@@ -255,7 +246,7 @@ __global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int 
         for (int s = 0; s < 4; ++s) {
           // U uniform on (0,1): 32 bits are ample, the law is cut off at (1-p)^gap = 2^-33
           const double u = ((double)o.c[s] + 0.5) * (1.0 / 4294967296.0);
-          const double gq = log(u) * m.inv_log1mp;
+          const double gq = log(u) * inv_log1mp;
           const int gap = gq < 1048576.0 ? (int)gq : 1048576;
           if (pos < lim) {
             pos += gap + 1;
@@ -323,56 +314,50 @@ __global__ void __launch_bounds__(TEST_TPB) k_mcc_test(MccDev m, unsigned int *l
   const double *teps = ntab ? s_tab : m.eps, *tsig = ntab ? s_tab + ntab : m.sig;
   unsigned int nc = lists_cnt[0];
   if (nc > cand_cap) nc = cand_cap;
+  const double psel = m.pk_dev[0];
   const unsigned int nc_pad = (nc + TEST_TPB - 1) / TEST_TPB * TEST_TPB;   // block-uniform trip count
   for (unsigned int t = blockIdx.x * TEST_TPB + threadIdx.x; t < nc_pad; t += gridDim.x * TEST_TPB) {
     if (t < nc) {
       const int64_t p = cand[t];
       Rng g(p, m.call, m.k0, m.k1, 1u);
-      const double U = g.u01();                                             // :260
-      int k = (int)floor(m.N * U + 1.0);                                    // :261
-      if (k > m.N) k = m.N;
-      const double delta = (double)k / m.N - U;                             // collide iff delta < P_k (:281)
-      // exact early-out before touching the row: P_k <= pk_dev[k] for every live row of the species
-      if (delta < m.pk_dev[k - 1]) {
-        const double vx = m.src.col[2][p], vy = m.src.col[3][p], vz = m.src.col[4][p];
-        const double px = m.src.col[0][p];                          // (dead rows carry x = NaN)
-        const double py = m.need_cell ? m.src.col[1][p] : px;       // uniform target density, no nu map: the cell is not needed
-        bool maybe = true;
-        if (m.tqm == 0.0) {   // second exact early-out with the row's own energy (target at rest: g = |v|)
-          const double g2 = (vx * vx + vy * vy) + vz * vz;
-          if (0.5 * m.m_eV * g2 <= m.eps_hi && delta >= m.pk_bound[k - 1]) maybe = false;
-        }
-        if (maybe && !is_dead(px)) {
-          int i, j;
-          double hx, hy;
-          cell1(px, m.g.dx, m.g.rdx, m.g.fast_div, i, hx);
-          cell1(py, m.g.dy, m.g.rdy, m.g.fast_div, j, hy);
-          if (m.need_cell && !cell_in_grid(i, j, m.g.nx, m.g.ny)) {
-            atomicOr(m.status, ISKB_ST_OOB);
-          } else {
-            const int64_t node = m.need_cell ? (int64_t)(i - 1) + (int64_t)(j - 1) * m.g.nx : 0;   // lower-left node :252-253
-            const double dens = m.need_cell ? m.tn[node] : m.n0max;
-            if (dens >= 0) {                                                      // :254-257
-              const ProcDev pc = m.proc[k - 1];
-              // neutral target (tqm == 0): (0*E)*dt contributes exactly +0 for any finite E, so E is not
-              // read -- the field solve of the previous step may still be writing it on the field stream
-              const double2 e = m.tqm == 0.0 ? make_double2(0.0, 0.0) : m.E2[node];
-              double d[3];
-              d[0] = (m.tqm * e.x) * m.dt - vx;                                   // :266-267
-              d[1] = (m.tqm * e.y) * m.dt - vy;
-              d[2] = (m.tqm * 0.0) * m.dt - vz;
-              const double gg = norm3(d);
-              const double eps = 0.5 * m.m_eV * (gg * gg);                        // :268
+      const double tsel = g.u01() * psel;                                   // process k iff tsel in [cum_{k-1}, cum_k)
+      const double vx = m.src.col[2][p], vy = m.src.col[3][p], vz = m.src.col[4][p];
+      const double px = m.src.col[0][p];                          // (dead rows carry x = NaN)
+      const double py = m.need_cell ? m.src.col[1][p] : px;       // uniform target density, no nu map: the cell is not needed
+      if (!is_dead(px)) {
+        int i, j;
+        double hx, hy;
+        cell1(px, m.g.dx, m.g.rdx, m.g.fast_div, i, hx);
+        cell1(py, m.g.dy, m.g.rdy, m.g.fast_div, j, hy);
+        if (m.need_cell && !cell_in_grid(i, j, m.g.nx, m.g.ny)) {
+          atomicOr(m.status, ISKB_ST_OOB);
+        } else {
+          const int64_t node = m.need_cell ? (int64_t)(i - 1) + (int64_t)(j - 1) * m.g.nx : 0;   // lower-left node :252-253
+          const double dens = m.need_cell ? m.tn[node] : m.n0max;
+          if (dens >= 0) {                                                      // :254-257
+            // neutral target (tqm == 0): (0*E)*dt contributes exactly +0 for any finite E, so E is not
+            // read -- the field solve of the previous step may still be writing it on the field stream
+            const double2 e = m.tqm == 0.0 ? make_double2(0.0, 0.0) : m.E2[node];
+            double d[3];
+            d[0] = (m.tqm * e.x) * m.dt - vx;                                   // :266-267
+            d[1] = (m.tqm * e.y) * m.dt - vy;
+            d[2] = (m.tqm * 0.0) * m.dt - vz;
+            const double gg = norm3(d);
+            const double eps = 0.5 * m.m_eV * (gg * gg);                        // :268
+            double cum = 0.0;
+            int hit = 0;
+            for (int k = 0; k < m.N; ++k) {
+              const ProcDev pc = m.proc[k];
               const double skg = xsec_eval(teps + pc.offset, tsig + pc.offset, pc.len, eps) * gg;
-              double Pk = 1.0 - exp(-dens * skg * m.dt);                          // :271
-              Pk /= m.p_cand;                                                     // :272  N*max_Pt
-              if (Pk > 1.0) atomicOr(m.status, ISKB_ST_PK);                       // :273-279
-              else if (delta < Pk) {                                              // :281  U > k/N - P_k
-                const unsigned slot = atomicAdd(&s_nhit, 1u);                     // block-local staging
-                s_hit[slot] = make_uint2((uint32_t)p, (uint32_t)k);
-                atomicAdd(&s_proc[k - 1], 1u);
-                if (m.nu) atomicAdd(&m.nu[node + (int64_t)(k - 1) * m.g.nx * m.g.ny], 1.0f);   // :283
-              }
+              cum += 1.0 - exp(-dens * skg * m.dt);                             // :271  P_k
+              if (!hit && tsel < cum) hit = k + 1;
+            }
+            if (cum > psel) atomicOr(m.status, ISKB_ST_PK);                     // :273-279: the bound does not hold for this row
+            else if (hit) {
+              const unsigned slot = atomicAdd(&s_nhit, 1u);                     // block-local staging
+              s_hit[slot] = make_uint2((uint32_t)p, (uint32_t)hit);
+              atomicAdd(&s_proc[hit - 1], 1u);
+              if (m.nu) atomicAdd(&m.nu[node + (int64_t)(hit - 1) * m.g.nx * m.g.ny], 1.0f);   // :283
             }
           }
         }
@@ -473,25 +458,15 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st, int 
   m.mr2 = mc->tm / (src->m + mc->tm);
   m.m_eV = mc->m_eV;
   m.dt = dt;
-  m.p_cand = N * max_Pt;
-  const double pc32 = m.p_cand * 4294967296.0;
-  m.p_cand_u32 = pc32 >= 4294967295.0 ? 0xffffffffu : (uint32_t)pc32;
-  m.inv_log1mp = m.p_cand < 1.0 ? 1.0 / log1p(-m.p_cand) : 0.0;   // p = 1: every gap is 0
-  // exact pruning bounds: sup over [0, eps_hi] of sigma_k(eps)*g(eps) (interior maxima of the
-  // piecewise (a + b*eps)*sqrt(eps) included), at the largest target density
-  m.eps_hi = mc->eps_hi;
-  for (int k = 0; k < N; ++k) {
-    const double pk = (1.0 - exp(-mc->max_n0 * mc->sup_sigma_g[(size_t)k] * dt)) / m.p_cand;
-    m.pk_bound[k] = pk * (1.0 + 1e-9) + 1e-300;
-  }
-  for (int k = 0; k < N; ++k) {
-    m.sup_sg[k] = mc->sup_sigma_g[(size_t)k];
-    m.sig_last[k] = mc->sig_last[(size_t)k];
-  }
+  m.sup_total = mc->sup_total;
+  m.sig_last_total = 0.0;
+  for (int k = 0; k < N; ++k) m.sig_last_total += mc->sig_last[(size_t)k];
   m.n0max = mc->max_n0;
+  m.p_cand = std::fmin(1.0, std::fmax(0.0, mc->max_n0 * mc->sup_total * dt));   // the device adds the speed bound (k_snapshot_begin)
   m.need_cell = (mc->uniform_n && !count_nu && mc->tq == 0.0) ? 0 : 1;
   m.vmax2 = src->d_vmax2;
   if (!mc->d_pk) CU_TRY(cudaMalloc(&mc->d_pk, 8 * sizeof(double)));
+  if (mc->max_n0 < 0.0) m.p_cand = 0.0;
   m.pk_dev = mc->d_pk;
   m.k0 = (uint32_t)mc->seed;
   m.k1 = (uint32_t)(mc->seed >> 32) ^ (0x9E3779B9u * (uint32_t)(c->rank + 1));
@@ -515,7 +490,7 @@ int32_t mcc_launch(iskb_mcc *mc, double dt, bool count_nu, cudaStream_t st, int 
   }
   const unsigned int cand_cap = (unsigned int)src->cap;
   const int64_t bound = src->counts_stale ? src->cap : src->h_nslots;
-  int64_t exp_cand = (int64_t)(m.p_cand * (double)bound * 1.05) + 1024;
+  int64_t exp_cand = (int64_t)(m.p_cand * (double)bound * 1.25) + 1024;
   if (phase & 1) {
   k_snapshot_begin<<<1, 1, 0, st>>>(src->d_cnt, mc->d_lists_cnt, m);
   LAUNCH_CHECK(c);
@@ -620,6 +595,24 @@ extern "C" int32_t iskb_mcc_create(iskb_ctx *c, iskb_species *source, double tar
     }
     mc->sup_sigma_g[(size_t)k] = sup;
     mc->sig_last.push_back(sigma[p.offset + p.len - 1]);   // sigma_k(last knot): Flat() beyond the table, so sigma*g <= sig_last*|v|max there
+  }
+  {   // supremum of the SUM over the processes (the candidate probability of the null-collision selection)
+    auto tot = [&](double ee) {
+      double sg = 0.0;
+      for (const MccProc &p : mc->procs) sg += xsec_eval_host(eps + p.offset, sigma + p.offset, p.len, ee);
+      return sg;
+    };
+    double sup = 0.0;
+    for (size_t q = 0; q + 1 < e.size(); ++q) {
+      const double e0 = e[q], e1 = e[q + 1], s0 = tot(e0), s1 = tot(e1);
+      sup = std::fmax(sup, std::fmax(s0 * alpha * sqrt(e0), s1 * alpha * sqrt(e1)));
+      const double b = (s1 - s0) / (e1 - e0), a = s0 - b * e0;   // every sigma_k is linear on [e0, e1]
+      if (b < 0.0 && a > 0.0) {
+        const double es = -a / (3.0 * b);
+        if (es > e0 && es < e1) sup = std::fmax(sup, (a + b * es) * alpha * sqrt(es));
+      }
+    }
+    mc->sup_total = sup;
   }
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   mc->max_n0 = -INFINITY;
