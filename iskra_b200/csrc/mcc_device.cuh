@@ -70,9 +70,11 @@ __device__ void diffuse_reflection(const double *v, Rng &g, double *out) {     /
 
 __device__ __forceinline__ void raise_vmax(const SpDev &s, const double *v) {
   const unsigned long long b = (unsigned long long)__double_as_longlong((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
-  if (b > *(volatile unsigned long long *)s.vmax2) atomicMax(s.vmax2, b);   // almost never taken: same-address atomics are slow
+  // almost never taken: same-address atomics are slow.  Plain L2 loads (not volatile): a stale bound only costs a redundant
+  // atomicMax, and the compiler may issue the two loads ahead of the kinematics instead of at the end of the dependent chain
+  if (b > __ldcg(s.vmax2)) atomicMax(s.vmax2, b);
   const unsigned long long bz = (unsigned long long)__double_as_longlong(v[2] * v[2]);   // kept for the lean advance (advance_tile.cu)
-  if (bz > *(volatile unsigned long long *)s.vz2max) atomicMax(s.vz2max, bz);
+  if (bz > __ldcg(s.vz2max)) atomicMax(s.vz2max, bz);
 }
 
 __device__ bool append_row(const SpDev &s, double x, double y, const double *v, int *status) {
