@@ -882,6 +882,9 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
         }
       }
       if (tile_dir) {
+        if (s->n_in_ufix) {   // nobody asked for the density of the previous step: species.n keeps an older one
+          s->n_in_ufix = false;
+        }
         CU_TRY(cudaMemsetAsync(s->d_ufix, 0, nn * sizeof(long long), c->stream));
         ISKB_TRY(launch_advance_tile(s, dt, c->after_push[0], c->after_push[1], move[k]));
         ISKB_TRY(tile_stats_snapshot(c, s));

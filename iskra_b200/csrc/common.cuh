@@ -215,6 +215,7 @@ struct iskb_species {
   uint32_t *d_tbase = nullptr;              // [ntiles*NCODE] destination bases of a re-grouping launch
   uint32_t *d_seg = nullptr;                // scan scratch of the re-group (3*ntiles+3 words + partials)
   uint32_t *d_tstart = nullptr, *d_tailbase = nullptr, *d_tn = nullptr;   // tail merge of a MOVE (advance_tile.cu)
+  bool n_in_ufix = false;                   // species.n of the last fused step not formed yet (particles.cu)
   int64_t tail_rows = 0;                    // rows of the unsorted tail at the latest snapshot (sizes the merge grid)
   uint8_t *d_code = nullptr, *alt_code = nullptr;   // per row: where its position lies relative to its storage tile
   uint2 *d_mlist = nullptr;                 // rows outside their tile's window: (source row, destination row)

@@ -208,17 +208,21 @@ struct RhoFix {
   long long z[8];
   int ns;
 };
-__global__ void k_rho_fixed_local(RhoFix f, const double *__restrict__ V, double inv_scale, long long *rho_int, int64_t nn) {
+// The per-species densities (species.n) are formed from the fixed-point sums only when somebody asks for them
+// (iskb_species_density_download): two node arrays less to write per step.  One rank: rho directly; several ranks:
+// the integer charge sum first (all-reduced as integers), k_rho_fixed_final afterwards.
+__global__ void k_rho_fixed_local(RhoFix f, const double *__restrict__ V, double q0_over_scale, long long *rho_int, double *rho,
+                                  int64_t nn) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nn; k += (int64_t)gridDim.x * blockDim.x) {
-    const double v = V[k];
     long long r = 0;
-    for (int s = 0; s < f.ns; ++s) {
-      const long long u = f.u[s][k];
-      f.n[s][k] = __ddiv_rn(__dmul_rn((double)u, inv_scale), v);
-      r += f.z[s] * u;
-    }
-    rho_int[k] = r;
+    for (int s = 0; s < f.ns; ++s) r += f.z[s] * f.u[s][k];
+    if (rho) rho[k] = __ddiv_rn(__dmul_rn((double)r, q0_over_scale), V[k]);
+    else rho_int[k] = r;
   }
+}
+__global__ void k_density_fixed(const long long *__restrict__ u, const double *__restrict__ V, double inv_scale, double *n, int64_t nn) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nn; k += (int64_t)gridDim.x * blockDim.x)
+    n[k] = __ddiv_rn(__dmul_rn((double)u[k], inv_scale), V[k]);
 }
 __global__ void k_rho_fixed_final(const long long *__restrict__ rho_int, const double *__restrict__ V, double q0_over_scale,
                                   double *rho, int64_t nn) {
@@ -467,6 +471,13 @@ extern "C" int32_t iskb_species_density_download(iskb_species *sp, double *n_out
   ISKB_TRY(need_grid(sp));
   iskb_ctx *c = sp->ctx;
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  if (sp->n_in_ufix) {   // fused tiled step: the density of the last step still sits in the fixed-point sums
+    int blocks = (int)((nn + TPB - 1) / TPB);
+    if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
+    k_density_fixed<<<blocks, TPB, 0, c->stream>>>(sp->d_ufix, c->d_V, 1.0 / c->fscale, sp->d_n, nn);
+    LAUNCH_CHECK(c);
+    sp->n_in_ufix = false;
+  }
   CU_TRY(cudaMemcpyAsync(n_out, sp->d_n, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(cudaStreamSynchronize(c->stream));
   return ISKB_OK;
@@ -520,13 +531,18 @@ int32_t launch_rho_finalize_fixed(iskb_ctx *c, const std::vector<iskb_species *>
     f.u[s] = sp[s]->d_ufix;
     f.n[s] = sp[s]->d_n;
     f.z[s] = (long long)llround(sp[s]->q / c->q0);
+    sp[s]->n_in_ufix = true;   // species.n of this step: formed on demand from the sums (until the next step zeroes them)
   }
   int blocks = (int)((nn + TPB - 1) / TPB);
   if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
-  k_rho_fixed_local<<<blocks, TPB, 0, c->stream>>>(f, c->d_V, 1.0 / c->fscale, c->d_rho_int, nn);
-  LAUNCH_CHECK(c);
-  if (c->n_ranks > 1) ISKB_TRY(comm_allreduce_sum_i64(c, c->d_rho_int, nn));
-  k_rho_fixed_final<<<blocks, TPB, 0, c->stream>>>(c->d_rho_int, c->d_V, c->q0 / c->fscale, c->d_rho, nn);
+  if (c->n_ranks > 1) {
+    k_rho_fixed_local<<<blocks, TPB, 0, c->stream>>>(f, c->d_V, c->q0 / c->fscale, c->d_rho_int, nullptr, nn);
+    LAUNCH_CHECK(c);
+    ISKB_TRY(comm_allreduce_sum_i64(c, c->d_rho_int, nn));
+    k_rho_fixed_final<<<blocks, TPB, 0, c->stream>>>(c->d_rho_int, c->d_V, c->q0 / c->fscale, c->d_rho, nn);
+  } else {
+    k_rho_fixed_local<<<blocks, TPB, 0, c->stream>>>(f, c->d_V, c->q0 / c->fscale, nullptr, c->d_rho, nn);
+  }
   LAUNCH_CHECK(c);
   return ISKB_OK;
 }

@@ -5,14 +5,19 @@ The reference's `@field` / `@particle` registrations copy every record into a ho
 registration stores a *fetch closure*; the device -> host copy happens only when `save_record` asks for the record
 (on demand), so a step that saves nothing moves nothing.  Record names, openPMD paths and attributes are the reference's.
 
-File format: openPMD-HDF5 (`prefix/hdf5/data<i>.h5`) through h5py when that is installed; this image has no HDF5 library,
-so the default sink writes the same paths and attributes into `prefix/hdf5/data<i>.npz` (+ `.attrs.json`).
+File format: openPMD-HDF5, `prefix/hdf5/data<i>.h5` like hdf5.jl:47-66 -- through h5py when that is installed, else through
+the pure-Python classic-layout writer in hdf5_min.py (this image has no HDF5 library; see the note there about
+validation).  `SINK = "npz"` writes the same paths and attributes into `data<i>.npz` + `.attrs.json` instead.
 """
 import datetime
 import json
 import os
 
 import numpy as np
+
+from . import hdf5_min
+
+SINK = "h5"      # "h5": openPMD-HDF5 (h5py if present, else hdf5_min); "npz": numpy archive + json attributes
 
 # ---- openpmd/root.jl -------------------------------------------------------------------------------
 # unitDimension = powers of (length, mass, time, current, temperature, amount, luminosity); unitSI = 1 for SI strings
@@ -170,6 +175,22 @@ class _H5Sink:
         self.f.close()
 
 
+class _MinH5Sink:
+    """openPMD-HDF5 without an HDF5 library (hdf5_min.Writer)"""
+
+    def __init__(self, path):
+        self.w = hdf5_min.Writer(path + ".h5")
+
+    def write(self, name, array):
+        self.w.write(name, np.asarray(array))
+
+    def set_attrs(self, name, attrs):
+        self.w.set_attrs(name, attrs)
+
+    def close(self):
+        self.w.close()
+
+
 class Iteration:
     """the HDF5 group `data/<i>` handed to the callback of new_iteration  hdf5.jl:47-66"""
 
@@ -181,11 +202,14 @@ def new_iteration(prefix, i, t, dt, f):
     """new_iteration(f, prefix, i, t, dt)  hdf5.jl:47-66: opens prefix/hdf5/data<i>, calls f(it), closes"""
     os.makedirs(os.path.join(prefix, "hdf5"), exist_ok=True)
     path = os.path.join(prefix, "hdf5", "data%d" % i)
-    try:
-        import h5py
-        sink = _H5Sink(path, h5py)
-    except ImportError:
+    if SINK == "npz":
         sink = _NpzSink(path)
+    else:
+        try:
+            import h5py
+            sink = _H5Sink(path, h5py)
+        except ImportError:
+            sink = _MinH5Sink(path)
     base = "data/%d/" % i
     root = dict(ROOT)
     root["date"] = datetime.datetime.now().strftime("%Y/%m/%d %H:%M")
@@ -239,3 +263,24 @@ def load_npz(path):
     arrays = {k.replace("|", "/"): v for k, v in np.load(path + ".npz").items()}
     with open(path + ".attrs.json") as f:
         return arrays, json.load(f)
+
+
+def load(path):
+    """Reads back one iteration written by new_iteration (either sink): {openPMD path: array}, {path: attributes};
+    paths without leading or trailing slashes, "" is the root."""
+    import os as _os
+    if _os.path.exists(path + ".h5"):
+        try:
+            import h5py
+        except ImportError:
+            arrays, attrs = hdf5_min.read(path + ".h5")
+            return ({k.strip("/"): v for k, v in arrays.items()},
+                    {k.strip("/"): {a: (v.tolist() if isinstance(v, np.ndarray) else (v.item() if isinstance(v, np.generic) else v))
+                                    for a, v in d.items()} for k, d in attrs.items()})
+        arrays, attrs = {}, {}
+        with h5py.File(path + ".h5", "r") as f:
+            attrs[""] = dict(f.attrs)
+            f.visititems(lambda n, o: (attrs.__setitem__(n, dict(o.attrs)), arrays.__setitem__(n, o[()]) if hasattr(o, "shape") else None))
+        return arrays, attrs
+    arrays, attrs = load_npz(path)
+    return {k.strip("/"): v for k, v in arrays.items()}, {k.strip("/"): v for k, v in attrs.items()}

@@ -15,7 +15,9 @@ class _S:
     name, np, m, q = "e-", 5, 2.0, -1.0
 
 
-def test_registry_paths_and_attributes(tmp_path):
+@pytest.mark.parametrize("sink", ["h5", "npz"])
+def test_registry_paths_and_attributes(tmp_path, sink, monkeypatch):
+    monkeypatch.setattr(DG, "SINK", sink)
     DG.records.clear()
     calls = []
     rho = np.arange(12.0).reshape(4, 3)
@@ -38,8 +40,9 @@ def test_registry_paths_and_attributes(tmp_path):
         DG.save_record(it, "missing")
     path = DG.new_iteration(str(tmp_path / "run"), 7, 0.5, 0.1, save)
     assert calls == ["rho"]                                       # fetched exactly once, when saved
-    arrays, attrs = DG.load_npz(path)
-    assert path.endswith("hdf5/data7")
+    arrays, attrs = DG.load(path)
+    import os
+    assert path.endswith("hdf5/data7") and os.path.exists(path + "." + sink)
     assert np.array_equal(arrays["data/7/fields/rho"], rho)
     assert np.array_equal(arrays["data/7/fields/E/y"], E[:, :, 1])
     assert np.array_equal(arrays["data/7/particles/e-/position/x"], np.arange(10.0).reshape(5, 2)[:, 0])
@@ -47,12 +50,13 @@ def test_registry_paths_and_attributes(tmp_path):
     assert "data/7/particles/e-/mass" not in arrays                                    # constant record: attributes only
     assert attrs["data/7/particles/e-/mass"]["value"] == 2.0 and attrs["data/7/particles/e-/mass"]["shape"] == [5]
     assert attrs["data/7/particles/e-/weighting"]["macroWeighted"] == 1
-    assert attrs["/"]["openPMD"] == "1.1.0" and attrs["/"]["meshesPath"] == "fields/" and attrs["/"]["particlesPath"] == "particles/"
-    assert attrs["data/7/"] == {"dt": 0.1, "time": 0.5, "timeUnitSI": 1.0}
+    assert attrs[""]["openPMD"] == "1.1.0" and attrs[""]["meshesPath"] == "fields/" and attrs[""]["particlesPath"] == "particles/"
+    assert attrs["data/7"] == {"dt": 0.1, "time": 0.5, "timeUnitSI": 1.0}
     assert attrs["data/7/fields/rho"]["unitDimension"] == [-2.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0]      # C/m^2 = m^-2 s A
     assert attrs["data/7/fields/rho"]["gridSpacing"] == [0.5, 0.25] and attrs["data/7/fields/rho"]["axisLabels"] == "xy"
-    assert attrs["data/7/fields/E/x"]["unitSI"] == 1.0 and attrs["data/7/fields/"]["fieldSolverParameters"] == "Nagel"
-    assert attrs["data/7/particles/"]["particlePush"] == "Boris"
+    assert attrs["data/7/fields/E/x"]["unitSI"] == 1.0 and attrs["data/7/fields"]["fieldSolverParameters"] == "Nagel"
+    assert attrs["data/7/fields"]["fieldBoundary"] == ["open"] * 4
+    assert attrs["data/7/particles"]["particlePush"] == "Boris"
 
 
 @pytest.mark.gpu
@@ -88,7 +92,7 @@ def test_records_of_a_running_solve_equal_the_device_state(tmp_path):
         PIC.solve(cfg, dt, 3, after_push=(ib._lib.BND_WRAP, ib._lib.BND_WRAP))
     finally:
         PIC.hooks.after_loop = lambda *a: None
-    arrays, attrs = DG.load_npz(saved[0])
+    arrays, attrs = DG.load(saved[0])
     rho, phi, E = g._rt.fields()
     b = "data/3/"
     assert np.array_equal(arrays[b + "fields/rho"], rho) and np.array_equal(arrays[b + "fields/phi"], phi)
