@@ -60,6 +60,7 @@ struct TileArgs {
   unsigned nchunks;
   // MOVE with tail merge: destination and key (tile, ntiles = stays in the tail, ntiles + 1 = dead) of tail row ns + k
   const uint32_t *taildst, *tailkey, *tstart, *tailbase, *tn;
+  int mark;                 // write the codes and counts a MOVE needs (always on a MOVE; in place only on the launch before one)
   uint2 *mlist;             // rows left to k_advance_list: (source row, destination row)
   unsigned *mlist_n;
   unsigned mlist_cap;
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
             // code of the new position seen from the tile the row is stored in after this launch
             int dtx = (int)sm.misc[2], dty = (int)sm.misc[3];
             if (MOVE && scode < 9u) { dtx += (int)(scode % 3u) - 1; dty += (int)(scode / 3u) - 1; }
-            ncode = rel_code((i - 1) >> 3, (j - 1) >> 3, dtx, dty);
+            if (MOVE || a.mark) ncode = rel_code((i - 1) >> 3, (j - 1) >> 3, dtx, dty);
             const int ri = i - 1 - ei0, rj = j - 1 - ej0;
             if ((unsigned)ri < (unsigned)(WE - 1) && (unsigned)rj < (unsigned)(WE - 1)) {
               ci = rj * WE + ri;
@@ -382,9 +383,10 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
           __syncwarp();
         }
       }
-      // ---- MARK: code of the new position + counts per (tile the row is stored in, code) ----
-      if (valid) (MOVE ? a.ocode : a.code)[dest] = (uint8_t)ncode;
-      {
+      // ---- MARK: code of the new position + counts per (tile the row is stored in, code); only the launch before a
+      // MOVE (and the MOVE itself) needs them ----
+      if (MOVE || a.mark) {
+        if (valid) (MOVE ? a.ocode : a.code)[dest] = (uint8_t)ncode;
         // counters of this tile and, on a MOVE, of its eight neighbours (rows that move there); rows that go to
         // the tail (FAR) or are parked (DEAD) belong to no tile any more
         const bool counted = valid && scode < 9u;
@@ -396,7 +398,8 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
       // ---- deposit rounds without atomics (advance_fused.cu).  The claim is per cell, so the winners' four corner
       // updates hit distinct nodes in every phase.  Measured alternatives (B200, C5 shard, ms per step): one claim round
       // followed by atomicAdd(double) on shared memory -- a compare-and-swap loop on sm_100a -- for the losers +0.11;
-      // match.any to merge equal cells in registers first costs ~2 cycles per distinct value (profiles/r1_microbench). ----
+      // match.any to merge equal cells in registers first costs ~2 cycles per distinct value (profiles/r1_microbench);
+      // one rho window and claim array per HALF warp (2 instead of 2.9 rounds for rows in random order) +0.09. ----
       {
         unsigned pend = __ballot_sync(0xffffffffu, dep_win);
         double *r0p = sm.rho + ci + (WRS - WE) * (ci >> 4);
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
       if (rb + 32 >= r1) {   // tile finished: flush its window, publish its counts, go to the next non-empty tile
         flush_rho(sm.rho, ei0, ej0, a.g.nx, a.ufix, a.fscale, lane);
         ei0 = NOT_ANCHORED;
+        if (MOVE || a.mark)
         for (int e = lane; e < (MOVE ? 9 * NCODE : NTC_INPLACE); e += 32) {
           const int sc = MOVE ? e / NCODE : CODE_STAY, nc = MOVE ? e % NCODE : e;
           const unsigned c = sm.tc[e];
@@ -842,7 +846,7 @@ int32_t tdir_build(iskb_species *sp, const uint32_t *sorted_keys, int64_t n) {
 }
 
 template <int MX, int MY, bool RZ, bool LEAN>
-static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
+static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move, bool mark) {
   iskb_ctx *c = sp->ctx;
   const TileGeom tg = tile_geom(c->g);
   TileArgs a;
@@ -874,6 +878,7 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
   a.vz2max = sp->d_vz2max;
   a.ticket = sp->d_ticket;
   a.nchunks = (unsigned)advance_chunks(c);
+  a.mark = (move || mark) ? 1 : 0;
   if (LEAN && !sp->vz2_known) {   // bound of v_z^2 (MCC pruning): the lean kernels do not see the column
     CU_TRY(cudaMemsetAsync(sp->d_vz2max, 0, sizeof(unsigned long long), c->stream));
     k_vz2max<<<c->n_sm * 4, 256, 0, c->stream>>>(sp->col[4], sp->d_cnt, sp->d_vz2max);
@@ -912,7 +917,7 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
     LAUNCH_CHECK(c);
     a.taildst = spare_idx; a.tailkey = spare_key; a.tstart = sp->d_tstart; a.tailbase = sp->d_tailbase; a.tn = sp->d_tn;
   }
-  CU_TRY(cudaMemsetAsync(sp->d_tcnt, 0, (size_t)tg.ntiles * NCODE * sizeof(uint32_t), c->stream));
+  if (a.mark) CU_TRY(cudaMemsetAsync(sp->d_tcnt, 0, (size_t)tg.ntiles * NCODE * sizeof(uint32_t), c->stream));
   CU_TRY(cudaMemsetAsync(sp->d_mlist_n, 0, sizeof(unsigned), c->stream));
   CU_TRY(cudaMemsetAsync(sp->d_ticket, 0, sizeof(unsigned), c->stream));
   ISKB_TRY(sp_vmax_reset(sp));
@@ -945,32 +950,32 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move) {
     sp->steps_since_move = 0;
   }
   sp->counts_stale = true;
-  sp->marks_valid = true;
+  sp->marks_valid = a.mark != 0;   // an unmarked launch leaves codes and counts of older positions behind
   return ISKB_OK;
 }
 
 template <bool RZ, bool LEAN>
-static int32_t launch_tile_rz(iskb_species *sp, double dt, int mx, int my, bool move) {
+static int32_t launch_tile_rz(iskb_species *sp, double dt, int mx, int my, bool move, bool mark) {
   switch (mx * 3 + my) {
-    case 0: return launch_tile_modes<0, 0, RZ, LEAN>(sp, dt, move);
-    case 1: return launch_tile_modes<0, 1, RZ, LEAN>(sp, dt, move);
-    case 2: return launch_tile_modes<0, 2, RZ, LEAN>(sp, dt, move);
-    case 3: return launch_tile_modes<1, 0, RZ, LEAN>(sp, dt, move);
-    case 4: return launch_tile_modes<1, 1, RZ, LEAN>(sp, dt, move);
-    case 5: return launch_tile_modes<1, 2, RZ, LEAN>(sp, dt, move);
-    case 6: return launch_tile_modes<2, 0, RZ, LEAN>(sp, dt, move);
-    case 7: return launch_tile_modes<2, 1, RZ, LEAN>(sp, dt, move);
-    default: return launch_tile_modes<2, 2, RZ, LEAN>(sp, dt, move);
+    case 0: return launch_tile_modes<0, 0, RZ, LEAN>(sp, dt, move, mark);
+    case 1: return launch_tile_modes<0, 1, RZ, LEAN>(sp, dt, move, mark);
+    case 2: return launch_tile_modes<0, 2, RZ, LEAN>(sp, dt, move, mark);
+    case 3: return launch_tile_modes<1, 0, RZ, LEAN>(sp, dt, move, mark);
+    case 4: return launch_tile_modes<1, 1, RZ, LEAN>(sp, dt, move, mark);
+    case 5: return launch_tile_modes<1, 2, RZ, LEAN>(sp, dt, move, mark);
+    case 6: return launch_tile_modes<2, 0, RZ, LEAN>(sp, dt, move, mark);
+    case 7: return launch_tile_modes<2, 1, RZ, LEAN>(sp, dt, move, mark);
+    default: return launch_tile_modes<2, 2, RZ, LEAN>(sp, dt, move, mark);
   }
 }
 
 // advance! + density of one species on the tile directory; `move` re-groups the rows on the way out
-int32_t launch_advance_tile(iskb_species *sp, double dt, int mode_x, int mode_y, bool move) {
+int32_t launch_advance_tile(iskb_species *sp, double dt, int mode_x, int mode_y, bool move, bool mark) {
   iskb_ctx *c = sp->ctx;
   ISKB_TRY(fields_join(c));
   if (!sp->tdir_valid) return iskb_fail(ISKB_E_INVALID, "tile directory not built (internal)");
   if (move && !sp->marks_valid) return iskb_fail(ISKB_E_INVALID, "re-group without valid marks (internal)");
-  if (c->pusher_rz) return launch_tile_rz<true, false>(sp, dt, mode_x, mode_y, move);   // the r-z transform rotates (v_x, v_z)
-  if (sp->wg_uniform && c->lean_ok) return launch_tile_rz<false, true>(sp, dt, mode_x, mode_y, move);
-  return launch_tile_rz<false, false>(sp, dt, mode_x, mode_y, move);
+  if (c->pusher_rz) return launch_tile_rz<true, false>(sp, dt, mode_x, mode_y, move, mark);   // the r-z transform rotates (v_x, v_z)
+  if (sp->wg_uniform && c->lean_ok) return launch_tile_rz<false, true>(sp, dt, mode_x, mode_y, move, mark);
+  return launch_tile_rz<false, false>(sp, dt, mode_x, mode_y, move, mark);
 }

@@ -648,8 +648,9 @@ extern "C" int32_t iskb_rho_allreduce(iskb_ctx *c) {
 // rate of the launch two steps back exceeds the threshold, when discarded rows make up more than 2 % of the
 // slots, or after sort_max_interval steps (fixed mode: every sort_interval steps).  The statistics travel
 // through an async copy + event, two steps late, so the host never waits for the step it has just queued.
-static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move) {
+static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move, bool *mark) {
   *move = false;
+  *mark = false;
   if (s->h_tstats) {
     const int slot = (int)(s->tstats_step & 1);   // the older of the two snapshots
     if (s->tstats_pending[slot]) {
@@ -679,17 +680,26 @@ static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move) {
     s->full_sorts++;
     s->miss_rate = s->tail_frac = s->dead_frac = 0.0;
     s->tstats_sort_mark = s->tstats_step;
+    // (the sort left valid marks behind; the launch of this step keeps them valid only if a MOVE is due right after it)
+    *mark = c->sort_miss_threshold > 0.0 ? (c->sort_max_interval > 0 && c->sort_max_interval <= 2 && s->drifting)
+                                         : c->sort_interval <= 2;
     return ISKB_OK;
   }
-  if (!s->marks_valid) return ISKB_OK;
+  // A MOVE needs the codes and counts of the launch before it (MARK).  Launches mark only when a MOVE is due at the
+  // next step: the periodic one is known a step ahead, a MOVE asked for by the statistics waits one marked launch.
   const int64_t since = s->steps_since_move + 1;
+  bool want, soon = false;
   if (c->sort_miss_threshold > 0.0) {
     // a species whose rows hardly ever leave their windows (ions) is not re-grouped just because time has passed
-    *move = s->miss_rate > c->sort_miss_threshold || s->dead_frac > 0.02 || s->tail_frac > 0.01 ||
-            (c->sort_max_interval > 0 && since >= c->sort_max_interval && s->drifting);
+    want = s->miss_rate > c->sort_miss_threshold || s->dead_frac > 0.02 || s->tail_frac > 0.01 ||
+           (c->sort_max_interval > 0 && since >= c->sort_max_interval && s->drifting);
+    soon = c->sort_max_interval > 0 && since + 1 >= c->sort_max_interval && s->drifting;
   } else {
-    *move = since >= c->sort_interval || s->tail_frac > 0.01;
+    want = since >= c->sort_interval || s->tail_frac > 0.01;
+    soon = since + 1 >= c->sort_interval;
   }
+  *move = want && s->marks_valid;
+  *mark = (want && !s->marks_valid) || soon;
   if (*move) {
     s->miss_rate = s->dead_frac = s->tail_frac = 0.0;
     s->tstats_sort_mark = s->tstats_step;
@@ -822,10 +832,10 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
     const bool tile_dir = tiled && !c->tracker && c->adv_path == 0 && c->g.fast_div;   // (a dh with an all-ones significand: simple kernels)
     const bool legacy = tiled && !tile_dir && !c->pusher_rz && (c->tracker || c->adv_path == 1);
     if (c->pusher_rz && c->tracker) return iskb_fail(ISKB_E_UNSUPPORTED, "surface tracker with the axial pusher");
-    bool move[64];
+    bool move[64], mark[64];
     if (species.size() > 64) return iskb_fail(ISKB_E_UNSUPPORTED, "more than 64 species");
     if (tile_dir) {
-      for (size_t k = 0; k < species.size(); ++k) ISKB_TRY(tile_policy(c, species[k], &move[k]));
+      for (size_t k = 0; k < species.size(); ++k) ISKB_TRY(tile_policy(c, species[k], &move[k], &mark[k]));
     } else if (legacy) {
       for (iskb_species *s : species) ISKB_TRY(maybe_sort(c, s));
     }
@@ -886,7 +896,7 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
           s->n_in_ufix = false;
         }
         CU_TRY(cudaMemsetAsync(s->d_ufix, 0, nn * sizeof(long long), c->stream));
-        ISKB_TRY(launch_advance_tile(s, dt, c->after_push[0], c->after_push[1], move[k]));
+        ISKB_TRY(launch_advance_tile(s, dt, c->after_push[0], c->after_push[1], move[k], mark[k]));
         ISKB_TRY(tile_stats_snapshot(c, s));
         s->steps_since_move++;
         s->steps_since_full++;

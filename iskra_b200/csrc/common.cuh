@@ -345,7 +345,7 @@ int32_t launch_advance_tracked(iskb_species *sp, double dt, int mode_x, int mode
 int32_t launch_advance_tiled_tracked(iskb_species *sp, double dt, int mode_x, int mode_y);
 int32_t launch_advance_tracked_list(iskb_species *sp, double dt, int mode_x, int mode_y);
 int32_t poisson_sigma_device(iskb_ctx *ctx, double **d_sigma_out);
-int32_t launch_advance_tile(iskb_species *sp, double dt, int mode_x, int mode_y, bool move);
+int32_t launch_advance_tile(iskb_species *sp, double dt, int mode_x, int mode_y, bool move, bool mark);
 int32_t tdir_build(iskb_species *sp, const uint32_t *sorted_keys, int64_t n);
 void tdir_free(iskb_species *sp);
 void sp_touch(iskb_species *sp);   // rows were changed outside the tile-aware advance: its marks no longer hold
