@@ -60,7 +60,7 @@ struct TileArgs {
   unsigned nchunks;
   // MOVE with tail merge: destination and key (tile, ntiles = stays in the tail, ntiles + 1 = dead) of tail row ns + k
   const uint32_t *taildst, *tailkey, *tstart, *tailbase, *tn;
-  int mark;                 // write the codes and counts a MOVE needs (always on a MOVE; in place only on the launch before one)
+  int mark;                 // write the codes and counts a MOVE needs: only on the launch before one
   uint2 *mlist;             // rows left to k_advance_list: (source row, destination row)
   unsigned *mlist_n;
   unsigned mlist_cap;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
             // code of the new position seen from the tile the row is stored in after this launch
             int dtx = (int)sm.misc[2], dty = (int)sm.misc[3];
             if (MOVE && scode < 9u) { dtx += (int)(scode % 3u) - 1; dty += (int)(scode / 3u) - 1; }
-            if (MOVE || a.mark) ncode = rel_code((i - 1) >> 3, (j - 1) >> 3, dtx, dty);
+            if (a.mark) ncode = rel_code((i - 1) >> 3, (j - 1) >> 3, dtx, dty);
             const int ri = i - 1 - ei0, rj = j - 1 - ej0;
             if ((unsigned)ri < (unsigned)(WE - 1) && (unsigned)rj < (unsigned)(WE - 1)) {
               ci = rj * WE + ri;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
       }
       // ---- MARK: code of the new position + counts per (tile the row is stored in, code); only the launch before a
       // MOVE (and the MOVE itself) needs them ----
-      if (MOVE || a.mark) {
+      if (a.mark) {
         if (valid) (MOVE ? a.ocode : a.code)[dest] = (uint8_t)ncode;
         // counters of this tile and, on a MOVE, of its eight neighbours (rows that move there); rows that go to
         // the tail (FAR) or are parked (DEAD) belong to no tile any more
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256, 3) k_advance_tile(const TileArgs a) {
       if (rb + 32 >= r1) {   // tile finished: flush its window, publish its counts, go to the next non-empty tile
         flush_rho(sm.rho, ei0, ej0, a.g.nx, a.ufix, a.fscale, lane);
         ei0 = NOT_ANCHORED;
-        if (MOVE || a.mark)
+        if (a.mark)
         for (int e = lane; e < (MOVE ? 9 * NCODE : NTC_INPLACE); e += 32) {
           const int sc = MOVE ? e / NCODE : CODE_STAY, nc = MOVE ? e % NCODE : e;
           const unsigned c = sm.tc[e];
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(256) k_advance_list(const TileArgs a) {
             atomicOr(a.status, ISKB_ST_OOB);
           }
         }
-        if (MOVE && key < a.ntiles) {   // MARK of a row that has just joined a tile
+        if (MOVE && a.mark && key < a.ntiles) {   // MARK of a row that has just joined a tile
           a.ocode[dst] = (uint8_t)ncode;
           atomicAdd(&a.tcnt[key * NCODE + ncode], 1u);
         }
@@ -878,7 +878,7 @@ static int32_t launch_tile_modes(iskb_species *sp, double dt, bool move, bool ma
   a.vz2max = sp->d_vz2max;
   a.ticket = sp->d_ticket;
   a.nchunks = (unsigned)advance_chunks(c);
-  a.mark = (move || mark) ? 1 : 0;
+  a.mark = mark ? 1 : 0;
   if (LEAN && !sp->vz2_known) {   // bound of v_z^2 (MCC pruning): the lean kernels do not see the column
     CU_TRY(cudaMemsetAsync(sp->d_vz2max, 0, sizeof(unsigned long long), c->stream));
     k_vz2max<<<c->n_sm * 4, 256, 0, c->stream>>>(sp->col[4], sp->d_cnt, sp->d_vz2max);

@@ -700,6 +700,8 @@ static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move, bool *mark)
   }
   *move = want && s->marks_valid;
   *mark = (want && !s->marks_valid) || soon;
+  if (*move)   // a MOVE marks only when the very next launch is a MOVE again (intervals of one or two steps)
+    *mark = c->sort_miss_threshold > 0.0 ? (c->sort_max_interval > 0 && c->sort_max_interval <= 2 && s->drifting) : c->sort_interval <= 2;
   if (*move) {
     s->miss_rate = s->dead_frac = s->tail_frac = 0.0;
     s->tstats_sort_mark = s->tstats_step;

@@ -665,18 +665,20 @@ __global__ void k_dense_gemv(const double *__restrict__ Ainv, const double *__re
 
 // calculate_electric_field!  generalized_poisson.jl:398-410 ; E2 = (Ex, Ey) per node
 __global__ void k_efield(int nx, int ny, double dx, double dy, const double *__restrict__ phi, double2 *E2) {
-  const int64_t nn = (int64_t)nx * ny;
-  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn;
-       n += (int64_t)gridDim.x * blockDim.x) {
-    const int i = (int)(n % nx), j = (int)(n / nx);
-    double ex, ey;
-    if (i == 0) ex = __ddiv_rn(__dsub_rn(phi[n], phi[n + 1]), dx);                      // :404
-    else if (i == nx - 1) ex = __ddiv_rn(__dsub_rn(phi[n - 1], phi[n]), dx);            // :405
-    else ex = __ddiv_rn(__dsub_rn(phi[n - 1], phi[n + 1]), __dmul_rn(2.0, dx));         // :402
-    if (j == 0) ey = __ddiv_rn(__dsub_rn(phi[n], phi[n + nx]), dy);                     // :406
-    else if (j == ny - 1) ey = __ddiv_rn(__dsub_rn(phi[n - nx], phi[n]), dy);           // :407
-    else ey = __ddiv_rn(__dsub_rn(phi[n - nx], phi[n + nx]), __dmul_rn(2.0, dy));       // :403
-    E2[n] = make_double2(ex, ey);
+  // one block row per grid row (no 64-bit div / mod per node); the quotients stay IEEE divisions like the reference's
+  const double dx2 = __dmul_rn(2.0, dx), dy2 = __dmul_rn(2.0, dy);
+  for (int j = blockIdx.y; j < ny; j += gridDim.y) {
+    const double *row = phi + (int64_t)j * nx;
+    const double *lo = j == 0 ? row : row - nx, *hi = j == ny - 1 ? row : row + nx;
+    const double dyj = (j == 0 || j == ny - 1) ? dy : dy2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+      double ex;
+      if (i == 0) ex = __ddiv_rn(__dsub_rn(row[0], row[1]), dx);                          // :404
+      else if (i == nx - 1) ex = __ddiv_rn(__dsub_rn(row[i - 1], row[i]), dx);            // :405
+      else ex = __ddiv_rn(__dsub_rn(row[i - 1], row[i + 1]), dx2);                        // :402
+      const double ey = __ddiv_rn(__dsub_rn(lo[i], hi[i]), dyj);                          // :403, :406, :407
+      E2[(int64_t)j * nx + i] = make_double2(ex, ey);
+    }
   }
 }
 
@@ -1042,7 +1044,10 @@ int32_t poisson_solve(iskb_ctx *c) {
       LAUNCH_CHECK(c);
     }
   }
-  k_efield<<<blocks_for(c, nn), TPB, 0, c->fstream>>>(nx, ny, c->g.dx, c->g.dy, c->d_phi, c->d_E2);
+  {
+    const dim3 eg((unsigned)std::min((nx + TPB - 1) / TPB, 8), (unsigned)std::min(ny, 65535));
+    k_efield<<<eg, TPB, 0, c->fstream>>>(nx, ny, c->g.dx, c->g.dy, c->d_phi, c->d_E2);
+  }
   LAUNCH_CHECK(c);
   CU_TRY(cudaEventRecord(c->ev_E, c->fstream));
   c->fields_pending = true;
