@@ -35,8 +35,8 @@ def parse():
     ap.add_argument("--particles-per-gpu", type=int, default=None)
     ap.add_argument("--cells", type=int, default=None)
     ap.add_argument("--sort-interval", type=int, default=4)
-    ap.add_argument("--sort-miss", type=float, default=0.005, help="adaptive re-group: window-miss fraction threshold (0 = fixed interval)")
-    ap.add_argument("--sort-max", type=int, default=5, help="re-group a drifting species at least every this many steps")
+    ap.add_argument("--sort-miss", type=float, default=0.02, help="adaptive re-group: window-miss fraction threshold (0 = fixed interval)")
+    ap.add_argument("--sort-max", type=int, default=6, help="re-group a drifting species at least every this many steps")
     ap.add_argument("--sort-full", type=int, default=0, help="force a FULL sort every this many steps (0: only when the unsorted tail exceeds 1 %% of the rows)")
     ap.add_argument("--advance-path", type=int, default=0, help="0: tile directory + incremental re-group, 1: per-warp windows + radix re-group")
     ap.add_argument("--no-lean", action="store_true", help="read and write every column (88 B per particle-step) even where v_z / wg cannot change")

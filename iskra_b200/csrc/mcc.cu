@@ -244,14 +244,13 @@ __global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int 
         const Philox4 o = philox4x32_10((uint32_t)row0, (uint32_t)(row0 >> 32), m.call, 0x40000000u + k, m.k0, m.k1);
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
+          if (pos >= lim) break;   // the FP64 log is most of this kernel: do not take it for gaps nobody needs
           // U uniform on (0,1): 32 bits are ample, the law is cut off at (1-p)^gap = 2^-33
           const double u = ((double)o.c[s] + 0.5) * (1.0 / 4294967296.0);
           const double gq = log(u) * inv_log1mp;
           const int gap = gq < 1048576.0 ? (int)gq : 1048576;
-          if (pos < lim) {
-            pos += gap + 1;
-            if (pos < lim) keep |= 1ull << pos;
-          }
+          pos += gap + 1;
+          if (pos < lim) keep |= 1ull << pos;
         }
       }
     }

@@ -559,12 +559,14 @@ __global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, co
 //   forward   y_q = (r_q - y_{q-1}) * m_q          A = -m_q, B = r_q*m_q      (m precomputed, [k + q*ma])
 //   backward  x_q = y_q - m_q * x_{q+1}            A = -m_q, B = y_q
 //   cyclic    x -= q*f, f = (x_0 + x_{mb-1}/gamma)*qden  (Sherman-Morrison): f is left in fout, the inverse transform applies it
-constexpr int TSEG = 32;   // 2047 modes x 32 segments = 2047 warps: the sweeps are latency bound, they need the loads in flight
-__global__ void __launch_bounds__(32 * TSEG) k_thomas_seg(int ma, int mb, const double *__restrict__ mt, const double *__restrict__ qden,
+constexpr int TSEG = 64;   // segments per system: the sweeps are latency bound, they need the loads in flight
+constexpr int TKL = 16;    // systems (modes) per block: 16 lanes x 8 B = one 128-byte line per row, and 2047 modes give 128 blocks
+                           // (32 modes per block were 64 blocks on 148 SMs: 70 us; this layout: see profiles/r2_launches_c5.txt)
+__global__ void __launch_bounds__(TKL * TSEG) k_thomas_seg(int ma, int mb, const double *__restrict__ mt, const double *__restrict__ qden,
                                                          const double *__restrict__ gam, double *W, double *fout) {
-  __shared__ double sA[TSEG][32], sB[TSEG][32];
-  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
-  const int k = blockIdx.x * 32 + lane;
+  __shared__ double sA[TSEG][TKL], sB[TSEG][TKL];
+  const int lane = threadIdx.x % TKL, seg = threadIdx.x / TKL;
+  const int k = blockIdx.x * TKL + lane;
   const bool act = k < ma;
   const int per = (mb + TSEG - 1) / TSEG;
   const int q0 = seg * per, q1 = min(mb, q0 + per);
@@ -1009,7 +1011,7 @@ int32_t poisson_solve(iskb_ctx *c) {
       k_dst_fft<1, 0><<<(ps.mb + 1) / 2, 512, fpad_host(M) * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, nullptr,
                                                                                 ps.d_w2, dst_scale, io);
       LAUNCH_CHECK(c);
-      k_thomas_seg<<<(ps.ma + 31) / 32, 32 * TSEG, 0, c->fstream>>>(ps.ma, ps.mb, ps.d_cpT, ps.d_qden, ps.d_gam, ps.d_w2,
+      k_thomas_seg<<<(ps.ma + TKL - 1) / TKL, TKL * TSEG, 0, c->fstream>>>(ps.ma, ps.mb, ps.d_cpT, ps.d_qden, ps.d_gam, ps.d_w2,
                                                                    ps.b_cyclic ? ps.d_fvec : nullptr);
       LAUNCH_CHECK(c);
       k_dst_fft<2, 1><<<(ps.mb + 1) / 2, 512, fpad_host(M) * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, ps.d_w2,
