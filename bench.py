@@ -18,6 +18,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: whatever NCCL has to say ("NCCL version ..." with NCCL_DEBUG=VERSION) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

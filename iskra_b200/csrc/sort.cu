@@ -298,6 +298,7 @@ struct Cols {
   double *out[6];
   const uint32_t *id_in;
   uint32_t *id_out;
+  double w0;   // weight a vacated slot is reset to (remove!, kinetic.jl:24)
 };
 
 // Each block moves a CONTIGUOUS range of destination rows: after a re-sort the sources of
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(256) k_permute(Cols c, const uint32_t *__restr
 #pragma unroll
       for (int q = 0; q < 6; ++q) v[q] = c.in[q][s];
       const uint32_t id = c.id_in[s];
+      if (is_dead(v[0])) v[5] = c.w0;   // a parked row is a free slot: whatever is created there later starts with the default weight
 #pragma unroll
       for (int q = 0; q < 6; ++q) c.out[q][k] = v[q];
       c.id_out[k] = id;
@@ -401,6 +403,7 @@ int32_t sort_by_keys(iskb_species *sp, int64_t n, int bits, uint32_t *perm_out_h
   }
   cols.id_in = sp->id;
   cols.id_out = sp->alt_id;
+  cols.w0 = sp->w0;
   constexpr int PERM_CHUNK = 512;
   int blocks = (int)((n + PERM_CHUNK - 1) / PERM_CHUNK);
   if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;

@@ -691,3 +691,31 @@ def test_remove_add_remove_particles_vs_oracle(ib):
     assert np.array_equal(np.sort(s2.id[:m]), np.sort(o2.id[:m]))
     assert np.array_equal(gx, ox) and np.array_equal(gy, oy) and np.array_equal(gw, ow)
     assert np.array_equal(np.sort(s2.id), np.arange(1, cap + 1))
+
+
+def test_vacated_slots_get_the_default_weight(ib):
+    """remove! resets the weight of the slot it vacates (kinetic.jl:24), so rows created later in those slots (add!,
+    sample!, ionisation) start with w0 -- also when the rows were discarded in bulk and parked by a compaction."""
+    PIC = ib.particle_in_cell
+    nx, ny, dx = 33, 33, 1e-3
+    g, cg = _grid_pair(ib, nx, ny, dx)
+    rng = np.random.default_rng(4)
+    n, w0 = 3000, 2.5
+    sp = PIC.create_kinetic_species("s", n + 500, -O.qe, O.me, w0)
+    sp.x[:n, 0] = rng.random(n) * (nx - 1) * dx * 1.3          # a quarter lies beyond the right edge
+    sp.x[:n, 1] = rng.random(n) * (ny - 1) * dx
+    sp.v[:n] = rng.standard_normal((n, 3))
+    sp.wg[:n] = 0.5 + rng.random(n)
+    sp.np = n
+    PIC.discard_(sp, g)
+    kept = sp.np
+    assert 0 < kept < n
+    src = PIC.create_kinetic_species("src", 400, -O.qe, O.me, w0)
+    src.x[:400] = rng.random((400, 2)) * (nx - 1) * dx
+    src.np = 400
+    src._push(g)
+    PIC.add_(src, sp)
+    assert sp.np == kept + 400
+    assert np.all(sp.wg[kept:kept + 400] == w0)
+    assert np.all(sp.wg[kept + 400:] == w0)
+    assert sorted(sp.id.tolist()) == list(range(1, n + 501))
