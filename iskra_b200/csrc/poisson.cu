@@ -153,6 +153,109 @@ bool invert_dense(std::vector<double> &A, int64_t n) {
   return true;
 }
 
+// ---- the same Gauss-Jordan on the device: same pivots (first largest |a| of the column), same arithmetic per element
+// (one multiply and one subtract, never contracted), so the inverse is bit-identical to invert_dense above.  The host version
+// is memory bound on one core (5 s at 2145 unknowns, 5 min at 8125 -- problem/13_seed.jl's grid); here one pivot is a
+// rank-1 update of 2 n^2 elements at HBM speed.
+__global__ void __launch_bounds__(1024) k_gj_pivot(const double *__restrict__ A, int64_t n, int64_t k, double amax, int64_t *piv,
+                                                   double *pval, int *singular) {
+  __shared__ double s_v[1024];
+  __shared__ int64_t s_i[1024];
+  double best = -1.0;
+  int64_t bi = n;
+  for (int64_t r = k + threadIdx.x; r < n; r += 1024) {
+    const double a = fabs(A[r + k * n]);
+    if (a > best) { best = a; bi = r; }          // rows ascend per thread: the first largest stays
+  }
+  s_v[threadIdx.x] = best; s_i[threadIdx.x] = bi;
+  __syncthreads();
+  for (int d = 512; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) {
+      const double ov = s_v[threadIdx.x + d];
+      const int64_t oi = s_i[threadIdx.x + d];
+      if (ov > s_v[threadIdx.x] || (ov == s_v[threadIdx.x] && oi < s_i[threadIdx.x])) { s_v[threadIdx.x] = ov; s_i[threadIdx.x] = oi; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (!(s_v[0] > 1e-13 * amax)) { *singular = 1; *piv = k; *pval = 1.0; }
+    else { *piv = s_i[0]; *pval = A[s_i[0] + k * n]; }
+  }
+}
+// swap rows k and piv, scale row k by 1/pivot; the scaled row is kept contiguous for the update
+__global__ void k_gj_rows(double *A, double *inv, int64_t n, int64_t k, const int64_t *__restrict__ piv, const double *__restrict__ pval,
+                          double *rowA, double *rowI) {
+  const int64_t p = *piv;
+  const double ip = 1.0 / *pval;
+  for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < n; col += (int64_t)gridDim.x * blockDim.x) {
+    double a = A[p + col * n], b = inv[p + col * n];
+    if (p != k) {
+      A[p + col * n] = A[k + col * n];
+      inv[p + col * n] = inv[k + col * n];
+    }
+    a = __dmul_rn(a, ip);
+    b = __dmul_rn(b, ip);
+    A[k + col * n] = a; inv[k + col * n] = b;
+    rowA[col] = a; rowI[col] = b;
+  }
+}
+__global__ void k_gj_colk(const double *__restrict__ A, int64_t n, int64_t k, double *colk) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) colk[r] = A[r + k * n];
+}
+__global__ void __launch_bounds__(256) k_gj_update(double *A, double *inv, int64_t n, int64_t k, const double *__restrict__ colk,
+                                                   const double *__restrict__ rowA, const double *__restrict__ rowI) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n || r == k) return;
+  const double f = colk[r];
+  if (f == 0.0) return;
+  for (int64_t col = blockIdx.y; col < n; col += gridDim.y) {
+    const double ak = rowA[col], ik = rowI[col];
+    if (ak != 0.0) A[r + col * n] = __dsub_rn(A[r + col * n], __dmul_rn(f, ak));
+    if (ik != 0.0) inv[r + col * n] = __dsub_rn(inv[r + col * n], __dmul_rn(f, ik));
+  }
+}
+__global__ void k_gj_identity(double *inv, int64_t n) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) inv[k + k * n] = 1.0;
+}
+
+// A (host, n*n column-major) -> its inverse in a new device buffer *d_inv_out
+int32_t invert_dense_device(iskb_ctx *c, const std::vector<double> &A, int64_t n, double **d_inv_out) {
+  double amax = 0.0;
+  for (double v : A) amax = std::fmax(amax, std::fabs(v));
+  double *dA = nullptr, *dI = nullptr, *d_work = nullptr, *d_pval = nullptr;
+  int64_t *d_piv = nullptr;
+  int *d_sing = nullptr;
+  const size_t bytes = (size_t)(n * n) * sizeof(double);
+  CU_TRY(cudaMalloc(&dA, bytes));
+  CU_TRY(cudaMalloc(&dI, bytes));
+  CU_TRY(cudaMalloc(&d_work, 3 * (size_t)n * sizeof(double)));
+  CU_TRY(cudaMalloc(&d_pval, sizeof(double)));
+  CU_TRY(cudaMalloc(&d_piv, sizeof(int64_t)));
+  CU_TRY(cudaMalloc(&d_sing, sizeof(int)));
+  cudaStream_t st = c->stream;
+  CU_TRY(cudaMemcpyAsync(dA, A.data(), bytes, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemsetAsync(dI, 0, bytes, st));
+  CU_TRY(cudaMemsetAsync(d_sing, 0, sizeof(int), st));
+  const int nb = (int)((n + 255) / 256);
+  k_gj_identity<<<nb, 256, 0, st>>>(dI, n);
+  double *colk = d_work, *rowA = d_work + n, *rowI = d_work + 2 * n;
+  const dim3 ug((unsigned)nb, (unsigned)std::min<int64_t>(n, 1024));
+  for (int64_t k = 0; k < n; ++k) {
+    k_gj_pivot<<<1, 1024, 0, st>>>(dA, n, k, amax, d_piv, d_pval, d_sing);
+    k_gj_rows<<<nb, 256, 0, st>>>(dA, dI, n, k, d_piv, d_pval, rowA, rowI);
+    k_gj_colk<<<nb, 256, 0, st>>>(dA, n, k, colk);
+    k_gj_update<<<ug, 256, 0, st>>>(dA, dI, n, k, colk, rowA, rowI);
+  }
+  int sing = 0;
+  CU_TRY(cudaMemcpyAsync(&sing, d_sing, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  CU_TRY(cudaGetLastError());
+  cudaFree(dA); cudaFree(d_work); cudaFree(d_pval); cudaFree(d_piv); cudaFree(d_sing);
+  if (sing) { cudaFree(dI); return iskb_fail(ISKB_E_SINGULAR, "dense Poisson operator is singular"); }
+  *d_inv_out = dI;
+  return ISKB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: closed-form orthonormal eigen-decompositions of the 1-D operators
 // ---------------------------------------------------------------------------------------------
@@ -756,7 +859,7 @@ static bool classify_axis(bool periodic, bool dir_lo, bool dir_hi, int n, AxisIn
 static int32_t prepare_dense(iskb_ctx *c) {
   PoissonState &ps = c->ps;
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
-  if (nn > 8192) return iskb_fail(ISKB_E_UNSUPPORTED,
+  if (nn > 16384) return iskb_fail(ISKB_E_UNSUPPORTED,
                                   "Dirichlet nodes are not whole edges and the grid (%lld nodes) is too large "
                                   "for the dense fallback", (long long)nn);
   std::vector<double> A, b;
@@ -796,8 +899,13 @@ static int32_t prepare_dense(iskb_ctx *c) {
     rowscale[(size_t)r] = sc;
     for (int64_t col = 0; col < nn; ++col) A[(size_t)(r + col * nn)] *= sc;
   }
-  if (!invert_dense(A, nn)) return iskb_fail(ISKB_E_SINGULAR, "dense Poisson operator is singular");
-  ISKB_TRY(upload(&ps.d_Ainv, A, c->stream));
+  if (nn >= 512) {   // same pivots, same arithmetic, on the device (below that the launches cost more than the host loop)
+    if (ps.d_Ainv) { cudaFree(ps.d_Ainv); ps.d_Ainv = nullptr; }
+    ISKB_TRY(invert_dense_device(c, A, nn, &ps.d_Ainv));
+  } else {
+    if (!invert_dense(A, nn)) return iskb_fail(ISKB_E_SINGULAR, "dense Poisson operator is singular");
+    ISKB_TRY(upload(&ps.d_Ainv, A, c->stream));
+  }
   ISKB_TRY(upload(&ps.d_rowscale, rowscale, c->stream));
   ps.nn_dense = nn;
   if (!ps.d_w1) CU_TRY(cudaMalloc(&ps.d_w1, nn * sizeof(double)));
@@ -1065,6 +1173,18 @@ extern "C" int32_t iskb_debug_invert_dense(double *A, int64_t n) {
   return ISKB_OK;
 }
 
+// test hook: the device-side inversion (bit-identical to the host one); A is n*n column-major, overwritten by its inverse
+extern "C" int32_t iskb_debug_invert_dense_device(iskb_ctx *c, double *A, int64_t n) {
+  if (!c || !A || n < 1) return iskb_fail(ISKB_E_INVALID, "bad arguments");
+  CU_TRY(cudaSetDevice(c->device));
+  std::vector<double> M(A, A + n * n);
+  double *d = nullptr;
+  ISKB_TRY(invert_dense_device(c, M, n, &d));
+  CU_TRY(cudaMemcpy(A, d, (size_t)(n * n) * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return ISKB_OK;
+}
+
 static int32_t sigma_pull(iskb_ctx *c);
 extern "C" int32_t iskb_poisson_create(iskb_ctx *c, double eps0) {
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "iskb_grid_set must be called first");
@@ -1259,7 +1379,7 @@ extern "C" int32_t iskb_phi_at(iskb_ctx *c, int32_t i, int32_t j, double *out) {
 extern "C" int32_t iskb_poisson_set_dense(iskb_ctx *c, const double *A, int64_t nn) {
   if (!c || !c->ps.created || !A) return iskb_fail(ISKB_E_INVALID, "no Poisson solver / operator");
   if (nn != (int64_t)c->g.nx * c->g.ny) return iskb_fail(ISKB_E_INVALID, "operator must be (nx*ny)^2");
-  if (nn > 8192) return iskb_fail(ISKB_E_UNSUPPORTED, "caller-assembled operators use the dense path (at most 8192 nodes)");
+  if (nn > 16384) return iskb_fail(ISKB_E_UNSUPPORTED, "caller-assembled operators use the dense path (at most 16384 nodes)");
   c->ps.custom_A.assign(A, A + nn * nn);
   c->ps.has_custom = true;
   c->ps.structure_dirty = true;

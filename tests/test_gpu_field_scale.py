@@ -99,3 +99,45 @@ def test_field_solve_residual_at_scale(ib, n, periodic, edges, path):
     assert np.abs(E[:, :, 0] - ex).max() <= 1e-13 * np.abs(ex).max()
     assert np.abs(E[:, :, 1] - ey).max() <= 1e-13 * np.abs(ey).max()
     assert np.all(E[:, :, 2] == 0.0)
+
+
+def test_device_dense_inversion_is_bit_identical_to_the_host_one(ib):
+    """The dense Poisson path inverts its operator on the device from 512 unknowns on (csrc/poisson.cu
+    invert_dense_device): same pivots, same arithmetic per element as the host Gauss-Jordan, so the two inverses agree
+    bit for bit -- on a random matrix, on a row-equilibrated axial operator with pivoting, and both flag a singular one."""
+    import ctypes as C
+    import time
+    from iskra_b200 import _lib as L
+    from oracle import axial_oracle as AX
+    g = ib.regular_grids.create_uniform_grid(np.arange(33) * 1e-3, np.arange(33) * 1e-3)      # a context to run on
+    host, dev = L.lib().iskb_debug_invert_dense, L.lib().iskb_debug_invert_dense_device
+    host.argtypes, host.restype = [C.POINTER(C.c_double), C.c_int64], C.c_int32
+    dev.argtypes, dev.restype = [C.c_void_p, C.POINTER(C.c_double), C.c_int64], C.c_int32
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rng = np.random.default_rng(1)
+    n = 700
+    M = rng.standard_normal((n, n))
+    M[rng.random((n, n)) < 0.5] = 0.0                       # zeros exercise the skipped updates
+    M = np.asfortranarray(M + 3.0 * np.diag(rng.standard_normal(n)))
+    A, B = M.copy(order="F"), M.copy(order="F")
+    assert host(dp(A), n) == 0 and dev(g._rt.h, dp(B), n) == 0
+    assert np.array_equal(A, B)
+    assert np.abs(B @ M - np.eye(n)).max() < 1e-8
+    og = AX.AxialGrid2(np.arange(25) * 0.0025, np.arange(49) * 0.0025)                       # 1225 unknowns
+    ps = AX.PoissonSolver(og, 1.0)
+    bot, top = np.zeros((25, 49), bool), np.zeros((25, 49), bool)
+    bot[:, 0], top[:, 48] = True, True
+    O.apply_dirichlet(ps, bot, 0.0)
+    O.apply_dirichlet(ps, top, 1.0)
+    As = np.asfortranarray(ps.A / np.abs(ps.A).max(axis=1)[:, None])
+    A, B = As.copy(order="F"), As.copy(order="F")
+    t0 = time.time()
+    assert host(dp(A), As.shape[0]) == 0
+    t1 = time.time()
+    assert dev(g._rt.h, dp(B), As.shape[0]) == 0
+    t2 = time.time()
+    assert np.array_equal(A, B) and np.abs(B @ As - np.eye(As.shape[0])).max() < 1e-12
+    print("dense inverse of %d unknowns: host %.2f s, device %.2f s" % (As.shape[0], t1 - t0, t2 - t1))
+    S = np.zeros((600, 600), order="F")
+    S[:599, :599] = np.eye(599)
+    assert dev(g._rt.h, dp(S), 600) == L.E_SINGULAR
