@@ -38,15 +38,27 @@ def parse():
     ap.add_argument("--particles-per-gpu", type=int, default=None)
     ap.add_argument("--cells", type=int, default=None)
     ap.add_argument("--sort-interval", type=int, default=4)
-    ap.add_argument("--sort-miss", type=float, default=0.02, help="adaptive re-group: window-miss fraction threshold (0 = fixed interval)")
-    ap.add_argument("--sort-max", type=int, default=6, help="re-group a drifting species at least every this many steps")
-    ap.add_argument("--sort-full", type=int, default=0, help="force a FULL sort every this many steps (0: only when the unsorted tail exceeds 1 %% of the rows)")
+    ap.add_argument("--sort-miss", type=float, default=None, help="adaptive re-group: window-miss fraction threshold (0 = fixed interval)")
+    ap.add_argument("--sort-max", type=int, default=None, help="re-group a drifting species at least every this many steps")
+    ap.add_argument("--sort-full", type=int, default=None, help="force a FULL sort every this many steps (0: only when the unsorted tail exceeds 1 %% of the rows)")
     ap.add_argument("--advance-path", type=int, default=0, help="0: tile directory + incremental re-group, 1: per-warp windows + radix re-group")
     ap.add_argument("--no-lean", action="store_true", help="read and write every column (88 B per particle-step) even where v_z / wg cannot change")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-particles", type=int, default=4_000_000)
-    return ap.parse_args()
+    a = ap.parse_args()
+    # re-ordering policy per advance path (measured sweeps: profiles/r2_policy_sweep.txt, profiles/r1c_ncu_tiled_c5_and_walls.md):
+    # tile directory (c5, c4): a re-group is one out-of-place advance launch -- every 6th step at the latest, no forced full sort;
+    # per-warp windows + radix re-group (surface tracker: walls; --advance-path 1; r-z on small grids): re-group when 3 % of the rows
+    # miss their window, full sort every 64 steps
+    legacy = a.workload in ("walls", "seed") or a.advance_path == 1
+    if a.sort_miss is None:
+        a.sort_miss = 0.03 if legacy else 0.02
+    if a.sort_max is None:
+        a.sort_max = 64 if legacy else 6
+    if a.sort_full is None:
+        a.sort_full = 64 if legacy else 0
+    return a
 
 
 def workload_defaults(a):

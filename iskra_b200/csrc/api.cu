@@ -831,7 +831,13 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
     const bool windows_fit = c->g.nx >= 20 && c->g.ny >= 20;   // small / quasi-1D grids use the simple kernels
     const bool tiled = c->sort_interval > 0 && windows_fit;
     // tile directory path: everything but the surface tracker (which still runs on the per-warp windows of advance_fused.cu)
-    const bool tile_dir = tiled && !c->tracker && c->adv_path == 0 && c->g.fast_div;   // (a dh with an all-ones significand: simple kernels)
+    // A warp owns whole tiles: a grid of a few tiles cannot feed 148 SMs (33 x 65 nodes = 32 tiles: 4e7 rows took 0.7 s per
+    // step).  Many rows on fewer than 2048 tiles go to the kernels that split by rows (per-warp windows / simple kernels).
+    int64_t rows_bound = 0;
+    for (const iskb_species *s : species) rows_bound += s->counts_stale ? s->cap : s->h_nslots;
+    const TileGeom tg0 = tile_geom(c->g);
+    const bool tiles_feed_gpu = (int64_t)tg0.tiles_x * tg0.tiles_y >= 2048 || rows_bound <= 4000000;
+    const bool tile_dir = tiled && !c->tracker && c->adv_path == 0 && c->g.fast_div && tiles_feed_gpu;   // (a dh with an all-ones significand: simple kernels)
     const bool legacy = tiled && !tile_dir && !c->pusher_rz && (c->tracker || c->adv_path == 1);
     if (c->pusher_rz && c->tracker) return iskb_fail(ISKB_E_UNSUPPORTED, "surface tracker with the axial pusher");
     bool move[64], mark[64];
