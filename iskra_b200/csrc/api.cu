@@ -341,7 +341,10 @@ extern "C" int32_t iskb_fields_download(iskb_ctx *c, double *rho, double *phi, d
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   double *tmp = nullptr;
-  if (rho) CU_TRY(cudaMemcpyAsync(rho, c->d_rho, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (rho) {
+    ISKB_TRY(rho_materialize(c));   // fused tiled step: rho is still in the fixed-point sums
+    CU_TRY(cudaMemcpyAsync(rho, c->d_rho, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
   if (phi) CU_TRY(cudaMemcpyAsync(phi, c->d_phi, nn * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (E) {
     CU_TRY(cudaMalloc(&tmp, 3 * nn * sizeof(double)));
@@ -359,7 +362,10 @@ extern "C" int32_t iskb_fields_upload(iskb_ctx *c, const double *rho, const doub
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   double *tmp = nullptr;
-  if (rho) CU_TRY(cudaMemcpyAsync(c->d_rho, rho, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (rho) {
+    c->rho_lazy = false;
+    CU_TRY(cudaMemcpyAsync(c->d_rho, rho, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
   if (phi) CU_TRY(cudaMemcpyAsync(c->d_phi, phi, nn * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (E) {
     CU_TRY(cudaMalloc(&tmp, 2 * nn * sizeof(double)));
@@ -840,6 +846,7 @@ extern "C" int32_t iskb_step(iskb_ctx *c, double dt, int32_t n_steps) {
     const bool tile_dir = tiled && !c->tracker && c->adv_path == 0 && c->g.fast_div && tiles_feed_gpu;   // (a dh with an all-ones significand: simple kernels)
     const bool legacy = tiled && !tile_dir && !c->pusher_rz && (c->tracker || c->adv_path == 1);
     if (c->pusher_rz && c->tracker) return iskb_fail(ISKB_E_UNSUPPORTED, "surface tracker with the axial pusher");
+    c->rho_lazy = false;   // the sums of the previous step are about to be zeroed
     bool move[64], mark[64];
     if (species.size() > 64) return iskb_fail(ISKB_E_UNSUPPORTED, "more than 64 species");
     if (tile_dir) {

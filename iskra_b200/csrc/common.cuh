@@ -156,6 +156,12 @@ struct iskb_ctx {
   double q0 = 0.0;                   // base charge: every active species carries an integer multiple of it (else 0)
   unsigned long long *d_see_counts = nullptr;   // emit! bookkeeping (see.cu)
   long long *d_rho_int = nullptr;    // sum_s Z_s * ufix_s, the quantity that is all-reduced
+  // rho of the last fused tiled step still sits in the fixed-point sums: the FFT solve reads it from there, everybody
+  // else calls rho_materialize first (particles.cu); void once the next step zeroes the sums
+  bool rho_lazy = false;
+  int rho_ns = 0;
+  const long long *rho_u[8] = {nullptr};
+  long long rho_z[8] = {0};
   bool lean_ok = true;               // iskb_set_lean(ctx, 0) forces the full 88 B/row kernels (A/B measurements)
   int adv_path = 0;                  // 0: tile directory (advance_tile.cu), 1: per-warp windows (advance_fused.cu)
   int pusher_rz = 0;                 // BorisPusher{:rz}: transform_from_cartesian_to_cylindrical! after the push
@@ -334,6 +340,7 @@ int32_t launch_advance(iskb_species *sp, double dt, int mode_x, int mode_y, bool
                        int64_t first_slot_from_cnt_begin);
 int32_t launch_rho_finalize(iskb_ctx *ctx, const std::vector<iskb_species *> *list = nullptr);
 int32_t launch_rho_finalize_fixed(iskb_ctx *ctx, const std::vector<iskb_species *> &list);
+int32_t rho_materialize(iskb_ctx *ctx);
 int32_t comm_allreduce_sum_i64(iskb_ctx *ctx, long long *d_buf, int64_t n);
 int32_t sp_vmax_unknown(iskb_species *sp);
 int32_t sp_vmax_reset(iskb_species *sp);

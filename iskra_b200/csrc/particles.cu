@@ -210,7 +210,7 @@ struct RhoFix {
 };
 // The per-species densities (species.n) are formed from the fixed-point sums only when somebody asks for them
 // (iskb_species_density_download): two node arrays less to write per step.  One rank: rho directly; several ranks:
-// the integer charge sum first (all-reduced as integers), k_rho_fixed_final afterwards.
+// the integer charge sum first (all-reduced as integers); rho itself is formed by its consumer (rho_materialize / the FFT solve).
 __global__ void k_rho_fixed_local(RhoFix f, const double *__restrict__ V, double q0_over_scale, long long *rho_int, double *rho,
                                   int64_t nn) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nn; k += (int64_t)gridDim.x * blockDim.x) {
@@ -223,11 +223,6 @@ __global__ void k_rho_fixed_local(RhoFix f, const double *__restrict__ V, double
 __global__ void k_density_fixed(const long long *__restrict__ u, const double *__restrict__ V, double inv_scale, double *n, int64_t nn) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nn; k += (int64_t)gridDim.x * blockDim.x)
     n[k] = __ddiv_rn(__dmul_rn((double)u[k], inv_scale), V[k]);
-}
-__global__ void k_rho_fixed_final(const long long *__restrict__ rho_int, const double *__restrict__ V, double q0_over_scale,
-                                  double *rho, int64_t nn) {
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nn; k += (int64_t)gridDim.x * blockDim.x)
-    rho[k] = __ddiv_rn(__dmul_rn((double)rho_int[k], q0_over_scale), V[k]);
 }
 
 // simple one-thread-per-particle advance! (gather + push + after_push [+ atomic deposit]);
@@ -486,12 +481,14 @@ extern "C" int32_t iskb_species_density_download(iskb_species *sp, double *n_out
 extern "C" int32_t iskb_rho_zero(iskb_ctx *c) {
   if (c) ISKB_TRY(fields_join(c));
   if (!c || !c->has_grid) return iskb_fail(ISKB_E_INVALID, "no grid");
+  c->rho_lazy = false;
   CU_TRY(cudaMemsetAsync(c->d_rho, 0, (int64_t)c->g.nx * c->g.ny * sizeof(double), c->stream));
   return ISKB_OK;
 }
 
 extern "C" int32_t iskb_rho_accumulate(iskb_ctx *c, iskb_species *sp) {
   if (c) ISKB_TRY(fields_join(c));
+  if (c) ISKB_TRY(rho_materialize(c));   // (rho of a fused step may still sit in the fixed-point sums)
   ISKB_TRY(need_grid(sp));
   const int64_t nn = (int64_t)c->g.nx * c->g.ny;
   int blocks = (int)((nn + TPB - 1) / TPB);
@@ -535,15 +532,34 @@ int32_t launch_rho_finalize_fixed(iskb_ctx *c, const std::vector<iskb_species *>
   }
   int blocks = (int)((nn + TPB - 1) / TPB);
   if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
+  // rho itself is formed where it is consumed: by the first transform of the FFT solve on its way in, or by
+  // rho_materialize for everybody else (download, dense / GEMM solve)
   if (c->n_ranks > 1) {
     k_rho_fixed_local<<<blocks, TPB, 0, c->stream>>>(f, c->d_V, c->q0 / c->fscale, c->d_rho_int, nullptr, nn);
     LAUNCH_CHECK(c);
     ISKB_TRY(comm_allreduce_sum_i64(c, c->d_rho_int, nn));
-    k_rho_fixed_final<<<blocks, TPB, 0, c->stream>>>(c->d_rho_int, c->d_V, c->q0 / c->fscale, c->d_rho, nn);
+    c->rho_ns = 1;
+    c->rho_u[0] = c->d_rho_int;
+    c->rho_z[0] = 1;
   } else {
-    k_rho_fixed_local<<<blocks, TPB, 0, c->stream>>>(f, c->d_V, c->q0 / c->fscale, nullptr, c->d_rho, nn);
+    c->rho_ns = f.ns;
+    for (int s = 0; s < f.ns; ++s) { c->rho_u[s] = f.u[s]; c->rho_z[s] = f.z[s]; }
   }
+  c->rho_lazy = true;
+  return ISKB_OK;
+}
+
+int32_t rho_materialize(iskb_ctx *c) {
+  if (!c->rho_lazy) return ISKB_OK;
+  const int64_t nn = (int64_t)c->g.nx * c->g.ny;
+  RhoFix f;
+  f.ns = c->rho_ns;
+  for (int s = 0; s < f.ns; ++s) { f.u[s] = c->rho_u[s]; f.n[s] = nullptr; f.z[s] = c->rho_z[s]; }
+  int blocks = (int)((nn + TPB - 1) / TPB);
+  if (blocks > c->n_sm * 8) blocks = c->n_sm * 8;
+  k_rho_fixed_local<<<blocks, TPB, 0, c->stream>>>(f, c->d_V, c->q0 / c->fscale, nullptr, c->d_rho, nn);
   LAUNCH_CHECK(c);
+  c->rho_lazy = false;
   return ISKB_OK;
 }
 

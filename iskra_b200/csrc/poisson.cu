@@ -549,6 +549,13 @@ struct FftIo {
   const double *qt;     // [k + q*ma] Sherman-Morrison vector (IN = 2, cyclic)
   const double *f;      // [ma] per-mode factor (IN = 2, cyclic); nullptr: no correction
   double *phi;
+  // IN = 1 with rho still in the fixed-point sums of the fused tiled step (particles.cu, rho_materialize): rho is formed on
+  // the way in with the expression of k_rho_fixed_local, so the solve reads the same bits whether or not rho was materialised
+  int ns;               // 0: read io.rho
+  const long long *u[8];
+  long long z[8];
+  const double *V;
+  double q0s;
 };
 
 template <int IN, int OUT>
@@ -564,7 +571,16 @@ __global__ void __launch_bounds__(512) k_dst_fft(int m, int ncols, int log2M, co
       const SolveDims &s = io.s;
       const int na = s.transposed ? s.ny : s.nx, nb = s.transposed ? s.nx : s.ny;
       const int a = s.a0 + p - 1, b = s.b0 + col;
-      double r = -(io.rho[node_of(s, a, b)]) * s.scale;
+      double rho_n;
+      if (io.ns) {
+        const int64_t n = node_of(s, a, b);
+        long long acc = 0;
+        for (int q = 0; q < io.ns; ++q) acc += io.z[q] * io.u[q][n];
+        rho_n = __ddiv_rn(__dmul_rn((double)acc, io.q0s), io.V[n]);
+      } else {
+        rho_n = io.rho[node_of(s, a, b)];
+      }
+      double r = -rho_n * s.scale;
       if (p == 1 || p == m || col == 0 || col == ncols - 1) {   // only the rim of the unknown block can touch a Dirichlet node
         if (a - 1 >= 0 && io.isdir[node_of(s, a - 1, b)]) r -= io.dval[node_of(s, a - 1, b)];
         if (a + 1 < na && io.isdir[node_of(s, a + 1, b)]) r -= io.dval[node_of(s, a + 1, b)];
@@ -1093,6 +1109,8 @@ int32_t poisson_prepare(iskb_ctx *c) {
 // on the field stream; main-stream users of phi / E call fields_join() first.
 int32_t poisson_solve(iskb_ctx *c) {
   ISKB_TRY(poisson_prepare(c));
+  // only the FFT path forms rho from the fixed-point sums on its way in
+  if (c->rho_lazy && !(c->ps.mode != 2 && c->ps.use_fft)) ISKB_TRY(rho_materialize(c));
   CU_TRY(cudaEventRecord(c->ev_rho, c->stream));
   CU_TRY(cudaStreamWaitEvent(c->fstream, c->ev_rho, 0));
   PoissonState &ps = c->ps;
@@ -1116,6 +1134,13 @@ int32_t poisson_solve(iskb_ctx *c) {
     if (ps.use_fft) {
       // rho --DST (rhs formed on the way in)--> w2[k + q*ma] --Thomas per mode, in place--> w2 --DST--> phi
       FftIo io{s, c->d_rho, ps.d_isdir, ps.d_dval, ps.d_qT, ps.b_cyclic ? ps.d_fvec : nullptr, c->d_phi};
+      io.ns = 0;
+      if (c->rho_lazy) {   // (every other path asked for rho_materialize above)
+        io.ns = c->rho_ns;
+        for (int q = 0; q < c->rho_ns; ++q) { io.u[q] = c->rho_u[q]; io.z[q] = c->rho_z[q]; }
+        io.V = c->d_V;
+        io.q0s = c->q0 / c->fscale;
+      }
       k_dst_fft<1, 0><<<(ps.mb + 1) / 2, 512, fpad_host(M) * sizeof(double2), c->fstream>>>(ps.ma, ps.mb, ps.fft_log2M, ps.d_tw, nullptr,
                                                                                 ps.d_w2, dst_scale, io);
       LAUNCH_CHECK(c);
