@@ -18,8 +18,7 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: whatever NCCL has to say ("NCCL version ..." with NCCL_DEBUG=VERSION) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_STDOUT_FD = 1
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -233,7 +232,7 @@ def run_reference(a):
                                                "single_thread_value = one thread, the reference's execution model"),
             "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -443,7 +442,7 @@ def run_b200(a):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(a, ppg, cells, world, {"setup_seconds": build_s}),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -505,8 +504,19 @@ def run_e2e(a, wl, torch, dist, world):
                     "H2D and live-count D2H, download x,v once; bytes are per-rank averages over the steps" % a.steps}
 
 
+def emit(line):
+    """the ONE line of stdout"""
+    sys.stdout.flush()
+    os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     args = parse()
+    # stdout carries exactly one JSON line: until it is printed, file descriptor 1 points at stderr, so whatever a library
+    # writes there ("NCCL version ..." at communicator creation, compiler chatter) cannot get in front of it
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
