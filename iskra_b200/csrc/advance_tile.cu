@@ -103,8 +103,9 @@ __device__ __forceinline__ int clamp_origin(int o, int n, int wn) {
 
 // Everything that leaves a warp goes into a 64-bit FIXED-POINT accumulator (value * fscale, rounded to nearest): integer
 // addition is associative, so the deposited weights do not depend on the order in which warps, tiles, list rows --
-// or ranks, the all-reduce is an integer sum too -- arrive (reproducible rho, run to run and for every
-// number of GPUs).  fscale is a power of two chosen on the host such that the sum over ALL slots of all species fits
+// or ranks, the all-reduce is an integer sum too -- arrive (rho reproducible from run to run, identical on
+// every rank).  The sums INSIDE a warp are FP64, so a different split of the rows over warps or ranks still differs by their
+// rounding (2e-13 of the largest node value between one and two GPUs, tests/multi_gpu).  fscale is a power of two chosen on the host such that the sum over ALL slots of all species fits
 // (api.cu): at the C5 shard one unit is 1.5e-11 of a particle weight, 1e-12 of a typical node value.
 __device__ __forceinline__ void add_fixed(long long *ufix, int64_t node, double v, double fscale) {
   atomicAdd((unsigned long long *)&ufix[node], (unsigned long long)__double2ll_rn(v * fscale));

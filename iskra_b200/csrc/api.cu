@@ -780,6 +780,7 @@ static int32_t fixed_point_setup(iskb_ctx *c, const std::vector<iskb_species *> 
     if (s->wmax <= 0.0) s->wmax = s->w0 > 0.0 ? s->w0 : 1.0;
     total += (fabs(zr) > 1.0 ? fabs(zr) : 1.0) * (double)s->cap * s->wmax;
   }
+  total *= (double)(c->n_ranks > 1 ? c->n_ranks : 1);   // the all-reduce adds the sums of every rank (slices of equal size)
   int e = 0;
   frexp(4.0e18 / total, &e);          // 2^(e-1) <= 4e18 / total < 2^e  (4e18 < 2^62)
   c->fscale = ldexp(1.0, e - 1);

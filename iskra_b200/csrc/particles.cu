@@ -201,7 +201,7 @@ __global__ void k_rho_finalize(RhoFin f, const double *__restrict__ V, double *r
 
 // The same from the fixed-point deposits of the tile path (advance_tile.cu, add_fixed): n_s = (ufix_s / fscale) ./ V and
 // rho from the INTEGER combination sum_s Z_s * ufix_s (Z_s = q_s / q0): that sum is what ranks all-reduce, so rho is
-// bit-identical for every number of GPUs and from run to run.
+// bit-identical on every rank and from run to run.
 struct RhoFix {
   const long long *u[8];
   double *n[8];
