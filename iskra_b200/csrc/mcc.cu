@@ -139,10 +139,12 @@ __global__ void k_snapshot_begin(int64_t *cnt, unsigned int *lists_cnt, MccDev m
   // candidate probability: p_sel >= sum_k P_k for EVERY live row.  1 - exp(-a) <= a, so n sup(sum sigma g) dt bounds
   // the sum; beyond the last knot every sigma_k is flat, so there sum sigma g <= sig_last_total*|v|max with the
   // species-wide bound of |v|^2 kept by the advance kernels (neutral target: g = |v|).  A row that still exceeds the
-  // bound (unknown speed bound, charged target) raises ISKB_ST_PK in the test phase like mcc.jl:273-279.
+  // bound raises ISKB_ST_PK in the test phase like mcc.jl:273-279; without a speed bound (unknown after an upload, charged
+  // target) the rate is the reference's N * max_Pt, so that the error needs what it needs there: P > N times the table bound.
   const double v2 = __longlong_as_double((long long)*m.vmax2);
   double sg = m.sup_total;
   if (m.tqm == 0.0 && v2 < 1e300) sg = fmax(sg, m.sig_last_total * sqrt(v2));
+  else sg *= m.N;   // no speed bound (first call after an upload, charged target): the reference's own margin, N times the table bound
   double psel = m.n0max * sg * m.dt * (1.0 + 1e-9);
   if (!(psel < 1.0)) psel = 1.0;
   if (!(psel > 0.0)) psel = 0.0;
