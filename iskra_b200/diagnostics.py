@@ -159,12 +159,19 @@ class _NpzSink:
             json.dump(self.attrs, f, indent=1, default=str)
 
 
+def _as_julia_wrote_it(array):
+    """HDF5.jl stores a column-major (nx, ny) array with the dimensions reversed: the file holds (ny, nx), x fastest
+    (hdf5.jl:93 `it[g] = output`).  The same bytes from a numpy (nx, ny) array are its transpose in C order."""
+    a = np.asarray(array)
+    return np.ascontiguousarray(a.T) if a.ndim >= 2 else a
+
+
 class _H5Sink:
     def __init__(self, path, h5py):
         self.f = h5py.File(path + ".h5", "w")
 
     def write(self, name, array):
-        self.f[name] = np.asarray(array)
+        self.f[name] = _as_julia_wrote_it(array)
 
     def set_attrs(self, name, attrs):
         node = self.f.require_group(name) if name not in self.f else self.f[name]
@@ -182,7 +189,7 @@ class _MinH5Sink:
         self.w = hdf5_min.Writer(path + ".h5")
 
     def write(self, name, array):
-        self.w.write(name, np.asarray(array))
+        self.w.write(name, _as_julia_wrote_it(array))
 
     def set_attrs(self, name, attrs):
         self.w.set_attrs(name, attrs)
@@ -267,20 +274,21 @@ def load_npz(path):
 
 def load(path):
     """Reads back one iteration written by new_iteration (either sink): {openPMD path: array}, {path: attributes};
-    paths without leading or trailing slashes, "" is the root."""
+    paths without leading or trailing slashes, "" is the root; field arrays come back as (nx, ny) whatever the file order."""
     import os as _os
     if _os.path.exists(path + ".h5"):
         try:
             import h5py
         except ImportError:
             arrays, attrs = hdf5_min.read(path + ".h5")
-            return ({k.strip("/"): v for k, v in arrays.items()},
+            return ({k.strip("/"): (v.T if v.ndim >= 2 else v) for k, v in arrays.items()},     # back to (nx, ny)
                     {k.strip("/"): {a: (v.tolist() if isinstance(v, np.ndarray) else (v.item() if isinstance(v, np.generic) else v))
                                     for a, v in d.items()} for k, d in attrs.items()})
         arrays, attrs = {}, {}
         with h5py.File(path + ".h5", "r") as f:
             attrs[""] = dict(f.attrs)
-            f.visititems(lambda n, o: (attrs.__setitem__(n, dict(o.attrs)), arrays.__setitem__(n, o[()]) if hasattr(o, "shape") else None))
+            f.visititems(lambda n, o: (attrs.__setitem__(n, dict(o.attrs)),
+                                       arrays.__setitem__(n, o[()].T if o.ndim >= 2 else o[()]) if hasattr(o, "shape") else None))
         return arrays, attrs
     arrays, attrs = load_npz(path)
     return {k.strip("/"): v for k, v in arrays.items()}, {k.strip("/"): v for k, v in attrs.items()}
