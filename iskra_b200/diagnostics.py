@@ -68,9 +68,13 @@ class FieldRecord:
 class ParticleRecord:
     """ParticleRecord  openpmd/particles.jl:17-66 ; fetch() -> (np,), (np, k) or a 1-element constant"""
 
-    def __init__(self, units, fetch, species, weighted=False, withcomponents=False, offset=0.0):
+    def __init__(self, units, fetch, species, weighted=False, withcomponents=False, offset=0.0, constant=None):
         dim, unit_si = usi(units)
         self.fetch, self.species, self.withcomponents = fetch, species, withcomponents
+        # the reference decides by the length of the REGISTERED buffer (hdf5.jl:74: a one-element input is a constant
+        # record, a per-row buffer -- full capacity there -- is a dataset even when one particle is alive); here the
+        # registration says it, None = by the size of what fetch returns
+        self.constant = constant
         self.metadata = {"unitDimension": dim, "timeOffset": float(offset), "macroWeighted": 1 if weighted else 0,
                          "weightingPower": 1.0, "unitSI": unit_si}
 
@@ -79,7 +83,7 @@ class ParticleRecord:
         if self.withcomponents:
             zz = np.zeros(data.shape[0])
             return {c: (data[:, n] if data.shape[1] > n else zz) for n, c in enumerate("xyz")}, False
-        return {" ": data}, data.size == 1
+        return {" ": data}, (data.size == 1 if self.constant is None else bool(self.constant))
 
 
 records = {}          # const records = Dict{String, Record}()  Diagnostics.jl:22
@@ -125,14 +129,14 @@ def register_solve_records(config):
             return out
         register_field("n" + sp.name, "1/m^2", dens, grid)
         n = sp.name
-        register_particle(n + "/id", "1", (lambda s=sp: s.id_ro[: s.np].copy()), sp)
-        register_particle(n + "/mass", "kg", (lambda s=sp: np.array([s.m])), sp)
-        register_particle(n + "/charge", "C", (lambda s=sp: np.array([s.q])), sp)
-        register_particle(n + "/weighting", "1", (lambda s=sp: s.wg_ro[: s.np].copy()), sp, weighted=True)
+        register_particle(n + "/id", "1", (lambda s=sp: s.id_ro[: s.np].copy()), sp, constant=False)
+        register_particle(n + "/mass", "kg", (lambda s=sp: np.array([s.m])), sp, constant=True)
+        register_particle(n + "/charge", "C", (lambda s=sp: np.array([s.q])), sp, constant=True)
+        register_particle(n + "/weighting", "1", (lambda s=sp: s.wg_ro[: s.np].copy()), sp, weighted=True, constant=False)
         register_particle(n + "/momentum", "kg*m/s", (lambda s=sp: s.m * s.v_ro[: s.np]), sp, withcomponents=True)
         register_particle(n + "/position", "m", (lambda s=sp: s.x_ro[: s.np].copy()), sp, withcomponents=True)
         for ax in "xyz":
-            register_particle(n + "/positionOffset/" + ax, "m", (lambda: np.array([0.0])), sp)
+            register_particle(n + "/positionOffset/" + ax, "m", (lambda: np.array([0.0])), sp, constant=True)
     for inter in config.interactions:
         if hasattr(inter, "last_nu") and getattr(inter, "collisions", None):
             src = inter.collisions[0].source
