@@ -116,3 +116,8 @@ def advance_circuit_(cir, V, dt):
         cir.i /= (L / dt + R / 2)
     cir.t += dt
     cir.probes = {"Q1": cir.q, "I1": cir.i, "V1": v(t), "Vext": vext}   # @probe :132-135
+    from . import diagnostics as DG
+    for key, units in (("Q1", "C"), ("I1", "A"), ("V1", "V"), ("Vext", "V")):
+        if not isinstance(DG.records.get(key), DG.ProbeRecord) or DG.records[key].owner is not cir:
+            DG.register_probe(key, (lambda k=key: cir.probes[k]), units)
+            DG.records[key].owner = cir

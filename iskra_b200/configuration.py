@@ -14,6 +14,14 @@ class Config:
         self.cells = None
 
 
+def create_fluid_species(name, mu, q, m, mx, my, T=300.0):
+    """create_fluid_species  problem/configuration.jl:104-108"""
+    import numpy as np
+
+    from . import particle_in_cell as PIC
+    return PIC.FluidSpecies(name, mu, q, m, np.zeros((mx, my)), T)
+
+
 def create_electrode(nodes, config_or_solver, grid=None, fixed=False, sigma=0.0, phi=0.0):
     """create_electrode  problem/configuration.jl:22-72.  Two call forms like the reference:
     create_electrode(nodes, config; ...) also registers the electrode with config.tracker (creating the

@@ -86,6 +86,18 @@ class ParticleRecord:
         return {" ": data}, (data.size == 1 if self.constant is None else bool(self.constant))
 
 
+class ProbeRecord:
+    """CircuitProbeRecord  Diagnostics/src/circuit.jl:1-19 ; fetch() -> one number, stored as a 1 x 1 dataset"""
+
+    def __init__(self, units, fetch, offset=0.0):
+        dim, unit_si = usi(units)
+        self.fetch, self.owner = fetch, None
+        self.metadata = {"unitDimension": dim, "timeOffset": float(offset), "axisLabels": ("", ""), "dataOrder": "C",
+                         "geometry": "cartesian", "geometryParameters": "", "gridGlobalOffset": (0.0, 0.0),
+                         "gridSpacing": (0.0, 0.0), "gridUnitSI": 1.0, "fieldSmoothing": "none", "position": (0.0, 0.0),
+                         "unitSI": unit_si}
+
+
 records = {}          # const records = Dict{String, Record}()  Diagnostics.jl:22
 _solve_keys = set()   # keys registered by register_solve_records: dropped when another solve() registers (their closures
                       # hold the previous run's species and device context alive otherwise)
@@ -99,6 +111,11 @@ def register_field(key, units, fetch, grid, **kw):
 def register_particle(key, units, fetch, species, **kw):
     """@particle key units data part [weighted=true] [withcomponents=true]  Diagnostics.jl:41-47"""
     records[key] = ParticleRecord(units, fetch, species, **kw)
+
+
+def register_probe(key, fetch, units, **kw):
+    """@probe key data units  Diagnostics/src/circuit.jl:25-31"""
+    records[key] = ProbeRecord(units, fetch, **kw)
 
 
 def register_solve_records(config):
@@ -241,6 +258,11 @@ def save_record(it, key):
     rec = records.get(key)
     if rec is None:
         print("Couldn't find diagnostic ", key)
+        return
+    if isinstance(rec, ProbeRecord):                                  # hdf5.jl:97-101
+        f = it.base + ROOT["meshesPath"] + key
+        it.sink.write(f, np.full((1, 1), float(rec.fetch())))
+        it.sink.set_attrs(f, rec.metadata)
         return
     if isinstance(rec, FieldRecord):
         f = it.base + ROOT["meshesPath"] + key

@@ -208,6 +208,13 @@ def thermal_speed(T, m):
     return math.sqrt(2 * kB * T / m)
 
 
+class DensitySource:
+    """DensitySource{D}  pic/sources.jl:3-6"""
+
+    def __init__(self, delta, grid):
+        self.delta, self.grid = np.asarray(delta, dtype=np.float64), grid
+
+
 def create_thermalized_beam(species, x, vb, dx=None, T=300.0, rate=1.0):
     """problem/configuration.jl:89-93"""
     vth = thermal_speed(T, species.m) * np.ones(3)
@@ -218,7 +225,13 @@ _sample_calls = [0]
 
 
 def sample_(src, species, dt, grid=None, seed=None):
-    """sample!(src, species, dt)  pic/sources.jl:24-34 -- drawn on the device (Philox)."""
+    """sample!(src, species, dt)  pic/sources.jl:24-34 -- drawn on the device (Philox); a DensitySource adds its
+    density to a fluid species on the host (:36-38)."""
+    if isinstance(src, DensitySource):
+        if not is_fluid(species):
+            raise TypeError("DensitySource feeds a FluidSpecies")
+        species.n += src.delta
+        return
     n = int(math.floor(src.rate * dt))            # :30
     species._push(grid)
     if seed is None:

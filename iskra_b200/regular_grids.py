@@ -38,6 +38,26 @@ class UniformGrid:
 CartesianGrid = UniformGrid
 
 
+class StaggeredGrid:
+    """create_staggered_grid(g)  RegularGrids.jl:99-108: the cell-centred companion of g (nx+1 by ny+1 nodes, shifted by half a
+    cell).  The path never computes on it (config.cells is carried through solve untouched, ParticleInCell.jl:91), so it
+    is a host object: no device context."""
+
+    def __init__(self, g):
+        (x0, y0), (dx, dy), (nx, ny) = g.origin, g.dh, g.n
+        xs = np.linspace(x0 - dx / 2.0, x0 + (nx - 1) * dx + dx / 2.0, nx + 1)
+        ys = np.linspace(y0 - dy / 2.0, y0 + (ny - 1) * dy + dy / 2.0, ny + 1)
+        self.n, self.dh, self.origin, self.bcs = (nx + 1, ny + 1), (dx, dy), (float(xs[0]), float(ys[0])), g.bcs
+        self.coords = (np.repeat(xs[:, None], ny + 1, 1), np.repeat(ys[None, :], nx + 1, 0))
+
+    def size(self):
+        return self.n
+
+
+def create_staggered_grid(g):
+    return StaggeredGrid(g)
+
+
 class AxialGrid(UniformGrid):
     """AxialGrid{2} = UniformGrid{:rz,2}  RegularGrids.jl:18; create_axial_grid :84-97.  Coordinates (r, z); the node
     volumes are rings (cell_volume :40-53), uploaded once."""

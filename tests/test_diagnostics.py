@@ -102,3 +102,30 @@ def test_records_of_a_running_solve_equal_the_device_state(tmp_path):
     assert np.array_equal(np.sort(arrays[b + "particles/e-/id"]), np.arange(1, n + 1))
     assert attrs[b + "particles/e-/charge"]["value"] == -O.qe and attrs[b + "particles/e-/mass"]["shape"] == [n]
     assert arrays[b + "fields/ne-"].shape == (nx, ny) and arrays[b + "fields/ne-"].sum() > 0
+
+
+def test_probe_records_and_small_mirrors(tmp_path):
+    """@probe (Diagnostics/src/circuit.jl), create_staggered_grid (RegularGrids.jl:99-108), DensitySource / create_fluid_species
+    (sources.jl:3-6,36-38; configuration.jl:104-108): host-side pieces of problem/06_circuit.jl."""
+    from iskra_b200 import circuit as CIR
+    from iskra_b200 import configuration as CFG
+    from iskra_b200 import particle_in_cell as PIC
+    from iskra_b200 import regular_grids as RG
+    DG.records.clear()
+    cir = CIR.rlc(CIR.netlist([("V1", 3, "GND", lambda t: 2.0), ("L1", "N", "V", 1e-6), ("C1", "N", "V", 1e-6), ("R1", "G", "N", 1.0)]))
+    CIR.advance_circuit_(cir, None, 1e-8)
+    assert set(DG.records) >= {"Q1", "I1", "V1", "Vext"}
+    path = DG.new_iteration(str(tmp_path / "run"), 1, 1e-8, 1e-8, lambda it: [DG.save_record(it, k) for k in ("Q1", "I1", "V1", "Vext")])
+    arrays, attrs = DG.load(path)
+    assert arrays["data/1/fields/V1"].shape == (1, 1) and arrays["data/1/fields/V1"][0, 0] == 2.0
+    assert arrays["data/1/fields/I1"][0, 0] == cir.i
+    assert attrs["data/1/fields/I1"]["unitDimension"] == [0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0] and attrs["data/1/fields/I1"]["geometry"] == "cartesian"
+
+    class G:
+        origin, dh, n, bcs = (0.0, 1.0), (0.5, 0.25), (5, 3), None
+    c = RG.create_staggered_grid(G())
+    assert c.n == (6, 4) and c.origin == (-0.25, 0.875) and np.isclose(c.coords[0][-1, 0], 2.25) and np.isclose(c.coords[1][0, -1], 1.625)
+    O_ = CFG.create_fluid_species("O", 1.0, 0.0, 8.0, 4, 3)
+    PIC.init(PIC.DensitySource(2.0 * np.ones((4, 3)), None), O_, 1e-8)
+    PIC.init(PIC.DensitySource(0.5 * np.ones((4, 3)), None), O_, 1e-8)
+    assert O_.n.shape == (4, 3) and np.all(O_.n == 2.5) and O_.T == 300.0
