@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("script,steps", [("p10_two_streams", 30), ("p11_rf_discharge", 20), ("p12_avalanche", 20),
-                                          ("p07_boundaries", 20), ("p01_single_electron", 12), ("p06_circuit", 12), ("p13_seed", 12), ("p05_dsmc", 6), ("p_ts", 30)])
+                                          ("p07_boundaries", 20), ("p01_single_electron", 12), ("p04_mcc", 12), ("p06_circuit", 12), ("p13_seed", 12), ("p05_dsmc", 6), ("p_ts", 30)])
 def test_problem_script_runs(script, steps):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "problem", script + ".py"), "--steps", str(steps)],
                        capture_output=True, text=True, timeout=120, cwd=os.path.join(ROOT, "problem"))
