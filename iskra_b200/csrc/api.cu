@@ -710,6 +710,10 @@ static int32_t tile_policy(iskb_ctx *c, iskb_species *s, bool *move, bool *mark)
     *mark = c->sort_miss_threshold > 0.0 ? (c->sort_max_interval > 0 && c->sort_max_interval <= 2 && s->drifting) : c->sort_interval <= 2;
   if (*move) {
     s->miss_rate = s->dead_frac = s->tail_frac = 0.0;
+    // "drifting" is earned again after every re-group (by the first snapshots taken after it): electrons are back over the
+    // bar within two steps, ions -- whose strays pile up over ~100 steps and are then cured by ONE re-group -- are not, so
+    // they do not go on re-grouping every max_interval steps for the rest of the run (a 500-step run showed exactly that)
+    s->drifting = false;
     s->tstats_sort_mark = s->tstats_step;
     s->moves++;
   }
