@@ -232,3 +232,22 @@ def test_header_ctypes_and_julia_glue_agree_on_names_and_arity():
         assert n == decl[name], "Julia ccall of %s lists %d argument types, the header declares %d" % (name, n, decl[name])
         seen.add(name)
     assert len(seen) >= 40
+
+
+def test_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the C oracle on the host cores) needs no GPU; stdout must carry ONE JSON line with the
+    contract's keys, whatever libraries print while it runs (file descriptor 1 points at stderr until the line is out)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-particles", "100000"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "particle-steps/s" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
