@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(256) k_mcc_select(MccDev m, unsigned int *list
 // the C5 step: 3.82 -> 3.77 ms -- most of the selection was already hidden behind the field solve on the
 // side stream.  k_mcc_select (one draw per row) remains for p = 0 / p = 1.  One Philox call yields four gaps;
 // counter = (first row of the chunk, call, 0x40000000 + k), disjoint from the per-row streams (draws 0, 1, ...).
-constexpr int SKIP_ROWS = 64;
+constexpr int SKIP_ROWS = 256;   // rows per thread: one Philox call (four gaps) is the fixed cost of a chunk, and at p = 0.5 % (ions)
+                                 // a 64-row chunk held 0.3 candidates -- the kernel was all fixed cost (30 us for 3e5 candidates)
+constexpr int SKIP_WORDS = SKIP_ROWS / 64;
 __global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int *lists_cnt, uint32_t *cand,
                                                          unsigned int cand_cap) {
   __shared__ unsigned int s_warp[8];
@@ -238,7 +240,9 @@ __global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int 
   for (int64_t c0 = (int64_t)blockIdx.x * 256; c0 < nchunk; c0 += (int64_t)gridDim.x * 256) {
     const int64_t ch = c0 + threadIdx.x;
     const int64_t row0 = ch * SKIP_ROWS;
-    unsigned long long keep = 0;
+    unsigned long long keep[SKIP_WORDS];
+#pragma unroll
+    for (int w = 0; w < SKIP_WORDS; ++w) keep[w] = 0;
     if (ch < nchunk) {
       const int lim = n - row0 < SKIP_ROWS ? (int)(n - row0) : SKIP_ROWS;
       int pos = -1;
@@ -252,11 +256,17 @@ __global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int 
           const double gq = log(u) * inv_log1mp;
           const int gap = gq < 1048576.0 ? (int)gq : 1048576;
           pos += gap + 1;
-          if (pos < lim) keep |= 1ull << pos;
+          if (pos < lim) {
+#pragma unroll
+            for (int w = 0; w < SKIP_WORDS; ++w)
+              if ((pos >> 6) == w) keep[w] |= 1ull << (pos & 63);
+          }
         }
       }
     }
-    const unsigned cnt = __popcll(keep);
+    unsigned cnt = 0;
+#pragma unroll
+    for (int w = 0; w < SKIP_WORDS; ++w) cnt += __popcll(keep[w]);
     my_cand += cnt;
     unsigned incl = cnt;
 #pragma unroll
@@ -277,12 +287,16 @@ __global__ void __launch_bounds__(256) k_mcc_select_skip(MccDev m, unsigned int 
     }
     __syncthreads();
     unsigned slot = s_base + s_warp[warp] + incl - cnt;
-    while (keep) {
-      const int b = __ffsll((long long)keep) - 1;
-      keep &= keep - 1;
-      if (slot < cand_cap) cand[slot] = (uint32_t)(row0 + b);
-      else atomicOr(m.status, ISKB_ST_CAPACITY);
-      ++slot;
+#pragma unroll
+    for (int w = 0; w < SKIP_WORDS; ++w) {
+      unsigned long long kw = keep[w];
+      while (kw) {
+        const int b = __ffsll((long long)kw) - 1;
+        kw &= kw - 1;
+        if (slot < cand_cap) cand[slot] = (uint32_t)(row0 + 64 * w + b);
+        else atomicOr(m.status, ISKB_ST_CAPACITY);
+        ++slot;
+      }
     }
     __syncthreads();
   }
